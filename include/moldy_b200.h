@@ -1,0 +1,220 @@
+/*
+ * moldy_b200.h -- C ABI of libmoldy_b200.so, the B200-native replacement for
+ * Moldy's force-evaluation hot path (force.c / kernel.c / ewald.c).
+ *
+ * Two layers, both plain C (pointers and sizes only, no torch/C++ types):
+ *
+ *  (A) Moldy's own symbols.  Linking libmoldy_b200.so in place of force.o,
+ *      kernel.o and ewald.o (moldy_SOURCES, src/Makefile.am:17) leaves the rest
+ *      of Moldy unchanged.  Each prototype cites the definition it replaces.
+ *  (B) mdb_* : the device-resident engine underneath (A), for callers that keep
+ *      positions and forces in HBM (bench.py `value`, multi-GPU ranks that
+ *      all-reduce the packed result with NCCL).
+ *
+ * Struct layouts below MUST stay byte-identical to src/structs.h / src/defs.h of
+ * the reference (LP64); tests/test_abi.py checks sizeof() against the Python
+ * mirror (moldy_b200/abi.py) and against the reference build.
+ */
+#ifndef MOLDY_B200_H
+#define MOLDY_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ types -- */
+#define MDB_NPOTP   8      /* src/defs.h:126   NPOTP                           */
+#define MDB_L_NAME  128    /* src/defs.h:139   L_name                          */
+#define MDB_L_SPEC  32     /* src/defs.h:140   L_spec                          */
+#define MDB_L_SITE  8      /* src/defs.h:141   L_site                          */
+#define MDB_NPE     2      /* src/defs.h:144   NPE: real-space & Ewald PE      */
+
+typedef double real;                 /* src/defs.h:259 */
+typedef int    boolean;              /* src/defs.h:260 */
+typedef real   vec_mt[3];            /* src/defs.h:266 */
+typedef vec_mt *vec_mp;
+typedef real   quat_mt[4];
+typedef quat_mt *quat_mp;
+typedef real   mat_mt[3][3];
+typedef vec_mt *mat_mp;
+
+/* src/structs.h:27-85.  The hot path reads: cutoff, subcell, alpha, k_cutoff,
+ * strict_cutoff, molpbc, surface_dipole(not here: accel.c), rdf_interval,
+ * begin_rdf, istep, limit. */
+typedef struct {
+   char     title[MDB_L_NAME];
+   long     istep, nsteps;
+   double   step;
+   boolean  print_sysdef, new_sysdef, molpbc, reset_averages;
+   int      scale_options;
+   boolean  surface_dipole, lattice_start;
+   char     sysdef[MDB_L_NAME], restart_file[MDB_L_NAME], save_file[MDB_L_NAME],
+            dump_file[MDB_L_NAME], backup_file[MDB_L_NAME], temp_file[MDB_L_NAME];
+   int      spare[20];
+   boolean  nosymmetric_rot;
+   double   ewald_accuracy;
+   double   ttmass, rtmass;
+   int      const_pressure;
+   int      const_temp;
+   boolean  xdr_write, strict_cutoff;
+   int      strain_mask;
+   int      nbins;
+   unsigned long seed;
+   int      page_width, page_length;
+   long     scale_interval, scale_end, begin_average, average_interval,
+            begin_dump, dump_offset, dump_interval;
+   int      dump_level, maxdumps;
+   long     backup_interval, roll_interval, print_interval, begin_rdf,
+            rdf_interval, rdf_out;
+   double   temp, pressure, pmass, cutoff, subcell, density, alpha, k_cutoff,
+            limit, cpu_limit;
+} contr_mt, *contr_mp;
+
+/* src/structs.h:87-118 */
+typedef struct {
+   int      nsites, nmols, nmols_r, nspecies, max_id, d_of_f;
+   int      ptype, n_potpar;
+   vec_mp   c_of_m, mom, momp;
+   quat_mp  quat, amom, amomp;
+   mat_mp   h, hmom, hmomp;
+   real     ts, tsmom;
+   real     H_0;
+   real     rs, rsmom;
+} system_mt, *system_mp;
+
+/* src/structs.h:121-145 */
+typedef struct {
+   real     inertia[3], mass, dipole, charge;
+   int      nsites, nmols;
+   int      rdof, framework;
+   char     name[MDB_L_SPEC];
+   int      *site_id;
+   vec_mp   p_f_sites;
+   vec_mp   c_of_m, mom, momp;
+   quat_mp  quat, amom, amomp;
+} spec_mt, *spec_mp;
+
+/* src/structs.h:147-154 */
+typedef struct {
+   double   mass, charge;
+   char     name[MDB_L_SITE];
+   int      flag;
+   int      pad;
+} site_mt, *site_mp;
+
+/* src/structs.h:156-161 */
+typedef struct {
+   int      flag;
+   int      pad;
+   real     p[MDB_NPOTP];
+} pot_mt, *pot_mp;
+
+/* src/structs.h:163-184 */
+typedef struct { char *name; int npar; } pots_mt;
+typedef struct { int m, l, t, q; } dim_mt, *dim_mp;
+
+/* ------------------------------------------- (A) Moldy's own entry points -- */
+
+/* Real-space link-cell site-site forces.  Replaces src/force.c:1108-1320
+ * (force_calc) and everything it calls (fill_cells, neighbour_list,
+ * site_neighbour_list, force_inner, kernel).  Accumulates (+=) into
+ * site_force[3][>=nsites], *pe and the upper triangle of stress; reads the
+ * globals `control`, `ithread`, `nthreads` (src/main.c:83-84). */
+void force_calc(real **site, real **site_force, system_mt *system, spec_mt *species,
+                real *chg, pot_mt *potpar, double *pe, mat_mt stress);
+
+/* Reciprocal-space Ewald sum.  Replaces src/ewald.c:280-589.  `pe` is the
+ * caller's pe+1 (src/accel.c:526). */
+void ewald(real **site, real **site_force, system_mp system, spec_mt *species,
+           real *chg, double *pe, real (*stress)[3]);
+
+/* Vector pair-potential evaluation, src/kernel.c:157-463: for j in [jmin,nnab)
+ * forceij[j] = -phi'(r_j)/r_j and *pe += sum phi(r_j).  Runs on the GPU (same
+ * device function as the pair kernel). */
+void kernel(int jmin, int nnab, real *forceij, double *pe, real *r_sqr, real *nab_chg,
+            double chg, double norm, double alpha, int ptype, real **pot);
+
+/* Single-pair potential energy, src/force.c:632-650. */
+double poteval(real *potpar, double r, int ptype, double chgsq);
+
+/* -int_{rc}^{inf} r^2 U(r) dr, src/kernel.c:103-151. */
+double dist_pot(real *potpar, double cutoff, int ptype);
+
+/* Potential name table / parameter dimensions, src/kernel.c:61-84 (read by
+ * input.c, output.c, convert.c). */
+extern const pots_mt potspec[];
+extern const dim_mt  pot_dim[][MDB_NPOTP];
+
+/* --------------------------------------- (B) device-resident engine (mdb_) -- */
+
+typedef struct mdb_engine mdb_engine;
+
+/* Flat description of what force_calc()/ewald() extract from system_mt/spec_mt/
+ * pot_mt/control.  All arrays are HOST pointers, copied by mdb_configure. */
+typedef struct {
+   int          nsites;        /* system->nsites                                    */
+   int          nsites_xf;     /* non-framework sites (frameworks are sorted last)  */
+   int          max_id;        /* system->max_id                                    */
+   int          ptype;         /* system->ptype, index into potspec[]               */
+   int          n_potpar;      /* system->n_potpar                                  */
+   const int    *site_type;    /* [nsites] site id, src/force.c:1185-1191           */
+   const int    *site_mol;     /* [nsites] molecule index (TOO_CLOSE test) or NULL  */
+   const double *chg;          /* [nsites]                                          */
+   const double *potpar;       /* [max_id*max_id*MDB_NPOTP], row i*max_id+j         */
+   double       h[9];          /* MD cell matrix, row major                         */
+   double       cutoff, subcell, alpha, k_cutoff;
+   int          strict_cutoff;
+   int          do_recip;      /* build k-space tables (alpha > ALPHAMIN)           */
+} mdb_config;
+
+/* Result block in HBM: [fx(N) | fy(N) | fz(N) | pe_real, pe_recip | stress[9] | pad]
+ * (stress row-major, upper triangle only, as the reference writes it). */
+#define MDB_OUT_SCALARS 16
+size_t      mdb_out_doubles(int nsites);
+
+mdb_engine *mdb_create(int device);
+void        mdb_destroy(mdb_engine *e);
+const char *mdb_last_error(void);
+
+/* (Re)build everything that depends on the system definition, the cell matrix
+ * and the control cut-offs: link-cell grid, neighbour stencil, k-vector tables.
+ * Returns 0, or -1 with mdb_last_error() set. */
+int  mdb_configure(mdb_engine *e, const mdb_config *cfg);
+
+/* Work partition of this process, the reference's ithread/nthreads
+ * (src/force.c:856, src/ewald.c:495-496). */
+void mdb_set_partition(mdb_engine *e, int ithread, int nthreads);
+
+/* Positions: three HOST rows of nsites doubles (copied H2D on `stream`), or
+ * three DEVICE rows already resident in HBM. */
+int  mdb_set_sites_host(mdb_engine *e, const double *x, const double *y, const double *z, void *stream);
+int  mdb_set_sites_device(mdb_engine *e, const double *dx, const double *dy, const double *dz, void *stream);
+
+/* Hot path.  `d_out` is a DEVICE buffer of mdb_out_doubles(nsites) doubles that
+ * is accumulated into (+=); zero it with mdb_zero_out first.  Everything is
+ * enqueued on `stream` (a cudaStream_t); nothing synchronises. */
+int  mdb_zero_out(mdb_engine *e, double *d_out, void *stream);
+int  mdb_build_cells(mdb_engine *e, void *stream);
+int  mdb_force_real(mdb_engine *e, double *d_out, void *stream);
+int  mdb_force_recip(mdb_engine *e, double *d_out, void *stream);
+
+/* Device->host copy of a result block (synchronises `stream`). */
+int  mdb_read_out(mdb_engine *e, const double *d_out, double *h_out, void *stream);
+
+/* Introspection used by the parity tests and bench.py. */
+int    mdb_grid(const mdb_engine *e, int nxyz[3]);           /* link-cell grid          */
+int    mdb_n_neighbour_cells(const mdb_engine *e);            /* half list, as NABORS/2  */
+int    mdb_n_kvectors(const mdb_engine *e);                   /* nhkl                    */
+int    mdb_get_cell_ids(mdb_engine *e, int *h_cell, void *stream);   /* [nsites], NCELL()  */
+double mdb_pair_count(mdb_engine *e, void *stream);           /* pairs handed to kernel() per step */
+long   mdb_kernel_launches(const mdb_engine *e);              /* our kernels launched so far */
+int    mdb_too_close(mdb_engine *e, int pair[2], void *stream);/* count of r^2<0.25 inter-molecular pairs */
+size_t mdb_sizeof(const char *struct_name);                   /* "contr_mt", "system_mt", ... */
+double mdb_fp64_peak_probe(int device, int iters);            /* measured DFMA rate, flop/s */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOLDY_B200_H */

@@ -1,0 +1,192 @@
+// mdb_cells.cu -- GPU link-cell builder (HBM-bound).
+//
+//   k_cell_ids     per site: scaled coordinate hinv.r, safe binning, cell count
+//   k_scan_*       exclusive scan of the per-cell counts -> cell_start[ncells+1]
+//   k_fill         site -> slot inside its cell (atomic cursor)
+//   k_sort_gather  per cell: order the slots by site index (deterministic),
+//                  gather {x,y,z,q}, type, cell id into cell-sorted SoA
+//
+// Cell assignment must be bit-identical to the reference (src/force.c:119-137
+// cellbin, :460-472 fill_cells, product order of mat_vec_mul src/matrix.c:76-83):
+// all arithmetic uses explicit round-to-nearest mul/add intrinsics so that nvcc
+// cannot contract a*b+c into an FMA.
+#include "mdb_internal.h"
+
+static constexpr int CB = 256;
+
+__device__ __forceinline__ int safe_bin(double rc, int nc, double fnc, double eps, int *bad)
+{
+   const double lo = __dadd_rn(-0.5, eps), hi = __dadd_rn(0.5, -eps);
+   if (rc < lo || rc >= hi) {
+      if (rc < lo && rc >= __dadd_rn(-0.5, -eps))
+         rc = -0.5;
+      else if (rc >= hi && rc <= __dadd_rn(0.5, eps))
+         rc = hi;
+      else
+         *bad = 1;                       // "Co-ordinate out of range in BIN"
+   }
+   int ibin = (int)floor(__dmul_rn(__dadd_rn(rc, 0.5), fnc));
+   if (ibin >= nc || ibin < 0) {
+      *bad = 1;                          // "Rounding problem in BIN"
+      ibin = min(max(ibin, 0), nc - 1);  // keep the run alive; the host reports the error
+   }
+   return ibin;
+}
+
+__global__ void __launch_bounds__(CB) k_cell_ids(CellParams P, int n, const double *__restrict__ x,
+                                                 const double *__restrict__ y, const double *__restrict__ z,
+                                                 int *__restrict__ cell, int *__restrict__ count,
+                                                 unsigned long long *__restrict__ counters)
+{
+   int i = blockIdx.x * CB + threadIdx.x;
+   if (i >= n) return;
+   double a0 = x[i], a1 = y[i], a2 = z[i];
+   double s0 = __dadd_rn(__dadd_rn(__dmul_rn(P.hinv[0], a0), __dmul_rn(P.hinv[1], a1)), __dmul_rn(P.hinv[2], a2));
+   double s1 = __dadd_rn(__dadd_rn(__dmul_rn(P.hinv[3], a0), __dmul_rn(P.hinv[4], a1)), __dmul_rn(P.hinv[5], a2));
+   double s2 = __dadd_rn(__dadd_rn(__dmul_rn(P.hinv[6], a0), __dmul_rn(P.hinv[7], a1)), __dmul_rn(P.hinv[8], a2));
+   int bad = 0;
+   int ix = safe_bin(s0, P.nx, P.fnx, P.eps, &bad);
+   int iy = safe_bin(s1, P.ny, P.fny, P.eps, &bad);
+   int iz = safe_bin(s2, P.nz, P.fnz, P.eps, &bad);
+   int c = iz + P.nz * (iy + P.ny * ix);
+   cell[i] = c;
+   atomicAdd(&count[c], 1);
+   if (bad) atomicAdd(&counters[2], 1ULL);
+}
+
+// ---- exclusive scan, three passes over tiles of SCAN_TILE ints ---------------
+static constexpr int SCAN_T = 256, SCAN_PER = 8, SCAN_TILE = SCAN_T * SCAN_PER;
+
+__device__ __forceinline__ int block_excl_scan(int v, int *total)
+{
+   __shared__ int wsum[SCAN_T / 32];
+   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+   int inc = v;
+#pragma unroll
+   for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+   }
+   if (lane == 31) wsum[w] = inc;
+   __syncthreads();
+   if (w == 0) {
+      int s = lane < SCAN_T / 32 ? wsum[lane] : 0;
+#pragma unroll
+      for (int d = 1; d < SCAN_T / 32; d <<= 1) {
+         int t = __shfl_up_sync(0xffffffffu, s, d);
+         if (lane >= d) s += t;
+      }
+      if (lane < SCAN_T / 32) wsum[lane] = s;
+   }
+   __syncthreads();
+   int base = w ? wsum[w - 1] : 0;
+   *total = wsum[SCAN_T / 32 - 1];
+   __syncthreads();
+   return base + inc - v;
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_scan_tiles(const int *__restrict__ in, int n, int *__restrict__ tile_sum)
+{
+   int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER;
+   int s = 0;
+#pragma unroll
+   for (int j = 0; j < SCAN_PER; j++) s += (base + j < n) ? in[base + j] : 0;
+   int tot;
+   block_excl_scan(s, &tot);
+   if (threadIdx.x == 0) tile_sum[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_scan_sums(int *__restrict__ tile_sum, int ntiles)
+{  // single block; ntiles is small (ncells / 2048)
+   __shared__ int carry;
+   if (threadIdx.x == 0) carry = 0;
+   __syncthreads();
+   for (int b = 0; b < ntiles; b += SCAN_T) {
+      int i = b + threadIdx.x;
+      int v = i < ntiles ? tile_sum[i] : 0;
+      int tot;
+      int ex = block_excl_scan(v, &tot);
+      if (i < ntiles) tile_sum[i] = carry + ex;
+      __syncthreads();
+      if (threadIdx.x == 0) carry += tot;
+      __syncthreads();
+   }
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_scan_apply(const int *__restrict__ in, int n, const int *__restrict__ tile_sum,
+                                                        int *__restrict__ out)
+{
+   int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER;
+   int v[SCAN_PER], s = 0;
+#pragma unroll
+   for (int j = 0; j < SCAN_PER; j++) {
+      v[j] = (base + j < n) ? in[base + j] : 0;
+      s += v[j];
+   }
+   int tot;
+   int ex = block_excl_scan(s, &tot) + tile_sum[blockIdx.x];
+#pragma unroll
+   for (int j = 0; j < SCAN_PER; j++) {
+      if (base + j < n) out[base + j] = ex;
+      ex += v[j];
+   }
+   if (base <= n - 1 && n - 1 < base + SCAN_PER) out[n] = ex;   // cell_start[ncells] = nsites
+}
+
+__global__ void __launch_bounds__(CB) k_fill(int n, const int *__restrict__ cell, const int *__restrict__ start,
+                                             int *__restrict__ cursor, int *__restrict__ order)
+{
+   int i = blockIdx.x * CB + threadIdx.x;
+   if (i >= n) return;
+   int c = cell[i];
+   order[start[c] + atomicAdd(&cursor[c], 1)] = i;
+}
+
+__global__ void __launch_bounds__(CB) k_sort_gather(int ncells, const int *__restrict__ start, int *__restrict__ order,
+                                                    const double *__restrict__ x, const double *__restrict__ y,
+                                                    const double *__restrict__ z, const double *__restrict__ q,
+                                                    const int *__restrict__ type, double4 *__restrict__ posq,
+                                                    int *__restrict__ stype, int *__restrict__ scell)
+{
+   int c = blockIdx.x * CB + threadIdx.x;
+   if (c >= ncells) return;
+   int b = start[c], e = start[c + 1];
+   for (int i = b + 1; i < e; i++) {     // insertion sort, a handful of sites per cell
+      int v = order[i], j = i - 1;
+      while (j >= b && order[j] > v) {
+         order[j + 1] = order[j];
+         j--;
+      }
+      order[j + 1] = v;
+   }
+   for (int s = b; s < e; s++) {
+      int o = order[s];
+      posq[s] = make_double4(x[o], y[o], z[o], q[o]);
+      stype[s] = type[o];
+      scell[s] = c;
+   }
+}
+
+int mdb_launch_cells(mdb_engine *e, cudaStream_t st)
+{
+   const int n = e->cfg.nsites, nc = e->ncells;
+   CellParams P;
+   for (int i = 0; i < 9; i++) P.hinv[i] = e->T.hinv[i];
+   P.nx = e->T.nx; P.ny = e->T.ny; P.nz = e->T.nz; P.ncells = nc;
+   P.fnx = P.nx; P.fny = P.ny; P.fnz = P.nz;
+   P.eps = 8.0 * 2.220446049250313e-16;                 // 8 * precision(), src/force.c:437
+   MDB_CUDA(cudaMemsetAsync(e->d_count, 0, sizeof(int) * (size_t)(nc + 1), st));
+   k_cell_ids<<<(n + CB - 1) / CB, CB, 0, st>>>(P, n, e->d_x, e->d_y, e->d_z, e->d_cell, e->d_count, e->d_counters);
+   int ntiles = (nc + SCAN_TILE - 1) / SCAN_TILE;
+   k_scan_tiles<<<ntiles, SCAN_T, 0, st>>>(e->d_count, nc, e->d_scan_tmp);
+   k_scan_sums<<<1, SCAN_T, 0, st>>>(e->d_scan_tmp, ntiles);
+   k_scan_apply<<<ntiles, SCAN_T, 0, st>>>(e->d_count, nc, e->d_scan_tmp, e->d_start);
+   MDB_CUDA(cudaMemsetAsync(e->d_count, 0, sizeof(int) * (size_t)(nc + 1), st));   // now the fill cursor
+   k_fill<<<(n + CB - 1) / CB, CB, 0, st>>>(n, e->d_cell, e->d_start, e->d_count, e->d_order);
+   k_sort_gather<<<(nc + CB - 1) / CB, CB, 0, st>>>(nc, e->d_start, e->d_order, e->d_x, e->d_y, e->d_z, e->d_chg,
+                                                   e->d_type, e->d_posq, e->d_stype, e->d_scell);
+   e->launches += 6;
+   MDB_CUDA(cudaGetLastError());
+   e->cells_valid = true;
+   return 0;
+}

@@ -1,0 +1,341 @@
+// mdb_engine.cu -- layer (B) of include/moldy_b200.h: the device-resident engine.
+// Owns every HBM buffer of the hot path; all work is enqueued on the caller's
+// stream.  HBM layout (N sites, C link cells):
+//   x,y,z[N]            positions, original site order (caller's rows)
+//   type[N], mol[N], chg[N], ptab[max_id^2][8]          static per system
+//   cell[N], count[C+1], start[C+1], order[N]           link-cell tables
+//   posq[N] (double4 x,y,z,q), stype[N], scell[N]       cell-sorted SoA, z-fastest cell order
+//   runs[], hk[], slot tables, coef[nslots][8], ppart[slabs][nslots][4]
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include "mdb_internal.h"
+
+#define FREE(p) do { if (p) { cudaFree(p); (p) = nullptr; } } while (0)
+
+extern "C" size_t mdb_out_doubles(int nsites) { return 3 * (size_t)nsites + MDB_OUT_SCALARS; }
+
+extern "C" mdb_engine *mdb_create(int device)
+{
+   int ndev = 0;
+   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) {
+      mdb_set_error("mdb_create: no such CUDA device (libmoldy_b200 has no CPU path)");
+      return nullptr;
+   }
+   if (cudaSetDevice(device) != cudaSuccess) {
+      mdb_set_error("mdb_create: cudaSetDevice failed");
+      return nullptr;
+   }
+   mdb_engine *e = new mdb_engine();
+   e->device = device;
+   if (cudaMalloc(&e->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess) {
+      mdb_set_error("mdb_create: cudaMalloc failed");
+      delete e;
+      return nullptr;
+   }
+   cudaMemset(e->d_counters, 0, 8 * sizeof(unsigned long long));
+   return e;
+}
+
+static void free_system(mdb_engine *e)
+{
+   FREE(e->d_type); FREE(e->d_mol); FREE(e->d_chg); FREE(e->d_ptab);
+   FREE(e->own_xyz); FREE(e->d_cell); FREE(e->d_order); FREE(e->d_posq);
+   FREE(e->d_stype); FREE(e->d_scell);
+   e->d_x = e->d_y = e->d_z = nullptr;
+}
+static void free_grid(mdb_engine *e)
+{
+   FREE(e->d_count); FREE(e->d_start); FREE(e->d_scan_tmp); FREE(e->d_runs);
+   e->cells_cap = 0;
+}
+static void free_recip(mdb_engine *e)
+{
+   FREE(e->d_hk); FREE(e->d_hk_valid); FREE(e->d_slot_flags); FREE(e->d_ppart);
+   FREE(e->d_coef_tot); FREE(e->d_coef_nf); FREE(e->d_kpartials);
+   e->ppart_cap = 0;
+}
+
+extern "C" void mdb_destroy(mdb_engine *e)
+{
+   if (!e) return;
+   cudaSetDevice(e->device);
+   free_system(e); free_grid(e); free_recip(e);
+   FREE(e->d_partials); FREE(e->d_counters); FREE(e->d_out_own);
+   if (e->h_stage) cudaFreeHost(e->h_stage);
+   delete e;
+}
+
+extern "C" void mdb_set_partition(mdb_engine *e, int ithread, int nthreads)
+{
+   e->ithread = ithread;
+   e->nthreads = nthreads < 1 ? 1 : nthreads;
+}
+
+template <class T>
+static int upload(T **dst, const T *src, size_t n)
+{
+   if (*dst) cudaFree(*dst);
+   *dst = nullptr;
+   if (n == 0) return 0;
+   MDB_CUDA(cudaMalloc(dst, sizeof(T) * n));
+   MDB_CUDA(cudaMemcpy(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice));
+   return 0;
+}
+
+extern "C" int mdb_configure(mdb_engine *e, const mdb_config *cfg)
+{
+   MDB_CUDA(cudaSetDevice(e->device));
+   const int n = cfg->nsites;
+   if (n <= 0 || cfg->max_id <= 0) { mdb_set_error("mdb_configure: empty system"); return -1; }
+   if (cfg->ptype < 0 || cfg->ptype > 6 || cfg->ptype == 5) {
+      mdb_set_error("KERNEL called with unknown potential type");
+      return -1;
+   }
+   const bool new_system = !e->configured || e->cfg.nsites != n || e->cfg.max_id != cfg->max_id;
+   e->cfg = *cfg;
+   e->cfg.site_type = nullptr; e->cfg.site_mol = nullptr; e->cfg.chg = nullptr; e->cfg.potpar = nullptr;
+   e->cells_valid = false;
+
+   // ---- static per-site data ----
+   e->h_type.assign(cfg->site_type, cfg->site_type + n);
+   if (cfg->site_mol) e->h_mol.assign(cfg->site_mol, cfg->site_mol + n);
+   else { e->h_mol.resize(n); for (int i = 0; i < n; i++) e->h_mol[i] = i; }
+   e->h_chg.assign(cfg->chg, cfg->chg + n);
+   const int np = cfg->max_id * cfg->max_id * MDB_NPOTP;
+   e->h_potpar.assign(cfg->potpar, cfg->potpar + np);
+   for (int i = 0; i < n; i++)
+      if (e->h_type[i] < 0 || e->h_type[i] >= cfg->max_id) {
+         mdb_set_error("mdb_configure: site id out of range");
+         return -1;
+      }
+   // pair table as the kernel wants it (LJ: sigma^2 and 6 eps precomputed, src/kernel.c:206-210)
+   std::vector<double> ptab(e->h_potpar);
+   if (cfg->ptype == 0)
+      for (int k = 0; k < cfg->max_id * cfg->max_id; k++) {
+         double *p = &ptab[(size_t)k * MDB_NPOTP];
+         p[2] = 6.0 * p[0];
+         p[1] = p[1] * p[1];
+      }
+   if (new_system) {
+      free_system(e);
+      MDB_CUDA(cudaMalloc(&e->own_xyz, sizeof(double) * 3 * (size_t)n));
+      MDB_CUDA(cudaMalloc(&e->d_cell, sizeof(int) * (size_t)n));
+      MDB_CUDA(cudaMalloc(&e->d_order, sizeof(int) * (size_t)n));
+      MDB_CUDA(cudaMalloc(&e->d_posq, sizeof(double4) * (size_t)n));
+      MDB_CUDA(cudaMalloc(&e->d_stype, sizeof(int) * (size_t)n));
+      MDB_CUDA(cudaMalloc(&e->d_scell, sizeof(int) * (size_t)n));
+      e->sites_set = false;
+   }
+   if (upload(&e->d_type, e->h_type.data(), n)) return -1;
+   if (upload(&e->d_mol, e->h_mol.data(), n)) return -1;
+   if (upload(&e->d_chg, e->h_chg.data(), n)) return -1;
+   if (upload(&e->d_ptab, ptab.data(), ptab.size())) return -1;
+
+   // ---- link-cell grid + stencil ----
+   std::string err;
+   if (!mdb_build_real_tables(e->cfg, e->T, err)) { mdb_set_error(err); return -1; }
+   e->ncells = e->T.nx * e->T.ny * e->T.nz;
+   if (e->ncells + 1 > e->cells_cap) {
+      free_grid(e);
+      e->cells_cap = e->ncells + 1;
+      MDB_CUDA(cudaMalloc(&e->d_count, sizeof(int) * (size_t)e->cells_cap));
+      MDB_CUDA(cudaMalloc(&e->d_start, sizeof(int) * (size_t)e->cells_cap));
+      MDB_CUDA(cudaMalloc(&e->d_scan_tmp, sizeof(int) * (size_t)(e->cells_cap / 2048 + 2)));
+   }
+   e->nruns = (int)e->T.runs.size();
+   if (upload(&e->d_runs, e->T.runs.data(), e->T.runs.size())) return -1;
+
+   // ---- reciprocal space ----
+   if (cfg->do_recip) {
+      if (!mdb_build_recip_tables(e->cfg, e->T, err)) { mdb_set_error(err); return -1; }
+      HostTables &T = e->T;
+      for (size_t v = 0; v < T.hk_valid.size(); v++) T.hk[T.hk_valid[v]].pad = (int)v;
+      for (auto &d : T.hk) if (d.nl == 0) d.pad = -1;
+      std::vector<int> slotinfo(2 * (size_t)T.nslots);
+      for (int s = 0; s < T.nslots; s++) slotinfo[s] = T.slot_flags[s];
+      for (size_t i = 0; i < T.hk.size(); i++)
+         for (int l = 0; l < T.hk[i].nl; l++) slotinfo[T.nslots + T.hk[i].slot0 + l] = (int)i;
+      if (upload(&e->d_hk, T.hk.data(), T.hk.size())) return -1;
+      if (upload(&e->d_hk_valid, T.hk_valid.data(), T.hk_valid.size())) return -1;
+      if (upload(&e->d_slot_flags, slotinfo.data(), slotinfo.size())) return -1;
+      // site slabs for k_sfac: enough blocks to fill 148 SMs about twice
+      const int nlc = (T.lmax + 1 + 7) / 8;
+      const int hkb = nlc <= 1 ? 256 : nlc <= 2 ? 128 : nlc <= 4 ? 64 : 32;
+      const int ncol_blocks = std::max(1, ((int)T.hk_valid.size() + hkb - 1) / hkb);
+      int want = std::max(1, (2 * 148 + ncol_blocks - 1) / ncol_blocks);
+      int slab = (n + want - 1) / want;
+      slab = std::max(32, ((slab + 31) / 32) * 32);
+      e->slab_sites = slab;
+      const int nxf = cfg->nsites_xf;
+      e->n_slabs_nf = (nxf + slab - 1) / slab;
+      e->n_slabs = e->n_slabs_nf + (n - nxf + slab - 1) / slab;
+      const size_t pp = (size_t)e->n_slabs * T.nslots * 4;
+      if (pp > e->ppart_cap) {
+         FREE(e->d_ppart);
+         MDB_CUDA(cudaMalloc(&e->d_ppart, sizeof(double) * pp));
+         e->ppart_cap = pp;
+      }
+      FREE(e->d_coef_tot); FREE(e->d_coef_nf); FREE(e->d_kpartials);
+      MDB_CUDA(cudaMalloc(&e->d_coef_tot, sizeof(double) * 8 * (size_t)std::max(T.nslots, 1)));
+      MDB_CUDA(cudaMalloc(&e->d_coef_nf, sizeof(double) * 8 * (size_t)std::max(T.nslots, 1)));
+      MDB_CUDA(cudaMalloc(&e->d_kpartials, sizeof(double) * 8 * (size_t)(T.nslots / 256 + 1)));
+   } else {
+      e->T.nhkl = 0; e->T.hk.clear(); e->T.hk_valid.clear(); e->T.nslots = 0;
+   }
+   e->configured = true;
+   return 0;
+}
+
+extern "C" int mdb_set_sites_host(mdb_engine *e, const double *x, const double *y, const double *z, void *stream)
+{
+   cudaStream_t st = (cudaStream_t)stream;
+   const size_t n = e->cfg.nsites;
+   MDB_CUDA(cudaMemcpyAsync(e->own_xyz, x, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+   MDB_CUDA(cudaMemcpyAsync(e->own_xyz + n, y, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+   MDB_CUDA(cudaMemcpyAsync(e->own_xyz + 2 * n, z, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+   e->d_x = e->own_xyz; e->d_y = e->own_xyz + n; e->d_z = e->own_xyz + 2 * n;
+   e->sites_set = true; e->cells_valid = false;
+   return 0;
+}
+
+extern "C" int mdb_set_sites_device(mdb_engine *e, const double *dx, const double *dy, const double *dz, void *stream)
+{
+   (void)stream;
+   e->d_x = const_cast<double *>(dx); e->d_y = const_cast<double *>(dy); e->d_z = const_cast<double *>(dz);
+   e->sites_set = true; e->cells_valid = false;
+   return 0;
+}
+
+extern "C" int mdb_zero_out(mdb_engine *e, double *d_out, void *stream)
+{
+   MDB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * mdb_out_doubles(e->cfg.nsites), (cudaStream_t)stream));
+   return 0;
+}
+
+extern "C" int mdb_build_cells(mdb_engine *e, void *stream)
+{
+   if (!e->configured || !e->sites_set) { mdb_set_error("mdb_build_cells: engine not configured / no sites"); return -1; }
+   return mdb_launch_cells(e, (cudaStream_t)stream);
+}
+
+extern "C" int mdb_force_real(mdb_engine *e, double *d_out, void *stream)
+{
+   if (!e->configured || !e->sites_set) { mdb_set_error("mdb_force_real: engine not configured / no sites"); return -1; }
+   if (!e->cells_valid && mdb_launch_cells(e, (cudaStream_t)stream)) return -1;
+   return mdb_launch_pair(e, d_out, (cudaStream_t)stream);
+}
+
+extern "C" int mdb_force_recip(mdb_engine *e, double *d_out, void *stream)
+{
+   if (!e->configured || !e->sites_set) { mdb_set_error("mdb_force_recip: engine not configured / no sites"); return -1; }
+   if (!e->cfg.do_recip) return 0;
+   return mdb_launch_recip(e, d_out, (cudaStream_t)stream);
+}
+
+extern "C" int mdb_read_out(mdb_engine *e, const double *d_out, double *h_out, void *stream)
+{
+   cudaStream_t st = (cudaStream_t)stream;
+   MDB_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(double) * mdb_out_doubles(e->cfg.nsites), cudaMemcpyDeviceToHost, st));
+   MDB_CUDA(cudaStreamSynchronize(st));
+   return 0;
+}
+
+extern "C" int mdb_grid(const mdb_engine *e, int nxyz[3])
+{
+   nxyz[0] = e->T.nx; nxyz[1] = e->T.ny; nxyz[2] = e->T.nz;
+   return e->ncells;
+}
+extern "C" int mdb_n_neighbour_cells(const mdb_engine *e) { return (int)e->T.half_list.size() / 3; }
+extern "C" int mdb_n_kvectors(const mdb_engine *e) { return e->T.nhkl; }
+extern "C" long mdb_kernel_launches(const mdb_engine *e) { return e->launches; }
+
+extern "C" int mdb_get_cell_ids(mdb_engine *e, int *h_cell, void *stream)
+{
+   cudaStream_t st = (cudaStream_t)stream;
+   if (!e->cells_valid && mdb_build_cells(e, stream)) return -1;
+   MDB_CUDA(cudaMemcpyAsync(h_cell, e->d_cell, sizeof(int) * (size_t)e->cfg.nsites, cudaMemcpyDeviceToHost, st));
+   MDB_CUDA(cudaStreamSynchronize(st));
+   return 0;
+}
+
+static int read_counters(mdb_engine *e, unsigned long long c[8], bool reset, cudaStream_t st)
+{
+   MDB_CUDA(cudaMemcpyAsync(c, e->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+   MDB_CUDA(cudaStreamSynchronize(st));
+   if (reset) MDB_CUDA(cudaMemsetAsync(e->d_counters, 0, 8 * sizeof(unsigned long long), st));
+   return 0;
+}
+
+// pairs handed to kernel() per step = half the visits counted since the last call
+extern "C" double mdb_pair_count(mdb_engine *e, void *stream)
+{
+   unsigned long long c[8];
+   if (read_counters(e, c, false, (cudaStream_t)stream)) return -1.0;
+   unsigned long long z = 0;
+   cudaMemcpyAsync(e->d_counters, &z, sizeof z, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+   cudaStreamSynchronize((cudaStream_t)stream);
+   return 0.5 * (double)c[0];
+}
+
+extern "C" int mdb_too_close(mdb_engine *e, int pair[2], void *stream)
+{
+   unsigned long long c[8];
+   if (read_counters(e, c, false, (cudaStream_t)stream)) return -1;
+   pair[0] = (int)(c[3] >> 32); pair[1] = (int)(c[3] & 0xffffffffu);
+   unsigned long long z[3] = {0, 0, 0};
+   cudaMemcpyAsync(e->d_counters + 1, z, sizeof z, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+   cudaStreamSynchronize((cudaStream_t)stream);
+   // every inter-molecular close pair is visited from both ends; [2] = bin errors
+   return (int)(c[1] / 2) + (c[2] ? (1 << 30) : 0);
+}
+
+extern "C" size_t mdb_sizeof(const char *name)
+{
+   if (!strcmp(name, "contr_mt")) return sizeof(contr_mt);
+   if (!strcmp(name, "system_mt")) return sizeof(system_mt);
+   if (!strcmp(name, "spec_mt")) return sizeof(spec_mt);
+   if (!strcmp(name, "site_mt")) return sizeof(site_mt);
+   if (!strcmp(name, "pot_mt")) return sizeof(pot_mt);
+   if (!strcmp(name, "mdb_config")) return sizeof(mdb_config);
+   if (!strcmp(name, "HkDesc")) return sizeof(HkDesc);
+   return 0;
+}
+
+// ---- FP64 roofline probe: a pure dependent-chain-free DFMA loop ----------------
+__global__ void __launch_bounds__(256) k_dfma_probe(double *out, int iters, double a, double b)
+{
+   double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+   for (int i = 0; i < iters; i++) {
+      v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
+      v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
+   }
+   out[blockIdx.x * blockDim.x + threadIdx.x] = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
+}
+
+extern "C" double mdb_fp64_peak_probe(int device, int iters)
+{
+   if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+   cudaDeviceProp prop;
+   cudaGetDeviceProperties(&prop, device);
+   const int blocks = prop.multiProcessorCount * 8, threads = 256;
+   double *d = nullptr;
+   if (cudaMalloc(&d, sizeof(double) * blocks * threads) != cudaSuccess) return -1.0;
+   cudaEvent_t e0, e1;
+   cudaEventCreate(&e0); cudaEventCreate(&e1);
+   k_dfma_probe<<<blocks, threads>>>(d, iters / 8, 0.999999, 1e-9);
+   double best = 0.0;
+   for (int rep = 0; rep < 5; rep++) {
+      cudaEventRecord(e0);
+      k_dfma_probe<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      double flops = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3);
+      best = std::max(best, flops);
+   }
+   cudaEventDestroy(e0); cudaEventDestroy(e1);
+   cudaFree(d);
+   return best;
+}

@@ -1,0 +1,133 @@
+// mdb_internal.h -- engine state shared by the translation units of libmoldy_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "moldy_b200.h"
+
+#define MDB_PI 3.14159265358979323846            /* src/defs.h:184 */
+#define MDB_TOO_CLOSE 0.25                       /* src/force.c:89 */
+#define MDB_ALPHAMIN 1e-7                        /* src/defs.h:181 */
+#define MDB_EPS0 (0.25 / MDB_PI)                 /* src/defs.h:227 */
+
+// ---- host-side tables ------------------------------------------------------
+struct StencilRun {            // one contiguous z-run of neighbour cells in column (dx,dy)
+   int dx, dy, dzlo, dzhi;     // full stencil = H u (-H), H = reference half list
+};
+
+struct HkDesc {                // one (h,k) column of the reciprocal lattice (traversal order)
+   double kx, ky, kzt;         // src/ewald.c:445-447
+   int    nl;                  // number of l-slots 0..nl-1 (0: nothing inside the cutoff)
+   int    slot0;               // first row of this column in the per-slot arrays
+   int    h, k;
+   int    code;                // how (cos,sin)(h a*.r + k b*.r) follows from the previous column
+   int    pad;
+};
+enum { HK_DIRECT = 0, HK_NEWH = 1, HK_KUP = 2, HK_KDOWN0 = 3, HK_KDOWN = 4 };
+
+struct HostTables {
+   // real space
+   int nx = 0, ny = 0, nz = 0;
+   double hinv[9];
+   std::vector<int> half_list;            // (ix,iy,iz) triplets of the reference half list
+   std::vector<StencilRun> runs;          // full stencil as z-runs
+   double reloc[27][3];                   // src/force.c:1284-1293
+   // reciprocal space
+   int hmax = 0, kmax = 0, lmax = 0, nhkl = 0;
+   double astar[3], bstar[3], cstar[3];
+   double vol = 0;
+   std::vector<HkDesc> hk;                // traversal order, includes empty columns
+   std::vector<int> hk_valid;             // indices into hk with nl > 0 (sorted by nl, descending)
+   std::vector<int> slot_flags;           // per slot: bit0 = +l inside cutoff, bit1 = -l inside
+   int nslots = 0;
+};
+
+// ---- device-side parameter blocks (passed by value to kernels) --------------
+struct CellParams {
+   double hinv[9];
+   int nx, ny, nz, ncells;
+   double fnx, fny, fnz, eps;
+};
+
+struct PairParams {
+   int nx, ny, nz, nruns;
+   double reloc[27][3];
+   double alpha, norm, cutoffsq, cutoff100sq;
+   int max_id, strict;
+   int s_lo, s_hi;                        // slice of cell-sorted sites owned by this rank
+};
+
+struct KspaceParams {
+   double astar[3], bstar[3], cstar[3];
+   double cz2;                            // cstar[2]
+   double r4alpha;                        // -1/(4 alpha^2)
+   double pref;                           // 2/(EPS0 vol)
+   int hmax, kmax, lmax, nlslots;         // nlslots = lmax+1
+   int nsites, nsites_xf;
+};
+
+struct mdb_engine {
+   int device = 0;
+   bool configured = false;
+   mdb_config cfg{};
+   std::vector<int> h_type, h_mol;
+   std::vector<double> h_chg, h_potpar;
+   HostTables T;
+   int ithread = 0, nthreads = 1;
+   long launches = 0;
+
+   // static per-system device data
+   int *d_type = nullptr, *d_mol = nullptr;
+   double *d_chg = nullptr, *d_ptab = nullptr;
+   // positions (original site order); owned unless borrowed
+   double *d_x = nullptr, *d_y = nullptr, *d_z = nullptr;
+   double *own_xyz = nullptr;
+   bool sites_set = false, cells_valid = false;
+   // link cells
+   int ncells = 0, cells_cap = 0;
+   int *d_cell = nullptr, *d_count = nullptr, *d_start = nullptr, *d_order = nullptr;
+   int *d_scan_tmp = nullptr;
+   double4 *d_posq = nullptr;
+   int *d_stype = nullptr, *d_scell = nullptr;
+   StencilRun *d_runs = nullptr;
+   int nruns = 0;
+   // reductions / diagnostics
+   double *d_partials = nullptr; int partials_cap = 0;
+   unsigned long long *d_counters = nullptr;      // [0]=pair visits [1]=too close [2]=bin errors [3..4]=example pair
+   // k-space
+   HkDesc *d_hk = nullptr; int *d_hk_valid = nullptr; int *d_slot_flags = nullptr;
+   double *d_ppart = nullptr; size_t ppart_cap = 0;
+   double *d_coef_tot = nullptr, *d_coef_nf = nullptr;
+   double *d_kpartials = nullptr;
+   int n_slabs = 0, n_slabs_nf = 0, slab_sites = 0;
+
+   // pinned staging for host-facing calls
+   double *h_stage = nullptr; size_t stage_cap = 0;
+   double *d_out_own = nullptr; size_t out_cap = 0;
+};
+
+// ---- host setup (mdb_host.cpp) ---------------------------------------------
+void mdb_invert3(const double a[9], double b[9]);
+double mdb_det3(const double a[9]);
+bool mdb_build_real_tables(const mdb_config &c, HostTables &T, std::string &err);
+bool mdb_build_recip_tables(const mdb_config &c, HostTables &T, std::string &err);
+double mdb_err_fn(double x);
+void mdb_set_error(const std::string &s);
+
+// ---- kernels launchers (mdb_cells.cu / mdb_pair.cu / mdb_kspace.cu) --------
+int mdb_launch_cells(mdb_engine *e, cudaStream_t st);
+int mdb_launch_pair(mdb_engine *e, double *d_out, cudaStream_t st);
+int mdb_launch_recip(mdb_engine *e, double *d_out, cudaStream_t st);
+int mdb_launch_kernel_vec(int jmin, int nnab, double *forceij, double *pe, const double *r_sqr,
+                          const double *nab_chg, double chg, double norm, double alpha, int ptype,
+                          double *const *pot);
+
+#define MDB_CUDA(call)                                                                   \
+   do {                                                                                  \
+      cudaError_t _e = (call);                                                           \
+      if (_e != cudaSuccess) {                                                           \
+         mdb_set_error(std::string(#call) + ": " + cudaGetErrorString(_e));              \
+         return -1;                                                                      \
+      }                                                                                  \
+   } while (0)

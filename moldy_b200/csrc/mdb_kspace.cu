@@ -1,0 +1,354 @@
+// mdb_kspace.cu -- reciprocal-space Ewald sum (replaces the k-vector loop of
+// ewald(), src/ewald.c:469-583: trig_recur, qsincos, sum, energy/stress, forces).
+//
+// The reference walks the k-vector list and, per k, makes three passes over
+// N-long trig arrays (HBM-bound, N x (hmax+kmax+lmax) doubles of tables).  Here
+// the phase factor is kept factorised,
+//        exp(i k.r) = E_hk(r) * E_l(r),   E_hk = E_h E_k,
+// and a k-vector pair (h,k,+l),(h,k,-l) shares its four real products
+//        P1 = sum c_hk C_l   P2 = sum s_hk S_l   P3 = sum s_hk C_l   P4 = sum c_hk S_l
+// (C_l = q cos(l c*.r), S_l = q sin(l c*.r)):  C(+-l) = P1 -+ P2,  S(+-l) = P3 +- P4.
+//
+//  k_sfac    structure factors: thread owns one (h,k) column and up to 8 l-slots
+//            (32 FP64 accumulators), sites stream through shared memory in
+//            chunks with their E_h/E_k/E_l power tables built by recurrence.
+//            2 DFMA per (site,k-vector).  Per-slab partial sums, no atomics.
+//  k_sfin    fixed-order slab reduction -> C,S per k; energy, stress
+//            (src/ewald.c:511-553) and the eight back-projection coefficients
+//            per l-slot.
+//  k_kforce  forces: thread owns a site, walks the (h,k) columns by recurrence
+//            and accumulates X,Y,Xz,Yz over the l-slots: 4 DFMA + one complex
+//            recurrence step per slot (2 k-vectors); f += k (s X + c Y) ...
+//            (src/ewald.c:558-579).
+// Framework sites (src/ewald.c:528-579) are handled by keeping their slabs
+// separate in k_sfac and using the non-framework-only coefficient set for them.
+#include "mdb_internal.h"
+
+static constexpr int KT = 256;          // threads per block (k_sfac)
+static constexpr int SC = 32;           // sites per shared-memory chunk
+static constexpr int LCH = 8;           // l-slots per thread
+static constexpr int KF = 128;          // threads per block (k_kforce)
+
+struct SfacArgs {
+   KspaceParams K;
+   int HKB, NLC;                        // (h,k) columns per block, l-chunks
+   int nvalid, rank, nranks;
+   int nslots, slab_sites, n_slabs_nf;
+};
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b)
+{
+   return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.y, b.x, a.x * b.y));
+}
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b)   // a * conj(b)
+{
+   return make_double2(fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -a.x * b.y));
+}
+
+__global__ void __launch_bounds__(KT)
+k_sfac(SfacArgs A, const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
+       const double *__restrict__ chg, const HkDesc *__restrict__ hk, const int *__restrict__ hk_valid,
+       double *__restrict__ ppart)
+{
+   extern __shared__ double2 smem[];
+   const KspaceParams &K = A.K;
+   const int NL = K.nlslots, NH = K.hmax + 1, NK = K.kmax + 1;
+   double2 *sA = smem;                          // [SC][HKB]
+   double2 *sB = sA + SC * A.HKB;               // [SC][NL]
+   double2 *sH = sB + SC * NL;                  // [SC][NH]
+   double2 *sK = sH + SC * NH;                  // [SC][NK]
+
+   const int tid = threadIdx.x;
+   const int hkl = tid % A.HKB, lc = tid / A.HKB;
+   // this thread's (h,k) column: i-th entry of the rank's interleaved share of the valid list
+   const int ient = blockIdx.x * A.HKB + hkl;
+   const int v = A.rank + A.nranks * ient;
+   const bool have = v < A.nvalid && lc < A.NLC;
+   int h = 0, ka = 0, ksgn = 1, nl = 0, slot0 = 0;
+   if (v < A.nvalid) {
+      const HkDesc d = hk[hk_valid[v]];
+      h = d.h; ka = abs(d.k); ksgn = d.k < 0 ? -1 : 1; nl = d.nl; slot0 = d.slot0;
+   }
+   const int l0 = lc * LCH;
+   const int lcnt = have ? min(max(nl - l0, 0), LCH) : 0;
+   const int wl = __reduce_max_sync(0xffffffffu, lcnt);       // warp-uniform trip count
+
+   // slab -> site range (framework sites live in their own slabs)
+   const int slab = blockIdx.y;
+   int s0, s1;
+   if (slab < A.n_slabs_nf) {
+      s0 = slab * A.slab_sites;
+      s1 = min(s0 + A.slab_sites, K.nsites_xf);
+   } else {
+      s0 = K.nsites_xf + (slab - A.n_slabs_nf) * A.slab_sites;
+      s1 = min(s0 + A.slab_sites, K.nsites);
+   }
+
+   double acc[LCH][4];
+#pragma unroll
+   for (int j = 0; j < LCH; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
+
+   for (int base = s0; base < s1; base += SC) {
+      // phase 1: power tables of the three base phase factors, one (site,axis) per thread
+      if (tid < 3 * SC) {
+         const int sl = tid % SC, axis = tid / SC, g = base + sl;
+         double q = 0.0, kr = 0.0;
+         const double *ks = axis == 0 ? K.astar : axis == 1 ? K.bstar : K.cstar;
+         if (g < s1) {
+            kr = ks[0] * x[g] + ks[1] * y[g] + ks[2] * z[g];
+            q = chg[g];
+         }
+         double s1v, c1v;
+         sincos(kr, &s1v, &c1v);
+         const double2 e1 = make_double2(c1v, s1v);
+         double2 *tab = axis == 0 ? sH + sl * NH : axis == 1 ? sK + sl * NK : sB + sl * NL;
+         const int nmax = axis == 0 ? NH : axis == 1 ? NK : NL;
+         const double amp = axis == 2 ? q : 1.0;
+         double2 e = make_double2(1.0, 0.0);
+         tab[0] = make_double2(amp, 0.0);
+         for (int m = 1; m < nmax; m++) {
+            e = cmul(e, e1);
+            tab[m] = make_double2(amp * e.x, amp * e.y);
+         }
+      }
+      __syncthreads();
+      // phase 2: E_hk = E_h * E_k (conjugate for k < 0) for this thread's column
+      for (int sl = lc; sl < SC; sl += KT / A.HKB) {
+         const double2 eh = sH[sl * NH + h], ek = sK[sl * NK + ka];
+         sA[sl * A.HKB + hkl] = ksgn > 0 ? cmul(eh, ek) : cmulc(eh, ek);
+      }
+      __syncthreads();
+      // phase 3: rank-1 updates, 4 DFMA per (site, l-slot)
+      if (wl > 0) {
+#pragma unroll 2
+         for (int sl = 0; sl < SC; sl++) {
+            const double2 a = sA[sl * A.HKB + hkl];
+            const double2 *bp = sB + sl * NL + l0;
+#pragma unroll
+            for (int j = 0; j < LCH; j++) {
+               if (j < wl) {
+                  const double2 b = bp[j];
+                  acc[j][0] = fma(a.x, b.x, acc[j][0]);
+                  acc[j][1] = fma(a.y, b.y, acc[j][1]);
+                  acc[j][2] = fma(a.y, b.x, acc[j][2]);
+                  acc[j][3] = fma(a.x, b.y, acc[j][3]);
+               }
+            }
+         }
+      }
+      __syncthreads();
+   }
+#pragma unroll
+   for (int j = 0; j < LCH; j++)
+      if (j < lcnt) {
+         double *o = ppart + ((size_t)slab * A.nslots + slot0 + l0 + j) * 4;
+         o[0] = acc[j][0]; o[1] = acc[j][1]; o[2] = acc[j][2]; o[3] = acc[j][3];
+      }
+}
+
+// ---- per k-vector: energy, stress, back-projection coefficients --------------
+struct SfinArgs {
+   KspaceParams K;
+   int nslots, n_slabs, n_slabs_nf, rank, nranks, framework;
+};
+
+__global__ void __launch_bounds__(256)
+k_sfin(SfinArgs A, const HkDesc *__restrict__ hk, const int *__restrict__ slot_hk,
+       const int *__restrict__ slot_flags, const double *__restrict__ ppart, double *__restrict__ coef_tot,
+       double *__restrict__ coef_nf, double *__restrict__ kpartials)
+{
+   const KspaceParams &K = A.K;
+   const int slot = blockIdx.x * 256 + threadIdx.x;
+   double red[7] = {0, 0, 0, 0, 0, 0, 0};
+   if (slot < A.nslots) {
+      const HkDesc d = hk[slot_hk[slot]];
+      const bool mine = (d.pad % A.nranks) == A.rank;          // pad = position in the valid list
+      double ct[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cn[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (mine) {
+         const int l = slot - d.slot0, flags = slot_flags[slot];
+         double pn[4] = {0, 0, 0, 0}, pf[4] = {0, 0, 0, 0};
+         for (int sb = 0; sb < A.n_slabs; sb++) {
+            const double *p = ppart + ((size_t)sb * A.nslots + slot) * 4;
+            double *dst = sb < A.n_slabs_nf ? pn : pf;
+            dst[0] += p[0]; dst[1] += p[1]; dst[2] += p[2]; dst[3] += p[3];
+         }
+         double Ct[2] = {0, 0}, St[2] = {0, 0}, Cn2[2] = {0, 0}, Sn2[2] = {0, 0};
+#pragma unroll
+         for (int sg = 0; sg < 2; sg++) {
+            if (!(flags & (1 << sg))) continue;
+            const double sgn = sg == 0 ? 1.0 : -1.0;
+            const double Cn = pn[0] - sgn * pn[1], Sn = pn[2] + sgn * pn[3];
+            const double Cf = pf[0] - sgn * pf[1], Sf = pf[2] + sgn * pf[3];
+            const double kx = d.kx, ky = d.ky, kz = d.kzt + (sg == 0 ? l : -l) * K.cz2;
+            const double ksq = kx * kx + ky * ky + kz * kz;
+            const double coeff = K.pref * exp(ksq * K.r4alpha) / ksq;
+            const double coeff2 = 2.0 * (1.0 - ksq * K.r4alpha) / ksq;
+            const double pe_k = 0.5 * coeff * (Cn * (Cn + Cf + Cf) + Sn * (Sn + Sf + Sf));
+            red[0] += pe_k;
+            red[1] += pe_k - pe_k * coeff2 * kx * kx;
+            red[2] -= pe_k * coeff2 * kx * ky;
+            red[3] -= pe_k * coeff2 * kx * kz;
+            red[4] += pe_k - pe_k * coeff2 * ky * ky;
+            red[5] -= pe_k * coeff2 * ky * kz;
+            red[6] += pe_k - pe_k * coeff2 * kz * kz;
+            Ct[sg] = coeff * (Cn + Cf); St[sg] = coeff * (Sn + Sf);
+            Cn2[sg] = coeff * Cn;       Sn2[sg] = coeff * Sn;
+         }
+         const double fl = (double)l;
+         ct[0] = Ct[0] + Ct[1]; ct[1] = St[0] + St[1]; ct[2] = Ct[0] - Ct[1]; ct[3] = St[0] - St[1];
+         ct[4] = fl * ct[2]; ct[5] = fl * ct[1]; ct[6] = fl * ct[0]; ct[7] = fl * ct[3];
+         cn[0] = Cn2[0] + Cn2[1]; cn[1] = Sn2[0] + Sn2[1]; cn[2] = Cn2[0] - Cn2[1]; cn[3] = Sn2[0] - Sn2[1];
+         cn[4] = fl * cn[2]; cn[5] = fl * cn[1]; cn[6] = fl * cn[0]; cn[7] = fl * cn[3];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) coef_tot[(size_t)slot * 8 + k] = ct[k];
+      if (A.framework)
+#pragma unroll
+         for (int k = 0; k < 8; k++) coef_nf[(size_t)slot * 8 + k] = cn[k];
+   }
+   __shared__ double sm[8][7];
+   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+   for (int k = 0; k < 7; k++) {
+      double t = red[k];
+#pragma unroll
+      for (int dd = 16; dd > 0; dd >>= 1) t += __shfl_xor_sync(0xffffffffu, t, dd);
+      if (lane == 0) sm[w][k] = t;
+   }
+   __syncthreads();
+   if (threadIdx.x < 7) {
+      double t = 0;
+      for (int k = 0; k < 8; k++) t += sm[k][threadIdx.x];
+      kpartials[(size_t)blockIdx.x * 8 + threadIdx.x] = t;
+   }
+}
+
+__global__ void __launch_bounds__(256) k_recip_finish(const double *__restrict__ kpartials, int nblocks, int nsites,
+                                                      double *__restrict__ out)
+{
+   __shared__ double sm[256];
+   double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+   for (int b = threadIdx.x; b < nblocks; b += 256)
+#pragma unroll
+      for (int k = 0; k < 7; k++) acc[k] += kpartials[(size_t)b * 8 + k];
+   double tot[7];
+   for (int k = 0; k < 7; k++) {
+      sm[threadIdx.x] = acc[k];
+      __syncthreads();
+      for (int d = 128; d > 0; d >>= 1) {
+         if (threadIdx.x < d) sm[threadIdx.x] += sm[threadIdx.x + d];
+         __syncthreads();
+      }
+      tot[k] = sm[0];
+      __syncthreads();
+   }
+   if (threadIdx.x == 0) {
+      double *sc = out + 3 * (size_t)nsites;
+      sc[1] += tot[0];
+      sc[2 + 0] += tot[1]; sc[2 + 1] += tot[2]; sc[2 + 2] += tot[3];
+      sc[2 + 4] += tot[4]; sc[2 + 5] += tot[5]; sc[2 + 8] += tot[6];
+   }
+}
+
+// ---- forces -------------------------------------------------------------------
+__global__ void __launch_bounds__(KF)
+k_kforce(KspaceParams K, int i0, int i1, int nhk, int rank, int nranks, const double *__restrict__ x,
+         const double *__restrict__ y, const double *__restrict__ z, const double *__restrict__ chg,
+         const HkDesc *__restrict__ hk, const double *__restrict__ coef, double *__restrict__ out)
+{
+   const int i = i0 + blockIdx.x * KF + threadIdx.x;
+   if (i >= i1) return;
+   const double q = chg[i];
+   if (q == 0.0) return;
+   const double xi = x[i], yi = y[i], zi = z[i];
+   double2 ea, eb, ec;
+   sincos(K.astar[0] * xi + K.astar[1] * yi + K.astar[2] * zi, &ea.y, &ea.x);
+   sincos(K.bstar[0] * xi + K.bstar[1] * yi + K.bstar[2] * zi, &eb.y, &eb.x);
+   sincos(K.cstar[0] * xi + K.cstar[1] * yi + K.cstar[2] * zi, &ec.y, &ec.x);
+   double2 eh = make_double2(1.0, 0.0), ehk = eh;
+   double fx = 0, fy = 0, fz = 0;
+   for (int c = 0; c < nhk; c++) {
+      const HkDesc d = hk[c];
+      switch (d.code) {
+         case HK_NEWH:   if (d.h > 0) eh = cmul(eh, ea); ehk = eh; break;
+         case HK_KUP:    ehk = cmul(ehk, eb); break;
+         case HK_KDOWN0: ehk = cmulc(eh, eb); break;
+         default:        ehk = cmulc(ehk, eb); break;
+      }
+      if (d.nl == 0 || (d.pad % nranks) != rank) continue;
+      const double4 *cf = reinterpret_cast<const double4 *>(coef + (size_t)d.slot0 * 8);
+      double2 el = make_double2(q, 0.0);
+      double X = 0, Y = 0, Xz = 0, Yz = 0;
+      for (int l = 0; l < d.nl; l++) {
+         const double4 a = cf[2 * l], b = cf[2 * l + 1];
+         X = fma(el.x, a.x, fma(el.y, a.w, X));
+         Y = fma(el.y, a.z, fma(-el.x, a.y, Y));
+         Xz = fma(el.x, b.x, fma(el.y, b.y, Xz));
+         Yz = fma(el.y, b.z, fma(-el.x, b.w, Yz));
+         el = cmul(el, ec);
+      }
+      const double T = fma(ehk.y, X, ehk.x * Y), Tz = fma(ehk.y, Xz, ehk.x * Yz);
+      fx = fma(d.kx, T, fx);
+      fy = fma(d.ky, T, fy);
+      fz = fma(d.kzt, T, fma(K.cz2, Tz, fz));
+   }
+   out[i] += fx;
+   out[(size_t)K.nsites + i] += fy;
+   out[2 * (size_t)K.nsites + i] += fz;
+}
+
+int mdb_launch_recip(mdb_engine *e, double *d_out, cudaStream_t st)
+{
+   const mdb_config &c = e->cfg;
+   const HostTables &T = e->T;
+   const int nvalid = (int)T.hk_valid.size();
+   if (nvalid == 0) return 0;
+   KspaceParams K;
+   for (int a = 0; a < 3; a++) { K.astar[a] = T.astar[a]; K.bstar[a] = T.bstar[a]; K.cstar[a] = T.cstar[a]; }
+   K.cz2 = T.cstar[2];
+   K.r4alpha = -1.0 / (4.0 * c.alpha * c.alpha);
+   K.pref = 2.0 / (MDB_EPS0 * T.vol);
+   K.hmax = T.hmax; K.kmax = T.kmax; K.lmax = T.lmax; K.nlslots = T.lmax + 1;
+   K.nsites = c.nsites; K.nsites_xf = c.nsites_xf;
+
+   SfacArgs A;
+   A.K = K;
+   A.NLC = (K.nlslots + LCH - 1) / LCH;
+   if (A.NLC > 8) {
+      mdb_set_error("k_cutoff gives lmax > 63: not supported by this build of k_sfac");
+      return -1;
+   }
+   A.HKB = A.NLC <= 1 ? 256 : A.NLC <= 2 ? 128 : A.NLC <= 4 ? 64 : 32;
+   A.nvalid = nvalid; A.rank = e->ithread; A.nranks = e->nthreads;
+   A.nslots = T.nslots; A.slab_sites = e->slab_sites; A.n_slabs_nf = e->n_slabs_nf;
+   const int my_cols = (nvalid - e->ithread + e->nthreads - 1) / e->nthreads;
+   const size_t shm = sizeof(double2) * (size_t)SC * (A.HKB + K.nlslots + K.hmax + 1 + K.kmax + 1);
+   if (my_cols > 0) {
+      static size_t shm_set = 0;
+      if (shm > shm_set) {
+         MDB_CUDA(cudaFuncSetAttribute(k_sfac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+         shm_set = shm;
+      }
+      dim3 g((my_cols + A.HKB - 1) / A.HKB, e->n_slabs);
+      k_sfac<<<g, KT, shm, st>>>(A, e->d_x, e->d_y, e->d_z, e->d_chg, e->d_hk, e->d_hk_valid, e->d_ppart);
+      e->launches++;
+   }
+   SfinArgs F;
+   F.K = K; F.nslots = T.nslots; F.n_slabs = e->n_slabs; F.n_slabs_nf = e->n_slabs_nf;
+   F.rank = e->ithread; F.nranks = e->nthreads; F.framework = c.nsites_xf < c.nsites;
+   const int fb = (T.nslots + 255) / 256;
+   k_sfin<<<fb, 256, 0, st>>>(F, e->d_hk, e->d_slot_flags + T.nslots, e->d_slot_flags, e->d_ppart, e->d_coef_tot,
+                              e->d_coef_nf, e->d_kpartials);
+   k_recip_finish<<<1, 256, 0, st>>>(e->d_kpartials, fb, c.nsites, d_out);
+   const int nhk = (int)T.hk.size();
+   if (c.nsites_xf > 0)
+      k_kforce<<<(c.nsites_xf + KF - 1) / KF, KF, 0, st>>>(K, 0, c.nsites_xf, nhk, e->ithread, e->nthreads, e->d_x,
+                                                          e->d_y, e->d_z, e->d_chg, e->d_hk, e->d_coef_tot, d_out);
+   if (c.nsites_xf < c.nsites)
+      k_kforce<<<(c.nsites - c.nsites_xf + KF - 1) / KF, KF, 0, st>>>(K, c.nsites_xf, c.nsites, nhk, e->ithread,
+                                                                      e->nthreads, e->d_x, e->d_y, e->d_z, e->d_chg,
+                                                                      e->d_hk, e->d_coef_nf, d_out);
+   e->launches += 3 + (c.nsites_xf < c.nsites ? 1 : 0);
+   MDB_CUDA(cudaGetLastError());
+   return 0;
+}

@@ -1,0 +1,399 @@
+// moldy_abi.cu -- layer (A) of include/moldy_b200.h: Moldy's own entry points
+// (force_calc, ewald, kernel, poteval, dist_pot, potspec, pot_dim) on top of the
+// device engine.  Linked in place of force.o / kernel.o / ewald.o the rest of
+// Moldy is unchanged.  There is no CPU path: if no CUDA device
+// can be opened every entry point reports FATAL through Moldy's message().
+//
+// Calling contract reproduced: the caller owns and zeroes
+// site_force / pe / stress; we only accumulate (+=); pe[0] gets the real-space
+// energy minus the intramolecular correction, the caller's pe+1 gets the
+// reciprocal-space energy minus self energy plus sheet term; only the upper
+// triangle of stress is touched; rank-0-only constants follow `ithread`.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "mdb_internal.h"
+
+#define CONV_E_KJ (0.001 * 6.0221367e23 * 1.6605402e-27 * 1.0e4)     /* src/defs.h:229 */
+#define CONV_Q_E  (4.07497263794495e-14 * 1.e-3 * 1.05482230112e-05 / 1.60217733e-19)
+
+enum { SEV_INFO = 0, SEV_WARNING = 1, SEV_ERROR = 2, SEV_FATAL = 3 };       /* src/messages.h */
+
+extern "C" {
+// Globals owned by Moldy's main.c (src/main.c:83-84).  Weak here so that a host
+// that is not Moldy (ctypes, bench.py) still resolves them; Moldy's own strong
+// definitions win when the library is linked into the program.
+__attribute__((weak)) contr_mt control;
+__attribute__((weak)) int ithread = 0;
+__attribute__((weak)) int nthreads = 1;
+
+// Moldy's message()/note() (src/output.c:131,175); weak fall-backs print the same tags.
+__attribute__((weak)) void note(char *text, ...)
+{
+   if (ithread > 0) return;
+   va_list ap;
+   va_start(ap, text);
+   printf(" *I* ");
+   vprintf(text, ap);
+   printf("\n");
+   va_end(ap);
+}
+__attribute__((weak)) void message(int *nerrs, ...)
+{
+   static const char *tag[] = {" *I* ", " *W* ", " *E* ", " *F* "};
+   va_list ap;
+   va_start(ap, nerrs);
+   char *buff = va_arg(ap, char *);
+   int sev = va_arg(ap, int);
+   char *fmt = va_arg(ap, char *);
+   (void)buff;
+   if (ithread == 0 || abs(sev) == SEV_FATAL) {
+      printf("%s", tag[abs(sev) & 3]);
+      vprintf(fmt, ap);
+      printf("\n");
+   }
+   va_end(ap);
+   if (sev >= SEV_ERROR && nerrs) (*nerrs)++;
+   if (abs(sev) == SEV_FATAL) { fflush(stdout); exit(3); }
+}
+contr_mt *mdb_control(void) { return &control; }
+void mdb_set_thread(int it, int nt) { ithread = it; nthreads = nt; }
+
+const pots_mt potspec[] = {{(char *)"lennard-jones", 2}, {(char *)"buckingham", 3}, {(char *)"mcy", 4},
+                           {(char *)"generic", 6},       {(char *)"hiw", 3},
+                           {(char *)"reserved for developer", 1}, {(char *)"morse", 7}, {0, 0}};
+const dim_mt pot_dim[][MDB_NPOTP] = {
+   {{1, 2, -2}, {0, 1, 0}},
+   {{1, 8, -2}, {1, 2, -2}, {0, -1, 0}},
+   {{1, 2, -2}, {0, -1, 0}, {1, 2, -2}, {0, -1, 0}},
+   {{1, 2, -2}, {0, -1, 0}, {1, 14, -2}, {1, 6, -2}, {1, 8, -2}, {1, 10, -2}},
+   {{1, 6, -2}, {1, 8, -2}, {1, 14, -2}},
+   {{0, 0, 0}},
+   {{1, 2, -2}, {0, 1, 0}, {0, -1, 0}, {1, 8, -2}, {1, 2, -2}, {0, -1, 0}, {0, 1, 0}}};
+}
+
+#define FATAL_MSG(...) message((int *)0, (char *)0, SEV_FATAL, (char *)__VA_ARGS__)
+
+// ---- process-wide state (the reference keeps the same in function statics) -----
+struct AbiState {
+   mdb_engine *eng = nullptr;
+   cudaStream_t stream = nullptr;
+   bool real_init = false, recip_init = false;
+   double eintra = 0, self_energy = 0, sheet_energy = 0;
+   int onabor = 0, onx = 0, ony = 0, onz = 0;
+   std::vector<int> type, mol;
+   std::vector<double> potflat, chg;
+   mdb_config cfg{};
+   bool have_cfg = false;
+   const void *last_sites = nullptr;
+   bool sites_fresh = false;
+   double *d_out = nullptr; size_t out_cap = 0;
+   double *h_out = nullptr; size_t hout_cap = 0;
+   bool rdf_warned = false;
+};
+static AbiState G;
+
+static void ensure_engine()
+{
+   if (G.eng) return;
+   int dev = 0;
+   const char *s = getenv("MOLDY_B200_DEVICE");
+   if (!s) s = getenv("LOCAL_RANK");
+   if (s) dev = atoi(s);
+   G.eng = mdb_create(dev);
+   if (!G.eng) FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+   if (cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking) != cudaSuccess)
+      FATAL_MSG("libmoldy_b200: cannot create CUDA stream");
+}
+
+static int count_xf_sites(const system_mt *system, const spec_mt *species)
+{
+   int n = 0;
+   for (const spec_mt *sp = species; sp < species + system->nspecies && !sp->framework; sp++)
+      n += sp->nsites * sp->nmols;
+   return n;
+}
+
+// Flatten system/species/potpar/control into mdb_config and (re)configure the engine
+// when anything that shapes the tables changed (cell matrix changes every step under
+// constant-stress dynamics; everything else is constant in a Moldy run).
+static void sync_config(system_mt *system, spec_mt *species, const real *chg, const pot_mt *potpar)
+{
+   ensure_engine();
+   const int n = system->nsites, max_id = system->max_id;
+   if (control.molpbc)
+      FATAL_MSG("libmoldy_b200: molecular-cutoff=1 is not supported by the GPU force path");
+   int nfw = 0;
+   for (int i = 0; i < system->nspecies; i++) nfw += species[i].framework ? species[i].nmols : 0;
+   if (nfw > 1) FATAL_MSG("Multiple framework molecules are not supported");     /* src/force.c:1218 */
+
+   mdb_config c{};
+   c.nsites = n; c.nsites_xf = count_xf_sites(system, species);
+   c.max_id = max_id; c.ptype = system->ptype; c.n_potpar = system->n_potpar;
+   for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) c.h[3 * i + j] = system->h[i][j];
+   c.cutoff = control.cutoff; c.subcell = control.subcell; c.alpha = control.alpha;
+   c.k_cutoff = control.k_cutoff; c.strict_cutoff = control.strict_cutoff;
+   c.do_recip = control.alpha > MDB_ALPHAMIN;
+
+   bool changed = !G.have_cfg || c.nsites != G.cfg.nsites || c.nsites_xf != G.cfg.nsites_xf ||
+                  c.max_id != G.cfg.max_id || c.ptype != G.cfg.ptype || memcmp(c.h, G.cfg.h, sizeof c.h) ||
+                  c.cutoff != G.cfg.cutoff || c.subcell != G.cfg.subcell || c.alpha != G.cfg.alpha ||
+                  c.k_cutoff != G.cfg.k_cutoff || c.strict_cutoff != G.cfg.strict_cutoff ||
+                  c.do_recip != G.cfg.do_recip;
+   if ((int)G.type.size() != n) {
+      // site id and molecule maps (src/force.c:1173-1191)
+      G.type.resize(n); G.mol.resize(n);
+      int js = 0, jm = 0;
+      for (const spec_mt *sp = species; sp < species + system->nspecies; sp++)
+         for (int im = 0; im < sp->nmols; im++, jm++)
+            for (int is = 0; is < sp->nsites; is++, js++) { G.type[js] = sp->site_id[is]; G.mol[js] = jm; }
+      changed = true;
+   }
+   if ((int)G.chg.size() != n || memcmp(G.chg.data(), chg, sizeof(double) * n)) {
+      G.chg.assign(chg, chg + n);
+      changed = true;
+   }
+   if (potpar) {
+      std::vector<double> flat((size_t)max_id * max_id * MDB_NPOTP);
+      for (int k = 0; k < max_id * max_id; k++) memcpy(&flat[(size_t)k * MDB_NPOTP], potpar[k].p, sizeof(double) * MDB_NPOTP);
+      if (flat != G.potflat) { G.potflat.swap(flat); changed = true; }
+   } else if (G.potflat.size() != (size_t)max_id * max_id * MDB_NPOTP) {
+      G.potflat.assign((size_t)max_id * max_id * MDB_NPOTP, 0.0);
+      changed = true;
+   }
+   if (!changed) return;
+   c.site_type = G.type.data(); c.site_mol = G.mol.data(); c.chg = G.chg.data(); c.potpar = G.potflat.data();
+   if (mdb_configure(G.eng, &c)) FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+   G.cfg = c;
+   G.have_cfg = true;
+   G.sites_fresh = false;
+   const size_t need = mdb_out_doubles(n);
+   if (need > G.out_cap) {
+      if (G.d_out) cudaFree(G.d_out);
+      if (G.h_out) cudaFreeHost(G.h_out);
+      if (cudaMalloc(&G.d_out, sizeof(double) * need) != cudaSuccess ||
+          cudaMallocHost(&G.h_out, sizeof(double) * need) != cudaSuccess)
+         FATAL_MSG("libmoldy_b200: out of device/pinned memory for %d sites", n);
+      G.out_cap = need;
+   }
+}
+
+static void push_sites(real **site)
+{
+   if (G.sites_fresh && G.last_sites == (const void *)site[0] && !getenv("MOLDY_B200_ALWAYS_UPLOAD")) return;
+   if (mdb_set_sites_host(G.eng, site[0], site[1], site[2], G.stream)) FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+   G.last_sites = site[0];
+}
+
+static void pull_and_accumulate(real **site_force, double *pe, real (*stress)[3], int n)
+{
+   if (mdb_read_out(G.eng, G.d_out, G.h_out, G.stream)) FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+   for (int a = 0; a < 3; a++) {
+      real *dst = site_force[a];
+      const double *src = G.h_out + (size_t)a * n;
+      for (int i = 0; i < n; i++) dst[i] += src[i];
+   }
+   const double *sc = G.h_out + 3 * (size_t)n;
+   (void)pe;
+   stress[0][0] += sc[2]; stress[0][1] += sc[3]; stress[0][2] += sc[4];
+   stress[1][1] += sc[6]; stress[1][2] += sc[7]; stress[2][2] += sc[10];
+}
+
+extern "C" void force_calc(real **site, real **site_force, system_mt *system, spec_mt *species, real *chg,
+                           pot_mt *potpar, double *pe, mat_mt stress)
+{
+   sync_config(system, species, chg, potpar);
+   mdb_set_partition(G.eng, ithread, nthreads);
+   const int n = system->nsites;
+
+   if (!G.real_init) {                                   /* src/force.c:1158-1169 */
+      int isite = 0;
+      for (spec_mt *sp = species; sp < species + system->nspecies; sp++) {
+         if (!sp->framework) {
+            double e = 0.0;
+            for (int js = 0; js < sp->nsites; js++)
+               for (int is = js + 1; is < sp->nsites; is++) {
+                  const double *a = sp->p_f_sites[is], *b = sp->p_f_sites[js];
+                  double r = sqrt((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) +
+                                  (a[2] - b[2]) * (a[2] - b[2]));
+                  e += poteval(potpar[sp->site_id[js] * system->max_id + sp->site_id[is]].p, r, system->ptype,
+                               chg[isite + is] * chg[isite + js]);
+               }
+            G.eintra += sp->nmols * e;
+         }
+         isite += sp->nmols * sp->nsites;
+      }
+      note((char *)"Intramolecular potential energy correction = %g", G.eintra * CONV_E_KJ);
+      G.real_init = true;
+   }
+   if (ithread == 0) *pe -= G.eintra;
+
+   const int nhalf = mdb_n_neighbour_cells(G.eng);
+   if (nhalf != G.onabor) {                              /* src/force.c:218-223 */
+      note((char *)"Neighbour list contains %d cells", 2 * nhalf);
+      G.onabor = nhalf;
+   }
+   int g[3];
+   const int ncells = mdb_grid(G.eng, g);
+   if (g[0] != G.onx || g[1] != G.ony || g[2] != G.onz) { /* src/force.c:1240-1243 */
+      note((char *)"MD cell divided into %d subcells (%dx%dx%d)", ncells, g[0], g[1], g[2]);
+      G.onx = g[0]; G.ony = g[1]; G.onz = g[2];
+   }
+
+   G.sites_fresh = false;
+   push_sites(site);
+   if (mdb_zero_out(G.eng, G.d_out, G.stream) || mdb_build_cells(G.eng, G.stream) ||
+       mdb_force_real(G.eng, G.d_out, G.stream))
+      FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+   pull_and_accumulate(site_force, pe, stress, n);
+   *pe += G.h_out[3 * (size_t)n];
+   G.sites_fresh = true;
+
+   int pr[2];
+   const int tc = mdb_too_close(G.eng, pr, G.stream);
+   if (tc & (1 << 30))
+      message((int *)0, (char *)0, SEV_ERROR, (char *)"Co-ordinate out of range in BIN (fill_cells)");
+   if (tc & ~(1 << 30))                                  /* src/force.c:944-946 */
+      message((int *)0, (char *)0, SEV_WARNING, (char *)"Sites %d and %d closer than %fA.", pr[0], pr[1],
+              sqrt(MDB_TOO_CLOSE));
+
+   if (control.rdf_interval > 0 && control.istep >= control.begin_rdf &&
+       control.istep % control.rdf_interval == 0 && !G.rdf_warned) {
+      message((int *)0, (char *)0, SEV_WARNING,
+              (char *)"libmoldy_b200: RDF accumulation inside force_calc is not implemented; rdf data will be empty");
+      G.rdf_warned = true;
+   }
+}
+
+extern "C" void ewald(real **site, real **site_force, system_mp system, spec_mt *species, real *chg, double *pe,
+                      real (*stress)[3])
+{
+   sync_config(system, species, chg, nullptr);
+   mdb_set_partition(G.eng, ithread, nthreads);
+   const int n = system->nsites;
+   double h9[9];
+   for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) h9[3 * i + j] = system->h[i][j];
+   const double vol = mdb_det3(h9);
+
+   if (!G.recip_init) {                                  /* src/ewald.c:367-425 */
+      double sqsq = 0, sq = 0, last_intra = 0;
+      int ssite = 0;
+      spec_mt *sp = species;
+      while (sp < species + system->nspecies && !sp->framework) {
+         double intra = 0.0;
+         for (int is = 0; is < sp->nsites; is++)
+            for (int js = is + 1; js < sp->nsites; js++) {
+               const double *a = sp->p_f_sites[is], *b = sp->p_f_sites[js];
+               double r = sqrt((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) +
+                               (a[2] - b[2]) * (a[2] - b[2]));
+               intra += chg[ssite + is] * chg[ssite + js] * mdb_err_fn(control.alpha * r) / r;
+            }
+         G.self_energy += sp->nmols * intra;
+         ssite += sp->nsites * sp->nmols;
+         sp++;
+      }
+      const int nsitesxf = ssite;
+      const bool frame = sp != species + system->nspecies;
+      int is = 0;
+      for (; is < nsitesxf; is++) { sq += chg[is]; sqsq += chg[is] * chg[is]; }
+      G.self_energy += control.alpha / sqrt(MDB_PI) * sqsq;
+      const double sqxf = sq;
+      for (; is < n; is++) sq += chg[is];
+      if (frame) {
+         G.sheet_energy = MDB_PI * (sq - sqxf) * (sq - sqxf) / (2.0 * control.alpha * control.alpha);
+         message((int *)0, (char *)0, SEV_INFO,
+                 (char *)"Framework has net electric charge of %.2g - correction of %g kJ/mol added",
+                 (sq - sqxf) * CONV_Q_E, G.sheet_energy / vol * CONV_E_KJ);
+      }
+      if (fabs(sq) * CONV_Q_E > 1.0e-5) {
+         last_intra = MDB_PI * sq * sq / (2.0 * control.alpha * control.alpha);
+         G.sheet_energy -= last_intra;
+         message((int *)0, (char *)0, SEV_WARNING,
+                 (char *)"System has net electric charge of %.2g - correction of %g kJ/mol added", sq * CONV_Q_E,
+                 last_intra / vol * CONV_E_KJ);
+      }
+      note((char *)"Ewald self-energy = %f kJ/mol", G.self_energy * CONV_E_KJ);
+      note((char *)"%d K-vectors included in reciprocal-space sum", mdb_n_kvectors(G.eng));
+      G.recip_init = true;
+   }
+   if (ithread == 0) {                                   /* src/ewald.c:427-433 */
+      *pe -= G.self_energy;
+      *pe += G.sheet_energy / vol;
+      for (int i = 0; i < 3; i++) stress[i][i] += G.sheet_energy / vol;
+   }
+
+   push_sites(site);
+   G.sites_fresh = false;
+   if (mdb_zero_out(G.eng, G.d_out, G.stream) || mdb_force_recip(G.eng, G.d_out, G.stream))
+      FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+   pull_and_accumulate(site_force, pe, stress, n);
+   *pe += G.h_out[3 * (size_t)n + 1];
+}
+
+extern "C" void kernel(int jmin, int nnab, real *forceij, double *pe, real *r_sqr, real *nab_chg, double chg,
+                       double norm, double alpha, int ptype, real **pot)
+{
+   ensure_engine();
+   if (ptype < 0 || ptype > 6 || ptype == 5)
+      FATAL_MSG("KERNEL called with unknown potential type %d", ptype);   /* src/kernel.c:186 */
+   if (mdb_launch_kernel_vec(jmin, nnab, forceij, pe, r_sqr, nab_chg, chg, norm, alpha, ptype, pot))
+      FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+}
+
+extern "C" double poteval(real *potpar, double r, int ptype, double chgsq)
+{
+   double pe = 0.0, norm = 2.0 * control.alpha / sqrt(MDB_PI);
+   real chgsq_r = chgsq, f, rr = r * r;
+   real *pp[MDB_NPOTP];
+   for (int i = 0; i < MDB_NPOTP; i++) pp[i] = potpar + i;
+   kernel(0, 1, &f, &pe, &rr, &chgsq_r, 1.0, norm, control.alpha, ptype, pp);
+   return pe;
+}
+
+// Closed forms of -int_rc^inf r^2 U(r) dr per potential (initialisation only).
+extern "C" double dist_pot(real *p, double rc, int ptype)
+{
+   const double tol = 1.0e-7;
+   const double rc2 = rc * rc, rc3 = rc2 * rc;
+   auto exp_tail = [&](double b) { return rc2 / b + 2 * rc / (b * b) + 2.0 / (b * b * b); };
+   switch (ptype) {
+      default:
+         FATAL_MSG("KERNEL called with unknown potential type %d", ptype);
+      case 0: { double s2 = p[1] * p[1] / rc; return p[0] * s2 * s2 * s2 / 3.0; }
+      case 1:
+         if (p[2] > tol) return p[0] / (3.0 * rc3) - p[1] * exp(-p[2] * rc) * exp_tail(p[2]);
+         return p[0] / (3.0 * rc3);
+      case 2:
+         if (p[3] > tol) return p[2] * exp_tail(p[3]) * exp(-p[3] * rc);
+         return 0.0;
+      case 3: {
+         double tail = -p[2] / (9.0 * rc3 * rc3 * rc3) + p[3] / rc + p[4] / (3.0 * rc3) + p[5] / (5.0 * rc2 * rc3);
+         if (p[1] > tol) return -p[0] * exp(-p[1] * rc) * exp_tail(p[1]) + tail;
+         return tail;
+      }
+      case 6:
+         if (p[5] != 0.0) return p[3] / (3.0 * rc3) + 2.0 * p[4] * exp_tail(p[5]) * exp(-p[5] * (rc - p[6]));
+         return p[3] / (3.0 * rc3);
+      case 4:
+         return -p[0] / rc - p[1] / rc3 / 3.0 - p[2] / (rc3 * rc3 * rc3) / 9.0;
+   }
+}
+
+// ---- test/bench accessors ------------------------------------------------------
+extern "C" mdb_engine *mdb_abi_engine(void) { ensure_engine(); return G.eng; }
+extern "C" void *mdb_abi_stream(void) { ensure_engine(); return (void *)G.stream; }
+extern "C" void mdb_abi_constants(double out[3]) { out[0] = G.eintra; out[1] = G.self_energy; out[2] = G.sheet_energy; }
+extern "C" void mdb_abi_reset(void)
+{  // forget first-call state so one process can run several systems (tests only;
+   // the reference needs a fresh process for that)
+   G.real_init = G.recip_init = false;
+   G.eintra = G.self_energy = G.sheet_energy = 0;
+   G.onabor = G.onx = G.ony = G.onz = 0;
+   G.type.clear(); G.mol.clear(); G.chg.clear(); G.potflat.clear();
+   G.have_cfg = false; G.sites_fresh = false; G.last_sites = nullptr; G.rdf_warned = false;
+}

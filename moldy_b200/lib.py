@@ -1,0 +1,295 @@
+"""ctypes binding of libmoldy_b200.so and the Python mirror of the reference's
+operator interface for the hot path.
+
+Two call levels, as in include/moldy_b200.h:
+
+* `force_calc(...)` / `ewald(...)` / `kernel(...)` / `poteval(...)` / `dist_pot(...)`
+  take the same arguments, in the same order and with the same accumulate-into
+  semantics as the reference functions (src/force.c:1108, src/ewald.c:280,
+  src/kernel.c:157,103, src/force.c:632), with numpy arrays standing in for the
+  C arrays.  `eval_forces()` sequences them the way src/accel.c:488-535 does.
+* `Engine` wraps the device-resident mdb_* layer for callers that keep data in HBM.
+
+There is no fallback: importing works anywhere, but every compute call needs
+the CUDA library and a GPU and raises/aborts loudly otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .systems import MoldySystem
+
+_LIB = None
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmoldy_b200.so")
+
+DP = C.POINTER(C.c_double)
+IP = C.POINTER(C.c_int)
+
+
+class mdb_config(C.Structure):
+    _fields_ = [
+        ("nsites", C.c_int), ("nsites_xf", C.c_int), ("max_id", C.c_int), ("ptype", C.c_int),
+        ("n_potpar", C.c_int),
+        ("site_type", IP), ("site_mol", IP), ("chg", DP), ("potpar", DP),
+        ("h", C.c_double * 9),
+        ("cutoff", C.c_double), ("subcell", C.c_double), ("alpha", C.c_double), ("k_cutoff", C.c_double),
+        ("strict_cutoff", C.c_int), ("do_recip", C.c_int),
+    ]
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library; fail loudly when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m moldy_b200.build` "
+            "(nvcc, sm_100a).  moldy_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    L.mdb_last_error.restype = C.c_char_p
+    L.mdb_create.restype = C.c_void_p
+    L.mdb_create.argtypes = [C.c_int]
+    L.mdb_destroy.argtypes = [C.c_void_p]
+    L.mdb_out_doubles.restype = C.c_size_t
+    L.mdb_out_doubles.argtypes = [C.c_int]
+    L.mdb_configure.argtypes = [C.c_void_p, C.POINTER(mdb_config)]
+    L.mdb_set_partition.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.mdb_set_sites_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mdb_set_sites_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    for f in ("mdb_zero_out", "mdb_force_real", "mdb_force_recip"):
+        getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mdb_build_cells.argtypes = [C.c_void_p, C.c_void_p]
+    L.mdb_read_out.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mdb_grid.argtypes = [C.c_void_p, IP]
+    L.mdb_n_neighbour_cells.argtypes = [C.c_void_p]
+    L.mdb_n_kvectors.argtypes = [C.c_void_p]
+    L.mdb_get_cell_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mdb_pair_count.restype = C.c_double
+    L.mdb_pair_count.argtypes = [C.c_void_p, C.c_void_p]
+    L.mdb_kernel_launches.restype = C.c_long
+    L.mdb_kernel_launches.argtypes = [C.c_void_p]
+    L.mdb_too_close.argtypes = [C.c_void_p, IP, C.c_void_p]
+    L.mdb_sizeof.restype = C.c_size_t
+    L.mdb_sizeof.argtypes = [C.c_char_p]
+    L.mdb_fp64_peak_probe.restype = C.c_double
+    L.mdb_fp64_peak_probe.argtypes = [C.c_int, C.c_int]
+    L.mdb_control.restype = C.POINTER(abi.contr_mt)
+    L.mdb_abi_engine.restype = C.c_void_p
+    L.mdb_abi_stream.restype = C.c_void_p
+    L.mdb_abi_constants.argtypes = [DP]
+    L.poteval.restype = C.c_double
+    L.poteval.argtypes = [DP, C.c_double, C.c_int, C.c_double]
+    L.dist_pot.restype = C.c_double
+    L.dist_pot.argtypes = [DP, C.c_double, C.c_int]
+    L.kernel.argtypes = [C.c_int, C.c_int, DP, DP, DP, DP, C.c_double, C.c_double, C.c_double, C.c_int,
+                         C.POINTER(DP)]
+    _LIB = L
+    return L
+
+
+def _err(L):
+    return L.mdb_last_error().decode()
+
+
+# ---------------------------------------------------------------------------
+# Moldy-level interface (same names / argument meaning as the reference)
+# ---------------------------------------------------------------------------
+def control() -> abi.contr_mt:
+    """The library's view of Moldy's global `control` record."""
+    return load().mdb_control().contents
+
+
+def set_thread(ithread: int, nthreads: int):
+    load().mdb_set_thread(ithread, nthreads)
+
+
+def _rows(block: np.ndarray):
+    assert block.dtype == np.float64 and block.flags.c_contiguous and block.shape[0] == 3
+    stride = block.strides[0]
+    return (DP * 3)(*[C.cast(block.ctypes.data + stride * i, DP) for i in range(3)])
+
+
+def force_calc(site, site_force, system, species, chg, potpar, pe, stress):
+    """force_calc(site, site_force, system, species, chg, potpar, pe, stress):
+    real-space forces accumulated into site_force[3][nsarray], pe[0], stress."""
+    L = load()
+    L.force_calc(_rows(site), _rows(site_force), C.byref(system), species,
+                 chg.ctypes.data_as(DP), potpar, pe.ctypes.data_as(DP),
+                 stress.ctypes.data_as(C.POINTER(abi.vec_mt)))
+
+
+def ewald(site, site_force, system, species, chg, pe, stress):
+    """ewald(site, site_force, system, species, chg, pe, stress): reciprocal-space
+    part; `pe` is the caller's pe+1 (a length-1 view)."""
+    L = load()
+    L.ewald(_rows(site), _rows(site_force), C.byref(system), species, chg.ctypes.data_as(DP),
+            pe.ctypes.data_as(DP), stress.ctypes.data_as(C.POINTER(abi.vec_mt)))
+
+
+def kernel(jmin, nnab, forceij, pe, r_sqr, nab_chg, chg, norm, alpha, ptype, pot):
+    """kernel(): vector pair-potential evaluation; pot is [n_potpar][nnab]."""
+    L = load()
+    pot = np.ascontiguousarray(pot, dtype=np.float64)
+    rows = (DP * 8)(*[C.cast(pot.ctypes.data + pot.strides[0] * min(i, pot.shape[0] - 1), DP) for i in range(8)])
+    L.kernel(jmin, nnab, forceij.ctypes.data_as(DP), pe.ctypes.data_as(DP), r_sqr.ctypes.data_as(DP),
+             nab_chg.ctypes.data_as(DP), chg, norm, alpha, ptype, rows)
+
+
+def poteval(potpar, r, ptype, chgsq):
+    p = np.ascontiguousarray(potpar, dtype=np.float64)
+    return load().poteval(p.ctypes.data_as(DP), r, ptype, chgsq)
+
+
+def dist_pot(potpar, cutoff, ptype):
+    p = np.ascontiguousarray(potpar, dtype=np.float64)
+    return load().dist_pot(p.ctypes.data_as(DP), cutoff, ptype)
+
+
+def eval_forces(ms: MoldySystem, real=True, recip=True, sites=None, ithread=0, nthreads=1):
+    """The hot-path part of eval_forces() (src/accel.c:488-535) for one
+    configuration through the Moldy-level C ABI with HOST buffers."""
+    L = load()
+    ms.control.fill(control())
+    set_thread(ithread, nthreads)
+    sysm, spec, pot = ms.cstructs()
+    n = ms.nsites
+    nsa = abi.nsarray(n)
+    site = np.ascontiguousarray(ms.make_sites() if sites is None else sites)
+    force = np.zeros((3, nsa))
+    chg = ms.charges()
+    pe = np.zeros(2)
+    stress = np.zeros((3, 3))
+    if real:
+        force_calc(site, force, sysm, spec, chg, pot, pe[0:1], stress)
+    if recip and ms.control.alpha > 1e-7:
+        ewald(site, force, sysm, spec, chg, pe[1:2], stress)
+    return dict(force=force[:, :n].copy(), pe=pe, stress=stress)
+
+
+def reset():
+    """Forget the Moldy-level first-call state (lets one test process run several systems)."""
+    load().mdb_abi_reset()
+
+
+# ---------------------------------------------------------------------------
+# Device-resident engine
+# ---------------------------------------------------------------------------
+class Engine:
+    def __init__(self, device: int = 0):
+        self.L = load()
+        self.h = self.L.mdb_create(device)
+        if not self.h:
+            raise RuntimeError("mdb_create failed: " + _err(self.L))
+        self.n = 0
+        self._keep = None
+
+    def close(self):
+        if self.h:
+            self.L.mdb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what}: {_err(self.L)}")
+
+    def configure(self, ms: MoldySystem):
+        cfg = mdb_config()
+        sd = ms.sysdef
+        ids = np.ascontiguousarray(ms.site_ids(), dtype=np.int32)
+        mol = np.ascontiguousarray(ms.molmap(), dtype=np.int32)
+        chg = np.ascontiguousarray(ms.charges())
+        pot = np.ascontiguousarray(sd.potpar.reshape(-1), dtype=np.float64)
+        cfg.nsites, cfg.nsites_xf = ms.nsites, ms.nsites_xf
+        cfg.max_id, cfg.ptype, cfg.n_potpar = sd.max_id, sd.ptype, sd.n_potpar
+        cfg.site_type = ids.ctypes.data_as(IP)
+        cfg.site_mol = mol.ctypes.data_as(IP)
+        cfg.chg = chg.ctypes.data_as(DP)
+        cfg.potpar = pot.ctypes.data_as(DP)
+        for i in range(9):
+            cfg.h[i] = float(ms.h.reshape(-1)[i])
+        c = ms.control
+        cfg.cutoff, cfg.subcell, cfg.alpha, cfg.k_cutoff = c.cutoff, c.subcell, c.alpha, c.k_cutoff
+        cfg.strict_cutoff = c.strict_cutoff
+        cfg.do_recip = int(c.alpha > 1e-7)
+        self._keep = (ids, mol, chg, pot)
+        self._chk(self.L.mdb_configure(self.h, C.byref(cfg)), "mdb_configure")
+        self.n = ms.nsites
+
+    def out_doubles(self):
+        return self.L.mdb_out_doubles(self.n)
+
+    def set_partition(self, ithread, nthreads):
+        self.L.mdb_set_partition(self.h, ithread, nthreads)
+
+    def set_sites_host(self, site_block: np.ndarray, stream=0):
+        r = [site_block.ctypes.data + site_block.strides[0] * i for i in range(3)]
+        self._chk(self.L.mdb_set_sites_host(self.h, r[0], r[1], r[2], stream), "mdb_set_sites_host")
+
+    def set_sites_host_ptrs(self, px, py, pz, stream=0):
+        self._chk(self.L.mdb_set_sites_host(self.h, px, py, pz, stream), "mdb_set_sites_host")
+
+    def set_sites_device(self, px, py, pz, stream=0):
+        self._chk(self.L.mdb_set_sites_device(self.h, px, py, pz, stream), "mdb_set_sites_device")
+
+    def zero_out(self, d_out, stream=0):
+        self._chk(self.L.mdb_zero_out(self.h, d_out, stream), "mdb_zero_out")
+
+    def build_cells(self, stream=0):
+        self._chk(self.L.mdb_build_cells(self.h, stream), "mdb_build_cells")
+
+    def force_real(self, d_out, stream=0):
+        self._chk(self.L.mdb_force_real(self.h, d_out, stream), "mdb_force_real")
+
+    def force_recip(self, d_out, stream=0):
+        self._chk(self.L.mdb_force_recip(self.h, d_out, stream), "mdb_force_recip")
+
+    def read_out(self, d_out, stream=0) -> np.ndarray:
+        h = np.empty(self.out_doubles())
+        self._chk(self.L.mdb_read_out(self.h, d_out, h.ctypes.data, stream), "mdb_read_out")
+        return h
+
+    def grid(self):
+        g = (C.c_int * 3)()
+        nc = self.L.mdb_grid(self.h, g)
+        return nc, tuple(g)
+
+    def n_neighbour_cells(self):
+        return self.L.mdb_n_neighbour_cells(self.h)
+
+    def n_kvectors(self):
+        return self.L.mdb_n_kvectors(self.h)
+
+    def cell_ids(self, stream=0) -> np.ndarray:
+        out = np.empty(self.n, dtype=np.int32)
+        self._chk(self.L.mdb_get_cell_ids(self.h, out.ctypes.data, stream), "mdb_get_cell_ids")
+        return out
+
+    def pair_count(self, stream=0) -> float:
+        return self.L.mdb_pair_count(self.h, stream)
+
+    def launches(self) -> int:
+        return self.L.mdb_kernel_launches(self.h)
+
+    def too_close(self, stream=0):
+        p = (C.c_int * 2)()
+        n = self.L.mdb_too_close(self.h, p, stream)
+        return n, (p[0], p[1])
+
+
+def unpack(h_out: np.ndarray, n: int):
+    """Split a result block into forces[3,N], pe[2], stress[3,3]."""
+    f = h_out[:3 * n].reshape(3, n).copy()
+    pe = h_out[3 * n:3 * n + 2].copy()
+    stress = h_out[3 * n + 2:3 * n + 11].reshape(3, 3).copy()
+    return f, pe, stress

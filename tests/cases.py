@@ -1,0 +1,115 @@
+"""Parity systems shared by the CPU (`-m "not gpu"`) and GPU (`-m gpu`) tests and by
+tests/golden/make_fixtures.py.  Every entry returns a fresh MoldySystem; all
+are small enough for the reference to evaluate in well under a second, and
+together they cover every potential form of src/kernel.c, Coulomb on/off,
+strict/lazy cut-off, orthorhombic/triclinic cells, multi-species systems and a
+framework species."""
+import numpy as np
+
+from moldy_b200 import systems
+from moldy_b200.systems import Control, build, KCAL_TIME_UNIT
+
+SPEC_HIW = """
+Water 60
+1 0 0 0 16 -0.8 O
+2 0.7569503 0 -0.5858822 1 0.4 H
+2 -0.7569503 0 -0.5858822
+Ion 6
+3 0 0 0 52 0 X
+end
+hiw
+1 1 -120 800 900000
+1 2 30 -10 300
+2 2 5 2 50
+1 3 -900 2500 5200000
+2 3 450 -300 8000
+3 3 0 0 9000000
+end
+"""
+
+SPEC_MORSE = """
+Metal 40
+1 0 0 0 55.8 1.2 M
+Oxide 60
+2 0 0 0 16 -0.8 O
+end
+morse
+1 1 0.3 1.8 6.0 20 0 0 0
+1 2 0.3 2.9 6.2 30 9.5 2.0 1.9
+2 2 0.3 3.6 5.5 70 0 0 0
+end
+"""
+
+SPEC_MORSE_NEUTRAL = SPEC_MORSE.replace("55.8 1.2 M", "55.8 0 M").replace("16 -0.8 O", "16 0 O")
+
+
+def hiw():
+    return build(SPEC_HIW, Control(subcell=2.2, density=1.0), time_unit=KCAL_TIME_UNIT, seed=11, jitter=0.1)
+
+
+def morse():
+    return build(SPEC_MORSE, Control(subcell=2.0, density=3.2), time_unit=KCAL_TIME_UNIT, seed=12, jitter=0.1)
+
+
+def morse_nocoul():
+    return build(SPEC_MORSE_NEUTRAL, Control(cutoff=7.0, subcell=2.0, density=3.2),
+                 time_unit=KCAL_TIME_UNIT, seed=13, jitter=0.1)
+
+
+def argon_lazy():
+    ms = systems.argon(seed=5)
+    ms.control.strict_cutoff = 0
+    return ms
+
+
+def quartz_auto():
+    """Triclinic Buckingham crystal with all three Ewald parameters derived."""
+    return systems.quartz(n=3, pinned_cutoff=False)
+
+
+def mcy_auto():
+    return systems.mgcl2(explicit=False)
+
+
+def tip4p_tiny_box():
+    """A box so small that the stencil reaches the periodic images of the
+    reference cell itself (self-image pairs, SURVEY 8a' item 1)."""
+    ms = systems.tips2()
+    ms.control.cutoff = 10.5
+    ms.control.alpha = 0.32
+    ms.control.k_cutoff = 2.4
+    ms.control.subcell = 3.2
+    return ms
+
+
+GOLDEN_CASES = {
+    "argon": systems.argon,
+    "argon_lazy": argon_lazy,
+    "tip4p": systems.tip4p,
+    "tip4p_2": lambda: systems.tip4p(2),
+    "tips2": systems.tips2,
+    "tips2_tinybox": tip4p_tiny_box,
+    "mgcl2": systems.mgcl2,
+    "mgcl2_auto": mcy_auto,
+    "quartz": systems.quartz,
+    "quartz_auto": quartz_auto,
+    "slab_framework": systems.slab,
+    "hiw": hiw,
+    "morse": morse,
+    "morse_nocoul": morse_nocoul,
+}
+
+# start-up scalars the reference's own example outputs pin:
+# name -> (subcells, neighbour cells (2 x half list), Ewald self energy kJ/mol, k-vectors)
+EXAMPLE_GOLDENS = {
+    "argon": (729, 912, None, None),            # src/examples/argon-example.out:58-60
+    "tip4p": (512, 204, 1722.888659, 1102),     # src/examples/tip4p-example.out:65-68
+    "tips2": (125, 94, 968.356089, 570),        # src/examples/tips2-example.out:65-68
+    "mgcl2": (3375, 486, 11332.778403, 1484),   # src/examples/mgclh2o-example.out:79-82
+    "quartz": (None, None, 457724.399972, 833), # src/examples/quartz-example.out:68-69
+}
+
+
+def rel_rms(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.sqrt(((a - b) ** 2).sum() / max((b ** 2).sum(), 1e-300)))
