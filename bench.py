@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- Moldy force-evaluation hot path on B200 (contract: see DESIGN.md section 7).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n REPL]
+
+A "step" is one full force evaluation of the synthetic TIP4P system (256-molecule
+equilibrated cell replicated n^3 with jitter; n=10 -> 1 024 000 sites, the ~10^6-site
+configuration BASELINE.json's metric is quoted on): link-cell build + real-space pair
+kernel + reciprocal-space Ewald (structure factors, energy/stress, forces), i.e. what
+force_calc() + ewald() do per MD step.
+
+`value`   steps/s with positions already resident in HBM (CUDA events per step, max
+          over ranks; for N>1 the system is the same -- strong scaling -- each rank owns
+          a slice of the cell-sorted sites and of the (h,k) columns and the packed
+          [forces|pe|stress] block is all-reduced with NCCL inside the timed step).
+`e2e`     the same metric through Moldy's own entry points force_calc()+ewald() of
+          libmoldy_b200.so with HOST (pinned) buffers: H2D of the site rows and D2H of
+          the force rows inside the timed region (N=1), or through
+          moldy_b200.spmd.SpmdForces (N>1).
+`--impl reference` times the reference's own CPU code (oracle/_ref, built from
+          /root/reference with its own flags) on all host cores, replicated-data SPMD
+          exactly as parallel.c runs it (rank p of P evaluates cells p mod P and its
+          block of k-vectors), on a bounded 1/S sample of the ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_PAIR = 59          # LJ + erfc-Coulomb pair, mk_r_sqr + kernel + mk_forces
+FLOP_PER_SITEK = 18         # qsincos + sum + force per (site, k-vector)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=10, help="replication factor of the 256-water cell (10 -> 1.024M sites)")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the bounded reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], None, set(), []
+        for r in self.rows:
+            t = [x.strip() for x in r.split(",")]
+            if len(t) < 7:
+                continue
+            try:
+                sm.append(float(t[0])); mx = float(t[1]); pw.append(float(t[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], t[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- reference arm
+def _ref_worker(args):
+    """One SPMD rank of the reference (runs in its own process: function statics)."""
+    n, ithread, nthreads, fast = args
+    sys.path.insert(0, ROOT)
+    from moldy_b200 import systems
+    from oracle import ref
+    ms = systems.tip4p(n)
+    r = ref.RefLib(fast=fast)
+    r.set_thread(ithread, nthreads)
+    site = ms.make_sites()
+    t0 = time.perf_counter()
+    r.run(ms, sites=site)
+    return time.perf_counter() - t0
+
+
+def reference_sample(n: int, target_s: float, steps: int = 1):
+    """Time the reference's replicated-data SPMD step on all usable host cores on a
+    bounded sample.  Full step on P cores = every rank p<P does cells p mod P and
+    k-block p.  We run P processes as ranks p of P*S (each does 1/(P*S) of the work),
+    plus one calibration with (almost) no work to separate the non-partitioned
+    overhead (trig tables, cell lists, potp expansion), and extrapolate
+        t_step(P cores) = t_over + S * (t_sample - t_over)."""
+    import multiprocessing as mp
+    from moldy_b200 import systems
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    nsites = 1024 * n ** 3
+    mem_per_rank = 1.7e9 * nsites / 1.024e6 + 0.4e9
+    try:
+        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except (ValueError, OSError):
+        avail = 32e9
+    P = int(max(1, min(ncpu, 64, 0.6 * avail // mem_per_rank)))
+    # serial cost model from the survey probe (541 s at 1.024M sites, ~N^1.5)
+    serial_est = 541.0 * (nsites / 1.024e6) ** 1.5 / 1.6      # fast-math build is ~1.6x quicker
+    S = max(1, int(round(serial_est / (P * target_s))))
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(P) as pool:
+        t_over = max(pool.map(_ref_worker, [(n, 0, 1 << 24, True)] * min(P, 2)))
+        samples = []
+        for _ in range(steps):
+            samples.append(max(pool.map(_ref_worker, [(n, p * S, P * S, True) for p in range(P)])))
+    t_sample = statistics.median(samples)
+    t_step = t_over + S * max(t_sample - t_over, 0.0)
+    return dict(value=1.0 / t_step, unit="steps/s", cores=P, kind="reference",
+                sample=f"ranks p*{S} (p<{P}) of a {P * S}-way replicated-data SPMD split of one step "
+                       f"(1/{S} of every core's share) + a no-work calibration run; "
+                       f"t_over={t_over:.2f}s t_sample={t_sample:.2f}s -> t_step({P} cores)={t_step:.1f}s; "
+                       f"oracle/_ref/libmoldyref_fast.so = reference force.c/kernel.c/ewald.c, gcc -O2 -ffast-math"), t_step
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref
+    if not ref.available(fast=True):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libmoldyref_fast.so not built"}))
+        return
+    cb, t_step = reference_sample(a.n, a.cpu_seconds, steps=max(1, min(a.steps, 2)))
+    nsites = 1024 * a.n ** 3
+    line = {"metric": "md_force_steps_per_s", "value": cb["value"], "unit": "steps/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": workload_config(a.n, nsites, None), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(n, nsites, ms):
+    cfg = {"workload": f"TIP4P water, 256-molecule equilibrated cell replicated {n}x{n}x{n} = {nsites} sites, "
+                       "real-space link-cell + reciprocal-space Ewald (force_calc + ewald)",
+           "l2_flush": "256 MiB device memset between steps, outside the per-step CUDA-event brackets"}
+    if ms is not None:
+        cfg.update({"cutoff_A": ms.control.cutoff, "alpha": ms.control.alpha, "k_cutoff": ms.control.k_cutoff,
+                    "subcell_A": ms.control.subcell})
+    return cfg
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from moldy_b200 import lib, systems
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; moldy_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    ms = systems.tip4p(a.n)
+    N = ms.nsites
+    site = ms.make_sites()
+    eng = lib.Engine(local)
+    eng.configure(ms)
+    eng.set_partition(rank, world)
+    st = torch.cuda.current_stream().cuda_stream
+    xyz = torch.from_numpy(np.ascontiguousarray(site[:, :N])).cuda()
+    out = torch.zeros(eng.out_doubles(), dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    eng.set_sites_device(xyz[0].data_ptr(), xyz[1].data_ptr(), xyz[2].data_ptr(), st)
+
+    def step(ev=None):
+        eng.zero_out(out.data_ptr(), st)
+        if ev: ev[0].record()
+        eng.build_cells(st)
+        if ev: ev[1].record()
+        eng.force_real(out.data_ptr(), st)
+        if ev: ev[2].record()
+        eng.force_recip(out.data_ptr(), st)
+        if ev: ev[3].record()
+        if world > 1:
+            dist.all_reduce(out)
+        if ev: ev[4].record()
+
+    for _ in range(a.warmup):
+        step()
+    torch.cuda.synchronize()
+    eng.pair_count(st)                        # reset the visit counter
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(a.steps)]
+    l0 = eng.launches()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for i in range(a.steps):
+        flush.zero_()
+        step(evs[i])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.launches() - l0
+    ph = np.array([[e[k].elapsed_time(e[k + 1]) for k in range(4)] for e in evs])     # ms: cells, pair, recip, allreduce
+    tot_ms = float(sum(e[0].elapsed_time(e[4]) for e in evs))
+    t = torch.tensor([tot_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot_ms = float(t.item())
+    pairs_rank = eng.pair_count(st) / a.steps
+    pr = torch.tensor([pairs_rank], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(pr)
+    pairs = float(pr.item())
+    nhkl = eng.n_kvectors()
+    ms_step = tot_ms / a.steps
+    value = 1e3 / ms_step
+
+    # ---- end-to-end through the public host-buffer API --------------------------------
+    e2e = measure_e2e(a, ms, site, world, rank, local)
+
+    if rank == 0:
+        pair_ms = float(ph[:, 1].mean())
+        peak = lib.load().mdb_fp64_peak_probe(local, 100000)
+        achieved = FLOP_PER_PAIR * (pairs / world) / (pair_ms * 1e-3)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        roof = {"bound": "fp64", "kernel": "k_pair<LJ,coulomb> (real-space pair kernel, FP64 CUDA cores; no tensor-core "
+                "or HBM roofline applies: ~36 B/site are reused for ~12 000 pair visits)",
+                "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_source": "FP64 DFMA rate measured in this run by mdb_fp64_peak_probe (MEASURED_PEAKS.json holds "
+                               "no FP64 figure; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2)",
+                "algorithmic_flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs / world,
+                "avg_launch_ms": pair_ms, "traffic": TRAFFIC.get(a.n),
+                "hbm_peak_gbs_measured": peaks.get("hbm_gbs")}
+        line = {"metric": "md_force_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(a.n, N, ms),
+                "site_pairs_per_s": pairs / (ms_step * 1e-3), "site_pairs_per_step": pairs,
+                "k_vectors": nhkl, "site_k_terms_per_s": N * nhkl / (ms_step * 1e-3),
+                "phase_ms": {"cells": float(ph[:, 0].mean()), "pair": pair_ms, "recip": float(ph[:, 2].mean()),
+                             "allreduce": float(ph[:, 3].mean())},
+                "recip_roofline": {"bound": "fp64", "achieved": FLOP_PER_SITEK * N * nhkl / world / (ph[:, 2].mean() * 1e-3) / 1e12,
+                                   "peak": peak / 1e12, "unit": "TFLOP/s",
+                                   "frac": FLOP_PER_SITEK * N * nhkl / world / (ph[:, 2].mean() * 1e-3) / peak},
+                "roofline": roof, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "wall_s_timed_region": t_wall}
+        if world == 1 and not a.no_cpu_baseline:
+            from oracle import ref
+            if ref.available(fast=True):
+                line["cpu_baseline"], _ = reference_sample(a.n, a.cpu_seconds)
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": "steps/s", "cores": 0, "kind": "reference",
+                                        "sample": "oracle/_ref not built on this box"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# dram__bytes_read+write per k_pair launch from the ncu --set full capture committed under profiles/
+TRAFFIC = {}
+
+
+def measure_e2e(a, ms, site, world, rank, local):
+    import numpy as np
+    import torch
+    from moldy_b200 import abi, lib
+    N = ms.nsites
+    nsa = abi.nsarray(N)
+    steps = max(2, min(a.steps, 5))
+    if world == 1:
+        # Moldy's own entry points, host buffers in pinned memory
+        ms.control.fill(lib.control())
+        lib.set_thread(0, 1)
+        sysm, spec, pot = ms.cstructs()
+        hs = torch.empty((3, nsa), dtype=torch.float64).pin_memory()
+        hf = torch.empty((3, nsa), dtype=torch.float64).pin_memory()
+        hs.numpy()[:] = site
+        s_np, f_np = hs.numpy(), hf.numpy()
+        chg = ms.charges()
+        pe = np.zeros(2)
+        stress = np.zeros((3, 3))
+
+        def one():
+            f_np[:] = 0.0
+            pe[:] = 0.0
+            stress[:] = 0.0
+            lib.force_calc(s_np, f_np, sysm, spec, chg, pot, pe[0:1], stress)
+            lib.ewald(s_np, f_np, sysm, spec, chg, pe[1:2], stress)
+
+        lib.reset()
+        one(); one()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one()
+        dt = (time.perf_counter() - t0) / steps
+        return {"value": 1.0 / dt, "unit": "steps/s", "ms_per_step": 1e3 * dt,
+                "h2d_bytes_per_step": 3 * N * 8, "d2h_bytes_per_step": 2 * (3 * N + 16) * 8,
+                "api": "force_calc()+ewald() of libmoldy_b200.so, pinned host site/site_force rows"}
+    from moldy_b200 import spmd
+    ev = spmd.SpmdForces(ms, rank, world, local)
+    hs = torch.from_numpy(np.ascontiguousarray(site[:, :N])).pin_memory()
+    ev.step(hs); ev.step(hs)
+    import torch.distributed as dist
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ev.step(hs)
+    dist.barrier()
+    dt = (time.perf_counter() - t0) / steps
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    return {"value": 1.0 / dt, "unit": "steps/s", "ms_per_step": 1e3 * dt,
+            "h2d_bytes_per_step": 3 * N * 8 * world, "d2h_bytes_per_step": (3 * N + 16) * 8 * world,
+            "api": "moldy_b200.spmd.SpmdForces.step(pinned host sites) -> host [forces|pe|stress] on every rank"}
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

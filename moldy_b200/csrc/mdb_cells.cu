@@ -145,8 +145,9 @@ __global__ void __launch_bounds__(CB) k_fill(int n, const int *__restrict__ cell
 __global__ void __launch_bounds__(CB) k_sort_gather(int ncells, const int *__restrict__ start, int *__restrict__ order,
                                                     const double *__restrict__ x, const double *__restrict__ y,
                                                     const double *__restrict__ z, const double *__restrict__ q,
-                                                    const int *__restrict__ type, double4 *__restrict__ posq,
-                                                    int *__restrict__ stype, int *__restrict__ scell)
+                                                    const int *__restrict__ type, int nsites_xf,
+                                                    double4 *__restrict__ posq, int *__restrict__ stype,
+                                                    int *__restrict__ scell)
 {
    int c = blockIdx.x * CB + threadIdx.x;
    if (c >= ncells) return;
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(CB) k_sort_gather(int ncells, const int *__res
    for (int s = b; s < e; s++) {
       int o = order[s];
       posq[s] = make_double4(x[o], y[o], z[o], q[o]);
-      stype[s] = type[o];
+      stype[s] = type[o] | (o >= nsites_xf ? 0x40000000 : 0);   // bit 30: framework site
       scell[s] = c;
    }
 }
@@ -184,7 +185,7 @@ int mdb_launch_cells(mdb_engine *e, cudaStream_t st)
    MDB_CUDA(cudaMemsetAsync(e->d_count, 0, sizeof(int) * (size_t)(nc + 1), st));   // now the fill cursor
    k_fill<<<(n + CB - 1) / CB, CB, 0, st>>>(n, e->d_cell, e->d_start, e->d_count, e->d_order);
    k_sort_gather<<<(nc + CB - 1) / CB, CB, 0, st>>>(nc, e->d_start, e->d_order, e->d_x, e->d_y, e->d_z, e->d_chg,
-                                                   e->d_type, e->d_posq, e->d_stype, e->d_scell);
+                                                   e->d_type, e->cfg.nsites_xf, e->d_posq, e->d_stype, e->d_scell);
    e->launches += 6;
    MDB_CUDA(cudaGetLastError());
    e->cells_valid = true;

@@ -40,10 +40,12 @@ k_pair(PairParams P, int nsites, const double4 *__restrict__ posq, const int *__
    const int s = P.s_lo + blockIdx.x * PB + threadIdx.x;
    const bool active = s < P.s_hi;
    double4 pi = make_double4(0, 0, 0, 0);
-   int cx = 0, cy = 0, cz = 0, ti = 0;
+   int cx = 0, cy = 0, cz = 0, ti = 0, fwi = 0;
    if (active) {
       pi = posq[s];
       ti = stype[s];
+      fwi = ti >> 30;                     // framework flag rides in bit 30 of the sorted type
+      ti &= 0x3fffffff;
       int c = scell[s];
       cz = c % P.nz;
       int t = c / P.nz;
@@ -79,7 +81,10 @@ k_pair(PairParams P, int nsites, const double4 *__restrict__ posq, const int *__
             for (int j = jb; j < je; j++) {
                if (central && j == s) { visits--; continue; }
                const double4 pj = posq[j];
-               const int tj = stype[j];
+               int tj = stype[j];
+               // framework sites never interact with each other (src/force.c:904-912)
+               if (fwi & (tj >> 30)) { visits--; continue; }
+               tj &= 0x3fffffff;
                const double dx = pj.x - sx, dy = pj.y - sy, dz = pj.z - sz;
                double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
                if (r2 < MDB_TOO_CLOSE) {

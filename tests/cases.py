@@ -110,6 +110,18 @@ EXAMPLE_GOLDENS = {
 }
 
 
+# the example systems exactly as the reference's start-up builds them (box from the
+# density, not from the 6-digit cell printed in a text-mode save file)
+EXAMPLE_SYSTEMS = {
+    "argon": systems.argon,
+    "tip4p": lambda: systems.tip4p(equilibrated=False),
+    "tips2": lambda: systems.tips2(equilibrated=False),
+    "mgcl2": lambda: systems.build(systems.SPEC_MGCL2, Control(cutoff=6.25, k_cutoff=3.0, alpha=0.45, density=1.0),
+                                   time_unit=KCAL_TIME_UNIT),
+    "quartz": systems.quartz,
+}
+
+
 def rel_rms(a, b):
     a, b = np.asarray(a), np.asarray(b)
     return float(np.sqrt(((a - b) ** 2).sum() / max((b ** 2).sum(), 1e-300)))

@@ -65,7 +65,7 @@ def test_cell_assignment_bit_exact(name, golden_dir):
 def test_startup_scalars_match_example_outputs(name):
     """#subcells, #neighbour cells and #k-vectors printed by the reference's 1996
     sample outputs (the only goldens its tree holds for this path)."""
-    ms = cases.GOLDEN_CASES[name]()
+    ms = cases.EXAMPLE_SYSTEMS[name]()
     sub, nab, self_e, nk = cases.EXAMPLE_GOLDENS[name]
     eng = lib.Engine(0)
     eng.configure(ms)
