@@ -50,7 +50,7 @@ def load() -> C.CDLL:
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with `python -m moldy_b200.build` "
             "(nvcc, sm_100a).  moldy_b200 has no CPU fallback.")
-    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    L = C.CDLL(LIB_PATH)
     L.mdb_last_error.restype = C.c_char_p
     L.mdb_create.restype = C.c_void_p
     L.mdb_create.argtypes = [C.c_int]

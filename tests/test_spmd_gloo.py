@@ -1,0 +1,84 @@
+"""CPU tests (-m "not gpu"): the N>1 path of the replicated-data layer on the
+`gloo` backend, world_size 2.  Each rank evaluates its slice of the step with the
+oracle standing in for the GPU kernels (same ithread/nthreads partition contract),
+packs the [forces | pe | stress] block the way the engine lays it out in HBM, and
+moldy_b200.spmd.combine() all-reduces it -- the par_dsum/par_rsum of
+src/accel.c:531-535.  Every rank must end up with the single-rank result,
+bit-identical across ranks (Moldy's DESYNC check, src/main.c:262-273)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port_no, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from moldy_b200 import spmd
+    from oracle import port
+    from tests import cases
+    ms = cases.GOLDEN_CASES["tips2"]()
+    n = ms.nsites
+    part = port.run(ms, ithread=rank, nthreads=world)
+    block = torch.zeros(3 * n + 16, dtype=torch.float64)
+    block[:3 * n] = torch.from_numpy(part["force"].reshape(-1))
+    block[3 * n:3 * n + 2] = torch.from_numpy(part["pe"])
+    block[3 * n + 2:3 * n + 11] = torch.from_numpy(part["stress"].reshape(-1))
+    spmd.combine(block)
+    gathered = [torch.zeros_like(block) for _ in range(world)]
+    dist.all_gather(gathered, block)
+    same = all(torch.equal(gathered[0], g) for g in gathered)
+    if rank == 0:
+        q.put((block.numpy().copy(), same))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_allreduce_reproduces_single_rank():
+    from oracle import port
+    from tests import cases
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port_no, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    block, same = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert same, "ranks disagree after the all-reduce"
+    ms = cases.GOLDEN_CASES["tips2"]()
+    n = ms.nsites
+    whole = port.run(ms)
+    assert cases.rel_rms(block[:3 * n].reshape(3, n), whole["force"]) < 1e-13
+    assert np.allclose(block[3 * n:3 * n + 2], whole["pe"], rtol=1e-12)
+    assert np.allclose(block[3 * n + 2:3 * n + 11].reshape(3, 3), whole["stress"], rtol=1e-11, atol=1e-9)
+
+
+def test_partition_helpers_cover_everything_once():
+    from moldy_b200 import spmd
+    for n, w in ((1024000, 8), (1000, 3), (7, 8)):
+        sl = [spmd.site_slice(n, r, w) for r in range(w)]
+        assert sl[0][0] == 0 and sl[-1][1] == n
+        assert all(sl[i][1] == sl[i + 1][0] for i in range(w - 1))
+    owners = [spmd.column_owner(v, 4) for v in range(103)]
+    assert sorted(set(owners)) == [0, 1, 2, 3]
+    assert max(np.bincount(owners)) - min(np.bincount(owners)) <= 1
