@@ -52,7 +52,7 @@ static void free_grid(mdb_engine *e)
 static void free_recip(mdb_engine *e)
 {
    FREE(e->d_hk); FREE(e->d_hk_valid); FREE(e->d_slot_flags); FREE(e->d_ppart);
-   FREE(e->d_coef_tot); FREE(e->d_coef_nf); FREE(e->d_kpartials);
+   FREE(e->d_coef_tot); FREE(e->d_coef_nf); FREE(e->d_kpartials); FREE(e->d_cidx); FREE(e->d_sfac_blocks);
    e->ppart_cap = 0;
 }
 
@@ -156,6 +156,14 @@ extern "C" int mdb_configure(mdb_engine *e, const mdb_config *cfg)
       for (int s = 0; s < T.nslots; s++) slotinfo[s] = T.slot_flags[s];
       for (size_t i = 0; i < T.hk.size(); i++)
          for (int l = 0; l < T.hk[i].nl; l++) slotinfo[T.nslots + T.hk[i].slot0 + l] = (int)i;
+      std::vector<int> cidx;
+      for (int i = 0; i < n; i++) {
+         if (i == cfg->nsites_xf) e->n_charged_nf = (int)cidx.size();
+         if (e->h_chg[i] != 0.0) cidx.push_back(i);
+      }
+      if (cfg->nsites_xf >= n) e->n_charged_nf = (int)cidx.size();
+      e->n_charged = (int)cidx.size();
+      if (upload(&e->d_cidx, cidx.data(), cidx.size())) return -1;
       if (upload(&e->d_hk, T.hk.data(), T.hk.size())) return -1;
       if (upload(&e->d_hk_valid, T.hk_valid.data(), T.hk_valid.size())) return -1;
       if (upload(&e->d_slot_flags, slotinfo.data(), slotinfo.size())) return -1;
@@ -167,9 +175,13 @@ extern "C" int mdb_configure(mdb_engine *e, const mdb_config *cfg)
       int slab = (n + want - 1) / want;
       slab = std::max(32, ((slab + 31) / 32) * 32);
       e->slab_sites = slab;
-      const int nxf = cfg->nsites_xf;
-      e->n_slabs_nf = (nxf + slab - 1) / slab;
-      e->n_slabs = e->n_slabs_nf + (n - nxf + slab - 1) / slab;
+      // slabs partition the compacted charged-site list (framework sites in their own slabs)
+      slab = (e->n_charged + want - 1) / want;
+      slab = std::max(32, ((slab + 31) / 32) * 32);
+      e->slab_sites = slab;
+      e->n_slabs_nf = (e->n_charged_nf + slab - 1) / slab;
+      e->n_slabs = e->n_slabs_nf + (e->n_charged - e->n_charged_nf + slab - 1) / slab;
+      e->sfac_rank = -1;
       const size_t pp = (size_t)e->n_slabs * T.nslots * 4;
       if (pp > e->ppart_cap) {
          FREE(e->d_ppart);

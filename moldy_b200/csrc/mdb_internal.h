@@ -99,6 +99,9 @@ struct mdb_engine {
    HkDesc *d_hk = nullptr; int *d_hk_valid = nullptr; int *d_slot_flags = nullptr;
    double *d_ppart = nullptr; size_t ppart_cap = 0;
    double *d_coef_tot = nullptr, *d_coef_nf = nullptr;
+   int *d_cidx = nullptr;                 // charged sites (non-framework first), original indices
+   int n_charged = 0, n_charged_nf = 0;
+   void *d_sfac_blocks = nullptr; int n_sfac_blocks = 0, sfac_rank = -1, sfac_nranks = -1;
    double *d_kpartials = nullptr;
    int n_slabs = 0, n_slabs_nf = 0, slab_sites = 0;
 

@@ -22,6 +22,7 @@
 //            (src/ewald.c:558-579).
 // Framework sites (src/ewald.c:528-579) are handled by keeping their slabs
 // separate in k_sfac and using the non-framework-only coefficient set for them.
+#include <algorithm>
 #include "mdb_internal.h"
 
 static constexpr int KT = 256;          // threads per block (k_sfac)
@@ -31,10 +32,15 @@ static constexpr int KF = 128;          // threads per block (k_kforce)
 
 struct SfacArgs {
    KspaceParams K;
-   int HKB, NLC;                        // (h,k) columns per block, l-chunks
+   int HKB;                             // shared-memory row stride of the E_hk tile (max columns per block)
    int nvalid, rank, nranks;
    int nslots, slab_sites, n_slabs_nf;
+   int nc_nf, nc;                       // charged sites: non-framework count, total
 };
+
+// per-block work descriptor of k_sfac: columns e0..e0+hkb-1 of this rank's share of the
+// (nl-sorted) valid list, split over nlc l-chunks of lch slots each (hkb*nlc <= 256)
+struct SfacBlock { int e0, hkb, nlc, lch; };
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b)
 {
@@ -46,7 +52,8 @@ __device__ __forceinline__ double2 cmulc(double2 a, double2 b)   // a * conj(b)
 }
 
 __global__ void __launch_bounds__(KT)
-k_sfac(SfacArgs A, const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
+k_sfac(SfacArgs A, const SfacBlock *__restrict__ blocks, const int *__restrict__ cidx,
+       const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
        const double *__restrict__ chg, const HkDesc *__restrict__ hk, const int *__restrict__ hk_valid,
        double *__restrict__ ppart)
 {
@@ -58,30 +65,31 @@ k_sfac(SfacArgs A, const double *__restrict__ x, const double *__restrict__ y, c
    double2 *sH = sB + SC * NL;                  // [SC][NH]
    double2 *sK = sH + SC * NH;                  // [SC][NK]
 
+   const SfacBlock B = blocks[blockIdx.x];
    const int tid = threadIdx.x;
-   const int hkl = tid % A.HKB, lc = tid / A.HKB;
-   // this thread's (h,k) column: i-th entry of the rank's interleaved share of the valid list
-   const int ient = blockIdx.x * A.HKB + hkl;
-   const int v = A.rank + A.nranks * ient;
-   const bool have = v < A.nvalid && lc < A.NLC;
+   const int hkl = tid % B.hkb, lc = tid / B.hkb;
+   // this thread's (h,k) column: entry of the rank's interleaved share of the valid list
+   const int v = A.rank + A.nranks * (B.e0 + hkl);
+   const bool have = v < A.nvalid && lc < B.nlc;
    int h = 0, ka = 0, ksgn = 1, nl = 0, slot0 = 0;
    if (v < A.nvalid) {
       const HkDesc d = hk[hk_valid[v]];
       h = d.h; ka = abs(d.k); ksgn = d.k < 0 ? -1 : 1; nl = d.nl; slot0 = d.slot0;
    }
-   const int l0 = lc * LCH;
-   const int lcnt = have ? min(max(nl - l0, 0), LCH) : 0;
+   const int l0 = lc * B.lch;
+   const int lcnt = have ? min(max(nl - l0, 0), B.lch) : 0;
    const int wl = __reduce_max_sync(0xffffffffu, lcnt);       // warp-uniform trip count
+   const int ngen = KT / B.hkb;                               // threads per column in phase 2
 
-   // slab -> site range (framework sites live in their own slabs)
+   // slab -> range of the compacted charged-site list (framework sites in their own slabs)
    const int slab = blockIdx.y;
    int s0, s1;
    if (slab < A.n_slabs_nf) {
       s0 = slab * A.slab_sites;
-      s1 = min(s0 + A.slab_sites, K.nsites_xf);
+      s1 = min(s0 + A.slab_sites, A.nc_nf);
    } else {
-      s0 = K.nsites_xf + (slab - A.n_slabs_nf) * A.slab_sites;
-      s1 = min(s0 + A.slab_sites, K.nsites);
+      s0 = A.nc_nf + (slab - A.n_slabs_nf) * A.slab_sites;
+      s1 = min(s0 + A.slab_sites, A.nc);
    }
 
    double acc[LCH][4];
@@ -95,8 +103,9 @@ k_sfac(SfacArgs A, const double *__restrict__ x, const double *__restrict__ y, c
          double q = 0.0, kr = 0.0;
          const double *ks = axis == 0 ? K.astar : axis == 1 ? K.bstar : K.cstar;
          if (g < s1) {
-            kr = ks[0] * x[g] + ks[1] * y[g] + ks[2] * z[g];
-            q = chg[g];
+            const int i = cidx[g];
+            kr = ks[0] * x[i] + ks[1] * y[i] + ks[2] * z[i];
+            q = chg[i];
          }
          double s1v, c1v;
          sincos(kr, &s1v, &c1v);
@@ -113,10 +122,11 @@ k_sfac(SfacArgs A, const double *__restrict__ x, const double *__restrict__ y, c
       }
       __syncthreads();
       // phase 2: E_hk = E_h * E_k (conjugate for k < 0) for this thread's column
-      for (int sl = lc; sl < SC; sl += KT / A.HKB) {
-         const double2 eh = sH[sl * NH + h], ek = sK[sl * NK + ka];
-         sA[sl * A.HKB + hkl] = ksgn > 0 ? cmul(eh, ek) : cmulc(eh, ek);
-      }
+      if (tid < ngen * B.hkb)
+         for (int sl = lc; sl < SC; sl += ngen) {
+            const double2 eh = sH[sl * NH + h], ek = sK[sl * NK + ka];
+            sA[sl * A.HKB + hkl] = ksgn > 0 ? cmul(eh, ek) : cmulc(eh, ek);
+         }
       __syncthreads();
       // phase 3: rank-1 updates, 4 DFMA per (site, l-slot)
       if (wl > 0) {
@@ -251,50 +261,95 @@ __global__ void __launch_bounds__(256) k_recip_finish(const double *__restrict__
 }
 
 // ---- forces -------------------------------------------------------------------
+// One thread per CHARGED site (cidx: compacted list, uncharged sites get no k-space
+// force).  The (h,k) descriptors and their back-projection coefficients are the same
+// for every site, so the block stages them through shared memory in batches
+// (coalesced copy, broadcast reads) instead of each warp fetching them from L2.
+struct KfArgs {
+   KspaceParams K;
+   int c0, c1;            // range in the compacted charged-site list
+   int nhk, rank, nranks;
+   int hb;                // descriptors per shared-memory batch
+   int max_slots;         // capacity of the coefficient stage (slots)
+};
+
 __global__ void __launch_bounds__(KF)
-k_kforce(KspaceParams K, int i0, int i1, int nhk, int rank, int nranks, const double *__restrict__ x,
-         const double *__restrict__ y, const double *__restrict__ z, const double *__restrict__ chg,
-         const HkDesc *__restrict__ hk, const double *__restrict__ coef, double *__restrict__ out)
+k_kforce(KfArgs A, const int *__restrict__ cidx, const double *__restrict__ x, const double *__restrict__ y,
+         const double *__restrict__ z, const double *__restrict__ chg, const HkDesc *__restrict__ hk,
+         const double *__restrict__ coef, double *__restrict__ out)
 {
-   const int i = i0 + blockIdx.x * KF + threadIdx.x;
-   if (i >= i1) return;
-   const double q = chg[i];
-   if (q == 0.0) return;
-   const double xi = x[i], yi = y[i], zi = z[i];
+   extern __shared__ double2 smem[];
+   double4 *s_coef = reinterpret_cast<double4 *>(smem);                        // [max_slots][2]
+   HkDesc *s_hk = reinterpret_cast<HkDesc *>(s_coef + 2 * (size_t)A.max_slots); // [hb]
+   const KspaceParams &K = A.K;
+   const int t = A.c0 + blockIdx.x * KF + threadIdx.x;
+   const bool active = t < A.c1;
+   int i = 0;
+   double q = 0.0, xi = 0, yi = 0, zi = 0;
+   if (active) {
+      i = cidx[t];
+      q = chg[i]; xi = x[i]; yi = y[i]; zi = z[i];
+   }
    double2 ea, eb, ec;
    sincos(K.astar[0] * xi + K.astar[1] * yi + K.astar[2] * zi, &ea.y, &ea.x);
    sincos(K.bstar[0] * xi + K.bstar[1] * yi + K.bstar[2] * zi, &eb.y, &eb.x);
    sincos(K.cstar[0] * xi + K.cstar[1] * yi + K.cstar[2] * zi, &ec.y, &ec.x);
    double2 eh = make_double2(1.0, 0.0), ehk = eh;
    double fx = 0, fy = 0, fz = 0;
-   for (int c = 0; c < nhk; c++) {
-      const HkDesc d = hk[c];
-      switch (d.code) {
-         case HK_NEWH:   if (d.h > 0) eh = cmul(eh, ea); ehk = eh; break;
-         case HK_KUP:    ehk = cmul(ehk, eb); break;
-         case HK_KDOWN0: ehk = cmulc(eh, eb); break;
-         default:        ehk = cmulc(ehk, eb); break;
+
+   for (int c0 = 0; c0 < A.nhk; c0 += A.hb) {
+      const int nb = min(A.hb, A.nhk - c0);
+      __syncthreads();
+      if (threadIdx.x < nb) {
+         HkDesc d = hk[c0 + threadIdx.x];
+         if (d.nl > 0 && (d.pad % A.nranks) != A.rank) d.nl = -d.nl;     // not ours: keep slot count, skip work
+         s_hk[threadIdx.x] = d;
       }
-      if (d.nl == 0 || (d.pad % nranks) != rank) continue;
-      const double4 *cf = reinterpret_cast<const double4 *>(coef + (size_t)d.slot0 * 8);
-      double2 el = make_double2(q, 0.0);
-      double X = 0, Y = 0, Xz = 0, Yz = 0;
-      for (int l = 0; l < d.nl; l++) {
-         const double4 a = cf[2 * l], b = cf[2 * l + 1];
-         X = fma(el.x, a.x, fma(el.y, a.w, X));
-         Y = fma(el.y, a.z, fma(-el.x, a.y, Y));
-         Xz = fma(el.x, b.x, fma(el.y, b.y, Xz));
-         Yz = fma(el.y, b.z, fma(-el.x, b.w, Yz));
-         el = cmul(el, ec);
+      __syncthreads();
+      // slots of a batch are contiguous (slot0 grows along the traversal)
+      int slot_lo = 0, nsl = 0;
+      {
+         const HkDesc &f = s_hk[0], &l = s_hk[nb - 1];
+         slot_lo = f.slot0;
+         nsl = l.slot0 + abs(l.nl) - slot_lo;
       }
-      const double T = fma(ehk.y, X, ehk.x * Y), Tz = fma(ehk.y, Xz, ehk.x * Yz);
-      fx = fma(d.kx, T, fx);
-      fy = fma(d.ky, T, fy);
-      fz = fma(d.kzt, T, fma(K.cz2, Tz, fz));
+      const double4 *src = reinterpret_cast<const double4 *>(coef) + 2 * (size_t)slot_lo;
+      for (int k = threadIdx.x; k < 2 * nsl; k += KF) s_coef[k] = src[k];
+      __syncthreads();
+      if (!active) continue;
+      for (int c = 0; c < nb; c++) {
+         const HkDesc &d = s_hk[c];
+         switch (d.code) {
+            case HK_NEWH:   if (d.h > 0) eh = cmul(eh, ea); ehk = eh; break;
+            case HK_KUP:    ehk = cmul(ehk, eb); break;
+            case HK_KDOWN0: ehk = cmulc(eh, eb); break;
+            default:        ehk = cmulc(ehk, eb); break;
+         }
+         const int nl = d.nl;
+         if (nl <= 0) continue;
+         const double4 *cf = s_coef + 2 * (d.slot0 - slot_lo);
+         double2 el = make_double2(q, 0.0);
+         double X = 0, Y = 0, Xz = 0, Yz = 0;
+#pragma unroll 2
+         for (int l = 0; l < nl; l++) {
+            const double4 a = cf[2 * l], b = cf[2 * l + 1];
+            X = fma(el.x, a.x, fma(el.y, a.w, X));
+            Y = fma(el.y, a.z, fma(-el.x, a.y, Y));
+            Xz = fma(el.x, b.x, fma(el.y, b.y, Xz));
+            Yz = fma(el.y, b.z, fma(-el.x, b.w, Yz));
+            el = cmul(el, ec);
+         }
+         const double T = fma(ehk.y, X, ehk.x * Y), Tz = fma(ehk.y, Xz, ehk.x * Yz);
+         fx = fma(d.kx, T, fx);
+         fy = fma(d.ky, T, fy);
+         fz = fma(d.kzt, T, fma(K.cz2, Tz, fz));
+      }
    }
-   out[i] += fx;
-   out[(size_t)K.nsites + i] += fy;
-   out[2 * (size_t)K.nsites + i] += fz;
+   if (active) {
+      out[i] += fx;
+      out[(size_t)K.nsites + i] += fy;
+      out[2 * (size_t)K.nsites + i] += fz;
+   }
 }
 
 int mdb_launch_recip(mdb_engine *e, double *d_out, cudaStream_t st)
@@ -311,26 +366,45 @@ int mdb_launch_recip(mdb_engine *e, double *d_out, cudaStream_t st)
    K.hmax = T.hmax; K.kmax = T.kmax; K.lmax = T.lmax; K.nlslots = T.lmax + 1;
    K.nsites = c.nsites; K.nsites_xf = c.nsites_xf;
 
+   // (re)build the per-block work table when the partition changes
+   if (e->sfac_rank != e->ithread || e->sfac_nranks != e->nthreads || !e->d_sfac_blocks) {
+      std::vector<SfacBlock> blocks;
+      const int my_cols = nvalid > e->ithread ? (nvalid - e->ithread + e->nthreads - 1) / e->nthreads : 0;
+      int e0 = 0;
+      while (e0 < my_cols) {
+         const int nlmax = T.hk[T.hk_valid[e->ithread + e->nthreads * e0]].nl;
+         int nlc = std::max(2, (nlmax + LCH - 1) / LCH);
+         if (nlc > 8) { mdb_set_error("k_cutoff gives lmax > 63: not supported by this build of k_sfac"); return -1; }
+         const int hkb = KT / nlc;
+         blocks.push_back({e0, hkb, nlc, (nlmax + nlc - 1) / nlc});
+         e0 += hkb;
+      }
+      if (e->d_sfac_blocks) { cudaFree(e->d_sfac_blocks); e->d_sfac_blocks = nullptr; }
+      e->n_sfac_blocks = (int)blocks.size();
+      if (!blocks.empty()) {
+         MDB_CUDA(cudaMalloc(&e->d_sfac_blocks, sizeof(SfacBlock) * blocks.size()));
+         MDB_CUDA(cudaMemcpyAsync(e->d_sfac_blocks, blocks.data(), sizeof(SfacBlock) * blocks.size(),
+                                  cudaMemcpyHostToDevice, st));
+         MDB_CUDA(cudaStreamSynchronize(st));
+      }
+      e->sfac_rank = e->ithread; e->sfac_nranks = e->nthreads;
+   }
    SfacArgs A;
    A.K = K;
-   A.NLC = (K.nlslots + LCH - 1) / LCH;
-   if (A.NLC > 8) {
-      mdb_set_error("k_cutoff gives lmax > 63: not supported by this build of k_sfac");
-      return -1;
-   }
-   A.HKB = A.NLC <= 1 ? 256 : A.NLC <= 2 ? 128 : A.NLC <= 4 ? 64 : 32;
+   A.HKB = KT / 2;
    A.nvalid = nvalid; A.rank = e->ithread; A.nranks = e->nthreads;
    A.nslots = T.nslots; A.slab_sites = e->slab_sites; A.n_slabs_nf = e->n_slabs_nf;
-   const int my_cols = (nvalid - e->ithread + e->nthreads - 1) / e->nthreads;
+   A.nc_nf = e->n_charged_nf; A.nc = e->n_charged;
    const size_t shm = sizeof(double2) * (size_t)SC * (A.HKB + K.nlslots + K.hmax + 1 + K.kmax + 1);
-   if (my_cols > 0) {
+   if (e->n_sfac_blocks > 0 && e->n_slabs > 0) {
       static size_t shm_set = 0;
       if (shm > shm_set) {
          MDB_CUDA(cudaFuncSetAttribute(k_sfac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
          shm_set = shm;
       }
-      dim3 g((my_cols + A.HKB - 1) / A.HKB, e->n_slabs);
-      k_sfac<<<g, KT, shm, st>>>(A, e->d_x, e->d_y, e->d_z, e->d_chg, e->d_hk, e->d_hk_valid, e->d_ppart);
+      dim3 g(e->n_sfac_blocks, e->n_slabs);
+      k_sfac<<<g, KT, shm, st>>>(A, (const SfacBlock *)e->d_sfac_blocks, e->d_cidx, e->d_x, e->d_y, e->d_z, e->d_chg,
+                                 e->d_hk, e->d_hk_valid, e->d_ppart);
       e->launches++;
    }
    SfinArgs F;
@@ -340,14 +414,21 @@ int mdb_launch_recip(mdb_engine *e, double *d_out, cudaStream_t st)
    k_sfin<<<fb, 256, 0, st>>>(F, e->d_hk, e->d_slot_flags + T.nslots, e->d_slot_flags, e->d_ppart, e->d_coef_tot,
                               e->d_coef_nf, e->d_kpartials);
    k_recip_finish<<<1, 256, 0, st>>>(e->d_kpartials, fb, c.nsites, d_out);
-   const int nhk = (int)T.hk.size();
-   if (c.nsites_xf > 0)
-      k_kforce<<<(c.nsites_xf + KF - 1) / KF, KF, 0, st>>>(K, 0, c.nsites_xf, nhk, e->ithread, e->nthreads, e->d_x,
-                                                          e->d_y, e->d_z, e->d_chg, e->d_hk, e->d_coef_tot, d_out);
-   if (c.nsites_xf < c.nsites)
-      k_kforce<<<(c.nsites - c.nsites_xf + KF - 1) / KF, KF, 0, st>>>(K, c.nsites_xf, c.nsites, nhk, e->ithread,
-                                                                      e->nthreads, e->d_x, e->d_y, e->d_z, e->d_chg,
-                                                                      e->d_hk, e->d_coef_nf, d_out);
+   KfArgs Q;
+   Q.K = K; Q.nhk = (int)T.hk.size(); Q.rank = e->ithread; Q.nranks = e->nthreads;
+   Q.hb = std::max(1, std::min(16, 512 / K.nlslots));
+   Q.max_slots = Q.hb * K.nlslots;
+   const size_t kshm = sizeof(double4) * 2 * (size_t)Q.max_slots + sizeof(HkDesc) * (size_t)Q.hb;
+   if (e->n_charged_nf > 0) {
+      Q.c0 = 0; Q.c1 = e->n_charged_nf;
+      k_kforce<<<(Q.c1 - Q.c0 + KF - 1) / KF, KF, kshm, st>>>(Q, e->d_cidx, e->d_x, e->d_y, e->d_z, e->d_chg, e->d_hk,
+                                                             e->d_coef_tot, d_out);
+   }
+   if (e->n_charged > e->n_charged_nf) {
+      Q.c0 = e->n_charged_nf; Q.c1 = e->n_charged;
+      k_kforce<<<(Q.c1 - Q.c0 + KF - 1) / KF, KF, kshm, st>>>(Q, e->d_cidx, e->d_x, e->d_y, e->d_z, e->d_chg, e->d_hk,
+                                                             e->d_coef_nf, d_out);
+   }
    e->launches += 3 + (c.nsites_xf < c.nsites ? 1 : 0);
    MDB_CUDA(cudaGetLastError());
    return 0;

@@ -12,7 +12,31 @@
 #define MDB_LIBM_MATH 0        /* 1: fall back to libdevice (debugging) */
 #endif
 
-// 1/sqrt(x), x > 0 normal.  MUFU.RSQ64H seed (~2^-20) + two Newton steps.
+// Polynomial / reduction constants live in __constant__ memory so that DFMA takes
+// them as c[bank][offset] operands (a 64-bit immediate would cost two UMOVs per use).
+__constant__ double c_exp[16] = {
+   2.08767569878680989792e-09,  // 1/12!
+   2.50521083854417187751e-08,  // 1/11!
+   2.75573192239858906526e-07,  // 1/10!
+   2.75573192239858906526e-06,  // 1/9!
+   2.48015873015873015873e-05,  // 1/8!
+   1.98412698412698412698e-04,  // 1/7!
+   1.38888888888888888889e-03,  // 1/6!
+   8.33333333333333333333e-03,  // 1/5!
+   4.16666666666666666667e-02,  // 1/4!
+   1.66666666666666666667e-01,  // 1/3!
+   1.4426950408889634074,       // [10] log2(e)
+   6755399441055744.0,          // [11] 1.5 * 2^52
+   -6.93147180369123816490e-01, // [12] -ln2 (high part)
+   -1.90821492927058770002e-10, // [13] -ln2 (low part)
+   0.0, 0.0};
+__constant__ double c_as[6] = {0.254829592, -0.284496736, 1.421413741, -1.453152027, 1.061405429, 0.3275911};
+
+// 1/sqrt(x), x > 0 normal.  MUFU.RSQ64H seed + Newton: two quadratic steps (default)
+// or one cubic step (MDB_RSQRT_CUBIC, 5 instead of 7 FP64 ops).
+#ifndef MDB_RSQRT_CUBIC
+#define MDB_RSQRT_CUBIC 0
+#endif
 __device__ __forceinline__ double mdb_rsqrt(double x)
 {
 #if MDB_LIBM_MATH
@@ -20,12 +44,18 @@ __device__ __forceinline__ double mdb_rsqrt(double x)
 #else
    double y;
    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#if MDB_RSQRT_CUBIC
+   double e = fma(-x * y, y, 1.0);
+   double p = fma(0.375, e, 0.5);
+   return fma(y * e, p, y);
+#else
    double hx = 0.5 * x;
    double e = fma(-hx, y * y, 0.5);
    y = fma(y, e, y);
    e = fma(-hx, y * y, 0.5);
    y = fma(y, e, y);
    return y;
+#endif
 #endif
 }
 
@@ -45,35 +75,30 @@ __device__ __forceinline__ double mdb_rcp(double x)
 #endif
 }
 
-// exp(x) for x in [-700, 700] (clamped): n = rint(x log2e), r = x - n ln2 in
-// two pieces, degree-12 Taylor on |r| <= 0.3466 (remainder 1.7e-16), scale by
-// adding n to the exponent field.
+// exp(x) for x <= ~700: n = rint(x log2e), r = x - n ln2 in two pieces, degree-12
+// Taylor on |r| <= 0.3466 (remainder 1.7e-16), scale by adding n to the exponent
+// field.  x < -708 returns 0 through an integer test on the high word (no FP64
+// min/max); large positive x is the caller's responsibility (never occurs for
+// -a^2 r^2, -p r).
 __device__ __forceinline__ double mdb_exp(double x)
 {
 #if MDB_LIBM_MATH
    return exp(x);
 #else
-   x = fmin(fmax(x, -700.0), 700.0);
-   const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52
-   double t = fma(x, 1.4426950408889634074, MAGIC);
+   double t = fma(x, c_exp[10], c_exp[11]);
    int n = __double2loint(t);
-   double nf = t - MAGIC;
-   double r = fma(nf, -6.93147180369123816490e-01, x);
-   r = fma(nf, -1.90821492927058770002e-10, r);
-   double p = 2.08767569878680989792e-09;                   // 1/12!
-   p = fma(p, r, 2.50521083854417187751e-08);               // 1/11!
-   p = fma(p, r, 2.75573192239858906526e-07);               // 1/10!
-   p = fma(p, r, 2.75573192239858906526e-06);               // 1/9!
-   p = fma(p, r, 2.48015873015873015873e-05);               // 1/8!
-   p = fma(p, r, 1.98412698412698412698e-04);               // 1/7!
-   p = fma(p, r, 1.38888888888888888889e-03);               // 1/6!
-   p = fma(p, r, 8.33333333333333333333e-03);               // 1/5!
-   p = fma(p, r, 4.16666666666666666667e-02);               // 1/4!
-   p = fma(p, r, 1.66666666666666666667e-01);               // 1/3!
+   double nf = t - c_exp[11];
+   double r = fma(nf, c_exp[12], x);
+   r = fma(nf, c_exp[13], r);
+   double p = c_exp[0];
+#pragma unroll
+   for (int k = 1; k < 10; k++) p = fma(p, r, c_exp[k]);
    p = fma(p, r, 0.5);
    p = fma(p, r, 1.0);
    p = fma(p, r, 1.0);
-   return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+   int hi = __double2hiint(p) + (n << 20), lo = __double2loint(p);
+   const bool tiny = (unsigned)__double2hiint(x) > 0xc0862000u;     // x < -708
+   return __hiloint2double(tiny ? 0 : hi, tiny ? 0 : lo);
 #endif
 }
 
@@ -103,12 +128,10 @@ __device__ __forceinline__ PairOut mdb_pair_eval(double r2, double qq, const dou
       r_r = r = 0.0;
    }
    if (COUL) {
-      const double E1 = 0.254829592, E2 = -0.284496736, E3 = 1.421413741, E4 = -1.453152027,
-                   E5 = 1.061405429, PP = 0.3275911;
       double ar = alpha * r;
-      double tt = mdb_rcp(fma(PP, ar, 1.0));
+      double tt = mdb_rcp(fma(c_as[5], ar, 1.0));
       double e = qq * mdb_exp(-(ar * ar));
-      double poly = tt * fma(tt, fma(tt, fma(tt, fma(tt, E5, E4), E3), E2), E1);
+      double poly = tt * fma(tt, fma(tt, fma(tt, fma(tt, c_as[4], c_as[3]), c_as[2]), c_as[1]), c_as[0]);
       t = poly * e * r_r;
       erfc_term = fma(norm, e, t);
    }

@@ -20,7 +20,7 @@
 #include "mdb_internal.h"
 #include "mdb_math.cuh"
 
-static constexpr int PB = 128;           // threads per block
+static constexpr int PB = 32;            // one warp per block: no block-level barrier, no tail warps
 static constexpr int NRED = 8;           // pe + 6 stress + pad
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -30,7 +30,13 @@ __device__ __forceinline__ double warp_sum(double v)
    return v;
 }
 
-template <int PT, bool COUL, bool STRICT>
+// Each lane walks its own flattened sequence of stencil segments (run x z-piece):
+// when a lane exhausts a segment it advances on its own, so lanes with short and
+// long segments do not wait for each other run by run; the warp only needs the
+// total visit counts of its 32 sites to be similar (they are, to ~1 %).
+// Two visits (j, j+1) are evaluated per iteration for instruction-level
+// parallelism; the second is masked off at the end of a segment.
+template <int PT, bool COUL, bool STRICT, bool FW>
 __global__ void __launch_bounds__(PB)
 k_pair(PairParams P, int nsites, const double4 *__restrict__ posq, const int *__restrict__ stype,
        const int *__restrict__ scell, const int *__restrict__ cstart, const int *__restrict__ order,
@@ -55,60 +61,99 @@ k_pair(PairParams P, int nsites, const double4 *__restrict__ posq, const int *__
    const double *__restrict__ prow = ptab + (size_t)ti * P.max_id * MDB_NPOTP;
    double fx = 0, fy = 0, fz = 0, pe = 0;
    double w00 = 0, w01 = 0, w02 = 0, w11 = 0, w12 = 0, w22 = 0;
+   double gx = 0, gy = 0, gz = 0, sx = 0, sy = 0, sz = 0;
    unsigned int visits = 0;
+   // segment iterator
+   int r = 0, kk = 2, j = 0, je = 0, pend_j = 0, pend_je = 0, kimg = 13;
+   int col = 0, z0 = 0, z1 = 0, ii = 0, jj = 0;
+   bool done = !active;
 
-   if (active)
-      for (int r = 0; r < P.nruns; r++) {
-         const StencilRun run = runs[r];
-         int tx = cx + run.dx, ty = cy + run.dy, ii = 0, jj = 0;
-         if (tx < 0) { tx += P.nx; ii = -1; } else if (tx >= P.nx) { tx -= P.nx; ii = 1; }
-         if (ty < 0) { ty += P.ny; jj = -1; } else if (ty >= P.ny) { ty -= P.ny; jj = 1; }
-         const int col = (tx * P.ny + ty) * P.nz;
-         const int z0 = cz + run.dzlo, z1 = cz + run.dzhi;
-#pragma unroll 1
-         for (int kk = -1; kk <= 1; kk++) {
-            const int zoff = kk * P.nz;
-            const int a = max(z0, zoff), b = min(z1, zoff + P.nz - 1);
-            if (a > b) continue;
-            const int jb = cstart[col + a - zoff], je = cstart[col + b - zoff + 1];
-            const int kimg = 9 * (ii + 1) + 3 * (jj + 1) + (kk + 1);
-            const bool central = kimg == 13;
-            const double sx = pi.x - P.reloc[kimg][0], sy = pi.y - P.reloc[kimg][1],
-                         sz = pi.z - P.reloc[kimg][2];
-            double gx = 0, gy = 0, gz = 0;
-            visits += (unsigned)(je - jb);
-#pragma unroll 2
-            for (int j = jb; j < je; j++) {
-               if (central && j == s) { visits--; continue; }
-               const double4 pj = posq[j];
-               int tj = stype[j];
-               // framework sites never interact with each other (src/force.c:904-912)
-               if (fwi & (tj >> 30)) { visits--; continue; }
-               tj &= 0x3fffffff;
-               const double dx = pj.x - sx, dy = pj.y - sy, dz = pj.z - sz;
-               double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
-               if (r2 < MDB_TOO_CLOSE) {
-                  if (mol[order[s]] != mol[order[j]]) {
-                     atomicAdd(&counters[1], 1ULL);
-                     counters[3] = ((unsigned long long)(unsigned)order[s] << 32) | (unsigned)order[j];
-                  }
+   for (;;) {
+      if (!done && j >= je) {
+         // ---- close the finished segment: fold its force sum into F and the image virial
+         fx += gx; fy += gy; fz += gz;
+         if (kimg != 13) {
+            const double rx = -0.5 * P.reloc[kimg][0], ry = -0.5 * P.reloc[kimg][1], rz = -0.5 * P.reloc[kimg][2];
+            w00 = fma(rx, gx, w00); w01 = fma(ry, gx, w01); w02 = fma(rz, gx, w02);
+            w11 = fma(ry, gy, w11); w12 = fma(rz, gy, w12); w22 = fma(rz, gz, w22);
+         }
+         gx = gy = gz = 0.0;
+         if (pend_je > pend_j) {          // second half of the central segment (after the self site)
+            j = pend_j; je = pend_je; pend_je = 0;
+         } else {
+            pend_je = 0;
+            for (;;) {
+               kk++;
+               if (kk > 1 || kk * P.nz > z1) {      // open the next run
+                  if (r >= P.nruns) { done = true; break; }
+                  const StencilRun run = runs[r++];
+                  int tx = cx + run.dx, ty = cy + run.dy;
+                  ii = 0; jj = 0;
+                  if (tx < 0) { tx += P.nx; ii = -1; } else if (tx >= P.nx) { tx -= P.nx; ii = 1; }
+                  if (ty < 0) { ty += P.ny; jj = -1; } else if (ty >= P.ny) { ty -= P.ny; jj = 1; }
+                  col = (tx * P.ny + ty) * P.nz;
+                  z0 = cz + run.dzlo; z1 = cz + run.dzhi;
+                  kk = z0 < 0 ? -1 : 0;
                }
-               if (STRICT) r2 = r2 > P.cutoffsq ? P.cutoff100sq : r2;
-               const PairOut o = mdb_pair_eval<PT, COUL>(r2, pi.w * pj.w, prow + tj * MDB_NPOTP, P.alpha, P.norm);
-               pe += o.phi;
-               gx = fma(-o.fij, dx, gx);
-               gy = fma(-o.fij, dy, gy);
-               gz = fma(-o.fij, dz, gz);
-            }
-            fx += gx; fy += gy; fz += gz;
-            if (!central) {
-               const double rx = -0.5 * P.reloc[kimg][0], ry = -0.5 * P.reloc[kimg][1],
-                            rz = -0.5 * P.reloc[kimg][2];
-               w00 = fma(rx, gx, w00); w01 = fma(ry, gx, w01); w02 = fma(rz, gx, w02);
-               w11 = fma(ry, gy, w11); w12 = fma(rz, gy, w12); w22 = fma(rz, gz, w22);
+               const int zoff = kk * P.nz;
+               const int a = max(z0, zoff), b = min(z1, zoff + P.nz - 1);
+               if (a > b) continue;
+               const int jb = cstart[col + a - zoff], jn = cstart[col + b - zoff + 1];
+               if (jb == jn) continue;
+               kimg = 9 * (ii + 1) + 3 * (jj + 1) + (kk + 1);
+               sx = pi.x - P.reloc[kimg][0]; sy = pi.y - P.reloc[kimg][1]; sz = pi.z - P.reloc[kimg][2];
+               j = jb; je = jn;
+               visits += (unsigned)(jn - jb);
+               if (kimg == 13 && jb <= s && s < jn) {   // the reference cell itself: skip j == i
+                  visits--;
+                  je = s; pend_j = s + 1; pend_je = jn;
+                  if (j >= je) { j = pend_j; je = pend_je; pend_je = 0; }
+                  if (j >= je) continue;
+               }
+               break;
             }
          }
       }
+      if (__all_sync(0xffffffffu, done)) break;
+      if (!done) {
+         const bool two = j + 1 < je;
+         const int ja = j, jb2 = two ? j + 1 : j;
+         const double4 pa = posq[ja], pb = posq[jb2];
+         int ta = stype[ja], tb = stype[jb2];
+         double ma = 1.0, mb = two ? 1.0 : 0.0;
+         if (FW) {                         // framework sites never interact with each other (src/force.c:904-912)
+            if (fwi & (ta >> 30)) { ma = 0.0; visits--; }
+            if (two && (fwi & (tb >> 30))) { mb = 0.0; visits--; }
+            ta &= 0x3fffffff; tb &= 0x3fffffff;
+         }
+         const double dxa = pa.x - sx, dya = pa.y - sy, dza = pa.z - sz;
+         const double dxb = pb.x - sx, dyb = pb.y - sy, dzb = pb.z - sz;
+         double r2a = fma(dxa, dxa, fma(dya, dya, dza * dza));
+         double r2b = fma(dxb, dxb, fma(dyb, dyb, dzb * dzb));
+         if (min(__double2hiint(r2a), __double2hiint(r2b)) < 0x3fd00000) {      // r^2 < 0.25 (rare)
+            const int mi = mol[order[s]];
+            if (r2a < MDB_TOO_CLOSE && ma != 0.0 && mi != mol[order[ja]]) {
+               atomicAdd(&counters[1], 1ULL);
+               counters[3] = ((unsigned long long)(unsigned)order[s] << 32) | (unsigned)order[ja];
+            }
+            if (two && r2b < MDB_TOO_CLOSE && mb != 0.0 && mi != mol[order[jb2]]) {
+               atomicAdd(&counters[1], 1ULL);
+               counters[3] = ((unsigned long long)(unsigned)order[s] << 32) | (unsigned)order[jb2];
+            }
+         }
+         if (STRICT) {
+            r2a = r2a > P.cutoffsq ? P.cutoff100sq : r2a;
+            r2b = r2b > P.cutoffsq ? P.cutoff100sq : r2b;
+         }
+         const PairOut oa = mdb_pair_eval<PT, COUL>(r2a, pi.w * pa.w, prow + ta * MDB_NPOTP, P.alpha, P.norm);
+         const PairOut ob = mdb_pair_eval<PT, COUL>(r2b, pi.w * pb.w, prow + tb * MDB_NPOTP, P.alpha, P.norm);
+         const double fa = FW ? oa.fij * ma : oa.fij, fb = ob.fij * mb;
+         pe += (FW ? oa.phi * ma : oa.phi) + ob.phi * mb;
+         gx = fma(-fa, dxa, gx); gy = fma(-fa, dya, gy); gz = fma(-fa, dza, gz);
+         gx = fma(-fb, dxb, gx); gy = fma(-fb, dyb, gy); gz = fma(-fb, dzb, gz);
+         j += 2;
+      }
+   }
 
    if (active) {
       const int o = order[s];
@@ -118,32 +163,17 @@ k_pair(PairParams P, int nsites, const double4 *__restrict__ posq, const int *__
       w00 = fma(pi.x, fx, w00); w01 = fma(pi.y, fx, w01); w02 = fma(pi.z, fx, w02);
       w11 = fma(pi.y, fy, w11); w12 = fma(pi.z, fy, w12); w22 = fma(pi.z, fz, w22);
    }
-   // block reduction -> one row of partials per block (deterministic second stage)
-   __shared__ double red[PB / 32][NRED];
-   __shared__ unsigned int vred[PB / 32];
+   // warp reduction -> one row of partials per warp (deterministic second stage)
    double v[7] = {pe, w00, w01, w02, w11, w12, w22};
-   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
    for (int k = 0; k < 7; k++) {
-      double t = warp_sum(v[k]);
-      if (lane == 0) red[w][k] = t;
+      const double t = warp_sum(v[k]);
+      if (threadIdx.x == 0) partials[(size_t)blockIdx.x * NRED + k] = t;
    }
    unsigned int vs = visits;
 #pragma unroll
    for (int d = 16; d > 0; d >>= 1) vs += __shfl_xor_sync(0xffffffffu, vs, d);
-   if (lane == 0) vred[w] = vs;
-   __syncthreads();
-   if (threadIdx.x < 7) {
-      double t = 0;
-#pragma unroll
-      for (int k = 0; k < PB / 32; k++) t += red[k][threadIdx.x];
-      partials[(size_t)blockIdx.x * NRED + threadIdx.x] = t;
-   }
-   if (threadIdx.x == 0) {
-      unsigned long long t = 0;
-      for (int k = 0; k < PB / 32; k++) t += vred[k];
-      atomicAdd(&counters[0], t);
-   }
+   if (threadIdx.x == 0) atomicAdd(&counters[0], (unsigned long long)vs);
 }
 
 // Fixed-order sum of the per-block rows; adds 1/2 sum(phi) to pe_real and the six
@@ -175,17 +205,19 @@ __global__ void __launch_bounds__(256) k_pair_finish(const double *__restrict__ 
    }
 }
 
+#define PAIR_ARGS P, e->cfg.nsites, e->d_posq, e->d_stype, e->d_scell, e->d_start, e->d_order, e->d_mol, e->d_runs, \
+                  e->d_ptab, d_out, e->d_partials, e->d_counters
 template <int PT, bool COUL>
 static void launch_pair_t(bool strict, dim3 g, cudaStream_t st, PairParams &P, mdb_engine *e, double *d_out)
 {
-   if (strict)
-      k_pair<PT, COUL, true><<<g, PB, 0, st>>>(P, e->cfg.nsites, e->d_posq, e->d_stype, e->d_scell, e->d_start,
-                                               e->d_order, e->d_mol, e->d_runs, e->d_ptab, d_out, e->d_partials,
-                                               e->d_counters);
-   else
-      k_pair<PT, COUL, false><<<g, PB, 0, st>>>(P, e->cfg.nsites, e->d_posq, e->d_stype, e->d_scell, e->d_start,
-                                                e->d_order, e->d_mol, e->d_runs, e->d_ptab, d_out, e->d_partials,
-                                                e->d_counters);
+   const bool fw = e->cfg.nsites_xf < e->cfg.nsites;
+   if (strict) {
+      if (fw) k_pair<PT, COUL, true, true><<<g, PB, 0, st>>>(PAIR_ARGS);
+      else k_pair<PT, COUL, true, false><<<g, PB, 0, st>>>(PAIR_ARGS);
+   } else {
+      if (fw) k_pair<PT, COUL, false, true><<<g, PB, 0, st>>>(PAIR_ARGS);
+      else k_pair<PT, COUL, false, false><<<g, PB, 0, st>>>(PAIR_ARGS);
+   }
 }
 
 template <int PT>
