@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=10, help="replication factor of the 256-water cell (10 -> 1.024M sites)")
-    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the bounded reference sample")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the bounded reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -151,7 +151,7 @@ def run_reference(a):
         return
     from oracle import ref
     if not ref.available(fast=True):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libmoldyref_fast.so not built"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libmoldyref_fast.so not built"})
         return
     cb, t_step = reference_sample(a.n, a.cpu_seconds, steps=max(1, min(a.steps, 2)))
     nsites = 1024 * a.n ** 3
@@ -160,7 +160,7 @@ def run_reference(a):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
             "config": workload_config(a.n, nsites, None), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(n, nsites, ms):
@@ -291,7 +291,7 @@ def run_ours(a):
             else:
                 line["cpu_baseline"] = {"value": None, "unit": "steps/s", "cores": 0, "kind": "reference",
                                         "sample": "oracle/_ref not built on this box"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -355,7 +355,17 @@ def measure_e2e(a, ms, site, world, rank, local):
             "api": "moldy_b200.spmd.SpmdForces.step(pinned host sites) -> host [forces|pe|stress] on every rank"}
 
 
+def emit(line: dict):
+    """The one JSON line goes to the real stdout; everything else (Moldy's start-up notes
+    printed by the C library, NCCL chatter) is routed to stderr."""
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         run_reference(args)

@@ -187,6 +187,12 @@ int  mdb_configure(mdb_engine *e, const mdb_config *cfg);
  * (src/force.c:856, src/ewald.c:495-496). */
 void mdb_set_partition(mdb_engine *e, int ithread, int nthreads);
 
+/* Real-space kernel variant: 2 = one thread per site, full stencil; 3 = tiled (warp = batch of
+ * sites, lanes = neighbours), full stencil, bit-reproducible; 4 = tiled with Newton's third law
+ * (half stencil, red.global.add.f64 force accumulation; last-bit run-to-run variation).
+ * Default: environment MDB_PAIR_MODE, else 4 (fastest); use 3 for bit-reproducible runs. */
+void mdb_set_pair_mode(mdb_engine *e, int mode);
+
 /* Positions: three HOST rows of nsites doubles (copied H2D on `stream`), or
  * three DEVICE rows already resident in HBM. */
 int  mdb_set_sites_host(mdb_engine *e, const double *x, const double *y, const double *z, void *stream);

@@ -168,6 +168,38 @@ __global__ void __launch_bounds__(CB) k_sort_gather(int ncells, const int *__res
    }
 }
 
+// Batches of <= NI consecutive cell-sorted sites that share a z-column (cx,cy): the unit
+// of work of the tiled pair kernel.  One block scans the columns in order, so the batch
+// list (and with it every summation order downstream) is deterministic.
+__global__ void __launch_bounds__(SCAN_T) k_make_batches(int ncols, int nz, int ni, const int *__restrict__ start,
+                                                          int2 *__restrict__ batches, int *__restrict__ nbatch)
+{
+   __shared__ int carry;
+   if (threadIdx.x == 0) carry = 0;
+   __syncthreads();
+   for (int b = 0; b < ncols; b += SCAN_T) {
+      const int col = b + threadIdx.x;
+      int s0 = 0, cnt = 0;
+      if (col < ncols) { s0 = start[col * nz]; cnt = start[(col + 1) * nz] - s0; }
+      const int nb = (cnt + ni - 1) / ni;
+      int tot;
+      const int off = carry + block_excl_scan(nb, &tot);
+      for (int k = 0; k < nb; k++) batches[off + k] = make_int2(s0 + k * ni, min(ni, cnt - k * ni));
+      __syncthreads();
+      if (threadIdx.x == 0) carry += tot;
+      __syncthreads();
+   }
+   if (threadIdx.x == 0) *nbatch = carry;
+}
+
+int mdb_launch_batches(mdb_engine *e, cudaStream_t st)
+{
+   k_make_batches<<<1, SCAN_T, 0, st>>>(e->T.nx * e->T.ny, e->T.nz, MDB_NI, e->d_start, e->d_batches, e->d_nbatch);
+   e->launches += 1;
+   MDB_CUDA(cudaGetLastError());
+   return 0;
+}
+
 int mdb_launch_cells(mdb_engine *e, cudaStream_t st)
 {
    const int n = e->cfg.nsites, nc = e->ncells;
@@ -188,6 +220,7 @@ int mdb_launch_cells(mdb_engine *e, cudaStream_t st)
                                                    e->d_type, e->cfg.nsites_xf, e->d_posq, e->d_stype, e->d_scell);
    e->launches += 6;
    MDB_CUDA(cudaGetLastError());
+   if (e->pair_mode >= 3 && mdb_launch_batches(e, st)) return -1;
    e->cells_valid = true;
    return 0;
 }

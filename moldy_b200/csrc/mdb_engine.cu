@@ -7,6 +7,7 @@
 //   posq[N] (double4 x,y,z,q), stype[N], scell[N]       cell-sorted SoA, z-fastest cell order
 //   runs[], hk[], slot tables, coef[nslots][8], ppart[slabs][nslots][4]
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include "mdb_internal.h"
@@ -41,12 +42,13 @@ static void free_system(mdb_engine *e)
 {
    FREE(e->d_type); FREE(e->d_mol); FREE(e->d_chg); FREE(e->d_ptab);
    FREE(e->own_xyz); FREE(e->d_cell); FREE(e->d_order); FREE(e->d_posq);
-   FREE(e->d_stype); FREE(e->d_scell);
+   FREE(e->d_stype); FREE(e->d_scell); FREE(e->d_fs);
    e->d_x = e->d_y = e->d_z = nullptr;
 }
 static void free_grid(mdb_engine *e)
 {
-   FREE(e->d_count); FREE(e->d_start); FREE(e->d_scan_tmp); FREE(e->d_runs);
+   FREE(e->d_count); FREE(e->d_start); FREE(e->d_scan_tmp); FREE(e->d_runs); FREE(e->d_runs_half);
+   FREE(e->d_batches); FREE(e->d_nbatch); e->batch_cap = 0;
    e->cells_cap = 0;
 }
 static void free_recip(mdb_engine *e)
@@ -64,6 +66,12 @@ extern "C" void mdb_destroy(mdb_engine *e)
    FREE(e->d_partials); FREE(e->d_counters); FREE(e->d_out_own);
    if (e->h_stage) cudaFreeHost(e->h_stage);
    delete e;
+}
+
+extern "C" void mdb_set_pair_mode(mdb_engine *e, int mode)
+{
+   e->pair_mode = (mode == 2 || mode == 3) ? mode : 4;
+   e->cells_valid = false;
 }
 
 extern "C" void mdb_set_partition(mdb_engine *e, int ithread, int nthreads)
@@ -145,6 +153,26 @@ extern "C" int mdb_configure(mdb_engine *e, const mdb_config *cfg)
    }
    e->nruns = (int)e->T.runs.size();
    if (upload(&e->d_runs, e->T.runs.data(), e->T.runs.size())) return -1;
+   e->nruns_half = (int)e->T.runs_half.size();
+   if (upload(&e->d_runs_half, e->T.runs_half.data(), e->T.runs_half.size())) return -1;
+   {
+      const int need = n / MDB_NI + e->T.nx * e->T.ny + 8;
+      if (need > e->batch_cap) {
+         FREE(e->d_batches); FREE(e->d_nbatch);
+         MDB_CUDA(cudaMalloc(&e->d_batches, sizeof(int2) * (size_t)need));
+         MDB_CUDA(cudaMalloc(&e->d_nbatch, sizeof(int)));
+         e->batch_cap = need;
+      }
+      if (e->pair_mode < 0) {
+         const char *m = getenv("MDB_PAIR_MODE");
+         const int mm = m ? atoi(m) : 4;
+         e->pair_mode = (mm == 2 || mm == 3) ? mm : 4;
+      }
+      if (new_system) { FREE(e->d_fs); }
+      if (!e->d_fs) MDB_CUDA(cudaMalloc(&e->d_fs, sizeof(double) * 3 * (size_t)n));
+      for (auto &r : e->T.runs)
+         if (r.dzlo < -500 || r.dzhi > 500) { mdb_set_error("stencil z extent > 500 cells"); return -1; }
+   }
 
    // ---- reciprocal space ----
    if (cfg->do_recip) {
@@ -235,6 +263,7 @@ extern "C" int mdb_force_real(mdb_engine *e, double *d_out, void *stream)
 {
    if (!e->configured || !e->sites_set) { mdb_set_error("mdb_force_real: engine not configured / no sites"); return -1; }
    if (!e->cells_valid && mdb_launch_cells(e, (cudaStream_t)stream)) return -1;
+   if (e->pair_mode >= 3) return mdb_launch_pair_tiled(e, d_out, (cudaStream_t)stream);
    return mdb_launch_pair(e, d_out, (cudaStream_t)stream);
 }
 

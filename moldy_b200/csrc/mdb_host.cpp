@@ -218,18 +218,25 @@ bool mdb_build_real_tables(const mdb_config &c, HostTables &T, std::string &err)
       cols[{ix, iy}].push_back(iz);
       if (ix || iy || iz) cols[{-ix, -iy}].push_back(-iz);
    }
-   T.runs.clear();
-   for (auto &kv : cols) {
-      std::vector<int> &z = kv.second;
-      std::sort(z.begin(), z.end());
-      size_t i = 0;
-      while (i < z.size()) {
-         size_t j = i;
-         while (j + 1 < z.size() && z[j + 1] <= z[j] + 1) j++;
-         T.runs.push_back({kv.first.first, kv.first.second, z[i], z[j]});
-         i = j + 1;
+   std::map<std::pair<int, int>, std::vector<int>> hcols;
+   for (size_t i = 0; i < T.half_list.size(); i += 3)
+      hcols[{T.half_list[i], T.half_list[i + 1]}].push_back(T.half_list[i + 2]);
+   auto to_runs = [](std::map<std::pair<int, int>, std::vector<int>> &m, std::vector<StencilRun> &out) {
+      out.clear();
+      for (auto &kv : m) {
+         std::vector<int> &z = kv.second;
+         std::sort(z.begin(), z.end());
+         size_t i = 0;
+         while (i < z.size()) {
+            size_t j = i;
+            while (j + 1 < z.size() && z[j + 1] <= z[j] + 1) j++;
+            out.push_back({kv.first.first, kv.first.second, z[i], z[j]});
+            i = j + 1;
+         }
       }
-   }
+   };
+   to_runs(cols, T.runs);
+   to_runs(hcols, T.runs_half);
    int k = 0;
    for (int ii = -1; ii <= 1; ii++)
       for (int jj = -1; jj <= 1; jj++)

@@ -32,6 +32,7 @@ struct HostTables {
    double hinv[9];
    std::vector<int> half_list;            // (ix,iy,iz) triplets of the reference half list
    std::vector<StencilRun> runs;          // full stencil as z-runs
+   std::vector<StencilRun> runs_half;     // the reference half list itself as z-runs (Newton-3 kernel)
    double reloc[27][3];                   // src/force.c:1284-1293
    // reciprocal space
    int hmax = 0, kmax = 0, lmax = 0, nhkl = 0;
@@ -90,8 +91,11 @@ struct mdb_engine {
    int *d_scan_tmp = nullptr;
    double4 *d_posq = nullptr;
    int *d_stype = nullptr, *d_scell = nullptr;
-   StencilRun *d_runs = nullptr;
-   int nruns = 0;
+   StencilRun *d_runs = nullptr, *d_runs_half = nullptr;
+   int nruns = 0, nruns_half = 0;
+   int2 *d_batches = nullptr; int *d_nbatch = nullptr; int batch_cap = 0;   // i-site batches of the tiled pair kernel
+   double *d_fs = nullptr;                // [3N] cell-sorted force accumulator (Newton-3 mode)
+   int pair_mode = -1;                    // 2: per-thread full stencil, 3: tiled full stencil, 4: tiled Newton-3
    // reductions / diagnostics
    double *d_partials = nullptr; int partials_cap = 0;
    unsigned long long *d_counters = nullptr;      // [0]=pair visits [1]=too close [2]=bin errors [3..4]=example pair
@@ -121,6 +125,9 @@ void mdb_set_error(const std::string &s);
 // ---- kernels launchers (mdb_cells.cu / mdb_pair.cu / mdb_kspace.cu) --------
 int mdb_launch_cells(mdb_engine *e, cudaStream_t st);
 int mdb_launch_pair(mdb_engine *e, double *d_out, cudaStream_t st);
+int mdb_launch_pair_tiled(mdb_engine *e, double *d_out, cudaStream_t st);
+int mdb_launch_batches(mdb_engine *e, cudaStream_t st);
+static constexpr int MDB_NI = 4;          // i-sites per warp in the tiled pair kernel
 int mdb_launch_recip(mdb_engine *e, double *d_out, cudaStream_t st);
 int mdb_launch_kernel_vec(int jmin, int nnab, double *forceij, double *pe, const double *r_sqr,
                           const double *nab_chg, double chg, double norm, double alpha, int ptype,

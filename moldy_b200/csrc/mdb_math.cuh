@@ -32,46 +32,60 @@ __constant__ double c_exp[16] = {
    0.0, 0.0};
 __constant__ double c_as[6] = {0.254829592, -0.284496736, 1.421413741, -1.453152027, 1.061405429, 0.3275911};
 
-// 1/sqrt(x), x > 0 normal.  MUFU.RSQ64H seed + Newton: two quadratic steps (default)
-// or one cubic step (MDB_RSQRT_CUBIC, 5 instead of 7 FP64 ops).
-#ifndef MDB_RSQRT_CUBIC
-#define MDB_RSQRT_CUBIC 0
-#endif
-__device__ __forceinline__ double mdb_rsqrt(double x)
+// All helpers below work on NV independent values at once and are written
+// step-by-step across the NV lanes ("structure of arrays" in registers): ptxas keeps
+// that order, so the NV dependent DFMA chains are issued interleaved and the FP64
+// pipe (2 issue cycles per warp-instruction, ~8 cycles latency) stays busy even with
+// two or three resident warps per scheduler.
+#define MDB_V for (int k = 0; k < NV; k++)
+
+// 1/sqrt(x), x > 0 normal.  MUFU.RSQ64H seed (~2^-20) + two Newton steps.
+template <int NV>
+__device__ __forceinline__ void mdb_rsqrt_v(const double (&x)[NV], double (&y)[NV])
 {
 #if MDB_LIBM_MATH
-   return rsqrt(x);
+#pragma unroll
+   MDB_V y[k] = rsqrt(x[k]);
 #else
-   double y;
-   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-#if MDB_RSQRT_CUBIC
-   double e = fma(-x * y, y, 1.0);
-   double p = fma(0.375, e, 0.5);
-   return fma(y * e, p, y);
-#else
-   double hx = 0.5 * x;
-   double e = fma(-hx, y * y, 0.5);
-   y = fma(y, e, y);
-   e = fma(-hx, y * y, 0.5);
-   y = fma(y, e, y);
-   return y;
-#endif
+   double hx[NV], e[NV];
+#pragma unroll
+   MDB_V asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[k]) : "d"(x[k]));
+#pragma unroll
+   MDB_V hx[k] = 0.5 * x[k];
+#pragma unroll
+   MDB_V e[k] = y[k] * y[k];
+#pragma unroll
+   MDB_V e[k] = fma(-hx[k], e[k], 0.5);
+#pragma unroll
+   MDB_V y[k] = fma(y[k], e[k], y[k]);
+#pragma unroll
+   MDB_V e[k] = y[k] * y[k];
+#pragma unroll
+   MDB_V e[k] = fma(-hx[k], e[k], 0.5);
+#pragma unroll
+   MDB_V y[k] = fma(y[k], e[k], y[k]);
 #endif
 }
 
 // 1/x, x normal.  MUFU.RCP64H seed + two Newton steps.
-__device__ __forceinline__ double mdb_rcp(double x)
+template <int NV>
+__device__ __forceinline__ void mdb_rcp_v(const double (&x)[NV], double (&y)[NV])
 {
 #if MDB_LIBM_MATH
-   return 1.0 / x;
+#pragma unroll
+   MDB_V y[k] = 1.0 / x[k];
 #else
-   double y;
-   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-   double e = fma(-x, y, 1.0);
-   y = fma(y, e, y);
-   e = fma(-x, y, 1.0);
-   y = fma(y, e, y);
-   return y;
+   double e[NV];
+#pragma unroll
+   MDB_V asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[k]) : "d"(x[k]));
+#pragma unroll
+   MDB_V e[k] = fma(-x[k], y[k], 1.0);
+#pragma unroll
+   MDB_V y[k] = fma(y[k], e[k], y[k]);
+#pragma unroll
+   MDB_V e[k] = fma(-x[k], y[k], 1.0);
+#pragma unroll
+   MDB_V y[k] = fma(y[k], e[k], y[k]);
 #endif
 }
 
@@ -80,25 +94,41 @@ __device__ __forceinline__ double mdb_rcp(double x)
 // field.  x < -708 returns 0 through an integer test on the high word (no FP64
 // min/max); large positive x is the caller's responsibility (never occurs for
 // -a^2 r^2, -p r).
-__device__ __forceinline__ double mdb_exp(double x)
+template <int NV>
+__device__ __forceinline__ void mdb_exp_v(const double (&x)[NV], double (&out)[NV])
 {
 #if MDB_LIBM_MATH
-   return exp(x);
-#else
-   double t = fma(x, c_exp[10], c_exp[11]);
-   int n = __double2loint(t);
-   double nf = t - c_exp[11];
-   double r = fma(nf, c_exp[12], x);
-   r = fma(nf, c_exp[13], r);
-   double p = c_exp[0];
 #pragma unroll
-   for (int k = 1; k < 10; k++) p = fma(p, r, c_exp[k]);
-   p = fma(p, r, 0.5);
-   p = fma(p, r, 1.0);
-   p = fma(p, r, 1.0);
-   int hi = __double2hiint(p) + (n << 20), lo = __double2loint(p);
-   const bool tiny = (unsigned)__double2hiint(x) > 0xc0862000u;     // x < -708
-   return __hiloint2double(tiny ? 0 : hi, tiny ? 0 : lo);
+   MDB_V out[k] = exp(x[k]);
+#else
+   double t[NV], r[NV], p[NV];
+#pragma unroll
+   MDB_V t[k] = fma(x[k], c_exp[10], c_exp[11]);
+#pragma unroll
+   MDB_V r[k] = t[k] - c_exp[11];
+#pragma unroll
+   MDB_V p[k] = fma(r[k], c_exp[12], x[k]);
+#pragma unroll
+   MDB_V r[k] = fma(r[k], c_exp[13], p[k]);
+#pragma unroll
+   MDB_V p[k] = fma(c_exp[0], r[k], c_exp[1]);
+#pragma unroll
+   for (int m = 2; m < 10; m++) {
+#pragma unroll
+      MDB_V p[k] = fma(p[k], r[k], c_exp[m]);
+   }
+#pragma unroll
+   MDB_V p[k] = fma(p[k], r[k], 0.5);
+#pragma unroll
+   MDB_V p[k] = fma(p[k], r[k], 1.0);
+#pragma unroll
+   MDB_V p[k] = fma(p[k], r[k], 1.0);
+#pragma unroll
+   MDB_V {
+      const int hi = __double2hiint(p[k]) + (__double2loint(t[k]) << 20), lo = __double2loint(p[k]);
+      const bool tiny = (unsigned)__double2hiint(x[k]) > 0xc0862000u;     // x < -708
+      out[k] = __hiloint2double(tiny ? 0 : hi, tiny ? 0 : lo);
+   }
 #endif
 }
 
@@ -113,71 +143,152 @@ enum { PT_LJ = 0, PT_E6 = 1, PT_MCY = 2, PT_GEN = 3, PT_HIW = 4, PT_RSV = 5, PT_
 
 struct PairOut { double fij, phi; };
 
+// NV pairs at once: r2[k], qq[k] = q_i q_j, p[k] -> parameter row of the (type_i,type_j) entry.
+template <int PT, bool COUL, int NV>
+__device__ __forceinline__ void mdb_pair_eval_v(const double (&r2)[NV], const double (&qq)[NV],
+                                                const double *const (&p)[NV], double alpha, double norm,
+                                                double (&fij)[NV], double (&phi)[NV])
+{
+   double r_r[NV], r[NV], r_sqr_r[NV], erfc_term[NV], t[NV];
+   if (COUL || PT != PT_LJ) {
+      mdb_rsqrt_v<NV>(r2, r_r);
+#pragma unroll
+      MDB_V r[k] = r2[k] * r_r[k];
+#pragma unroll
+      MDB_V r_sqr_r[k] = r_r[k] * r_r[k];
+   } else {
+      mdb_rcp_v<NV>(r2, r_sqr_r);
+#pragma unroll
+      MDB_V r_r[k] = r[k] = 0.0;
+   }
+#pragma unroll
+   MDB_V erfc_term[k] = t[k] = 0.0;
+   if (COUL) {
+      double ar[NV], u[NV], tt[NV], x[NV], e[NV], poly[NV];
+#pragma unroll
+      MDB_V ar[k] = alpha * r[k];
+#pragma unroll
+      MDB_V u[k] = fma(c_as[5], ar[k], 1.0);
+#pragma unroll
+      MDB_V x[k] = -(ar[k] * ar[k]);
+      mdb_rcp_v<NV>(u, tt);
+      mdb_exp_v<NV>(x, e);
+#pragma unroll
+      MDB_V e[k] = qq[k] * e[k];
+#pragma unroll
+      MDB_V poly[k] = fma(tt[k], c_as[4], c_as[3]);
+#pragma unroll
+      MDB_V poly[k] = fma(tt[k], poly[k], c_as[2]);
+#pragma unroll
+      MDB_V poly[k] = fma(tt[k], poly[k], c_as[1]);
+#pragma unroll
+      MDB_V poly[k] = fma(tt[k], poly[k], c_as[0]);
+#pragma unroll
+      MDB_V poly[k] = tt[k] * poly[k];
+#pragma unroll
+      MDB_V t[k] = poly[k] * e[k] * r_r[k];
+#pragma unroll
+      MDB_V erfc_term[k] = fma(norm, e[k], t[k]);
+   }
+   if (PT == PT_LJ) {                       // p[0]=eps, p[1]=sigma^2, p[2]=6 eps
+      double r6[NV], r12[NV];
+#pragma unroll
+      MDB_V r6[k] = p[k][1] * r_sqr_r[k];
+#pragma unroll
+      MDB_V r6[k] = r6[k] * r6[k] * r6[k];
+#pragma unroll
+      MDB_V r12[k] = r6[k] * r6[k];
+#pragma unroll
+      MDB_V phi[k] = t[k] + p[k][0] * (r12[k] - r6[k]);
+#pragma unroll
+      MDB_V fij[k] = r_sqr_r[k] * fma(p[k][2], fma(2.0, r12[k], -r6[k]), erfc_term[k]);
+   } else if (PT == PT_E6) {                // -p0/r^6 + p1 exp(-p2 r)
+      double x[NV], e1[NV], r6[NV];
+#pragma unroll
+      MDB_V x[k] = -p[k][2] * r[k];
+      mdb_exp_v<NV>(x, e1);
+#pragma unroll
+      MDB_V e1[k] = p[k][1] * e1[k];
+#pragma unroll
+      MDB_V r6[k] = p[k][0] * r_sqr_r[k] * r_sqr_r[k] * r_sqr_r[k];
+#pragma unroll
+      MDB_V phi[k] = t[k] - r6[k] + e1[k];
+#pragma unroll
+      MDB_V fij[k] = fma(r_sqr_r[k], fma(-6.0, r6[k], erfc_term[k]), p[k][2] * e1[k] * r_r[k]);
+   } else if (PT == PT_MCY) {               // p0 exp(-p1 r) - p2 exp(-p3 r)
+      double x1[NV], x2[NV], e1[NV], e2[NV];
+#pragma unroll
+      MDB_V { x1[k] = -p[k][1] * r[k]; x2[k] = -p[k][3] * r[k]; }
+      mdb_exp_v<NV>(x1, e1);
+      mdb_exp_v<NV>(x2, e2);
+#pragma unroll
+      MDB_V { e1[k] = p[k][0] * e1[k]; e2[k] = -p[k][2] * e2[k]; }
+#pragma unroll
+      MDB_V phi[k] = t[k] + e1[k] + e2[k];
+#pragma unroll
+      MDB_V fij[k] = fma(fma(p[k][1], e1[k], p[k][3] * e2[k]), r_r[k], erfc_term[k] * r_sqr_r[k]);
+   } else if (PT == PT_GEN) {               // p0 exp(-p1 r) + p2/r^12 - p3/r^4 - p4/r^6 - p5/r^8
+      double x[NV], e1[NV];
+#pragma unroll
+      MDB_V x[k] = -p[k][1] * r[k];
+      mdb_exp_v<NV>(x, e1);
+#pragma unroll
+      MDB_V {
+         e1[k] = p[k][0] * e1[k];
+         double r4 = r_sqr_r[k] * r_sqr_r[k];
+         double r6 = r_sqr_r[k] * r4;
+         const double r8 = p[k][5] * r4 * r4;
+         const double r12 = p[k][2] * r6 * r6;
+         r4 *= p[k][3];
+         r6 *= p[k][4];
+         phi[k] = t[k] + e1[k] + r12 - r4 - r6 - r8;
+         fij[k] = fma(r_sqr_r[k], 12.0 * r12 - 4.0 * r4 - 6.0 * r6 - 8.0 * r8 + erfc_term[k], p[k][1] * e1[k] * r_r[k]);
+      }
+   } else if (PT == PT_HIW) {               // p0/r^4 + p1/r^6 + p2/r^12
+#pragma unroll
+      MDB_V {
+         double r4 = r_sqr_r[k] * r_sqr_r[k];
+         double r6 = r_sqr_r[k] * r4;
+         const double r12 = p[k][2] * r6 * r6;
+         r6 *= p[k][1];
+         r4 *= p[k][0];
+         phi[k] = t[k] + r4 + r6 + r12;
+         fij[k] = r_sqr_r[k] * (4.0 * r4 + 6.0 * r6 + 12.0 * r12 + erfc_term[k]);
+      }
+   } else {                                 // PT_MOR: Busing-Ida-Gilbert + Morse
+      double x1[NV], x2[NV], x3[NV], e1[NV], e2[NV], e3[NV];
+#pragma unroll
+      MDB_V {
+         x1[k] = (p[k][1] - r[k]) * p[k][2];
+         x2[k] = -2.0 * p[k][5] * (r[k] - p[k][6]);
+         x3[k] = -p[k][5] * (r[k] - p[k][6]);
+      }
+      mdb_exp_v<NV>(x1, e1);
+      mdb_exp_v<NV>(x2, e2);
+      mdb_exp_v<NV>(x3, e3);
+#pragma unroll
+      MDB_V {
+         e1[k] = p[k][0] * e1[k];
+         e2[k] = p[k][4] * e2[k];
+         e3[k] = -p[k][4] * 2.0 * e3[k];
+         const double r6 = p[k][3] * r_sqr_r[k] * r_sqr_r[k] * r_sqr_r[k];
+         phi[k] = t[k] + e1[k] - r6 + e2[k] + e3[k];
+         fij[k] = fma(r_sqr_r[k], fma(-6.0, r6, erfc_term[k]),
+                      r_r[k] * (p[k][2] * e1[k] + (2.0 * p[k][5]) * e2[k] + p[k][5] * e3[k]));
+      }
+   }
+}
+
+// single pair (kernel() of the C ABI, per-thread pair kernel)
 template <int PT, bool COUL>
 __device__ __forceinline__ PairOut mdb_pair_eval(double r2, double qq, const double *__restrict__ p,
                                                  double alpha, double norm)
 {
+   const double r2v[1] = {r2}, qqv[1] = {qq};
+   const double *const pv[1] = {p};
+   double f[1], ph[1];
+   mdb_pair_eval_v<PT, COUL, 1>(r2v, qqv, pv, alpha, norm, f, ph);
    PairOut o;
-   double r_r, r, r_sqr_r, erfc_term = 0.0, t = 0.0;
-   if (COUL || PT != PT_LJ) {
-      r_r = mdb_rsqrt(r2);
-      r = r2 * r_r;
-      r_sqr_r = r_r * r_r;
-   } else {
-      r_sqr_r = mdb_rcp(r2);
-      r_r = r = 0.0;
-   }
-   if (COUL) {
-      double ar = alpha * r;
-      double tt = mdb_rcp(fma(c_as[5], ar, 1.0));
-      double e = qq * mdb_exp(-(ar * ar));
-      double poly = tt * fma(tt, fma(tt, fma(tt, fma(tt, c_as[4], c_as[3]), c_as[2]), c_as[1]), c_as[0]);
-      t = poly * e * r_r;
-      erfc_term = fma(norm, e, t);
-   }
-   if (PT == PT_LJ) {                       // p[0]=eps, p[1]=sigma^2, p[2]=6 eps
-      double r_6_r = p[1] * r_sqr_r;
-      r_6_r = r_6_r * r_6_r * r_6_r;
-      double r_12_r = r_6_r * r_6_r;
-      o.phi = t + p[0] * (r_12_r - r_6_r);
-      o.fij = r_sqr_r * fma(p[2], fma(2.0, r_12_r, -r_6_r), erfc_term);
-   } else if (PT == PT_E6) {                // -p0/r^6 + p1 exp(-p2 r)
-      double exp_f1 = p[1] * mdb_exp(-p[2] * r);
-      double r_6_r = p[0] * r_sqr_r * r_sqr_r * r_sqr_r;
-      o.phi = t - r_6_r + exp_f1;
-      o.fij = fma(r_sqr_r, fma(-6.0, r_6_r, erfc_term), p[2] * exp_f1 * r_r);
-   } else if (PT == PT_MCY) {               // p0 exp(-p1 r) - p2 exp(-p3 r)
-      double exp_f1 = p[0] * mdb_exp(-p[1] * r);
-      double exp_f2 = -p[2] * mdb_exp(-p[3] * r);
-      o.phi = t + exp_f1 + exp_f2;
-      o.fij = fma(fma(p[1], exp_f1, p[3] * exp_f2), r_r, erfc_term * r_sqr_r);
-   } else if (PT == PT_GEN) {               // p0 exp(-p1 r) + p2/r^12 - p3/r^4 - p4/r^6 - p5/r^8
-      double exp_f1 = p[0] * mdb_exp(-p[1] * r);
-      double r_4_r = r_sqr_r * r_sqr_r;
-      double r_6_r = r_sqr_r * r_4_r;
-      double r_8_r = p[5] * r_4_r * r_4_r;
-      double r_12_r = p[2] * r_6_r * r_6_r;
-      r_4_r *= p[3];
-      r_6_r *= p[4];
-      o.phi = t + exp_f1 + r_12_r - r_4_r - r_6_r - r_8_r;
-      o.fij = fma(r_sqr_r, 12.0 * r_12_r - 4.0 * r_4_r - 6.0 * r_6_r - 8.0 * r_8_r + erfc_term,
-                  p[1] * exp_f1 * r_r);
-   } else if (PT == PT_HIW) {               // p0/r^4 + p1/r^6 + p2/r^12
-      double r_4_r = r_sqr_r * r_sqr_r;
-      double r_6_r = r_sqr_r * r_4_r;
-      double r_12_r = p[2] * r_6_r * r_6_r;
-      r_6_r *= p[1];
-      r_4_r *= p[0];
-      o.phi = t + r_4_r + r_6_r + r_12_r;
-      o.fij = r_sqr_r * (4.0 * r_4_r + 6.0 * r_6_r + 12.0 * r_12_r + erfc_term);
-   } else {                                 // PT_MOR: Busing-Ida-Gilbert + Morse
-      double exp_f1 = p[0] * mdb_exp((p[1] - r) * p[2]);
-      double r_6_r = p[3] * r_sqr_r * r_sqr_r * r_sqr_r;
-      double exp_f2 = p[4] * mdb_exp(-2.0 * p[5] * (r - p[6]));
-      double exp_f3 = -p[4] * 2.0 * mdb_exp(-p[5] * (r - p[6]));
-      o.phi = t + exp_f1 - r_6_r + exp_f2 + exp_f3;
-      o.fij = fma(r_sqr_r, fma(-6.0, r_6_r, erfc_term),
-                  r_r * (p[2] * exp_f1 + (2.0 * p[5]) * exp_f2 + p[5] * exp_f3));
-   }
+   o.fij = f[0]; o.phi = ph[0];
    return o;
 }

@@ -1,0 +1,407 @@
+// mdb_pair_tiled.cu -- tiled FP64 real-space pair kernel (pair_mode 3 and 4).
+//
+// Same pair set and arithmetic as k_pair (mdb_pair.cu), different mapping:
+//   * a WARP owns a batch of <= NI consecutive cell-sorted sites i of one z-column;
+//     their data and force accumulators are warp-uniform registers;
+//   * the 32 LANES own neighbour sites j.  For 64 stencil runs at a time the warp
+//     builds, in shared memory, the list of contiguous j-segments that the union of
+//     the batch's windows covers (cells are sorted z-fastest, so a run is one
+//     contiguous range per periodic piece), prefix-sums their lengths and walks the
+//     flattened list 32 sites per step: lanes are always full, control flow is
+//     warp-uniform, each j is loaded once and reused for the NI sites i;
+//   * a (i,j) visit is masked by the exact window test  dzlo <= cz_j - cz_i <= dzhi
+//     (the batch spans ~2 cells, so ~10 % of the lane-visits are masked off).
+// mode 3 (full stencil): every reference pair is visited from both ends, forces are
+//   written by their owner only -> no atomics, bit-reproducible.
+// mode 4 (Newton-3): the reference's half list; the lane also accumulates the force
+//   on j over the NI visits and adds it to a cell-sorted accumulator with
+//   red.global.add.f64 (coalesced); results vary in the last bits run to run.
+#include "mdb_internal.h"
+#include "mdb_math.cuh"
+
+#ifndef MDB_TILED_MINB
+#define MDB_TILED_MINB 2
+#endif
+static constexpr int TW = 4;                   // warps per block
+static constexpr int RB = 64;                  // stencil runs per shared-memory pass
+static constexpr int NSLOT = 3 * RB;           // segment slots per pass (3 periodic pieces per run)
+static constexpr int NI = MDB_NI;
+static constexpr int NRED = 8;
+
+struct SegTable {
+   int jstart[NSLOT];
+   int pre[NSLOT + 1];
+   int colbase[NSLOT];
+   int pack[NSLOT];                            // kimg | zoffidx<<5 | selfcol<<7 | (dzlo+512)<<8 | (dzhi+512)<<18
+};
+
+__device__ __forceinline__ double wsum(double v)
+{
+#pragma unroll
+   for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+   return v;
+}
+
+template <int PT, bool COUL, bool STRICT, bool FW, bool N3>
+__global__ void __launch_bounds__(TW * 32, MDB_TILED_MINB)
+k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const int *__restrict__ stype,
+             const int *__restrict__ scell, const int *__restrict__ cstart, const int *__restrict__ order,
+             const int *__restrict__ mol, const StencilRun *__restrict__ runs, const double *__restrict__ ptab,
+             const int2 *__restrict__ batches, const int *__restrict__ nbatch_p, int rank, int nranks,
+             int ptab_in_smem,
+             double *__restrict__ out, double *__restrict__ fs, double *__restrict__ partials,
+             unsigned long long *__restrict__ counters)
+{
+   __shared__ SegTable s_seg[TW];
+   __shared__ double s_reloc[27][3];
+   extern __shared__ double s_ptab[];           // pair-parameter table (when it fits), else read through L1
+   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+   for (int k = threadIdx.x; k < 81; k += TW * 32) s_reloc[k / 3][k % 3] = P.reloc[k / 3][k % 3];
+   const int ntab = P.max_id * P.max_id * MDB_NPOTP;
+   if (ptab_in_smem)
+      for (int k = threadIdx.x; k < ntab; k += TW * 32) s_ptab[k] = ptab[k];
+   const double *__restrict__ tab = ptab_in_smem ? s_ptab : ptab;
+   __syncthreads();
+   SegTable &S = s_seg[w];
+
+   const int nbatch = *nbatch_p;
+   const long b_lo = (long)nbatch * rank / nranks, b_hi = (long)nbatch * (rank + 1) / nranks;
+   const long b = b_lo + (long)blockIdx.x * TW + w;
+   const size_t prow_id = (size_t)blockIdx.x * TW + w;
+   if (b >= b_hi) {                             // whole warp idle: still publish a zero row
+      if (lane < 7) partials[prow_id * NRED + lane] = 0.0;
+      return;
+   }
+   const int2 bt = batches[b];
+   const int s0 = bt.x, cnt = bt.y;
+
+   // ---- batch (warp-uniform) data
+   double pix[NI], piy[NI], piz[NI], piq[NI];
+   int czi[NI], tyi[NI], fwi[NI];
+   double fix[NI], fiy[NI], fiz[NI];
+   int cx, cy, cz_lo, cz_hi;
+   {
+      const int c0 = scell[s0];
+      cz_lo = c0 % P.nz;
+      const int t = c0 / P.nz;
+      cy = t % P.ny; cx = t / P.ny;
+      cz_hi = scell[s0 + cnt - 1] % P.nz;
+   }
+#pragma unroll
+   for (int k = 0; k < NI; k++) {
+      const int sk = s0 + min(k, cnt - 1);
+      const double4 p = posq[sk];
+      const int t = stype[sk];
+      pix[k] = p.x; piy[k] = p.y; piz[k] = p.z; piq[k] = p.w;
+      tyi[k] = t & 0x3fffffff; fwi[k] = t >> 30;
+      czi[k] = k < cnt ? scell[sk] % P.nz : (1 << 20);      // padded entries never pass the window test
+      fix[k] = fiy[k] = fiz[k] = 0.0;
+   }
+   double pe = 0, w00 = 0, w01 = 0, w02 = 0, w11 = 0, w12 = 0, w22 = 0;
+   unsigned int visits = 0;
+   const int nruns = P.nruns;
+
+   for (int rb = 0; rb < nruns; rb += RB) {
+      // ---- segment table for runs rb .. rb+RB-1: lane handles runs rb+lane and rb+32+lane
+      __syncwarp();
+      int total = 0, nseg = 0;
+#pragma unroll
+      for (int hh = 0; hh < RB / 32; hh++) {
+         const int lr = hh * 32 + lane, r = rb + lr;
+         int cnt3[3] = {0, 0, 0}, js3[3] = {0, 0, 0}, pk3[3] = {0, 0, 0}, colb = 0;
+         if (r < nruns) {
+            const StencilRun run = runs[r];
+            int tx = cx + run.dx, ty = cy + run.dy, ii = 0, jj = 0;
+            if (tx < 0) { tx += P.nx; ii = -1; } else if (tx >= P.nx) { tx -= P.nx; ii = 1; }
+            if (ty < 0) { ty += P.ny; jj = -1; } else if (ty >= P.ny) { ty -= P.ny; jj = 1; }
+            colb = (tx * P.ny + ty) * P.nz;
+            const int z0 = cz_lo + run.dzlo, z1 = cz_hi + run.dzhi;
+            const int selfcol = (run.dx == 0 && run.dy == 0) ? 1 : 0;
+#pragma unroll
+            for (int kk = -1; kk <= 1; kk++) {
+               const int zoff = kk * P.nz;
+               const int a = max(z0, zoff), bb = min(z1, zoff + P.nz - 1);
+               if (a <= bb) {
+                  const int jb = cstart[colb + a - zoff], jn = cstart[colb + bb - zoff + 1];
+                  js3[kk + 1] = jb; cnt3[kk + 1] = jn - jb;
+                  pk3[kk + 1] = (9 * (ii + 1) + 3 * (jj + 1) + (kk + 1)) | ((kk + 1) << 5) | (selfcol << 7) |
+                                ((run.dzlo + 512) << 8) | ((run.dzhi + 512) << 18);
+               }
+            }
+         }
+         // append the non-empty pieces (compacted) and their running prefix
+         const int ne = (cnt3[0] > 0) + (cnt3[1] > 0) + (cnt3[2] > 0);
+         const int tot = cnt3[0] + cnt3[1] + cnt3[2];
+         int inc = tot, ninc = ne;
+#pragma unroll
+         for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, d), u = __shfl_up_sync(0xffffffffu, ninc, d);
+            if (lane >= d) { inc += t; ninc += u; }
+         }
+         int base = total + inc - tot, slot = nseg + ninc - ne;
+#pragma unroll
+         for (int q = 0; q < 3; q++)
+            if (cnt3[q] > 0) {
+               S.jstart[slot] = js3[q]; S.colbase[slot] = colb; S.pack[slot] = pk3[q];
+               S.pre[slot] = base;
+               base += cnt3[q];
+               slot++;
+            }
+         total += __shfl_sync(0xffffffffu, inc, 31);
+         nseg += __shfl_sync(0xffffffffu, ninc, 31);
+      }
+      if (lane == 0) S.pre[nseg] = total;
+      __syncwarp();
+
+      // ---- walk the flattened j list, 32 sites per step; the loads of step n+1 are
+      // issued before the arithmetic of step n (uniform control flow makes this free)
+      int seg = 0;
+      int n_j = s0, n_pk = 13, n_tj = 0, n_cz = 0;
+      double4 n_pj = make_double4(0, 0, 0, 0);
+      bool n_valid = false;
+      auto fetch = [&](int base) {
+         const int p = base + lane;
+         n_valid = p < total;
+         const int pp = n_valid ? p : total - 1;
+         while (pp >= S.pre[seg + 1]) seg++;
+         n_j = S.jstart[seg] + (pp - S.pre[seg]);
+         n_pk = S.pack[seg];
+         n_pj = posq[n_j];
+         n_tj = stype[n_j];
+         n_cz = scell[n_j] - S.colbase[seg];
+      };
+      if (total > 0) fetch(0);
+      for (int base = 0; base < total; base += 32) {
+         const bool valid = n_valid;
+         const int j = n_j, pk = n_pk;
+         double4 pj = n_pj;
+         int tj = n_tj;
+         const int kimg = pk & 31;
+         const int dzlo = ((pk >> 8) & 1023) - 512, dzhi = ((pk >> 18) & 1023) - 512;
+         const int zj = n_cz + (((pk >> 5) & 3) - 1) * P.nz;
+         if (base + 32 < total) fetch(base + 32);
+         const int fwj = tj >> 30;
+         tj &= 0x3fffffff;
+         pj.x += s_reloc[kimg][0]; pj.y += s_reloc[kimg][1]; pj.z += s_reloc[kimg][2];
+         const bool central = kimg == 13;
+         const bool samecol = central && ((pk >> 7) & 1);
+         double gx = 0, gy = 0, gz = 0;
+         int close = 0;
+         double dx[NI], dy[NI], dzz[NI], r2[NI], qq[NI], fij[NI], phi[NI];
+         const double *prow[NI];
+         bool in[NI];
+#pragma unroll
+         for (int k = 0; k < NI; k++) {
+            const int dz = zj - czi[k];
+            in[k] = valid && dz >= dzlo && dz <= dzhi;
+            if (N3) in[k] = in[k] && !(samecol && dz == 0 && j <= s0 + k);   // same cell: each pair once
+            else in[k] = in[k] && !(central && j == s0 + k);                 // never pair a site with itself
+            if (FW) in[k] = in[k] && !(fwi[k] & fwj);
+            dx[k] = pj.x - pix[k]; dy[k] = pj.y - piy[k]; dzz[k] = pj.z - piz[k];
+            qq[k] = piq[k] * pj.w;
+            prow[k] = tab + (tyi[k] * P.max_id + tj) * MDB_NPOTP;
+         }
+#pragma unroll
+         for (int k = 0; k < NI; k++) r2[k] = fma(dx[k], dx[k], fma(dy[k], dy[k], dzz[k] * dzz[k]));
+#pragma unroll
+         for (int k = 0; k < NI; k++) {
+            close |= (in[k] && __double2hiint(r2[k]) < 0x3fd00000) ? (1 << k) : 0;   // r^2 < 0.25 (rare)
+            if (STRICT) r2[k] = r2[k] > P.cutoffsq ? P.cutoff100sq : r2[k];
+         }
+         mdb_pair_eval_v<PT, COUL, NI>(r2, qq, prow, P.alpha, P.norm, fij, phi);
+#pragma unroll
+         for (int k = 0; k < NI; k++) {
+            const double f = in[k] ? fij[k] : 0.0;
+            pe += in[k] ? phi[k] : 0.0;
+            visits += in[k] ? 1u : 0u;
+            fix[k] = fma(-f, dx[k], fix[k]); fiy[k] = fma(-f, dy[k], fiy[k]); fiz[k] = fma(-f, dzz[k], fiz[k]);
+            gx = fma(f, dx[k], gx); gy = fma(f, dy[k], gy); gz = fma(f, dzz[k], gz);
+         }
+         if (close) {                           // TOO_CLOSE diagnostics, off the hot path (src/force.c:939-949)
+            const int mj = mol[order[j]];
+            for (int k = 0; k < NI; k++)
+               if (((close >> k) & 1) && mol[order[s0 + k]] != mj) {
+                  atomicAdd(&counters[1], N3 ? 2ULL : 1ULL);
+                  counters[3] = ((unsigned long long)(unsigned)order[s0 + k] << 32) | (unsigned)order[j];
+               }
+         }
+         if (N3) {
+            if (valid) {
+               atomicAdd(&fs[j], gx);
+               atomicAdd(&fs[(size_t)nsites + j], gy);
+               atomicAdd(&fs[2 * (size_t)nsites + j], gz);
+            }
+         }
+         if (!central) {                        // Bekker image-force virial (src/force.c:983-991)
+            const double sc = N3 ? 1.0 : 0.5;
+            const double rx = sc * s_reloc[kimg][0], ry = sc * s_reloc[kimg][1], rz = sc * s_reloc[kimg][2];
+            w00 = fma(rx, gx, w00); w01 = fma(ry, gx, w01); w02 = fma(rz, gx, w02);
+            w11 = fma(ry, gy, w11); w12 = fma(rz, gy, w12); w22 = fma(rz, gz, w22);
+         }
+      }
+   }
+
+   // ---- forces on the batch sites: reduce the per-lane partial sums
+#pragma unroll
+   for (int k = 0; k < NI; k++) {
+      const double fx = wsum(fix[k]), fy = wsum(fiy[k]), fz = wsum(fiz[k]);
+      if (lane == 0 && k < cnt) {
+         if (N3) {
+            atomicAdd(&fs[s0 + k], fx);
+            atomicAdd(&fs[(size_t)nsites + s0 + k], fy);
+            atomicAdd(&fs[2 * (size_t)nsites + s0 + k], fz);
+         } else {
+            const int o = order[s0 + k];
+            out[o] += fx;
+            out[(size_t)nsites + o] += fy;
+            out[2 * (size_t)nsites + o] += fz;
+            w00 = fma(pix[k], fx, w00); w01 = fma(piy[k], fx, w01); w02 = fma(piz[k], fx, w02);
+            w11 = fma(piy[k], fy, w11); w12 = fma(piz[k], fy, w12); w22 = fma(piz[k], fz, w22);
+         }
+      }
+   }
+   double v[7] = {pe, w00, w01, w02, w11, w12, w22};
+#pragma unroll
+   for (int k = 0; k < 7; k++) {
+      const double t = wsum(v[k]);
+      if (lane == 0) partials[prow_id * NRED + k] = t;
+   }
+   unsigned int vs = visits;
+#pragma unroll
+   for (int d = 16; d > 0; d >>= 1) vs += __shfl_xor_sync(0xffffffffu, vs, d);
+   if (lane == 0) atomicAdd(&counters[0], (unsigned long long)vs * (N3 ? 2ULL : 1ULL));
+}
+
+// Newton-3 mode: move the cell-sorted accumulator back to the caller's site order and add the
+// site virial sum_i r_i (x) F_i (src/force.c:973-982), one row of partial sums per block.
+__global__ void __launch_bounds__(256) k_unsort_virial(int n, const double4 *__restrict__ posq,
+                                                       const int *__restrict__ order, const double *__restrict__ fs,
+                                                       double *__restrict__ out, double *__restrict__ partials)
+{
+   const int s = blockIdx.x * 256 + threadIdx.x;
+   double v[6] = {0, 0, 0, 0, 0, 0};
+   if (s < n) {
+      const double fx = fs[s], fy = fs[(size_t)n + s], fz = fs[2 * (size_t)n + s];
+      const double4 p = posq[s];
+      const int o = order[s];
+      out[o] += fx; out[(size_t)n + o] += fy; out[2 * (size_t)n + o] += fz;
+      v[0] = p.x * fx; v[1] = p.y * fx; v[2] = p.z * fx; v[3] = p.y * fy; v[4] = p.z * fy; v[5] = p.z * fz;
+   }
+   __shared__ double red[8][6];
+   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+   for (int k = 0; k < 6; k++) {
+      const double t = wsum(v[k]);
+      if (lane == 0) red[w][k] = t;
+   }
+   __syncthreads();
+   if (threadIdx.x < 6) {
+      double t = 0;
+      for (int k = 0; k < 8; k++) t += red[k][threadIdx.x];
+      partials[(size_t)blockIdx.x * NRED + 1 + threadIdx.x] = t;
+   }
+   if (threadIdx.x == 6) partials[(size_t)blockIdx.x * NRED] = 0.0;
+}
+
+// fixed-order sum of partial rows: out.pe_real += scale * sum(row[0]); stress += sum(row[1..6])
+__global__ void __launch_bounds__(1024) k_rows_finish(const double *__restrict__ partials, int nrows, int nsites,
+                                                      double pe_scale, double *__restrict__ out)
+{
+   __shared__ double sm[1024];
+   double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+   for (int b = threadIdx.x; b < nrows; b += 1024)
+#pragma unroll
+      for (int k = 0; k < 7; k++) acc[k] += partials[(size_t)b * NRED + k];
+   double tot[7];
+   for (int k = 0; k < 7; k++) {
+      sm[threadIdx.x] = acc[k];
+      __syncthreads();
+      for (int d = 512; d > 0; d >>= 1) {
+         if (threadIdx.x < d) sm[threadIdx.x] += sm[threadIdx.x + d];
+         __syncthreads();
+      }
+      tot[k] = sm[0];
+      __syncthreads();
+   }
+   if (threadIdx.x == 0) {
+      double *sc = out + 3 * (size_t)nsites;
+      sc[0] += pe_scale * tot[0];
+      sc[2 + 0] += tot[1]; sc[2 + 1] += tot[2]; sc[2 + 2] += tot[3];
+      sc[2 + 4] += tot[4]; sc[2 + 5] += tot[5]; sc[2 + 8] += tot[6];
+   }
+}
+
+#define TILED_ARGS P, c.nsites, e->d_posq, e->d_stype, e->d_scell, e->d_start, e->d_order, e->d_mol, runs, e->d_ptab, \
+                   e->d_batches, e->d_nbatch, e->ithread, e->nthreads, tab_smem, d_out, e->d_fs, e->d_partials, e->d_counters
+
+template <int PT, bool COUL>
+static void launch_tiled(bool strict, bool fw, bool n3, dim3 g, cudaStream_t st, PairParams &P, mdb_engine *e,
+                         const StencilRun *runs, double *d_out)
+{
+   const mdb_config &c = e->cfg;
+   const size_t tab_bytes = sizeof(double) * MDB_NPOTP * (size_t)c.max_id * c.max_id;
+   const int tab_smem = tab_bytes <= 24576 ? 1 : 0;
+   const size_t shm = tab_smem ? tab_bytes : 0;
+#define GO(S, F, N) k_pair_tiled<PT, COUL, S, F, N><<<g, TW * 32, shm, st>>>(TILED_ARGS)
+   if (strict) {
+      if (fw) { if (n3) GO(true, true, true); else GO(true, true, false); }
+      else    { if (n3) GO(true, false, true); else GO(true, false, false); }
+   } else {
+      if (fw) { if (n3) GO(false, true, true); else GO(false, true, false); }
+      else    { if (n3) GO(false, false, true); else GO(false, false, false); }
+   }
+#undef GO
+}
+
+int mdb_launch_pair_tiled(mdb_engine *e, double *d_out, cudaStream_t st)
+{
+   const mdb_config &c = e->cfg;
+   const bool n3 = e->pair_mode == 4;
+   PairParams P;
+   P.nx = e->T.nx; P.ny = e->T.ny; P.nz = e->T.nz;
+   P.nruns = n3 ? e->nruns_half : e->nruns;
+   const StencilRun *runs = n3 ? e->d_runs_half : e->d_runs;
+   for (int k = 0; k < 27; k++)
+      for (int a = 0; a < 3; a++) P.reloc[k][a] = e->T.reloc[k][a];
+   P.alpha = c.alpha;
+   P.norm = 2.0 * c.alpha / sqrt(MDB_PI);
+   P.cutoffsq = c.cutoff * c.cutoff;
+   P.cutoff100sq = 10000.0 * P.cutoffsq;
+   P.max_id = c.max_id;
+   P.strict = c.strict_cutoff;
+   P.s_lo = 0; P.s_hi = c.nsites;
+   // upper bound on this rank's batches (the exact count lives on the device)
+   const long nb_max = (long)c.nsites / NI + (long)e->T.nx * e->T.ny + 1;
+   const int my_max = (int)((nb_max + e->nthreads - 1) / e->nthreads) + 1;
+   const int nblocks = (my_max + TW - 1) / TW;
+   const int nrows_pair = nblocks * TW;
+   const int nblocks_u = (c.nsites + 255) / 256;
+   const int nrows = nrows_pair + (n3 ? nblocks_u : 0);
+   if (nrows > e->partials_cap) {
+      if (e->d_partials) cudaFree(e->d_partials);
+      MDB_CUDA(cudaMalloc(&e->d_partials, sizeof(double) * NRED * (size_t)nrows));
+      e->partials_cap = nrows;
+   }
+   if (n3) MDB_CUDA(cudaMemsetAsync(e->d_fs, 0, sizeof(double) * 3 * (size_t)c.nsites, st));
+   const bool coul = c.alpha > 0.0, strict = c.strict_cutoff != 0, fw = c.nsites_xf < c.nsites;
+   dim3 g(nblocks);
+#define PT_CASE(X) case X: if (coul) launch_tiled<X, true>(strict, fw, n3, g, st, P, e, runs, d_out); \
+                           else launch_tiled<X, false>(strict, fw, n3, g, st, P, e, runs, d_out); break
+   switch (c.ptype) {
+      PT_CASE(PT_LJ); PT_CASE(PT_E6); PT_CASE(PT_MCY); PT_CASE(PT_GEN); PT_CASE(PT_HIW); PT_CASE(PT_MOR);
+      default:
+         mdb_set_error("KERNEL called with unknown potential type");
+         return -1;
+   }
+#undef PT_CASE
+   e->launches += 1;
+   if (n3) {
+      k_unsort_virial<<<nblocks_u, 256, 0, st>>>(c.nsites, e->d_posq, e->d_order, e->d_fs, d_out,
+                                                 e->d_partials + (size_t)nrows_pair * NRED);
+      e->launches += 1;
+   }
+   k_rows_finish<<<1, 1024, 0, st>>>(e->d_partials, nrows, c.nsites, n3 ? 1.0 : 0.5, d_out);
+   e->launches += 1;
+   MDB_CUDA(cudaGetLastError());
+   return 0;
+}

@@ -59,6 +59,7 @@ def load() -> C.CDLL:
     L.mdb_out_doubles.argtypes = [C.c_int]
     L.mdb_configure.argtypes = [C.c_void_p, C.POINTER(mdb_config)]
     L.mdb_set_partition.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.mdb_set_pair_mode.argtypes = [C.c_void_p, C.c_int]
     L.mdb_set_sites_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mdb_set_sites_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     for f in ("mdb_zero_out", "mdb_force_real", "mdb_force_recip"):
@@ -231,6 +232,10 @@ class Engine:
 
     def set_partition(self, ithread, nthreads):
         self.L.mdb_set_partition(self.h, ithread, nthreads)
+
+    def set_pair_mode(self, mode: int):
+        """2: per-thread full stencil, 3: tiled full stencil (default), 4: tiled Newton-3."""
+        self.L.mdb_set_pair_mode(self.h, mode)
 
     def set_sites_host(self, site_block: np.ndarray, stream=0):
         r = [site_block.ctypes.data + site_block.strides[0] * i for i in range(3)]
