@@ -28,10 +28,11 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_lib(force: bool = False, verbose: bool = False, extra=()) -> str:
-    if not force and not _stale():
+def build_lib(force: bool = False, verbose: bool = False, extra=(), out: str = LIB, tag: str = "") -> str:
+    """extra: additional nvcc flags (e.g. -DMDB_TILED_MINB=3) for tuning variants written to `out`."""
+    if not force and out == LIB and not _stale():
         return LIB
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" + tag)
     os.makedirs(objdir, exist_ok=True)
     procs = []
     objs = []
@@ -44,14 +45,14 @@ def build_lib(force: bool = False, verbose: bool = False, extra=()) -> str:
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     fail = False
     for s, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if p.returncode != 0 or verbose:
-            sys.stderr.write(f"--- {s}\n{out}\n")
+            sys.stderr.write(f"--- {s}\n{log}\n")
         fail |= p.returncode != 0
     if fail:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-lcudart"])
-    return LIB
+    subprocess.check_call([NVCC, "-shared", "-o", out, *objs, "-lcudart"])
+    return out
 
 
 if __name__ == "__main__":

@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(256) k_kernel_vec(int jmin, int nnab, double *
    int j = jmin + blockIdx.x * 256 + threadIdx.x;
    double phi = 0.0;
    if (j < nnab) {
-      double p[MDB_NPOTP];
+      __align__(16) double p[MDB_NPOTP];
 #pragma unroll
       for (int k = 0; k < MDB_NPOTP; k++) p[k] = k < npar_rows ? pot[(size_t)k * nnab + j] : 0.0;
       if (PT == PT_LJ) { p[2] = 6.0 * p[0]; p[1] = p[1] * p[1]; }

@@ -20,7 +20,10 @@
 #include "mdb_math.cuh"
 
 #ifndef MDB_TILED_MINB
-#define MDB_TILED_MINB 2
+#define MDB_TILED_MINB 3
+#endif
+#ifndef MDB_TILED_NV
+#define MDB_TILED_NV 4                 /* pair evaluations interleaved at a time (<= NI) */
 #endif
 static constexpr int TW = 4;                   // warps per block
 static constexpr int RB = 64;                  // stencil runs per shared-memory pass
@@ -54,6 +57,8 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
 {
    __shared__ SegTable s_seg[TW];
    __shared__ double s_reloc[27][3];
+   __shared__ double4 s_ipos[TW][NI];            // batch sites: x,y,z,q   (warp-uniform, re-read per use to
+   __shared__ int4 s_iint[TW][NI];               //              cz,type,framework,-   keep them out of registers)
    extern __shared__ double s_ptab[];           // pair-parameter table (when it fits), else read through L1
    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
    for (int k = threadIdx.x; k < 81; k += TW * 32) s_reloc[k / 3][k % 3] = P.reloc[k / 3][k % 3];
@@ -76,8 +81,6 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
    const int s0 = bt.x, cnt = bt.y;
 
    // ---- batch (warp-uniform) data
-   double pix[NI], piy[NI], piz[NI], piq[NI];
-   int czi[NI], tyi[NI], fwi[NI];
    double fix[NI], fiy[NI], fiz[NI];
    int cx, cy, cz_lo, cz_hi;
    {
@@ -87,16 +90,18 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
       cy = t % P.ny; cx = t / P.ny;
       cz_hi = scell[s0 + cnt - 1] % P.nz;
    }
-#pragma unroll
-   for (int k = 0; k < NI; k++) {
-      const int sk = s0 + min(k, cnt - 1);
-      const double4 p = posq[sk];
+   if (lane < NI) {
+      const int k = lane, sk = s0 + min(k, cnt - 1);
+      s_ipos[w][k] = posq[sk];
       const int t = stype[sk];
-      pix[k] = p.x; piy[k] = p.y; piz[k] = p.z; piq[k] = p.w;
-      tyi[k] = t & 0x3fffffff; fwi[k] = t >> 30;
-      czi[k] = k < cnt ? scell[sk] % P.nz : (1 << 20);      // padded entries never pass the window test
-      fix[k] = fiy[k] = fiz[k] = 0.0;
+      // padded entries never pass the window test
+      s_iint[w][k] = make_int4(k < cnt ? scell[sk] % P.nz : (1 << 20), t & 0x3fffffff, t >> 30, 0);
    }
+#pragma unroll
+   for (int k = 0; k < NI; k++) fix[k] = fiy[k] = fiz[k] = 0.0;
+   __syncwarp();
+   const volatile double4 *ipos = s_ipos[w];
+   const volatile int4 *iint = s_iint[w];
    double pe = 0, w00 = 0, w01 = 0, w02 = 0, w11 = 0, w12 = 0, w22 = 0;
    unsigned int visits = 0;
    const int nruns = P.nruns;
@@ -192,14 +197,19 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
          bool in[NI];
 #pragma unroll
          for (int k = 0; k < NI; k++) {
-            const int dz = zj - czi[k];
+            const int czk = iint[k].x, tyk = iint[k].y;
+            const int dz = zj - czk;
             in[k] = valid && dz >= dzlo && dz <= dzhi;
             if (N3) in[k] = in[k] && !(samecol && dz == 0 && j <= s0 + k);   // same cell: each pair once
             else in[k] = in[k] && !(central && j == s0 + k);                 // never pair a site with itself
-            if (FW) in[k] = in[k] && !(fwi[k] & fwj);
-            dx[k] = pj.x - pix[k]; dy[k] = pj.y - piy[k]; dzz[k] = pj.z - piz[k];
-            qq[k] = piq[k] * pj.w;
-            prow[k] = tab + (tyi[k] * P.max_id + tj) * MDB_NPOTP;
+            if (FW) in[k] = in[k] && !(iint[k].z & fwj);
+            dx[k] = pj.x - ipos[k].x; dy[k] = pj.y - ipos[k].y; dzz[k] = pj.z - ipos[k].z;
+            qq[k] = ipos[k].w * pj.w;
+#ifdef MDB_EXP_NOPARAM
+            prow[k] = tab;
+#else
+            prow[k] = tab + (tyk * P.max_id + tj) * MDB_NPOTP;
+#endif
          }
 #pragma unroll
          for (int k = 0; k < NI; k++) r2[k] = fma(dx[k], dx[k], fma(dy[k], dy[k], dzz[k] * dzz[k]));
@@ -208,14 +218,32 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
             close |= (in[k] && __double2hiint(r2[k]) < 0x3fd00000) ? (1 << k) : 0;   // r^2 < 0.25 (rare)
             if (STRICT) r2[k] = r2[k] > P.cutoffsq ? P.cutoff100sq : r2[k];
          }
+#ifdef MDB_EXP_NOMATH
+#pragma unroll
+         for (int k = 0; k < NI; k++) { fij[k] = r2[k] * prow[k][0]; phi[k] = qq[k]; }
+#elif MDB_TILED_NV >= MDB_NI
          mdb_pair_eval_v<PT, COUL, NI>(r2, qq, prow, P.alpha, P.norm, fij, phi);
+#else
+#pragma unroll
+         for (int g = 0; g < NI; g += MDB_TILED_NV) {          // NV visits in flight at a time
+            double r2g[MDB_TILED_NV], qqg[MDB_TILED_NV], fg[MDB_TILED_NV], pg[MDB_TILED_NV];
+            const double *prg[MDB_TILED_NV];
+#pragma unroll
+            for (int k = 0; k < MDB_TILED_NV; k++) { r2g[k] = r2[g + k]; qqg[k] = qq[g + k]; prg[k] = prow[g + k]; }
+            mdb_pair_eval_v<PT, COUL, MDB_TILED_NV>(r2g, qqg, prg, P.alpha, P.norm, fg, pg);
+#pragma unroll
+            for (int k = 0; k < MDB_TILED_NV; k++) { fij[g + k] = fg[k]; phi[g + k] = pg[k]; }
+         }
+#endif
 #pragma unroll
          for (int k = 0; k < NI; k++) {
-            const double f = in[k] ? fij[k] : 0.0;
-            pe += in[k] ? phi[k] : 0.0;
-            visits += in[k] ? 1u : 0u;
-            fix[k] = fma(-f, dx[k], fix[k]); fiy[k] = fma(-f, dy[k], fiy[k]); fiz[k] = fma(-f, dzz[k], fiz[k]);
-            gx = fma(f, dx[k], gx); gy = fma(f, dy[k], gy); gz = fma(f, dzz[k], gz);
+            if (in[k]) {                         // predicated FP64 accumulation, no selects
+               const double f = fij[k];
+               pe += phi[k];
+               visits++;
+               fix[k] = fma(-f, dx[k], fix[k]); fiy[k] = fma(-f, dy[k], fiy[k]); fiz[k] = fma(-f, dzz[k], fiz[k]);
+               gx = fma(f, dx[k], gx); gy = fma(f, dy[k], gy); gz = fma(f, dzz[k], gz);
+            }
          }
          if (close) {                           // TOO_CLOSE diagnostics, off the hot path (src/force.c:939-949)
             const int mj = mol[order[j]];
@@ -225,6 +253,7 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
                   counters[3] = ((unsigned long long)(unsigned)order[s0 + k] << 32) | (unsigned)order[j];
                }
          }
+#ifndef MDB_EXP_NORED
          if (N3) {
             if (valid) {
                atomicAdd(&fs[j], gx);
@@ -232,6 +261,9 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
                atomicAdd(&fs[2 * (size_t)nsites + j], gz);
             }
          }
+#else
+         pe += gx + gy + gz;
+#endif
          if (!central) {                        // Bekker image-force virial (src/force.c:983-991)
             const double sc = N3 ? 1.0 : 0.5;
             const double rx = sc * s_reloc[kimg][0], ry = sc * s_reloc[kimg][1], rz = sc * s_reloc[kimg][2];
@@ -255,8 +287,9 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
             out[o] += fx;
             out[(size_t)nsites + o] += fy;
             out[2 * (size_t)nsites + o] += fz;
-            w00 = fma(pix[k], fx, w00); w01 = fma(piy[k], fx, w01); w02 = fma(piz[k], fx, w02);
-            w11 = fma(piy[k], fy, w11); w12 = fma(piz[k], fy, w12); w22 = fma(piz[k], fz, w22);
+            const double px = ipos[k].x, py = ipos[k].y, pz = ipos[k].z;
+            w00 = fma(px, fx, w00); w01 = fma(py, fx, w01); w02 = fma(pz, fx, w02);
+            w11 = fma(py, fy, w11); w12 = fma(pz, fy, w12); w22 = fma(pz, fz, w22);
          }
       }
    }
@@ -404,4 +437,52 @@ int mdb_launch_pair_tiled(mdb_engine *e, double *d_out, cudaStream_t st)
    e->launches += 1;
    MDB_CUDA(cudaGetLastError());
    return 0;
+}
+
+// ---- micro-benchmark: throughput of the pair arithmetic alone (no memory traffic) -----------------
+template <int NV>
+__global__ void __launch_bounds__(128) k_pairmath_probe(double *out, int iters, double alpha, double norm, double seed)
+{
+   double r2[NV], qq[NV], f[NV], ph[NV], acc = 0.0;
+   __shared__ double tabp[8];
+   if (threadIdx.x < 8) tabp[threadIdx.x] = 0.5 + 0.1 * threadIdx.x;
+   __syncthreads();
+   const double *pr[NV];
+#pragma unroll
+   for (int k = 0; k < NV; k++) { r2[k] = seed + 0.37 * k + 1e-3 * threadIdx.x; qq[k] = 0.3 + 0.01 * k; pr[k] = tabp; }
+   for (int i = 0; i < iters; i++) {
+      mdb_pair_eval_v<PT_LJ, true, NV>(r2, qq, pr, alpha, norm, f, ph);
+#pragma unroll
+      for (int k = 0; k < NV; k++) { acc += f[k] + ph[k]; r2[k] = fma(1e-9, f[k], r2[k]); }
+   }
+   out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+extern "C" double mdb_pair_math_probe(int device, int iters, int nv, int blocks_per_sm)
+{
+   if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+   cudaDeviceProp prop;
+   cudaGetDeviceProperties(&prop, device);
+   const int blocks = prop.multiProcessorCount * blocks_per_sm, threads = 128;
+   double *d = nullptr;
+   if (cudaMalloc(&d, sizeof(double) * blocks * threads) != cudaSuccess) return -1.0;
+   cudaEvent_t e0, e1;
+   cudaEventCreate(&e0); cudaEventCreate(&e1);
+   double best = 1e30;
+   for (int rep = 0; rep < 4; rep++) {
+      cudaEventRecord(e0);
+      if (nv == 1) k_pairmath_probe<1><<<blocks, threads>>>(d, iters, 0.12, 0.135, 9.0);
+      else if (nv == 2) k_pairmath_probe<2><<<blocks, threads>>>(d, iters, 0.12, 0.135, 9.0);
+      else if (nv == 4) k_pairmath_probe<4><<<blocks, threads>>>(d, iters, 0.12, 0.135, 9.0);
+      else k_pairmath_probe<8><<<blocks, threads>>>(d, iters, 0.12, 0.135, 9.0);
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      best = ms < best ? ms : best;
+   }
+   cudaEventDestroy(e0); cudaEventDestroy(e1);
+   cudaFree(d);
+   // pair evaluations per second
+   return (double)iters * (nv == 1 ? 1 : nv == 2 ? 2 : nv == 4 ? 4 : 8) * blocks * threads / (best * 1e-3);
 }

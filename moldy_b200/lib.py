@@ -24,7 +24,7 @@ from . import abi
 from .systems import MoldySystem
 
 _LIB = None
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmoldy_b200.so")
+LIB_PATH = os.environ.get("MOLDY_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmoldy_b200.so")
 
 DP = C.POINTER(C.c_double)
 IP = C.POINTER(C.c_int)
