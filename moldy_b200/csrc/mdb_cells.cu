@@ -169,33 +169,40 @@ __global__ void __launch_bounds__(CB) k_sort_gather(int ncells, const int *__res
 }
 
 // Batches of <= NI consecutive cell-sorted sites that share a z-column (cx,cy): the unit
-// of work of the tiled pair kernel.  One block scans the columns in order, so the batch
-// list (and with it every summation order downstream) is deterministic.
-__global__ void __launch_bounds__(SCAN_T) k_make_batches(int ncols, int nz, int ni, const int *__restrict__ start,
-                                                          int2 *__restrict__ batches, int *__restrict__ nbatch)
+// of work of the tiled pair kernel.  Per-column batch counts are scanned with the same
+// three-pass scan as the cell counts, so the batch list (and with it every summation
+// order downstream) is deterministic.
+__global__ void __launch_bounds__(CB) k_col_batches(int ncols, int nz, int ni, const int *__restrict__ start,
+                                                    int *__restrict__ nb)
 {
-   __shared__ int carry;
-   if (threadIdx.x == 0) carry = 0;
-   __syncthreads();
-   for (int b = 0; b < ncols; b += SCAN_T) {
-      const int col = b + threadIdx.x;
-      int s0 = 0, cnt = 0;
-      if (col < ncols) { s0 = start[col * nz]; cnt = start[(col + 1) * nz] - s0; }
-      const int nb = (cnt + ni - 1) / ni;
-      int tot;
-      const int off = carry + block_excl_scan(nb, &tot);
-      for (int k = 0; k < nb; k++) batches[off + k] = make_int2(s0 + k * ni, min(ni, cnt - k * ni));
-      __syncthreads();
-      if (threadIdx.x == 0) carry += tot;
-      __syncthreads();
-   }
-   if (threadIdx.x == 0) *nbatch = carry;
+   const int col = blockIdx.x * CB + threadIdx.x;
+   if (col < ncols) nb[col] = (start[(col + 1) * nz] - start[col * nz] + ni - 1) / ni;
+}
+
+__global__ void __launch_bounds__(CB) k_fill_batches(int ncols, int nz, int ni, const int *__restrict__ start,
+                                                     const int *__restrict__ off, int2 *__restrict__ batches,
+                                                     int *__restrict__ nbatch)
+{
+   const int col = blockIdx.x * CB + threadIdx.x;
+   if (col >= ncols) return;
+   const int s0 = start[col * nz], cnt = start[(col + 1) * nz] - s0, o = off[col];
+   const int nb = (cnt + ni - 1) / ni;
+   for (int k = 0; k < nb; k++) batches[o + k] = make_int2(s0 + k * ni, min(ni, cnt - k * ni));
+   if (col == ncols - 1) *nbatch = off[ncols];
 }
 
 int mdb_launch_batches(mdb_engine *e, cudaStream_t st)
 {
-   k_make_batches<<<1, SCAN_T, 0, st>>>(e->T.nx * e->T.ny, e->T.nz, MDB_NI, e->d_start, e->d_batches, e->d_nbatch);
-   e->launches += 1;
+   const int ncols = e->T.nx * e->T.ny;
+   int *nb = e->d_count, *off = e->d_count + ncols + 1;        // the cell-count array is free after the fill
+   if (2 * (ncols + 1) > e->cells_cap) { mdb_set_error("batch scratch too small"); return -1; }
+   const int ntiles = (ncols + SCAN_TILE - 1) / SCAN_TILE;
+   k_col_batches<<<(ncols + CB - 1) / CB, CB, 0, st>>>(ncols, e->T.nz, MDB_NI, e->d_start, nb);
+   k_scan_tiles<<<ntiles, SCAN_T, 0, st>>>(nb, ncols, e->d_scan_tmp);
+   k_scan_sums<<<1, SCAN_T, 0, st>>>(e->d_scan_tmp, ntiles);
+   k_scan_apply<<<ntiles, SCAN_T, 0, st>>>(nb, ncols, e->d_scan_tmp, off);
+   k_fill_batches<<<(ncols + CB - 1) / CB, CB, 0, st>>>(ncols, e->T.nz, MDB_NI, e->d_start, off, e->d_batches, e->d_nbatch);
+   e->launches += 5;
    MDB_CUDA(cudaGetLastError());
    return 0;
 }

@@ -144,9 +144,9 @@ extern "C" int mdb_configure(mdb_engine *e, const mdb_config *cfg)
    std::string err;
    if (!mdb_build_real_tables(e->cfg, e->T, err)) { mdb_set_error(err); return -1; }
    e->ncells = e->T.nx * e->T.ny * e->T.nz;
-   if (e->ncells + 1 > e->cells_cap) {
+   if (std::max(e->ncells + 1, 2 * (e->T.nx * e->T.ny + 1)) > e->cells_cap) {
       free_grid(e);
-      e->cells_cap = e->ncells + 1;
+      e->cells_cap = std::max(e->ncells + 1, 2 * (e->T.nx * e->T.ny + 1));
       MDB_CUDA(cudaMalloc(&e->d_count, sizeof(int) * (size_t)e->cells_cap));
       MDB_CUDA(cudaMalloc(&e->d_start, sizeof(int) * (size_t)e->cells_cap));
       MDB_CUDA(cudaMalloc(&e->d_scan_tmp, sizeof(int) * (size_t)(e->cells_cap / 2048 + 2)));

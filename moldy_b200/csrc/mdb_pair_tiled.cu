@@ -38,6 +38,24 @@ struct SegTable {
    int pack[NSLOT];                            // kimg | zoffidx<<5 | selfcol<<7 | (dzlo+512)<<8 | (dzhi+512)<<18
 };
 
+// 32-byte / 16-byte shared-memory loads the compiler must re-issue at every use (asm volatile):
+// keeps the warp-uniform batch data out of the register file.
+__device__ __forceinline__ double4 lds_d4(const double4 *p)
+{
+   double4 v;
+   const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+   asm volatile("ld.shared.v2.f64 {%0,%1}, [%4];\n\tld.shared.v2.f64 {%2,%3}, [%4+16];"
+                : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "r"(a));
+   return v;
+}
+__device__ __forceinline__ int4 lds_i4(const int4 *p)
+{
+   int4 v;
+   const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+   asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+   return v;
+}
+
 __device__ __forceinline__ double wsum(double v)
 {
 #pragma unroll
@@ -95,13 +113,14 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
       s_ipos[w][k] = posq[sk];
       const int t = stype[sk];
       // padded entries never pass the window test
-      s_iint[w][k] = make_int4(k < cnt ? scell[sk] % P.nz : (1 << 20), t & 0x3fffffff, t >> 30, 0);
+      s_iint[w][k] = make_int4(k < cnt ? scell[sk] % P.nz : (1 << 20), (t & 0x3fffffff) * P.max_id * MDB_NPOTP,
+                               t >> 30, k < cnt ? s0 + k : 0x7fffffff);
    }
 #pragma unroll
    for (int k = 0; k < NI; k++) fix[k] = fiy[k] = fiz[k] = 0.0;
    __syncwarp();
-   const volatile double4 *ipos = s_ipos[w];
-   const volatile int4 *iint = s_iint[w];
+   const double4 *ipos = s_ipos[w];
+   const int4 *iint = s_iint[w];
    double pe = 0, w00 = 0, w01 = 0, w02 = 0, w11 = 0, w12 = 0, w22 = 0;
    unsigned int visits = 0;
    const int nruns = P.nruns;
@@ -190,33 +209,48 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
          pj.x += s_reloc[kimg][0]; pj.y += s_reloc[kimg][1]; pj.z += s_reloc[kimg][2];
          const bool central = kimg == 13;
          const bool samecol = central && ((pk >> 7) & 1);
+         // window test per visit: dzlo_e <= cz_j - cz_i <= dzhi_e  and  jcut > s_i, where
+         //  * invalid (padding) lanes get an empty window,
+         //  * full stencil: jcut = j only in the central image, and j == s_i is the self pair;
+         //    written as (jcut - s_i) != 0 through jself,
+         //  * Newton-3: in the reference cell's own column the window starts at the cell itself
+         //    (dzlo = 0) and "same cell, j <= s_i" is excluded, which is exactly j > s_i.
+         const int dzhi_e = valid ? dzhi : -(1 << 28);
+         const int dzlo_e = (N3 && samecol) ? -(1 << 28) : dzlo;
+         const int jcut = N3 ? (samecol ? j : 0x7fffffff) : (central ? j : -1);
+         const int tjoff = tj * MDB_NPOTP;
          double gx = 0, gy = 0, gz = 0;
-         int close = 0;
          double dx[NI], dy[NI], dzz[NI], r2[NI], qq[NI], fij[NI], phi[NI];
          const double *prow[NI];
          bool in[NI];
 #pragma unroll
          for (int k = 0; k < NI; k++) {
-            const int czk = iint[k].x, tyk = iint[k].y;
-            const int dz = zj - czk;
-            in[k] = valid && dz >= dzlo && dz <= dzhi;
-            if (N3) in[k] = in[k] && !(samecol && dz == 0 && j <= s0 + k);   // same cell: each pair once
-            else in[k] = in[k] && !(central && j == s0 + k);                 // never pair a site with itself
-            if (FW) in[k] = in[k] && !(iint[k].z & fwj);
-            dx[k] = pj.x - ipos[k].x; dy[k] = pj.y - ipos[k].y; dzz[k] = pj.z - ipos[k].z;
-            qq[k] = ipos[k].w * pj.w;
+            const double4 pi = lds_d4(&ipos[k]);
+            const int4 ik = lds_i4(&iint[k]);          // cz, type row offset, framework flag, sorted index
+            const int dz = zj - ik.x;
+            in[k] = dz >= dzlo_e && dz <= dzhi_e && (N3 ? jcut > ik.w : jcut != ik.w);
+            if (FW) in[k] = in[k] && !(ik.z & fwj);
+            dx[k] = pj.x - pi.x; dy[k] = pj.y - pi.y; dzz[k] = pj.z - pi.z;
+            qq[k] = pi.w * pj.w;
 #ifdef MDB_EXP_NOPARAM
             prow[k] = tab;
 #else
-            prow[k] = tab + (tyk * P.max_id + tj) * MDB_NPOTP;
+            prow[k] = tab + (ik.y + tjoff);
 #endif
          }
 #pragma unroll
          for (int k = 0; k < NI; k++) r2[k] = fma(dx[k], dx[k], fma(dy[k], dy[k], dzz[k] * dzz[k]));
+         int r2min = __double2hiint(r2[0]);
 #pragma unroll
-         for (int k = 0; k < NI; k++) {
-            close |= (in[k] && __double2hiint(r2[k]) < 0x3fd00000) ? (1 << k) : 0;   // r^2 < 0.25 (rare)
-            if (STRICT) r2[k] = r2[k] > P.cutoffsq ? P.cutoff100sq : r2[k];
+         for (int k = 1; k < NI; k++) r2min = min(r2min, __double2hiint(r2[k]));
+         int close = 0;
+         if (r2min < 0x3fd00000) {                 // some r^2 < 0.25 in this step (rare): look closer
+#pragma unroll
+            for (int k = 0; k < NI; k++) close |= (in[k] && r2[k] < MDB_TOO_CLOSE) ? (1 << k) : 0;
+         }
+         if (STRICT) {
+#pragma unroll
+            for (int k = 0; k < NI; k++) r2[k] = r2[k] > P.cutoffsq ? P.cutoff100sq : r2[k];
          }
 #ifdef MDB_EXP_NOMATH
 #pragma unroll
@@ -287,7 +321,8 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
             out[o] += fx;
             out[(size_t)nsites + o] += fy;
             out[2 * (size_t)nsites + o] += fz;
-            const double px = ipos[k].x, py = ipos[k].y, pz = ipos[k].z;
+            const double4 pk4 = lds_d4(&ipos[k]);
+            const double px = pk4.x, py = pk4.y, pz = pk4.z;
             w00 = fma(px, fx, w00); w01 = fma(py, fx, w01); w02 = fma(pz, fx, w02);
             w11 = fma(py, fy, w11); w12 = fma(pz, fy, w12); w22 = fma(pz, fz, w22);
          }
@@ -336,20 +371,40 @@ __global__ void __launch_bounds__(256) k_unsort_virial(int n, const double4 *__r
    if (threadIdx.x == 6) partials[(size_t)blockIdx.x * NRED] = 0.0;
 }
 
-// fixed-order sum of partial rows: out.pe_real += scale * sum(row[0]); stress += sum(row[1..6])
-__global__ void __launch_bounds__(1024) k_rows_finish(const double *__restrict__ partials, int nrows, int nsites,
-                                                      double pe_scale, double *__restrict__ out)
+// fixed-order sum of partial rows, two stages: RS1 blocks each fold a contiguous span of rows
+// into one row, then one block folds those and adds pe_real (scaled) and the stress sums.
+static constexpr int RS1 = 128;
+__global__ void __launch_bounds__(256) k_rows_stage1(const double *__restrict__ partials, int nrows,
+                                                     double *__restrict__ rows1)
 {
-   __shared__ double sm[1024];
+   __shared__ double sm[256];
+   const int per = (nrows + RS1 - 1) / RS1;
+   const int r0 = blockIdx.x * per, r1 = min(nrows, r0 + per);
    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-   for (int b = threadIdx.x; b < nrows; b += 1024)
+   for (int b = r0 + threadIdx.x; b < r1; b += 256)
 #pragma unroll
       for (int k = 0; k < 7; k++) acc[k] += partials[(size_t)b * NRED + k];
-   double tot[7];
    for (int k = 0; k < 7; k++) {
       sm[threadIdx.x] = acc[k];
       __syncthreads();
-      for (int d = 512; d > 0; d >>= 1) {
+      for (int d = 128; d > 0; d >>= 1) {
+         if (threadIdx.x < d) sm[threadIdx.x] += sm[threadIdx.x + d];
+         __syncthreads();
+      }
+      if (threadIdx.x == 0) rows1[(size_t)blockIdx.x * NRED + k] = sm[0];
+      __syncthreads();
+   }
+}
+
+__global__ void __launch_bounds__(RS1) k_rows_finish(const double *__restrict__ rows1, int nsites, double pe_scale,
+                                                     double *__restrict__ out)
+{
+   __shared__ double sm[RS1];
+   double tot[7];
+   for (int k = 0; k < 7; k++) {
+      sm[threadIdx.x] = rows1[(size_t)threadIdx.x * NRED + k];
+      __syncthreads();
+      for (int d = RS1 / 2; d > 0; d >>= 1) {
          if (threadIdx.x < d) sm[threadIdx.x] += sm[threadIdx.x + d];
          __syncthreads();
       }
@@ -410,10 +465,10 @@ int mdb_launch_pair_tiled(mdb_engine *e, double *d_out, cudaStream_t st)
    const int nrows_pair = nblocks * TW;
    const int nblocks_u = (c.nsites + 255) / 256;
    const int nrows = nrows_pair + (n3 ? nblocks_u : 0);
-   if (nrows > e->partials_cap) {
+   if (nrows + RS1 > e->partials_cap) {
       if (e->d_partials) cudaFree(e->d_partials);
-      MDB_CUDA(cudaMalloc(&e->d_partials, sizeof(double) * NRED * (size_t)nrows));
-      e->partials_cap = nrows;
+      MDB_CUDA(cudaMalloc(&e->d_partials, sizeof(double) * NRED * (size_t)(nrows + RS1)));
+      e->partials_cap = nrows + RS1;
    }
    if (n3) MDB_CUDA(cudaMemsetAsync(e->d_fs, 0, sizeof(double) * 3 * (size_t)c.nsites, st));
    const bool coul = c.alpha > 0.0, strict = c.strict_cutoff != 0, fw = c.nsites_xf < c.nsites;
@@ -433,8 +488,10 @@ int mdb_launch_pair_tiled(mdb_engine *e, double *d_out, cudaStream_t st)
                                                  e->d_partials + (size_t)nrows_pair * NRED);
       e->launches += 1;
    }
-   k_rows_finish<<<1, 1024, 0, st>>>(e->d_partials, nrows, c.nsites, n3 ? 1.0 : 0.5, d_out);
-   e->launches += 1;
+   double *rows1 = e->d_partials + (size_t)nrows * NRED;
+   k_rows_stage1<<<RS1, 256, 0, st>>>(e->d_partials, nrows, rows1);
+   k_rows_finish<<<1, RS1, 0, st>>>(rows1, c.nsites, n3 ? 1.0 : 0.5, d_out);
+   e->launches += 2;
    MDB_CUDA(cudaGetLastError());
    return 0;
 }

@@ -14,6 +14,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <chrono>
+#include <thread>
 #include <vector>
 #include "mdb_internal.h"
 
@@ -189,14 +191,32 @@ static void push_sites(real **site)
    G.last_sites = site[0];
 }
 
+static double now_ms()
+{
+   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static const bool g_timing = getenv("MOLDY_B200_TIMING") != nullptr;
+
+// D2H of the result block into pinned memory, then site_force[a][i] += f (the caller's arrays
+// are only accumulated into, src/accel.c:488-535); the three rows are added by three threads.
 static void pull_and_accumulate(real **site_force, double *pe, real (*stress)[3], int n)
 {
+   const double t0 = now_ms();
    if (mdb_read_out(G.eng, G.d_out, G.h_out, G.stream)) FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
-   for (int a = 0; a < 3; a++) {
+   const double t1 = now_ms();
+   auto add_row = [&](int a) {
       real *dst = site_force[a];
       const double *src = G.h_out + (size_t)a * n;
       for (int i = 0; i < n; i++) dst[i] += src[i];
+   };
+   if (n >= 65536) {
+      std::thread th1(add_row, 1), th2(add_row, 2);
+      add_row(0);
+      th1.join(); th2.join();
+   } else {
+      for (int a = 0; a < 3; a++) add_row(a);
    }
+   if (g_timing) fprintf(stderr, "[moldy_b200] wait+D2H %.2f ms, host += %.2f ms\n", t1 - t0, now_ms() - t1);
    const double *sc = G.h_out + 3 * (size_t)n;
    (void)pe;
    stress[0][0] += sc[2]; stress[0][1] += sc[3]; stress[0][2] += sc[4];
@@ -206,7 +226,9 @@ static void pull_and_accumulate(real **site_force, double *pe, real (*stress)[3]
 extern "C" void force_calc(real **site, real **site_force, system_mt *system, spec_mt *species, real *chg,
                            pot_mt *potpar, double *pe, mat_mt stress)
 {
+   const double tc0 = now_ms();
    sync_config(system, species, chg, potpar);
+   if (g_timing) fprintf(stderr, "[moldy_b200] force_calc: sync_config %.2f ms\n", now_ms() - tc0);
    mdb_set_partition(G.eng, ithread, nthreads);
    const int n = system->nsites;
 
@@ -272,7 +294,9 @@ extern "C" void force_calc(real **site, real **site_force, system_mt *system, sp
 extern "C" void ewald(real **site, real **site_force, system_mp system, spec_mt *species, real *chg, double *pe,
                       real (*stress)[3])
 {
+   const double tc0 = now_ms();
    sync_config(system, species, chg, nullptr);
+   if (g_timing) fprintf(stderr, "[moldy_b200] ewald: sync_config %.2f ms\n", now_ms() - tc0);
    mdb_set_partition(G.eng, ithread, nthreads);
    const int n = system->nsites;
    double h9[9];
