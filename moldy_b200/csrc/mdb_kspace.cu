@@ -317,32 +317,77 @@ k_kforce(KfArgs A, const int *__restrict__ cidx, const double *__restrict__ x, c
       for (int k = threadIdx.x; k < 2 * nsl; k += KF) s_coef[k] = src[k];
       __syncthreads();
       if (!active) continue;
-      for (int c = 0; c < nb; c++) {
-         const HkDesc &d = s_hk[c];
-         switch (d.code) {
-            case HK_NEWH:   if (d.h > 0) eh = cmul(eh, ea); ehk = eh; break;
+      // two (h,k) columns per pass: they share the l-recurrence of E_l (4 of the 12 FP64 ops per
+      // slot) and give the scheduler eight independent accumulator chains
+      for (int c = 0; c < nb; c += 2) {
+         const HkDesc &d1 = s_hk[c];
+         const HkDesc &d2 = s_hk[min(c + 1, nb - 1)];
+         const bool two = c + 1 < nb;
+         double2 ehk1, ehk2;
+         switch (d1.code) {
+            case HK_NEWH:   if (d1.h > 0) eh = cmul(eh, ea); ehk = eh; break;
             case HK_KUP:    ehk = cmul(ehk, eb); break;
             case HK_KDOWN0: ehk = cmulc(eh, eb); break;
             default:        ehk = cmulc(ehk, eb); break;
          }
-         const int nl = d.nl;
-         if (nl <= 0) continue;
-         const double4 *cf = s_coef + 2 * (d.slot0 - slot_lo);
+         ehk1 = ehk;
+         if (two) {
+            switch (d2.code) {
+               case HK_NEWH:   if (d2.h > 0) eh = cmul(eh, ea); ehk = eh; break;
+               case HK_KUP:    ehk = cmul(ehk, eb); break;
+               case HK_KDOWN0: ehk = cmulc(eh, eb); break;
+               default:        ehk = cmulc(ehk, eb); break;
+            }
+         }
+         ehk2 = ehk;
+         const int nl1 = max(d1.nl, 0), nl2 = two ? max(d2.nl, 0) : 0;
+         if (nl1 + nl2 == 0) continue;
+         const double4 *cf1 = s_coef + 2 * (d1.slot0 - slot_lo);
+         const double4 *cf2 = s_coef + 2 * (d2.slot0 - slot_lo);
          double2 el = make_double2(q, 0.0);
-         double X = 0, Y = 0, Xz = 0, Yz = 0;
-#pragma unroll 2
-         for (int l = 0; l < nl; l++) {
-            const double4 a = cf[2 * l], b = cf[2 * l + 1];
-            X = fma(el.x, a.x, fma(el.y, a.w, X));
-            Y = fma(el.y, a.z, fma(-el.x, a.y, Y));
-            Xz = fma(el.x, b.x, fma(el.y, b.y, Xz));
-            Yz = fma(el.y, b.z, fma(-el.x, b.w, Yz));
+         double X1 = 0, Y1 = 0, Xz1 = 0, Yz1 = 0, X2 = 0, Y2 = 0, Xz2 = 0, Yz2 = 0;
+         const int nj = min(nl1, nl2);
+         int l = 0;
+         for (; l < nj; l++) {
+            const double4 a1 = cf1[2 * l], b1 = cf1[2 * l + 1], a2 = cf2[2 * l], b2 = cf2[2 * l + 1];
+            X1 = fma(el.x, a1.x, fma(el.y, a1.w, X1));
+            Y1 = fma(el.y, a1.z, fma(-el.x, a1.y, Y1));
+            Xz1 = fma(el.x, b1.x, fma(el.y, b1.y, Xz1));
+            Yz1 = fma(el.y, b1.z, fma(-el.x, b1.w, Yz1));
+            X2 = fma(el.x, a2.x, fma(el.y, a2.w, X2));
+            Y2 = fma(el.y, a2.z, fma(-el.x, a2.y, Y2));
+            Xz2 = fma(el.x, b2.x, fma(el.y, b2.y, Xz2));
+            Yz2 = fma(el.y, b2.z, fma(-el.x, b2.w, Yz2));
             el = cmul(el, ec);
          }
-         const double T = fma(ehk.y, X, ehk.x * Y), Tz = fma(ehk.y, Xz, ehk.x * Yz);
-         fx = fma(d.kx, T, fx);
-         fy = fma(d.ky, T, fy);
-         fz = fma(d.kzt, T, fma(K.cz2, Tz, fz));
+         for (; l < nl1; l++) {
+            const double4 a1 = cf1[2 * l], b1 = cf1[2 * l + 1];
+            X1 = fma(el.x, a1.x, fma(el.y, a1.w, X1));
+            Y1 = fma(el.y, a1.z, fma(-el.x, a1.y, Y1));
+            Xz1 = fma(el.x, b1.x, fma(el.y, b1.y, Xz1));
+            Yz1 = fma(el.y, b1.z, fma(-el.x, b1.w, Yz1));
+            el = cmul(el, ec);
+         }
+         for (; l < nl2; l++) {
+            const double4 a2 = cf2[2 * l], b2 = cf2[2 * l + 1];
+            X2 = fma(el.x, a2.x, fma(el.y, a2.w, X2));
+            Y2 = fma(el.y, a2.z, fma(-el.x, a2.y, Y2));
+            Xz2 = fma(el.x, b2.x, fma(el.y, b2.y, Xz2));
+            Yz2 = fma(el.y, b2.z, fma(-el.x, b2.w, Yz2));
+            el = cmul(el, ec);
+         }
+         if (nl1 > 0) {
+            const double T = fma(ehk1.y, X1, ehk1.x * Y1), Tz = fma(ehk1.y, Xz1, ehk1.x * Yz1);
+            fx = fma(d1.kx, T, fx);
+            fy = fma(d1.ky, T, fy);
+            fz = fma(d1.kzt, T, fma(K.cz2, Tz, fz));
+         }
+         if (nl2 > 0) {
+            const double T = fma(ehk2.y, X2, ehk2.x * Y2), Tz = fma(ehk2.y, Xz2, ehk2.x * Yz2);
+            fx = fma(d2.kx, T, fx);
+            fy = fma(d2.ky, T, fy);
+            fz = fma(d2.kzt, T, fma(K.cz2, Tz, fz));
+         }
       }
    }
    if (active) {
