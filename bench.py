@@ -178,7 +178,7 @@ def run_ours(a):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from moldy_b200 import lib, systems
+    from moldy_b200 import lib, spmd, systems
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -198,6 +198,7 @@ def run_ours(a):
     st = torch.cuda.current_stream().cuda_stream
     xyz = torch.from_numpy(np.ascontiguousarray(site[:, :N])).cuda()
     out = torch.zeros(eng.out_doubles(), dtype=torch.float64, device="cuda")
+    psum = torch.zeros(eng.recip_sum_doubles(), dtype=torch.float64, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     eng.set_sites_device(xyz[0].data_ptr(), xyz[1].data_ptr(), xyz[2].data_ptr(), st)
 
@@ -208,7 +209,7 @@ def run_ours(a):
         if ev: ev[1].record()
         eng.force_real(out.data_ptr(), st)
         if ev: ev[2].record()
-        eng.force_recip(out.data_ptr(), st)
+        spmd.recip_sites(eng, psum, out, st)          # N>1: site partition + all-reduce of S(k)
         if ev: ev[3].record()
         if world > 1:
             dist.all_reduce(out)

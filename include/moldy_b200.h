@@ -206,6 +206,14 @@ int  mdb_build_cells(mdb_engine *e, void *stream);
 int  mdb_force_real(mdb_engine *e, double *d_out, void *stream);
 int  mdb_force_recip(mdb_engine *e, double *d_out, void *stream);
 
+/* k-space cut by SITES instead of by (h,k) columns (multi-GPU, moldy_b200/spmd.py): pass 1 writes
+ * this rank's structure-factor sums (mdb_recip_sum_doubles() doubles) to the DEVICE buffer d_psum,
+ * the caller all-reduces d_psum over the ranks, pass 2 adds energy/stress (rank 0) and the forces
+ * on this rank's sites.  With one rank the pair equals mdb_force_recip. */
+size_t mdb_recip_sum_doubles(const mdb_engine *e);
+int  mdb_recip_partial(mdb_engine *e, double *d_psum, void *stream);
+int  mdb_recip_finish(mdb_engine *e, const double *d_psum, double *d_out, void *stream);
+
 /* Device->host copy of a result block (synchronises `stream`). */
 int  mdb_read_out(mdb_engine *e, const double *d_out, double *h_out, void *stream);
 

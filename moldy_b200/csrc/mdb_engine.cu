@@ -55,6 +55,7 @@ static void free_recip(mdb_engine *e)
 {
    FREE(e->d_hk); FREE(e->d_hk_valid); FREE(e->d_slot_flags); FREE(e->d_ppart);
    FREE(e->d_coef_tot); FREE(e->d_coef_nf); FREE(e->d_kpartials); FREE(e->d_cidx); FREE(e->d_sfac_blocks);
+   FREE(e->d_psum);
    e->ppart_cap = 0;
 }
 
@@ -195,31 +196,13 @@ extern "C" int mdb_configure(mdb_engine *e, const mdb_config *cfg)
       if (upload(&e->d_hk, T.hk.data(), T.hk.size())) return -1;
       if (upload(&e->d_hk_valid, T.hk_valid.data(), T.hk_valid.size())) return -1;
       if (upload(&e->d_slot_flags, slotinfo.data(), slotinfo.size())) return -1;
-      // site slabs for k_sfac: enough blocks to fill 148 SMs about twice
-      const int nlc = (T.lmax + 1 + 7) / 8;
-      const int hkb = nlc <= 1 ? 256 : nlc <= 2 ? 128 : nlc <= 4 ? 64 : 32;
-      const int ncol_blocks = std::max(1, ((int)T.hk_valid.size() + hkb - 1) / hkb);
-      int want = std::max(1, (2 * 148 + ncol_blocks - 1) / ncol_blocks);
-      int slab = (n + want - 1) / want;
-      slab = std::max(32, ((slab + 31) / 32) * 32);
-      e->slab_sites = slab;
-      // slabs partition the compacted charged-site list (framework sites in their own slabs)
-      slab = (e->n_charged + want - 1) / want;
-      slab = std::max(32, ((slab + 31) / 32) * 32);
-      e->slab_sites = slab;
-      e->n_slabs_nf = (e->n_charged_nf + slab - 1) / slab;
-      e->n_slabs = e->n_slabs_nf + (e->n_charged - e->n_charged_nf + slab - 1) / slab;
       e->sfac_rank = -1;
-      const size_t pp = (size_t)e->n_slabs * T.nslots * 4;
-      if (pp > e->ppart_cap) {
-         FREE(e->d_ppart);
-         MDB_CUDA(cudaMalloc(&e->d_ppart, sizeof(double) * pp));
-         e->ppart_cap = pp;
-      }
       FREE(e->d_coef_tot); FREE(e->d_coef_nf); FREE(e->d_kpartials);
       MDB_CUDA(cudaMalloc(&e->d_coef_tot, sizeof(double) * 8 * (size_t)std::max(T.nslots, 1)));
       MDB_CUDA(cudaMalloc(&e->d_coef_nf, sizeof(double) * 8 * (size_t)std::max(T.nslots, 1)));
       MDB_CUDA(cudaMalloc(&e->d_kpartials, sizeof(double) * 8 * (size_t)(T.nslots / 256 + 1)));
+      FREE(e->d_psum);
+      MDB_CUDA(cudaMalloc(&e->d_psum, sizeof(double) * 8 * (size_t)std::max(T.nslots, 1)));
    } else {
       e->T.nhkl = 0; e->T.hk.clear(); e->T.hk_valid.clear(); e->T.nslots = 0;
    }
@@ -272,6 +255,24 @@ extern "C" int mdb_force_recip(mdb_engine *e, double *d_out, void *stream)
    if (!e->configured || !e->sites_set) { mdb_set_error("mdb_force_recip: engine not configured / no sites"); return -1; }
    if (!e->cfg.do_recip) return 0;
    return mdb_launch_recip(e, d_out, (cudaStream_t)stream);
+}
+
+// k-space with the SITE partition (moldy_b200/spmd.py): pass 1 leaves this rank's structure-factor
+// sums in d_psum (mdb_recip_sum_doubles() doubles, device memory of the caller); the caller
+// all-reduces them over the ranks; pass 2 turns them into energy/stress (rank 0 only) and the
+// forces on this rank's sites.
+extern "C" size_t mdb_recip_sum_doubles(const mdb_engine *e) { return 8 * (size_t)std::max(e->T.nslots, 1); }
+extern "C" int mdb_recip_partial(mdb_engine *e, double *d_psum, void *stream)
+{
+   if (!e->configured || !e->sites_set) { mdb_set_error("mdb_recip_partial: engine not configured / no sites"); return -1; }
+   if (!e->cfg.do_recip) return 0;
+   return mdb_launch_recip_partial(e, d_psum, (cudaStream_t)stream);
+}
+extern "C" int mdb_recip_finish(mdb_engine *e, const double *d_psum, double *d_out, void *stream)
+{
+   if (!e->configured || !e->sites_set) { mdb_set_error("mdb_recip_finish: engine not configured / no sites"); return -1; }
+   if (!e->cfg.do_recip) return 0;
+   return mdb_launch_recip_finish(e, d_psum, d_out, (cudaStream_t)stream);
 }
 
 extern "C" int mdb_read_out(mdb_engine *e, const double *d_out, double *h_out, void *stream)

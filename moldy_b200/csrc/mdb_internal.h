@@ -107,6 +107,7 @@ struct mdb_engine {
    int n_charged = 0, n_charged_nf = 0;
    void *d_sfac_blocks = nullptr; int n_sfac_blocks = 0, sfac_rank = -1, sfac_nranks = -1;
    double *d_kpartials = nullptr;
+   double *d_psum = nullptr;              // [2][nslots][4] structure-factor sums (non-framework, framework)
    int n_slabs = 0, n_slabs_nf = 0, slab_sites = 0;
 
    // pinned staging for host-facing calls
@@ -129,6 +130,8 @@ int mdb_launch_pair_tiled(mdb_engine *e, double *d_out, cudaStream_t st);
 int mdb_launch_batches(mdb_engine *e, cudaStream_t st);
 static constexpr int MDB_NI = 4;          // i-sites per warp in the tiled pair kernel
 int mdb_launch_recip(mdb_engine *e, double *d_out, cudaStream_t st);
+int mdb_launch_recip_partial(mdb_engine *e, double *d_psum, cudaStream_t st);
+int mdb_launch_recip_finish(mdb_engine *e, const double *d_psum, double *d_out, cudaStream_t st);
 int mdb_launch_kernel_vec(int jmin, int nnab, double *forceij, double *pe, const double *r_sqr,
                           const double *nab_chg, double chg, double norm, double alpha, int ptype,
                           double *const *pot);

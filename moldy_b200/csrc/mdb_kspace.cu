@@ -35,7 +35,7 @@ struct SfacArgs {
    int HKB;                             // shared-memory row stride of the E_hk tile (max columns per block)
    int nvalid, rank, nranks;
    int nslots, slab_sites, n_slabs_nf;
-   int nc_nf, nc;                       // charged sites: non-framework count, total
+   int nf_lo, nf_hi, fw_lo, fw_hi;      // this rank's ranges in the compacted charged-site list
 };
 
 // per-block work descriptor of k_sfac: columns e0..e0+hkb-1 of this rank's share of the
@@ -85,11 +85,11 @@ k_sfac(SfacArgs A, const SfacBlock *__restrict__ blocks, const int *__restrict__
    const int slab = blockIdx.y;
    int s0, s1;
    if (slab < A.n_slabs_nf) {
-      s0 = slab * A.slab_sites;
-      s1 = min(s0 + A.slab_sites, A.nc_nf);
+      s0 = A.nf_lo + slab * A.slab_sites;
+      s1 = min(s0 + A.slab_sites, A.nf_hi);
    } else {
-      s0 = A.nc_nf + (slab - A.n_slabs_nf) * A.slab_sites;
-      s1 = min(s0 + A.slab_sites, A.nc);
+      s0 = A.fw_lo + (slab - A.n_slabs_nf) * A.slab_sites;
+      s1 = min(s0 + A.slab_sites, A.fw_hi);
    }
 
    double acc[LCH][4];
@@ -154,6 +154,20 @@ k_sfac(SfacArgs A, const SfacBlock *__restrict__ blocks, const int *__restrict__
          double *o = ppart + ((size_t)slab * A.nslots + slot0 + l0 + j) * 4;
          o[0] = acc[j][0]; o[1] = acc[j][1]; o[2] = acc[j][2]; o[3] = acc[j][3];
       }
+}
+
+// ---- fixed-order sum of the slab partials: psum[0] = non-framework slabs, psum[1] = framework slabs.
+// This 8*nslots block is what ranks all-reduce when k-space is partitioned by sites.
+__global__ void __launch_bounds__(256) k_slab_sum(int nslots, int n_slabs, int n_slabs_nf,
+                                                  const double *__restrict__ ppart, double *__restrict__ psum)
+{
+   const int t = blockIdx.x * 256 + threadIdx.x;            // one thread per (slot, component)
+   if (t >= nslots * 4) return;
+   double a = 0.0, b = 0.0;
+   for (int sb = 0; sb < n_slabs_nf; sb++) a += ppart[(size_t)sb * nslots * 4 + t];
+   for (int sb = n_slabs_nf; sb < n_slabs; sb++) b += ppart[(size_t)sb * nslots * 4 + t];
+   psum[t] = a;
+   psum[(size_t)nslots * 4 + t] = b;
 }
 
 // ---- per k-vector: energy, stress, back-projection coefficients --------------
@@ -397,27 +411,54 @@ k_kforce(KfArgs A, const int *__restrict__ cidx, const double *__restrict__ x, c
    }
 }
 
-int mdb_launch_recip(mdb_engine *e, double *d_out, cudaStream_t st)
+// How one rank's share of the k-space work is cut.
+//  column mode (Moldy's own scheme, src/ewald.c:495-496): all sites x every P-th (h,k) column;
+//              no exchange before the final force sum, but the per-site set-up is replicated.
+//  site mode   (the manual's "RIL" scheme, src/moldy.tex:3441-3466): own sites x all columns; the
+//              8*nslots structure-factor sums are all-reduced between the two passes; both
+//              passes then scale with 1/P.
+struct RecipPlan {
+   int col_rank, col_nranks;
+   int nf_lo, nf_hi, fw_lo, fw_hi;
+   int slab_sites, n_slabs_nf, n_slabs;
+   bool add_scalars;
+};
+
+static void kspace_params(const mdb_engine *e, KspaceParams &K)
 {
    const mdb_config &c = e->cfg;
    const HostTables &T = e->T;
-   const int nvalid = (int)T.hk_valid.size();
-   if (nvalid == 0) return 0;
-   KspaceParams K;
    for (int a = 0; a < 3; a++) { K.astar[a] = T.astar[a]; K.bstar[a] = T.bstar[a]; K.cstar[a] = T.cstar[a]; }
    K.cz2 = T.cstar[2];
    K.r4alpha = -1.0 / (4.0 * c.alpha * c.alpha);
    K.pref = 2.0 / (MDB_EPS0 * T.vol);
    K.hmax = T.hmax; K.kmax = T.kmax; K.lmax = T.lmax; K.nlslots = T.lmax + 1;
    K.nsites = c.nsites; K.nsites_xf = c.nsites_xf;
+}
 
-   // (re)build the per-block work table when the partition changes
-   if (e->sfac_rank != e->ithread || e->sfac_nranks != e->nthreads || !e->d_sfac_blocks) {
+static int make_plan(mdb_engine *e, bool by_sites, RecipPlan &P, cudaStream_t st)
+{
+   const HostTables &T = e->T;
+   const int nvalid = (int)T.hk_valid.size();
+   const int r = e->ithread, np = e->nthreads;
+   if (by_sites) {
+      P.col_rank = 0; P.col_nranks = 1;
+      const long nf = e->n_charged_nf, fw = e->n_charged - e->n_charged_nf;
+      P.nf_lo = (int)(nf * r / np); P.nf_hi = (int)(nf * (r + 1) / np);
+      P.fw_lo = e->n_charged_nf + (int)(fw * r / np); P.fw_hi = e->n_charged_nf + (int)(fw * (r + 1) / np);
+      P.add_scalars = r == 0;
+   } else {
+      P.col_rank = r; P.col_nranks = np;
+      P.nf_lo = 0; P.nf_hi = e->n_charged_nf; P.fw_lo = e->n_charged_nf; P.fw_hi = e->n_charged;
+      P.add_scalars = true;
+   }
+   // per-block column table for this column partition
+   if (e->sfac_rank != P.col_rank || e->sfac_nranks != P.col_nranks || !e->d_sfac_blocks) {
       std::vector<SfacBlock> blocks;
-      const int my_cols = nvalid > e->ithread ? (nvalid - e->ithread + e->nthreads - 1) / e->nthreads : 0;
+      const int my_cols = nvalid > P.col_rank ? (nvalid - P.col_rank + P.col_nranks - 1) / P.col_nranks : 0;
       int e0 = 0;
       while (e0 < my_cols) {
-         const int nlmax = T.hk[T.hk_valid[e->ithread + e->nthreads * e0]].nl;
+         const int nlmax = T.hk[T.hk_valid[P.col_rank + P.col_nranks * e0]].nl;
          int nlc = std::max(2, (nlmax + LCH - 1) / LCH);
          if (nlc > 8) { mdb_set_error("k_cutoff gives lmax > 63: not supported by this build of k_sfac"); return -1; }
          const int hkb = KT / nlc;
@@ -432,49 +473,115 @@ int mdb_launch_recip(mdb_engine *e, double *d_out, cudaStream_t st)
                                   cudaMemcpyHostToDevice, st));
          MDB_CUDA(cudaStreamSynchronize(st));
       }
-      e->sfac_rank = e->ithread; e->sfac_nranks = e->nthreads;
+      e->sfac_rank = P.col_rank; e->sfac_nranks = P.col_nranks;
    }
+   // site slabs: enough blocks for about two waves on 148 SMs x 2 resident blocks
+   const int own = (P.nf_hi - P.nf_lo) + (P.fw_hi - P.fw_lo);
+   const int want = std::max(1, (4 * 148 + std::max(1, e->n_sfac_blocks) - 1) / std::max(1, e->n_sfac_blocks));
+   int slab = (own + want - 1) / want;
+   slab = std::max(SC, ((slab + SC - 1) / SC) * SC);
+   P.slab_sites = slab;
+   P.n_slabs_nf = (P.nf_hi - P.nf_lo + slab - 1) / slab;
+   P.n_slabs = P.n_slabs_nf + (P.fw_hi - P.fw_lo + slab - 1) / slab;
+   const size_t pp = (size_t)std::max(1, P.n_slabs) * T.nslots * 4;
+   if (pp > e->ppart_cap) {
+      if (e->d_ppart) cudaFree(e->d_ppart);
+      MDB_CUDA(cudaMalloc(&e->d_ppart, sizeof(double) * pp));
+      e->ppart_cap = pp;
+   }
+   return 0;
+}
+
+// pass 1: structure-factor sums of this rank's share -> psum[2][nslots][4]
+static int recip_partial(mdb_engine *e, const RecipPlan &P, double *d_psum, cudaStream_t st)
+{
+   const HostTables &T = e->T;
    SfacArgs A;
-   A.K = K;
+   kspace_params(e, A.K);
    A.HKB = KT / 2;
-   A.nvalid = nvalid; A.rank = e->ithread; A.nranks = e->nthreads;
-   A.nslots = T.nslots; A.slab_sites = e->slab_sites; A.n_slabs_nf = e->n_slabs_nf;
-   A.nc_nf = e->n_charged_nf; A.nc = e->n_charged;
-   const size_t shm = sizeof(double2) * (size_t)SC * (A.HKB + K.nlslots + K.hmax + 1 + K.kmax + 1);
-   if (e->n_sfac_blocks > 0 && e->n_slabs > 0) {
+   A.nvalid = (int)T.hk_valid.size(); A.rank = P.col_rank; A.nranks = P.col_nranks;
+   A.nslots = T.nslots; A.slab_sites = P.slab_sites; A.n_slabs_nf = P.n_slabs_nf;
+   A.nf_lo = P.nf_lo; A.nf_hi = P.nf_hi; A.fw_lo = P.fw_lo; A.fw_hi = P.fw_hi;
+   const size_t shm = sizeof(double2) * (size_t)SC * (A.HKB + A.K.nlslots + A.K.hmax + 1 + A.K.kmax + 1);
+   if (P.col_nranks > 1)      // slots of other ranks' columns are never written: keep them defined
+      MDB_CUDA(cudaMemsetAsync(e->d_ppart, 0, sizeof(double) * (size_t)std::max(1, P.n_slabs) * T.nslots * 4, st));
+   if (e->n_sfac_blocks > 0 && P.n_slabs > 0) {
       static size_t shm_set = 0;
       if (shm > shm_set) {
          MDB_CUDA(cudaFuncSetAttribute(k_sfac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
          shm_set = shm;
       }
-      dim3 g(e->n_sfac_blocks, e->n_slabs);
+      dim3 g(e->n_sfac_blocks, P.n_slabs);
       k_sfac<<<g, KT, shm, st>>>(A, (const SfacBlock *)e->d_sfac_blocks, e->d_cidx, e->d_x, e->d_y, e->d_z, e->d_chg,
                                  e->d_hk, e->d_hk_valid, e->d_ppart);
       e->launches++;
    }
-   SfinArgs F;
-   F.K = K; F.nslots = T.nslots; F.n_slabs = e->n_slabs; F.n_slabs_nf = e->n_slabs_nf;
-   F.rank = e->ithread; F.nranks = e->nthreads; F.framework = c.nsites_xf < c.nsites;
-   const int fb = (T.nslots + 255) / 256;
-   k_sfin<<<fb, 256, 0, st>>>(F, e->d_hk, e->d_slot_flags + T.nslots, e->d_slot_flags, e->d_ppart, e->d_coef_tot,
-                              e->d_coef_nf, e->d_kpartials);
-   k_recip_finish<<<1, 256, 0, st>>>(e->d_kpartials, fb, c.nsites, d_out);
-   KfArgs Q;
-   Q.K = K; Q.nhk = (int)T.hk.size(); Q.rank = e->ithread; Q.nranks = e->nthreads;
-   Q.hb = std::max(1, std::min(16, 512 / K.nlslots));
-   Q.max_slots = Q.hb * K.nlslots;
-   const size_t kshm = sizeof(double4) * 2 * (size_t)Q.max_slots + sizeof(HkDesc) * (size_t)Q.hb;
-   if (e->n_charged_nf > 0) {
-      Q.c0 = 0; Q.c1 = e->n_charged_nf;
-      k_kforce<<<(Q.c1 - Q.c0 + KF - 1) / KF, KF, kshm, st>>>(Q, e->d_cidx, e->d_x, e->d_y, e->d_z, e->d_chg, e->d_hk,
-                                                             e->d_coef_tot, d_out);
-   }
-   if (e->n_charged > e->n_charged_nf) {
-      Q.c0 = e->n_charged_nf; Q.c1 = e->n_charged;
-      k_kforce<<<(Q.c1 - Q.c0 + KF - 1) / KF, KF, kshm, st>>>(Q, e->d_cidx, e->d_x, e->d_y, e->d_z, e->d_chg, e->d_hk,
-                                                             e->d_coef_nf, d_out);
-   }
-   e->launches += 3 + (c.nsites_xf < c.nsites ? 1 : 0);
+   k_slab_sum<<<(T.nslots * 4 + 255) / 256, 256, 0, st>>>(T.nslots, P.n_slabs, P.n_slabs_nf, e->d_ppart, d_psum);
+   e->launches++;
    MDB_CUDA(cudaGetLastError());
    return 0;
+}
+
+// pass 2: per-k energy/stress/coefficients from the (complete) sums, then forces on this rank's sites
+static int recip_finish(mdb_engine *e, const RecipPlan &P, const double *d_psum, double *d_out, cudaStream_t st)
+{
+   const mdb_config &c = e->cfg;
+   const HostTables &T = e->T;
+   SfinArgs F;
+   kspace_params(e, F.K);
+   F.nslots = T.nslots; F.n_slabs = 2; F.n_slabs_nf = 1;
+   F.rank = P.col_rank; F.nranks = P.col_nranks; F.framework = c.nsites_xf < c.nsites;
+   const int fb = (T.nslots + 255) / 256;
+   k_sfin<<<fb, 256, 0, st>>>(F, e->d_hk, e->d_slot_flags + T.nslots, e->d_slot_flags, d_psum, e->d_coef_tot,
+                              e->d_coef_nf, e->d_kpartials);
+   e->launches++;
+   if (P.add_scalars) {
+      k_recip_finish<<<1, 256, 0, st>>>(e->d_kpartials, fb, c.nsites, d_out);
+      e->launches++;
+   }
+   KfArgs Q;
+   Q.K = F.K; Q.nhk = (int)T.hk.size(); Q.rank = P.col_rank; Q.nranks = P.col_nranks;
+   Q.hb = std::max(1, std::min(16, 512 / F.K.nlslots));
+   Q.max_slots = Q.hb * F.K.nlslots;
+   const size_t kshm = sizeof(double4) * 2 * (size_t)Q.max_slots + sizeof(HkDesc) * (size_t)Q.hb;
+   if (P.nf_hi > P.nf_lo) {
+      Q.c0 = P.nf_lo; Q.c1 = P.nf_hi;
+      k_kforce<<<(Q.c1 - Q.c0 + KF - 1) / KF, KF, kshm, st>>>(Q, e->d_cidx, e->d_x, e->d_y, e->d_z, e->d_chg, e->d_hk,
+                                                             e->d_coef_tot, d_out);
+      e->launches++;
+   }
+   if (P.fw_hi > P.fw_lo) {
+      Q.c0 = P.fw_lo; Q.c1 = P.fw_hi;
+      k_kforce<<<(Q.c1 - Q.c0 + KF - 1) / KF, KF, kshm, st>>>(Q, e->d_cidx, e->d_x, e->d_y, e->d_z, e->d_chg, e->d_hk,
+                                                             e->d_coef_nf, d_out);
+      e->launches++;
+   }
+   MDB_CUDA(cudaGetLastError());
+   return 0;
+}
+
+// one call, no exchange: column partition (or everything, for a single rank)
+int mdb_launch_recip(mdb_engine *e, double *d_out, cudaStream_t st)
+{
+   if (e->T.hk_valid.empty()) return 0;
+   RecipPlan P;
+   if (make_plan(e, false, P, st)) return -1;
+   if (recip_partial(e, P, e->d_psum, st)) return -1;
+   return recip_finish(e, P, e->d_psum, d_out, st);
+}
+
+// split form for the site partition: the caller all-reduces d_psum between the two calls
+int mdb_launch_recip_partial(mdb_engine *e, double *d_psum, cudaStream_t st)
+{
+   if (e->T.hk_valid.empty()) return 0;
+   RecipPlan P;
+   if (make_plan(e, true, P, st)) return -1;
+   return recip_partial(e, P, d_psum, st);
+}
+int mdb_launch_recip_finish(mdb_engine *e, const double *d_psum, double *d_out, cudaStream_t st)
+{
+   if (e->T.hk_valid.empty()) return 0;
+   RecipPlan P;
+   if (make_plan(e, true, P, st)) return -1;
+   return recip_finish(e, P, d_psum, d_out, st);
 }

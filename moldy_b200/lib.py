@@ -65,6 +65,10 @@ def load() -> C.CDLL:
     for f in ("mdb_zero_out", "mdb_force_real", "mdb_force_recip"):
         getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.mdb_build_cells.argtypes = [C.c_void_p, C.c_void_p]
+    L.mdb_recip_sum_doubles.restype = C.c_size_t
+    L.mdb_recip_sum_doubles.argtypes = [C.c_void_p]
+    L.mdb_recip_partial.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mdb_recip_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mdb_read_out.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mdb_grid.argtypes = [C.c_void_p, IP]
     L.mdb_n_neighbour_cells.argtypes = [C.c_void_p]
@@ -258,6 +262,15 @@ class Engine:
 
     def force_recip(self, d_out, stream=0):
         self._chk(self.L.mdb_force_recip(self.h, d_out, stream), "mdb_force_recip")
+
+    def recip_sum_doubles(self) -> int:
+        return self.L.mdb_recip_sum_doubles(self.h)
+
+    def recip_partial(self, d_psum, stream=0):
+        self._chk(self.L.mdb_recip_partial(self.h, d_psum, stream), "mdb_recip_partial")
+
+    def recip_finish(self, d_psum, d_out, stream=0):
+        self._chk(self.L.mdb_recip_finish(self.h, d_psum, d_out, stream), "mdb_recip_finish")
 
     def read_out(self, d_out, stream=0) -> np.ndarray:
         h = np.empty(self.out_doubles())

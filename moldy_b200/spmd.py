@@ -7,12 +7,16 @@ replicated: ~0.1 ms at 10^6 sites); rank r of P owns
 
   * real space:  the r-th contiguous slice of the cell-sorted sites (full
     stencil, owner-computes: its partial force array is non-zero only there),
-  * k-space:     every P-th (h,k) column of the reciprocal lattice (structure
-    factors, energy/stress and back-projection for those k-vectors, all sites),
+  * k-space:     its slice of the (charged) sites for ALL k-vectors -- the manual's
+    "RIL" scheme (src/moldy.tex:3441-3466): the 8*nslots structure-factor sums are
+    all-reduced between the two passes (0.6-1.2 MB), so both the structure-factor
+    pass and the back-projection scale with 1/P.  (Moldy's shipped scheme, a block
+    of k-vectors per rank for all sites, src/ewald.c:495-496, is what the library
+    does when it is driven through force_calc()/ewald() with ithread/nthreads,
+    because no exchange is available there before the final sums.)
 
-exactly the reference's scheme (cells `icell = ithread mod nthreads`,
-src/force.c:856; a block of k-vectors, src/ewald.c:495-496) with a different
-but equally disjoint assignment.  The partial [forces | pe | stress] blocks are
+Real space follows the reference's scheme (cells `icell = ithread mod nthreads`,
+src/force.c:856) with a different but equally disjoint assignment.  The partial [forces | pe | stress] blocks are
 combined by ONE packed all-reduce (the reference issues three,
 src/accel.c:532-534); NCCL returns bit-identical sums on all ranks, which is what
 Moldy's DESYNC check (src/main.c:262-273) relies on.  Constants the reference
@@ -46,6 +50,17 @@ def column_owner(vpos: int, world: int) -> int:
     return vpos % world
 
 
+def recip_sites(eng, d_psum: torch.Tensor, d_out: torch.Tensor, stream: int, group=None):
+    """k-space with the site partition: pass 1 on own sites, all-reduce of the structure-factor
+    sums, pass 2 (energy/stress on rank 0, forces on own sites)."""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        eng.force_recip(d_out.data_ptr(), stream)
+        return
+    eng.recip_partial(d_psum.data_ptr(), stream)
+    dist.all_reduce(d_psum, op=dist.ReduceOp.SUM, group=group)
+    eng.recip_finish(d_psum.data_ptr(), d_out.data_ptr(), stream)
+
+
 class SpmdForces:
     """Host-buffer front end of the multi-GPU force evaluation (bench.py `e2e`, N>1)."""
 
@@ -58,6 +73,7 @@ class SpmdForces:
         self.n = ms.nsites
         self.d_xyz = torch.empty((3, self.n), dtype=torch.float64, device="cuda")
         self.d_out = torch.zeros(self.eng.out_doubles(), dtype=torch.float64, device="cuda")
+        self.d_psum = torch.zeros(self.eng.recip_sum_doubles(), dtype=torch.float64, device="cuda")
         self.h_out = torch.empty(self.eng.out_doubles(), dtype=torch.float64).pin_memory()
         self.eng.set_sites_device(self.d_xyz[0].data_ptr(), self.d_xyz[1].data_ptr(), self.d_xyz[2].data_ptr())
 
@@ -69,7 +85,7 @@ class SpmdForces:
         self.eng.zero_out(self.d_out.data_ptr(), st)
         self.eng.build_cells(st)
         self.eng.force_real(self.d_out.data_ptr(), st)
-        self.eng.force_recip(self.d_out.data_ptr(), st)
+        recip_sites(self.eng, self.d_psum, self.d_out, st)
         combine(self.d_out)
         self.h_out.copy_(self.d_out, non_blocking=True)
         torch.cuda.synchronize()

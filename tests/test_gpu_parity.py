@@ -143,6 +143,38 @@ def test_every_pair_kernel_variant_vs_golden(name, mode, golden_dir):
     eng.close()
 
 
+def test_site_partitioned_kspace_sums_to_whole():
+    """The multi-GPU k-space scheme emulated on one GPU: every rank's structure-factor sums are
+    added (the all-reduce), then every rank back-projects onto its own sites; the rank blocks
+    add up to the single-rank result (energy and stress come from rank 0 only)."""
+    import torch
+    ms = cases.GOLDEN_CASES["slab_framework"]()
+    n = ms.nsites
+    st = torch.cuda.current_stream().cuda_stream
+    eng = lib.Engine(0)
+    eng.configure(ms)
+    eng.set_sites_host(ms.make_sites())
+    whole = torch.zeros(eng.out_doubles(), dtype=torch.float64, device="cuda")
+    eng.force_recip(whole.data_ptr(), st)
+    P = 3
+    psums = []
+    for r in range(P):
+        eng.set_partition(r, P)
+        ps = torch.zeros(eng.recip_sum_doubles(), dtype=torch.float64, device="cuda")
+        eng.recip_partial(ps.data_ptr(), st)
+        psums.append(ps)
+    total = sum(psums)
+    parts = torch.zeros_like(whole)
+    for r in range(P):
+        eng.set_partition(r, P)
+        eng.recip_finish(total.data_ptr(), parts.data_ptr(), st)
+    torch.cuda.synchronize()
+    a, b = whole.cpu().numpy(), parts.cpu().numpy()
+    assert cases.rel_rms(b[:3 * n], a[:3 * n]) < 1e-13
+    assert np.allclose(b[3 * n:3 * n + 11], a[3 * n:3 * n + 11], rtol=1e-12, atol=1e-9)
+    eng.close()
+
+
 def test_deterministic_repeat():
     """pair_mode 3 (owner-computes, no atomics) is bit-reproducible run to run; the default
     Newton-3 mode accumulates with red.global.add.f64 and may differ in the last bits."""
