@@ -298,7 +298,7 @@ def run_ours(a):
 
 
 # dram__bytes_read+write per k_pair launch from the ncu --set full capture committed under profiles/
-TRAFFIC = {}
+TRAFFIC = {10: 102.4e6}    # bytes per k_pair_tiled launch at n=10 (profiles/r01_final_summary.md)
 
 
 def measure_e2e(a, ms, site, world, rank, local):
