@@ -264,8 +264,9 @@ def run_ours(a):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        roof = {"bound": "fp64", "kernel": "k_pair<LJ,coulomb> (real-space pair kernel, FP64 CUDA cores; no tensor-core "
-                "or HBM roofline applies: ~36 B/site are reused for ~12 000 pair visits)",
+        roof = {"bound": "fp64", "kernel": "k_pair_tiled<LJ,coulomb,newton3> (real-space pair kernel, FP64 CUDA cores; no "
+                "tensor-core or HBM roofline applies: ~36 B/site are reused for ~6 300 pair visits; `traffic` is "
+                "dram read+write bytes per launch from the ncu capture in profiles/)",
                 "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": "FP64 DFMA rate measured in this run by mdb_fp64_peak_probe (MEASURED_PEAKS.json holds "
                                "no FP64 figure; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2)",
