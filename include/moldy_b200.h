@@ -167,6 +167,8 @@ typedef struct {
    double       cutoff, subcell, alpha, k_cutoff;
    int          strict_cutoff;
    int          do_recip;      /* build k-space tables (alpha > ALPHAMIN)           */
+   int          molpbc;        /* control.molpbc: bin whole molecules by their c-of-m (src/force.c:456-484) */
+   int          nmols;         /* molecules (rows of the c-of-m array), needed when molpbc                  */
 } mdb_config;
 
 /* Result block in HBM: [fx(N) | fy(N) | fz(N) | pe_real, pe_recip | stress[9] | pad]
@@ -197,6 +199,10 @@ void mdb_set_pair_mode(mdb_engine *e, int mode);
  * three DEVICE rows already resident in HBM. */
 int  mdb_set_sites_host(mdb_engine *e, const double *x, const double *y, const double *z, void *stream);
 int  mdb_set_sites_device(mdb_engine *e, const double *dx, const double *dy, const double *dz, void *stream);
+
+/* molecular-cutoff mode only: the scaled centre-of-mass co-ordinates system->c_of_m[nmols][3]
+ * (HOST pointer, copied on `stream`); call before mdb_build_cells every step. */
+int  mdb_set_com_host(mdb_engine *e, const double *c_of_m, void *stream);
 
 /* Hot path.  `d_out` is a DEVICE buffer of mdb_out_doubles(nsites) doubles that
  * is accumulated into (+=); zero it with mdb_zero_out first.  Everything is

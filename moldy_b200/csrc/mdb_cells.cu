@@ -35,15 +35,24 @@ __device__ __forceinline__ int safe_bin(double rc, int nc, double fnc, double ep
 
 __global__ void __launch_bounds__(CB) k_cell_ids(CellParams P, int n, const double *__restrict__ x,
                                                  const double *__restrict__ y, const double *__restrict__ z,
+                                                 const int *__restrict__ mol, const double *__restrict__ com,
                                                  int *__restrict__ cell, int *__restrict__ count,
                                                  unsigned long long *__restrict__ counters)
 {
    int i = blockIdx.x * CB + threadIdx.x;
    if (i >= n) return;
-   double a0 = x[i], a1 = y[i], a2 = z[i];
-   double s0 = __dadd_rn(__dadd_rn(__dmul_rn(P.hinv[0], a0), __dmul_rn(P.hinv[1], a1)), __dmul_rn(P.hinv[2], a2));
-   double s1 = __dadd_rn(__dadd_rn(__dmul_rn(P.hinv[3], a0), __dmul_rn(P.hinv[4], a1)), __dmul_rn(P.hinv[5], a2));
-   double s2 = __dadd_rn(__dadd_rn(__dmul_rn(P.hinv[6], a0), __dmul_rn(P.hinv[7], a1)), __dmul_rn(P.hinv[8], a2));
+   double s0, s1, s2;
+   if (P.molpbc && i < P.nsites_xf) {
+      // molecular cut-off: the whole molecule goes into the cell of its (already scaled) centre of
+      // mass, src/force.c:474-484; framework sites are always binned one by one
+      const int m = mol[i];
+      s0 = com[3 * m]; s1 = com[3 * m + 1]; s2 = com[3 * m + 2];
+   } else {
+      const double a0 = x[i], a1 = y[i], a2 = z[i];
+      s0 = __dadd_rn(__dadd_rn(__dmul_rn(P.hinv[0], a0), __dmul_rn(P.hinv[1], a1)), __dmul_rn(P.hinv[2], a2));
+      s1 = __dadd_rn(__dadd_rn(__dmul_rn(P.hinv[3], a0), __dmul_rn(P.hinv[4], a1)), __dmul_rn(P.hinv[5], a2));
+      s2 = __dadd_rn(__dadd_rn(__dmul_rn(P.hinv[6], a0), __dmul_rn(P.hinv[7], a1)), __dmul_rn(P.hinv[8], a2));
+   }
    int bad = 0;
    int ix = safe_bin(s0, P.nx, P.fnx, P.eps, &bad);
    int iy = safe_bin(s1, P.ny, P.fny, P.eps, &bad);
@@ -215,8 +224,11 @@ int mdb_launch_cells(mdb_engine *e, cudaStream_t st)
    P.nx = e->T.nx; P.ny = e->T.ny; P.nz = e->T.nz; P.ncells = nc;
    P.fnx = P.nx; P.fny = P.ny; P.fnz = P.nz;
    P.eps = 8.0 * 2.220446049250313e-16;                 // 8 * precision(), src/force.c:437
+   P.molpbc = e->cfg.molpbc; P.nsites_xf = e->cfg.nsites_xf;
+   if (P.molpbc && !e->com_set) { mdb_set_error("molecular-cutoff mode: mdb_set_com_host was not called"); return -1; }
    MDB_CUDA(cudaMemsetAsync(e->d_count, 0, sizeof(int) * (size_t)(nc + 1), st));
-   k_cell_ids<<<(n + CB - 1) / CB, CB, 0, st>>>(P, n, e->d_x, e->d_y, e->d_z, e->d_cell, e->d_count, e->d_counters);
+   k_cell_ids<<<(n + CB - 1) / CB, CB, 0, st>>>(P, n, e->d_x, e->d_y, e->d_z, e->d_mol, e->d_com, e->d_cell, e->d_count,
+                                                e->d_counters);
    int ntiles = (nc + SCAN_TILE - 1) / SCAN_TILE;
    k_scan_tiles<<<ntiles, SCAN_T, 0, st>>>(e->d_count, nc, e->d_scan_tmp);
    k_scan_sums<<<1, SCAN_T, 0, st>>>(e->d_scan_tmp, ntiles);

@@ -42,7 +42,7 @@ static void free_system(mdb_engine *e)
 {
    FREE(e->d_type); FREE(e->d_mol); FREE(e->d_chg); FREE(e->d_ptab);
    FREE(e->own_xyz); FREE(e->d_cell); FREE(e->d_order); FREE(e->d_posq);
-   FREE(e->d_stype); FREE(e->d_scell); FREE(e->d_fs);
+   FREE(e->d_stype); FREE(e->d_scell); FREE(e->d_fs); FREE(e->d_com); e->com_cap = 0; e->com_set = false;
    e->d_x = e->d_y = e->d_z = nullptr;
 }
 static void free_grid(mdb_engine *e)
@@ -219,6 +219,20 @@ extern "C" int mdb_set_sites_host(mdb_engine *e, const double *x, const double *
    MDB_CUDA(cudaMemcpyAsync(e->own_xyz + 2 * n, z, sizeof(double) * n, cudaMemcpyHostToDevice, st));
    e->d_x = e->own_xyz; e->d_y = e->own_xyz + n; e->d_z = e->own_xyz + 2 * n;
    e->sites_set = true; e->cells_valid = false;
+   return 0;
+}
+
+extern "C" int mdb_set_com_host(mdb_engine *e, const double *c_of_m, void *stream)
+{
+   const int nm = e->cfg.nmols;
+   if (nm <= 0) { mdb_set_error("mdb_set_com_host: nmols not configured"); return -1; }
+   if (nm > e->com_cap) {
+      FREE(e->d_com);
+      MDB_CUDA(cudaMalloc(&e->d_com, sizeof(double) * 3 * (size_t)nm));
+      e->com_cap = nm;
+   }
+   MDB_CUDA(cudaMemcpyAsync(e->d_com, c_of_m, sizeof(double) * 3 * (size_t)nm, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+   e->com_set = true; e->cells_valid = false;
    return 0;
 }
 

@@ -49,6 +49,7 @@ struct CellParams {
    double hinv[9];
    int nx, ny, nz, ncells;
    double fnx, fny, fnz, eps;
+   int molpbc, nsites_xf;                 // molecular-cutoff binning for the non-framework sites
 };
 
 struct PairParams {
@@ -85,6 +86,7 @@ struct mdb_engine {
    double *d_x = nullptr, *d_y = nullptr, *d_z = nullptr;
    double *own_xyz = nullptr;
    bool sites_set = false, cells_valid = false;
+   double *d_com = nullptr; int com_cap = 0; bool com_set = false;   // scaled c-of-m (molecular-cutoff mode)
    // link cells
    int ncells = 0, cells_cap = 0;
    int *d_cell = nullptr, *d_count = nullptr, *d_start = nullptr, *d_order = nullptr;

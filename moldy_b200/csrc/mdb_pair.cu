@@ -253,7 +253,7 @@ int mdb_launch_pair(mdb_engine *e, double *d_out, cudaStream_t st)
       e->partials_cap = nblocks;
    }
    const bool coul = c.alpha > 0.0;                     // src/kernel.c:182
-   const bool strict = c.strict_cutoff != 0;            // src/force.c:951 (molpbc unsupported)
+   const bool strict = c.strict_cutoff != 0 && !c.molpbc; // src/force.c:951
    dim3 g(nblocks);
    switch (c.ptype) {
       case PT_LJ:  launch_pair_c<PT_LJ>(coul, strict, g, st, P, e, d_out); break;

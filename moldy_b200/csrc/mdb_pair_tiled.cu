@@ -471,7 +471,7 @@ int mdb_launch_pair_tiled(mdb_engine *e, double *d_out, cudaStream_t st)
       e->partials_cap = nrows + RS1;
    }
    if (n3) MDB_CUDA(cudaMemsetAsync(e->d_fs, 0, sizeof(double) * 3 * (size_t)c.nsites, st));
-   const bool coul = c.alpha > 0.0, strict = c.strict_cutoff != 0, fw = c.nsites_xf < c.nsites;
+   const bool coul = c.alpha > 0.0, strict = c.strict_cutoff != 0 && !c.molpbc, fw = c.nsites_xf < c.nsites;   // src/force.c:951
    dim3 g(nblocks);
 #define PT_CASE(X) case X: if (coul) launch_tiled<X, true>(strict, fw, n3, g, st, P, e, runs, d_out); \
                            else launch_tiled<X, false>(strict, fw, n3, g, st, P, e, runs, d_out); break

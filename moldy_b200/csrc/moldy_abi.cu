@@ -126,8 +126,6 @@ static void sync_config(system_mt *system, spec_mt *species, const real *chg, co
 {
    ensure_engine();
    const int n = system->nsites, max_id = system->max_id;
-   if (control.molpbc)
-      FATAL_MSG("libmoldy_b200: molecular-cutoff=1 is not supported by the GPU force path");
    int nfw = 0;
    for (int i = 0; i < system->nspecies; i++) nfw += species[i].framework ? species[i].nmols : 0;
    if (nfw > 1) FATAL_MSG("Multiple framework molecules are not supported");     /* src/force.c:1218 */
@@ -140,12 +138,13 @@ static void sync_config(system_mt *system, spec_mt *species, const real *chg, co
    c.cutoff = control.cutoff; c.subcell = control.subcell; c.alpha = control.alpha;
    c.k_cutoff = control.k_cutoff; c.strict_cutoff = control.strict_cutoff;
    c.do_recip = control.alpha > MDB_ALPHAMIN;
+   c.molpbc = control.molpbc ? 1 : 0; c.nmols = system->nmols;
 
    bool changed = !G.have_cfg || c.nsites != G.cfg.nsites || c.nsites_xf != G.cfg.nsites_xf ||
                   c.max_id != G.cfg.max_id || c.ptype != G.cfg.ptype || memcmp(c.h, G.cfg.h, sizeof c.h) ||
                   c.cutoff != G.cfg.cutoff || c.subcell != G.cfg.subcell || c.alpha != G.cfg.alpha ||
                   c.k_cutoff != G.cfg.k_cutoff || c.strict_cutoff != G.cfg.strict_cutoff ||
-                  c.do_recip != G.cfg.do_recip;
+                  c.do_recip != G.cfg.do_recip || c.molpbc != G.cfg.molpbc || c.nmols != G.cfg.nmols;
    if ((int)G.type.size() != n) {
       // site id and molecule maps (src/force.c:1173-1191)
       G.type.resize(n); G.mol.resize(n);
@@ -268,6 +267,8 @@ extern "C" void force_calc(real **site, real **site_force, system_mt *system, sp
 
    G.sites_fresh = false;
    push_sites(site);
+   if (control.molpbc && mdb_set_com_host(G.eng, &system->c_of_m[0][0], G.stream))
+      FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
    if (mdb_zero_out(G.eng, G.d_out, G.stream) || mdb_build_cells(G.eng, G.stream) ||
        mdb_force_real(G.eng, G.d_out, G.stream))
       FATAL_MSG("libmoldy_b200: %s", mdb_last_error());

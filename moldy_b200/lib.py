@@ -37,7 +37,7 @@ class mdb_config(C.Structure):
         ("site_type", IP), ("site_mol", IP), ("chg", DP), ("potpar", DP),
         ("h", C.c_double * 9),
         ("cutoff", C.c_double), ("subcell", C.c_double), ("alpha", C.c_double), ("k_cutoff", C.c_double),
-        ("strict_cutoff", C.c_int), ("do_recip", C.c_int),
+        ("strict_cutoff", C.c_int), ("do_recip", C.c_int), ("molpbc", C.c_int), ("nmols", C.c_int),
     ]
 
 
@@ -62,6 +62,7 @@ def load() -> C.CDLL:
     L.mdb_set_pair_mode.argtypes = [C.c_void_p, C.c_int]
     L.mdb_set_sites_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mdb_set_sites_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mdb_set_com_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     for f in ("mdb_zero_out", "mdb_force_real", "mdb_force_recip"):
         getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.mdb_build_cells.argtypes = [C.c_void_p, C.c_void_p]
@@ -164,7 +165,8 @@ def eval_forces(ms: MoldySystem, real=True, recip=True, sites=None, ithread=0, n
     sysm, spec, pot = ms.cstructs()
     n = ms.nsites
     nsa = abi.nsarray(n)
-    site = np.ascontiguousarray(ms.make_sites() if sites is None else sites)
+    # eval_forces() builds the sites with MOLPBC (no per-site wrap) when control.molpbc (src/accel.c:500-504)
+    site = np.ascontiguousarray(ms.make_sites(wrap=not ms.control.molpbc) if sites is None else sites)
     force = np.zeros((3, nsa))
     chg = ms.charges()
     pe = np.zeros(2)
@@ -227,6 +229,7 @@ class Engine:
         cfg.cutoff, cfg.subcell, cfg.alpha, cfg.k_cutoff = c.cutoff, c.subcell, c.alpha, c.k_cutoff
         cfg.strict_cutoff = c.strict_cutoff
         cfg.do_recip = int(c.alpha > 1e-7)
+        cfg.molpbc, cfg.nmols = int(c.molpbc), ms.nmols
         self._keep = (ids, mol, chg, pot)
         self._chk(self.L.mdb_configure(self.h, C.byref(cfg)), "mdb_configure")
         self.n = ms.nsites
@@ -244,6 +247,12 @@ class Engine:
     def set_sites_host(self, site_block: np.ndarray, stream=0):
         r = [site_block.ctypes.data + site_block.strides[0] * i for i in range(3)]
         self._chk(self.L.mdb_set_sites_host(self.h, r[0], r[1], r[2], stream), "mdb_set_sites_host")
+
+    def set_com_host(self, c_of_m: np.ndarray, stream=0):
+        """molecular-cutoff mode: scaled centre-of-mass co-ordinates [nmols,3]."""
+        com = np.ascontiguousarray(c_of_m, dtype=np.float64)
+        self._com_keep = com
+        self._chk(self.L.mdb_set_com_host(self.h, com.ctypes.data, stream), "mdb_set_com_host")
 
     def set_sites_host_ptrs(self, px, py, pz, stream=0):
         self._chk(self.L.mdb_set_sites_host(self.h, px, py, pz, stream), "mdb_set_sites_host")

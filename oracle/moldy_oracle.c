@@ -296,9 +296,15 @@ int orc_cell_ids(const orc_system *s, const double *x, const double *y, const do
    grid_dims(s, &nx, &ny, &nz);
    orc_invert3(s->h, hinv);
    for (i = 0; i < s->nsites; i++) {
-      double s0 = hinv[0] * x[i] + hinv[1] * y[i] + hinv[2] * z[i];
-      double s1 = hinv[3] * x[i] + hinv[4] * y[i] + hinv[5] * z[i];
-      double s2 = hinv[6] * x[i] + hinv[7] * y[i] + hinv[8] * z[i];
+      double s0, s1, s2;
+      if (s->molpbc && i < s->nsites_xf) {      /* whole molecule by its scaled c-of-m, force.c:474-484 */
+         const double *c = s->c_of_m + 3 * s->site_mol[i];
+         s0 = c[0]; s1 = c[1]; s2 = c[2];
+      } else {
+         s0 = hinv[0] * x[i] + hinv[1] * y[i] + hinv[2] * z[i];
+         s1 = hinv[3] * x[i] + hinv[4] * y[i] + hinv[5] * z[i];
+         s2 = hinv[6] * x[i] + hinv[7] * y[i] + hinv[8] * z[i];
+      }
       int bx = orc_cellbin(s0, nx, (double)nx, eps, &err);
       int by = orc_cellbin(s1, ny, (double)ny, eps, &err);
       int bz = orc_cellbin(s2, nz, (double)nz, eps, &err);
@@ -337,7 +343,19 @@ int orc_force_calc(const orc_system *s, const double *x, const double *y, const 
    {
       int *cur = (int *)malloc(sizeof(int) * (size_t)ncells);
       memcpy(cur, start, sizeof(int) * (size_t)ncells);
-      for (i = n - 1; i >= 0; i--) members[cur[cell[i]]++] = i;
+      /* list order = reverse insertion order: molecules from last to first; a per-site node list
+       * (site mode, framework) gives its sites in descending order, a per-molecule node (molpbc,
+       * force.c:474-484) keeps its sites ascending */
+      i = n - 1;
+      while (i >= 0) {
+         int lo = i, k;
+         while (lo > 0 && s->site_mol[lo - 1] == s->site_mol[i]) lo--;
+         if (s->molpbc && i < s->nsites_xf)
+            for (k = lo; k <= i; k++) members[cur[cell[k]]++] = k;
+         else
+            for (k = i; k >= lo; k--) members[cur[cell[k]]++] = k;
+         i = lo - 1;
+      }
       free(cur);
    }
    cap = 3 * 4 * 64 * 64 * 64;
@@ -409,7 +427,7 @@ int orc_force_calc(const orc_system *s, const double *x, const double *y, const 
          }
          for (j = jmin; j < jmax; j++)                      /* TOO_CLOSE, force.c:939-949 */
             if (r2[j] < 0.25 && s->site_mol[isite] != s->site_mol[nab[j]]) too_close++;
-         if (s->strict_cutoff)                              /* force.c:951-954 */
+         if (s->strict_cutoff && !s->molpbc)                /* force.c:951-954 */
             for (j = jmin; j < jmax; j++) if (r2[j] > rc2) r2[j] = rc2far;
          for (j = jmin; j < jmax; j++) {                    /* kernel + mk_forces */
             double f, phi;

@@ -26,6 +26,8 @@ typedef struct {
    /* control */
    double cutoff, subcell, alpha, k_cutoff;
    int strict_cutoff;
+   int molpbc;                     /* molecular cut-off: non-framework molecules binned by c-of-m */
+   const double *c_of_m;           /* [nmols][3] scaled centre-of-mass co-ordinates (molpbc only)  */
    /* replicated-data partition (the reference's globals ithread/nthreads) */
    int ithread, nthreads;
 } orc_system;

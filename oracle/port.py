@@ -20,7 +20,8 @@ class orc_system(C.Structure):
     _fields_ = [("nsites", C.c_int), ("nsites_xf", C.c_int), ("max_id", C.c_int), ("ptype", C.c_int),
                 ("n_potpar", C.c_int), ("site_type", IP), ("site_mol", IP), ("chg", DP), ("potpar", DP),
                 ("h", C.c_double * 9), ("cutoff", C.c_double), ("subcell", C.c_double), ("alpha", C.c_double),
-                ("k_cutoff", C.c_double), ("strict_cutoff", C.c_int), ("ithread", C.c_int), ("nthreads", C.c_int)]
+                ("k_cutoff", C.c_double), ("strict_cutoff", C.c_int), ("molpbc", C.c_int), ("c_of_m", DP),
+                ("ithread", C.c_int), ("nthreads", C.c_int)]
 
 
 class orc_result(C.Structure):
@@ -53,7 +54,8 @@ def _system(ms, ithread=0, nthreads=1):
     keep = dict(ids=np.ascontiguousarray(ms.site_ids(), dtype=np.int32),
                 mol=np.ascontiguousarray(ms.molmap(), dtype=np.int32),
                 chg=np.ascontiguousarray(ms.charges()),
-                pot=np.ascontiguousarray(sd.potpar.reshape(-1), dtype=np.float64))
+                pot=np.ascontiguousarray(sd.potpar.reshape(-1), dtype=np.float64),
+                com=np.ascontiguousarray(ms.c_of_m, dtype=np.float64))
     s = orc_system()
     s.nsites, s.nsites_xf = ms.nsites, ms.nsites_xf
     s.max_id, s.ptype, s.n_potpar = sd.max_id, sd.ptype, sd.n_potpar
@@ -65,6 +67,8 @@ def _system(ms, ithread=0, nthreads=1):
         s.h[i] = float(ms.h.reshape(-1)[i])
     c = ms.control
     s.cutoff, s.subcell, s.alpha, s.k_cutoff, s.strict_cutoff = c.cutoff, c.subcell, c.alpha, c.k_cutoff, c.strict_cutoff
+    s.molpbc = int(c.molpbc)
+    s.c_of_m = keep["com"].ctypes.data_as(DP)
     s.ithread, s.nthreads = ithread, nthreads
     return s, keep
 
@@ -95,7 +99,7 @@ def constants(ms):
 def cell_ids(ms, sites=None):
     L = load()
     s, keep = _system(ms)
-    site = np.ascontiguousarray(ms.make_sites() if sites is None else sites)
+    site = np.ascontiguousarray(ms.make_sites(wrap=not ms.control.molpbc) if sites is None else sites)
     n = ms.nsites
     x, y, z = (np.ascontiguousarray(site[i, :n]) for i in range(3))
     out = np.empty(n, dtype=np.int32)
@@ -106,7 +110,7 @@ def cell_ids(ms, sites=None):
 def run(ms, real=True, recip=True, sites=None, ithread=0, nthreads=1):
     L = load()
     s, keep = _system(ms, ithread, nthreads)
-    site = np.ascontiguousarray(ms.make_sites() if sites is None else sites)
+    site = np.ascontiguousarray(ms.make_sites(wrap=not ms.control.molpbc) if sites is None else sites)
     n = ms.nsites
     x, y, z = (np.ascontiguousarray(site[i, :n]) for i in range(3))
     f = np.zeros((3, n))

@@ -69,7 +69,7 @@ class RefLib:
         sysm, spec, pot = ms.cstructs()
         n = ms.nsites
         nsa = abi.nsarray(n)
-        site = np.ascontiguousarray(ms.make_sites() if sites is None else sites)
+        site = np.ascontiguousarray(ms.make_sites(wrap=not ms.control.molpbc) if sites is None else sites)
         force = np.zeros((3, nsa))
         chg = ms.charges()
         pe = (C.c_double * 2)(0.0, 0.0)
@@ -92,7 +92,7 @@ class RefLib:
         h = np.ascontiguousarray(ms.h)
         hinv = np.zeros((3, 3))
         self.lib.invert(h.ctypes.data_as(C.POINTER(abi.vec_mt)), hinv.ctypes.data_as(C.POINTER(abi.vec_mt)))
-        site = ms.make_sites() if sites is None else sites
+        site = ms.make_sites(wrap=not ms.control.molpbc) if sites is None else sites
         sub = ms.control.subcell if ms.control.subcell > 0 else ms.control.cutoff / 5.0
         nx = int(h[0, 0] / sub + 0.5)
         ny = int(h[1, 1] / sub + 0.5)
@@ -101,6 +101,11 @@ class RefLib:
         n = ms.nsites
         x, y, z = site[0, :n], site[1, :n], site[2, :n]
         s = [(hinv[i, 0] * x + hinv[i, 1] * y) + hinv[i, 2] * z for i in range(3)]
+        if ms.control.molpbc:                     # LOCATE(c_of_m[imol]) for non-framework molecules
+            nxf, mol = ms.nsites_xf, ms.molmap()
+            for i in range(3):
+                s[i] = s[i].copy()
+                s[i][:nxf] = ms.c_of_m[mol[:nxf], i]
         out = np.empty(n, dtype=np.int32)
         cb = self.lib.cellbin
         for i in range(n):

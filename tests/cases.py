@@ -82,6 +82,28 @@ def tip4p_tiny_box():
     return ms
 
 
+def tips2_molpbc():
+    """molecular-cutoff=1: whole molecules binned by their centre of mass, sites not wrapped."""
+    ms = systems.tips2()
+    ms.control.molpbc = 1
+    return ms
+
+
+def tip4p_molpbc_strict():
+    """molecular-cutoff=1 with strict-cutoff=1: strict stencil, but no r^2 clamp (src/force.c:951)."""
+    ms = systems.tip4p()
+    ms.control.molpbc = 1
+    ms.control.strict_cutoff = 1
+    return ms
+
+
+def tips2_strict():
+    """strict cut-off with Coulomb: the clamped pairs are evaluated at r = 100 rc."""
+    ms = systems.tips2()
+    ms.control.strict_cutoff = 1
+    return ms
+
+
 GOLDEN_CASES = {
     "argon": systems.argon,
     "argon_lazy": argon_lazy,
@@ -97,6 +119,9 @@ GOLDEN_CASES = {
     "hiw": hiw,
     "morse": morse,
     "morse_nocoul": morse_nocoul,
+    "tips2_molpbc": tips2_molpbc,
+    "tip4p_molpbc_strict": tip4p_molpbc_strict,
+    "tips2_strict": tips2_strict,
 }
 
 # start-up scalars the reference's own example outputs pin:

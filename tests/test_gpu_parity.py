@@ -55,7 +55,9 @@ def test_cell_assignment_bit_exact(name, golden_dir):
     gold = np.load(os.path.join(golden_dir, f"ref_{name}.npz"))
     eng = lib.Engine(0)
     eng.configure(ms)
-    eng.set_sites_host(ms.make_sites())
+    eng.set_sites_host(ms.make_sites(wrap=not ms.control.molpbc))
+    if ms.control.molpbc:
+        eng.set_com_host(ms.c_of_m)
     got = eng.cell_ids()
     assert np.array_equal(got, gold["cell"]), f"{name}: {np.count_nonzero(got != gold['cell'])} sites in the wrong cell"
     eng.close()
@@ -126,7 +128,9 @@ def test_every_pair_kernel_variant_vs_golden(name, mode, golden_dir):
     eng = lib.Engine(0)
     eng.set_pair_mode(mode)
     eng.configure(ms)
-    eng.set_sites_host(ms.make_sites())
+    eng.set_sites_host(ms.make_sites(wrap=not ms.control.molpbc))
+    if ms.control.molpbc:
+        eng.set_com_host(ms.c_of_m)
     st = torch.cuda.current_stream().cuda_stream
     out = torch.zeros(eng.out_doubles(), dtype=torch.float64, device="cuda")
     eng.build_cells(st)
