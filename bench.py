@@ -218,7 +218,6 @@ def run_ours(a):
     for _ in range(a.warmup):
         step()
     torch.cuda.synchronize()
-    eng.pair_count(st)                        # reset the visit counter
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(a.steps)]
     l0 = eng.launches()
     sampler = ClockSampler(local)
@@ -243,7 +242,7 @@ def run_ours(a):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     tot_ms = float(t.item())
-    pairs_rank = eng.pair_count(st) / a.steps
+    pairs_rank = eng.pair_count(st)            # pairs handed to kernel() per step by this rank (counting pass, untimed)
     pr = torch.tensor([pairs_rank], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(pr)

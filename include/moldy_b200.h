@@ -228,7 +228,8 @@ int    mdb_grid(const mdb_engine *e, int nxyz[3]);           /* link-cell grid  
 int    mdb_n_neighbour_cells(const mdb_engine *e);            /* half list, as NABORS/2  */
 int    mdb_n_kvectors(const mdb_engine *e);                   /* nhkl                    */
 int    mdb_get_cell_ids(mdb_engine *e, int *h_cell, void *stream);   /* [nsites], NCELL()  */
-double mdb_pair_count(mdb_engine *e, void *stream);           /* pairs handed to kernel() per step */
+double mdb_pair_count(mdb_engine *e, void *stream);           /* pairs handed to kernel() per force evaluation
+                                                                  (src/force.c:960) for the current sites */
 long   mdb_kernel_launches(const mdb_engine *e);              /* our kernels launched so far */
 int    mdb_too_close(mdb_engine *e, int pair[2], void *stream);/* count of r^2<0.25 inter-molecular pairs */
 size_t mdb_sizeof(const char *struct_name);                   /* "contr_mt", "system_mt", ... */

@@ -4,7 +4,7 @@
 //   k_scan_*       exclusive scan of the per-cell counts -> cell_start[ncells+1]
 //   k_fill         site -> slot inside its cell (atomic cursor)
 //   k_sort_gather  per cell: order the slots by site index (deterministic),
-//                  gather {x,y,z,q}, type, cell id into cell-sorted SoA
+//                  gather {x,y,z,q}, type, cell id, {type, z index} into cell-sorted SoA
 //
 // Cell assignment must be bit-identical to the reference (src/force.c:119-137
 // cellbin, :460-472 fill_cells, product order of mat_vec_mul src/matrix.c:76-83):
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(CB) k_sort_gather(int ncells, const int *__res
                                                     const double *__restrict__ z, const double *__restrict__ q,
                                                     const int *__restrict__ type, int nsites_xf,
                                                     double4 *__restrict__ posq, int *__restrict__ stype,
-                                                    int *__restrict__ scell)
+                                                    int *__restrict__ scell, int2 *__restrict__ sinfo, int nz)
 {
    int c = blockIdx.x * CB + threadIdx.x;
    if (c >= ncells) return;
@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(CB) k_sort_gather(int ncells, const int *__res
       posq[s] = make_double4(x[o], y[o], z[o], q[o]);
       stype[s] = type[o] | (o >= nsites_xf ? 0x40000000 : 0);   // bit 30: framework site
       scell[s] = c;
+      sinfo[s] = make_int2(stype[s], c % nz);                  // what the tiled pair kernel reads per neighbour
    }
 }
 
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(CB) k_fill_batches(int ncols, int nz, int ni, 
    if (col >= ncols) return;
    const int s0 = start[col * nz], cnt = start[(col + 1) * nz] - s0, o = off[col];
    const int nb = (cnt + ni - 1) / ni;
-   for (int k = 0; k < nb; k++) batches[o + k] = make_int2(s0 + k * ni, min(ni, cnt - k * ni));
+   for (int k = 0; k < nb; k++) batches[o + k] = make_int2(s0 + k * ni, min(ni, cnt - k * ni) | (col << 3));
    if (col == ncols - 1) *nbatch = off[ncols];
 }
 
@@ -236,7 +237,8 @@ int mdb_launch_cells(mdb_engine *e, cudaStream_t st)
    MDB_CUDA(cudaMemsetAsync(e->d_count, 0, sizeof(int) * (size_t)(nc + 1), st));   // now the fill cursor
    k_fill<<<(n + CB - 1) / CB, CB, 0, st>>>(n, e->d_cell, e->d_start, e->d_count, e->d_order);
    k_sort_gather<<<(nc + CB - 1) / CB, CB, 0, st>>>(nc, e->d_start, e->d_order, e->d_x, e->d_y, e->d_z, e->d_chg,
-                                                   e->d_type, e->cfg.nsites_xf, e->d_posq, e->d_stype, e->d_scell);
+                                                   e->d_type, e->cfg.nsites_xf, e->d_posq, e->d_stype, e->d_scell, e->d_sinfo,
+                                                   e->T.nz);
    e->launches += 6;
    MDB_CUDA(cudaGetLastError());
    if (e->pair_mode >= 3 && mdb_launch_batches(e, st)) return -1;

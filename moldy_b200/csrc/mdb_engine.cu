@@ -42,7 +42,7 @@ static void free_system(mdb_engine *e)
 {
    FREE(e->d_type); FREE(e->d_mol); FREE(e->d_chg); FREE(e->d_ptab);
    FREE(e->own_xyz); FREE(e->d_cell); FREE(e->d_order); FREE(e->d_posq);
-   FREE(e->d_stype); FREE(e->d_scell); FREE(e->d_fs); FREE(e->d_com); e->com_cap = 0; e->com_set = false;
+   FREE(e->d_stype); FREE(e->d_scell); FREE(e->d_sinfo); FREE(e->d_fs); FREE(e->d_com); e->com_cap = 0; e->com_set = false;
    e->d_x = e->d_y = e->d_z = nullptr;
 }
 static void free_grid(mdb_engine *e)
@@ -72,6 +72,7 @@ extern "C" void mdb_destroy(mdb_engine *e)
 extern "C" void mdb_set_pair_mode(mdb_engine *e, int mode)
 {
    e->pair_mode = (mode == 2 || mode == 3) ? mode : 4;
+   if (e->configured && sizeof(double) * e->h_potpar.size() > MDB_TILED_TAB_MAX) e->pair_mode = 2;
    e->cells_valid = false;
 }
 
@@ -134,6 +135,7 @@ extern "C" int mdb_configure(mdb_engine *e, const mdb_config *cfg)
       MDB_CUDA(cudaMalloc(&e->d_posq, sizeof(double4) * (size_t)n));
       MDB_CUDA(cudaMalloc(&e->d_stype, sizeof(int) * (size_t)n));
       MDB_CUDA(cudaMalloc(&e->d_scell, sizeof(int) * (size_t)n));
+      MDB_CUDA(cudaMalloc(&e->d_sinfo, sizeof(int2) * (size_t)n));
       e->sites_set = false;
    }
    if (upload(&e->d_type, e->h_type.data(), n)) return -1;
@@ -169,6 +171,8 @@ extern "C" int mdb_configure(mdb_engine *e, const mdb_config *cfg)
          const int mm = m ? atoi(m) : 4;
          e->pair_mode = (mm == 2 || mm == 3) ? mm : 4;
       }
+      // the tiled kernel keeps the pair table in shared memory; very many site types -> per-thread kernel
+      if (sizeof(double) * ptab.size() > MDB_TILED_TAB_MAX) e->pair_mode = 2;
       if (new_system) { FREE(e->d_fs); }
       if (!e->d_fs) MDB_CUDA(cudaMalloc(&e->d_fs, sizeof(double) * 3 * (size_t)n));
       for (auto &r : e->T.runs)
@@ -261,6 +265,7 @@ extern "C" int mdb_force_real(mdb_engine *e, double *d_out, void *stream)
    if (!e->configured || !e->sites_set) { mdb_set_error("mdb_force_real: engine not configured / no sites"); return -1; }
    if (!e->cells_valid && mdb_launch_cells(e, (cudaStream_t)stream)) return -1;
    if (e->pair_mode >= 3) return mdb_launch_pair_tiled(e, d_out, (cudaStream_t)stream);
+   e->pair_evals++;
    return mdb_launch_pair(e, d_out, (cudaStream_t)stream);
 }
 
@@ -323,15 +328,27 @@ static int read_counters(mdb_engine *e, unsigned long long c[8], bool reset, cud
    return 0;
 }
 
-// pairs handed to kernel() per step = half the visits counted since the last call
+// pairs handed to kernel() per force evaluation (src/force.c:960) for the current configuration.
+// Tiled modes: the force kernel's traversal and window tests re-run without the arithmetic;
+// mode 2: the visits counted by the force kernel itself, averaged over the evaluations since the last call.
 extern "C" double mdb_pair_count(mdb_engine *e, void *stream)
 {
-   unsigned long long c[8];
-   if (read_counters(e, c, false, (cudaStream_t)stream)) return -1.0;
-   unsigned long long z = 0;
-   cudaMemcpyAsync(e->d_counters, &z, sizeof z, cudaMemcpyHostToDevice, (cudaStream_t)stream);
-   cudaStreamSynchronize((cudaStream_t)stream);
-   return 0.5 * (double)c[0];
+   cudaStream_t st = (cudaStream_t)stream;
+   unsigned long long c[8], z = 0;
+   double evals = 1.0;
+   if (e->pair_mode >= 3) {
+      if (!e->configured || !e->sites_set) { mdb_set_error("mdb_pair_count: engine not configured / no sites"); return -1.0; }
+      if (!e->cells_valid && mdb_launch_cells(e, st)) return -1.0;
+      cudaMemcpyAsync(e->d_counters, &z, sizeof z, cudaMemcpyHostToDevice, st);
+      if (mdb_launch_pair_count_tiled(e, st)) return -1.0;
+   } else {
+      evals = e->pair_evals > 0 ? (double)e->pair_evals : 1.0;
+      e->pair_evals = 0;
+   }
+   if (read_counters(e, c, false, st)) return -1.0;
+   cudaMemcpyAsync(e->d_counters, &z, sizeof z, cudaMemcpyHostToDevice, st);
+   cudaStreamSynchronize(st);
+   return 0.5 * (double)c[0] / evals;
 }
 
 extern "C" int mdb_too_close(mdb_engine *e, int pair[2], void *stream)

@@ -93,6 +93,7 @@ struct mdb_engine {
    int *d_scan_tmp = nullptr;
    double4 *d_posq = nullptr;
    int *d_stype = nullptr, *d_scell = nullptr;
+   int2 *d_sinfo = nullptr;               // {type | framework bit 30, z index of the cell}, cell-sorted
    StencilRun *d_runs = nullptr, *d_runs_half = nullptr;
    int nruns = 0, nruns_half = 0;
    int2 *d_batches = nullptr; int *d_nbatch = nullptr; int batch_cap = 0;   // i-site batches of the tiled pair kernel
@@ -100,6 +101,7 @@ struct mdb_engine {
    int pair_mode = -1;                    // 2: per-thread full stencil, 3: tiled full stencil, 4: tiled Newton-3
    // reductions / diagnostics
    double *d_partials = nullptr; int partials_cap = 0;
+   long pair_evals = 0;                   // force evaluations since the visit counter was last read (mode 2)
    unsigned long long *d_counters = nullptr;      // [0]=pair visits [1]=too close [2]=bin errors [3..4]=example pair
    // k-space
    HkDesc *d_hk = nullptr; int *d_hk_valid = nullptr; int *d_slot_flags = nullptr;
@@ -129,6 +131,8 @@ void mdb_set_error(const std::string &s);
 int mdb_launch_cells(mdb_engine *e, cudaStream_t st);
 int mdb_launch_pair(mdb_engine *e, double *d_out, cudaStream_t st);
 int mdb_launch_pair_tiled(mdb_engine *e, double *d_out, cudaStream_t st);
+int mdb_launch_pair_count_tiled(mdb_engine *e, cudaStream_t st);
+static constexpr size_t MDB_TILED_TAB_MAX = 28 * 1024;   // pair table of the tiled kernel lives in shared memory
 int mdb_launch_batches(mdb_engine *e, cudaStream_t st);
 static constexpr int MDB_NI = 4;          // i-sites per warp in the tiled pair kernel
 int mdb_launch_recip(mdb_engine *e, double *d_out, cudaStream_t st);

@@ -287,7 +287,14 @@ struct KfArgs {
    int max_slots;         // capacity of the coefficient stage (slots)
 };
 
-__global__ void __launch_bounds__(KF)
+// NS sites per thread: the coefficient loads (8 broadcast LDS.128 per slot pair) are shared by NS
+// sites, which takes the shared-memory pipe off the critical path (at NS = 1 it is as busy as FP64)
+// and lets consecutive DFMAs share the coefficient operand (.reuse): a DFMA that reads three
+// distinct vector registers issues every 3.2 cycles on sm_100a, 2.1 otherwise (scripts/ubench2.cu).
+// Reading the coefficients through the uniform datapath instead (__constant__ chunks, LDCU -> UR
+// operands) was measured slower: LDCU.128 sustains only ~1 per 6 cycles per SM.
+template <int NS>
+__global__ void __launch_bounds__(KF, NS == 1 ? 4 : NS == 2 ? 3 : 2)
 k_kforce(KfArgs A, const int *__restrict__ cidx, const double *__restrict__ x, const double *__restrict__ y,
          const double *__restrict__ z, const double *__restrict__ chg, const HkDesc *__restrict__ hk,
          const double *__restrict__ coef, double *__restrict__ out)
@@ -296,20 +303,28 @@ k_kforce(KfArgs A, const int *__restrict__ cidx, const double *__restrict__ x, c
    double4 *s_coef = reinterpret_cast<double4 *>(smem);                        // [max_slots][2]
    HkDesc *s_hk = reinterpret_cast<HkDesc *>(s_coef + 2 * (size_t)A.max_slots); // [hb]
    const KspaceParams &K = A.K;
-   const int t = A.c0 + blockIdx.x * KF + threadIdx.x;
-   const bool active = t < A.c1;
-   int i = 0;
-   double q = 0.0, xi = 0, yi = 0, zi = 0;
-   if (active) {
-      i = cidx[t];
-      q = chg[i]; xi = x[i]; yi = y[i]; zi = z[i];
+   int i[NS];
+   bool active[NS];
+   double q[NS];
+   double2 ea[NS], eb[NS], ec[NS], eh[NS], ehk[NS];
+   double fx[NS], fy[NS], fz[NS];
+#pragma unroll
+   for (int s = 0; s < NS; s++) {
+      const int t = A.c0 + (blockIdx.x * NS + s) * KF + threadIdx.x;
+      active[s] = t < A.c1;
+      i[s] = 0;
+      double xi = 0, yi = 0, zi = 0;
+      q[s] = 0.0;
+      if (active[s]) {
+         i[s] = cidx[t];
+         q[s] = chg[i[s]]; xi = x[i[s]]; yi = y[i[s]]; zi = z[i[s]];
+      }
+      sincos(K.astar[0] * xi + K.astar[1] * yi + K.astar[2] * zi, &ea[s].y, &ea[s].x);
+      sincos(K.bstar[0] * xi + K.bstar[1] * yi + K.bstar[2] * zi, &eb[s].y, &eb[s].x);
+      sincos(K.cstar[0] * xi + K.cstar[1] * yi + K.cstar[2] * zi, &ec[s].y, &ec[s].x);
+      eh[s] = make_double2(1.0, 0.0); ehk[s] = eh[s];
+      fx[s] = fy[s] = fz[s] = 0.0;
    }
-   double2 ea, eb, ec;
-   sincos(K.astar[0] * xi + K.astar[1] * yi + K.astar[2] * zi, &ea.y, &ea.x);
-   sincos(K.bstar[0] * xi + K.bstar[1] * yi + K.bstar[2] * zi, &eb.y, &eb.x);
-   sincos(K.cstar[0] * xi + K.cstar[1] * yi + K.cstar[2] * zi, &ec.y, &ec.x);
-   double2 eh = make_double2(1.0, 0.0), ehk = eh;
-   double fx = 0, fy = 0, fz = 0;
 
    for (int c0 = 0; c0 < A.nhk; c0 += A.hb) {
       const int nb = min(A.hb, A.nhk - c0);
@@ -330,86 +345,112 @@ k_kforce(KfArgs A, const int *__restrict__ cidx, const double *__restrict__ x, c
       const double4 *src = reinterpret_cast<const double4 *>(coef) + 2 * (size_t)slot_lo;
       for (int k = threadIdx.x; k < 2 * nsl; k += KF) s_coef[k] = src[k];
       __syncthreads();
-      if (!active) continue;
       // two (h,k) columns per pass: they share the l-recurrence of E_l (4 of the 12 FP64 ops per
-      // slot) and give the scheduler eight independent accumulator chains
+      // slot) and give the scheduler 8 NS independent accumulator chains
       for (int c = 0; c < nb; c += 2) {
          const HkDesc &d1 = s_hk[c];
          const HkDesc &d2 = s_hk[min(c + 1, nb - 1)];
          const bool two = c + 1 < nb;
-         double2 ehk1, ehk2;
-         switch (d1.code) {
-            case HK_NEWH:   if (d1.h > 0) eh = cmul(eh, ea); ehk = eh; break;
-            case HK_KUP:    ehk = cmul(ehk, eb); break;
-            case HK_KDOWN0: ehk = cmulc(eh, eb); break;
-            default:        ehk = cmulc(ehk, eb); break;
-         }
-         ehk1 = ehk;
-         if (two) {
-            switch (d2.code) {
-               case HK_NEWH:   if (d2.h > 0) eh = cmul(eh, ea); ehk = eh; break;
-               case HK_KUP:    ehk = cmul(ehk, eb); break;
-               case HK_KDOWN0: ehk = cmulc(eh, eb); break;
-               default:        ehk = cmulc(ehk, eb); break;
+         double2 ehk1[NS], ehk2[NS];
+#pragma unroll
+         for (int s = 0; s < NS; s++) {
+            switch (d1.code) {
+               case HK_NEWH:   if (d1.h > 0) eh[s] = cmul(eh[s], ea[s]); ehk[s] = eh[s]; break;
+               case HK_KUP:    ehk[s] = cmul(ehk[s], eb[s]); break;
+               case HK_KDOWN0: ehk[s] = cmulc(eh[s], eb[s]); break;
+               default:        ehk[s] = cmulc(ehk[s], eb[s]); break;
             }
+            ehk1[s] = ehk[s];
+            if (two) {
+               switch (d2.code) {
+                  case HK_NEWH:   if (d2.h > 0) eh[s] = cmul(eh[s], ea[s]); ehk[s] = eh[s]; break;
+                  case HK_KUP:    ehk[s] = cmul(ehk[s], eb[s]); break;
+                  case HK_KDOWN0: ehk[s] = cmulc(eh[s], eb[s]); break;
+                  default:        ehk[s] = cmulc(ehk[s], eb[s]); break;
+               }
+            }
+            ehk2[s] = ehk[s];
          }
-         ehk2 = ehk;
          const int nl1 = max(d1.nl, 0), nl2 = two ? max(d2.nl, 0) : 0;
          if (nl1 + nl2 == 0) continue;
          const double4 *cf1 = s_coef + 2 * (d1.slot0 - slot_lo);
          const double4 *cf2 = s_coef + 2 * (d2.slot0 - slot_lo);
-         double2 el = make_double2(q, 0.0);
-         double X1 = 0, Y1 = 0, Xz1 = 0, Yz1 = 0, X2 = 0, Y2 = 0, Xz2 = 0, Yz2 = 0;
+         double2 el[NS];
+         double X1[NS], Y1[NS], Xz1[NS], Yz1[NS], X2[NS], Y2[NS], Xz2[NS], Yz2[NS];
+#pragma unroll
+         for (int s = 0; s < NS; s++) {
+            el[s] = make_double2(q[s], 0.0);
+            X1[s] = Y1[s] = Xz1[s] = Yz1[s] = X2[s] = Y2[s] = Xz2[s] = Yz2[s] = 0.0;
+         }
          const int nj = min(nl1, nl2);
          int l = 0;
+#pragma unroll 2
          for (; l < nj; l++) {
             const double4 a1 = cf1[2 * l], b1 = cf1[2 * l + 1], a2 = cf2[2 * l], b2 = cf2[2 * l + 1];
-            X1 = fma(el.x, a1.x, fma(el.y, a1.w, X1));
-            Y1 = fma(el.y, a1.z, fma(-el.x, a1.y, Y1));
-            Xz1 = fma(el.x, b1.x, fma(el.y, b1.y, Xz1));
-            Yz1 = fma(el.y, b1.z, fma(-el.x, b1.w, Yz1));
-            X2 = fma(el.x, a2.x, fma(el.y, a2.w, X2));
-            Y2 = fma(el.y, a2.z, fma(-el.x, a2.y, Y2));
-            Xz2 = fma(el.x, b2.x, fma(el.y, b2.y, Xz2));
-            Yz2 = fma(el.y, b2.z, fma(-el.x, b2.w, Yz2));
-            el = cmul(el, ec);
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+               X1[s] = fma(el[s].x, a1.x, fma(el[s].y, a1.w, X1[s]));
+               Y1[s] = fma(el[s].y, a1.z, fma(-el[s].x, a1.y, Y1[s]));
+               Xz1[s] = fma(el[s].x, b1.x, fma(el[s].y, b1.y, Xz1[s]));
+               Yz1[s] = fma(el[s].y, b1.z, fma(-el[s].x, b1.w, Yz1[s]));
+               X2[s] = fma(el[s].x, a2.x, fma(el[s].y, a2.w, X2[s]));
+               Y2[s] = fma(el[s].y, a2.z, fma(-el[s].x, a2.y, Y2[s]));
+               Xz2[s] = fma(el[s].x, b2.x, fma(el[s].y, b2.y, Xz2[s]));
+               Yz2[s] = fma(el[s].y, b2.z, fma(-el[s].x, b2.w, Yz2[s]));
+               el[s] = cmul(el[s], ec[s]);
+            }
          }
          for (; l < nl1; l++) {
             const double4 a1 = cf1[2 * l], b1 = cf1[2 * l + 1];
-            X1 = fma(el.x, a1.x, fma(el.y, a1.w, X1));
-            Y1 = fma(el.y, a1.z, fma(-el.x, a1.y, Y1));
-            Xz1 = fma(el.x, b1.x, fma(el.y, b1.y, Xz1));
-            Yz1 = fma(el.y, b1.z, fma(-el.x, b1.w, Yz1));
-            el = cmul(el, ec);
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+               X1[s] = fma(el[s].x, a1.x, fma(el[s].y, a1.w, X1[s]));
+               Y1[s] = fma(el[s].y, a1.z, fma(-el[s].x, a1.y, Y1[s]));
+               Xz1[s] = fma(el[s].x, b1.x, fma(el[s].y, b1.y, Xz1[s]));
+               Yz1[s] = fma(el[s].y, b1.z, fma(-el[s].x, b1.w, Yz1[s]));
+               el[s] = cmul(el[s], ec[s]);
+            }
          }
          for (; l < nl2; l++) {
             const double4 a2 = cf2[2 * l], b2 = cf2[2 * l + 1];
-            X2 = fma(el.x, a2.x, fma(el.y, a2.w, X2));
-            Y2 = fma(el.y, a2.z, fma(-el.x, a2.y, Y2));
-            Xz2 = fma(el.x, b2.x, fma(el.y, b2.y, Xz2));
-            Yz2 = fma(el.y, b2.z, fma(-el.x, b2.w, Yz2));
-            el = cmul(el, ec);
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+               X2[s] = fma(el[s].x, a2.x, fma(el[s].y, a2.w, X2[s]));
+               Y2[s] = fma(el[s].y, a2.z, fma(-el[s].x, a2.y, Y2[s]));
+               Xz2[s] = fma(el[s].x, b2.x, fma(el[s].y, b2.y, Xz2[s]));
+               Yz2[s] = fma(el[s].y, b2.z, fma(-el[s].x, b2.w, Yz2[s]));
+               el[s] = cmul(el[s], ec[s]);
+            }
          }
-         if (nl1 > 0) {
-            const double T = fma(ehk1.y, X1, ehk1.x * Y1), Tz = fma(ehk1.y, Xz1, ehk1.x * Yz1);
-            fx = fma(d1.kx, T, fx);
-            fy = fma(d1.ky, T, fy);
-            fz = fma(d1.kzt, T, fma(K.cz2, Tz, fz));
-         }
-         if (nl2 > 0) {
-            const double T = fma(ehk2.y, X2, ehk2.x * Y2), Tz = fma(ehk2.y, Xz2, ehk2.x * Yz2);
-            fx = fma(d2.kx, T, fx);
-            fy = fma(d2.ky, T, fy);
-            fz = fma(d2.kzt, T, fma(K.cz2, Tz, fz));
+#pragma unroll
+         for (int s = 0; s < NS; s++) {
+            if (nl1 > 0) {
+               const double T = fma(ehk1[s].y, X1[s], ehk1[s].x * Y1[s]), Tz = fma(ehk1[s].y, Xz1[s], ehk1[s].x * Yz1[s]);
+               fx[s] = fma(d1.kx, T, fx[s]);
+               fy[s] = fma(d1.ky, T, fy[s]);
+               fz[s] = fma(d1.kzt, T, fma(K.cz2, Tz, fz[s]));
+            }
+            if (nl2 > 0) {
+               const double T = fma(ehk2[s].y, X2[s], ehk2[s].x * Y2[s]), Tz = fma(ehk2[s].y, Xz2[s], ehk2[s].x * Yz2[s]);
+               fx[s] = fma(d2.kx, T, fx[s]);
+               fy[s] = fma(d2.ky, T, fy[s]);
+               fz[s] = fma(d2.kzt, T, fma(K.cz2, Tz, fz[s]));
+            }
          }
       }
    }
-   if (active) {
-      out[i] += fx;
-      out[(size_t)K.nsites + i] += fy;
-      out[2 * (size_t)K.nsites + i] += fz;
-   }
+#pragma unroll
+   for (int s = 0; s < NS; s++)
+      if (active[s]) {
+         out[i[s]] += fx[s];
+         out[(size_t)K.nsites + i[s]] += fy[s];
+         out[2 * (size_t)K.nsites + i[s]] += fz[s];
+      }
 }
+
+#ifndef MDB_KF_NS
+#define MDB_KF_NS 2
+#endif
 
 // How one rank's share of the k-space work is cut.
 //  column mode (Moldy's own scheme, src/ewald.c:495-496): all sites x every P-th (h,k) column;
@@ -546,14 +587,14 @@ static int recip_finish(mdb_engine *e, const RecipPlan &P, const double *d_psum,
    const size_t kshm = sizeof(double4) * 2 * (size_t)Q.max_slots + sizeof(HkDesc) * (size_t)Q.hb;
    if (P.nf_hi > P.nf_lo) {
       Q.c0 = P.nf_lo; Q.c1 = P.nf_hi;
-      k_kforce<<<(Q.c1 - Q.c0 + KF - 1) / KF, KF, kshm, st>>>(Q, e->d_cidx, e->d_x, e->d_y, e->d_z, e->d_chg, e->d_hk,
-                                                             e->d_coef_tot, d_out);
+      k_kforce<MDB_KF_NS><<<(Q.c1 - Q.c0 + KF * MDB_KF_NS - 1) / (KF * MDB_KF_NS), KF, kshm, st>>>(
+         Q, e->d_cidx, e->d_x, e->d_y, e->d_z, e->d_chg, e->d_hk, e->d_coef_tot, d_out);
       e->launches++;
    }
    if (P.fw_hi > P.fw_lo) {
       Q.c0 = P.fw_lo; Q.c1 = P.fw_hi;
-      k_kforce<<<(Q.c1 - Q.c0 + KF - 1) / KF, KF, kshm, st>>>(Q, e->d_cidx, e->d_x, e->d_y, e->d_z, e->d_chg, e->d_hk,
-                                                             e->d_coef_nf, d_out);
+      k_kforce<MDB_KF_NS><<<(Q.c1 - Q.c0 + KF * MDB_KF_NS - 1) / (KF * MDB_KF_NS), KF, kshm, st>>>(
+         Q, e->d_cidx, e->d_x, e->d_y, e->d_z, e->d_chg, e->d_hk, e->d_coef_nf, d_out);
       e->launches++;
    }
    MDB_CUDA(cudaGetLastError());

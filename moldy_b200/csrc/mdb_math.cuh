@@ -32,6 +32,36 @@ __constant__ double c_exp[16] = {
    0.0, 0.0};
 __constant__ double c_as[6] = {0.254829592, -0.284496736, 1.421413741, -1.453152027, 1.061405429, 0.3275911};
 
+// Table-driven exp for the tiled pair kernel: x = n ln2/64 + r, exp(x) = 2^(n>>6) * 2^((n&63)/64) * e^r,
+// |r| <= ln2/128 so a degree-5 Taylor polynomial leaves r^6/720 < 3.5e-17.  10 FP64 ops instead of 15;
+// the 64-entry table is copied to shared memory by the kernel (one LDS.64 per evaluation).
+__constant__ double c_expt[8] = {
+   0x1.71547652b82fep+6,        // [0] 64 log2(e)
+   6755399441055744.0,          // [1] 1.5 * 2^52
+   -0x1.62e42fee00000p-7,       // [2] -ln2/64 (high part, 21 significant bits: n * hi is exact)
+   -0x1.a39ef35793c76p-39,      // [3] -ln2/64 (low part)
+   8.33333333333333333333e-03,  // [4] 1/5!
+   4.16666666666666666667e-02,  // [5] 1/4!
+   1.66666666666666666667e-01,  // [6] 1/3!
+   0.0};
+__constant__ double c_exp2tab[64] = {
+   0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
+   0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
+   0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+   0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
+   0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
+   0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+   0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
+   0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
+   0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+   0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
+   0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
+   0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+   0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
+   0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
+   0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+   0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
+
 // All helpers below work on NV independent values at once and are written
 // step-by-step across the NV lanes ("structure of arrays" in registers): ptxas keeps
 // that order, so the NV dependent DFMA chains are issued interleaved and the FP64
@@ -129,6 +159,54 @@ __device__ __forceinline__ void mdb_exp_v(const double (&x)[NV], double (&out)[N
 #endif
 }
 
+// exp(x) through the shared-memory copy of c_exp2tab at 32-bit shared address `e2s` (see c_expt).
+// x below -708 gives ~2^-1022 (the integer part is clamped) instead of 0: either vanishes in every sum.
+template <int NV>
+__device__ __forceinline__ void mdb_exp_tab_v(const double (&x)[NV], double (&out)[NV], unsigned e2s)
+{
+   double t[NV], r[NV], p[NV], T[NV];
+   int n[NV];
+#pragma unroll
+   MDB_V t[k] = fma(x[k], c_expt[0], c_expt[1]);
+#pragma unroll
+   MDB_V {
+      n[k] = max(__double2loint(t[k]), -65408);
+      asm("ld.shared.f64 %0, [%1];" : "=d"(T[k]) : "r"(e2s + (unsigned)(n[k] & 63) * 8u));
+   }
+#pragma unroll
+   MDB_V r[k] = t[k] - c_expt[1];
+#pragma unroll
+   MDB_V p[k] = fma(r[k], c_expt[2], x[k]);
+#pragma unroll
+   MDB_V r[k] = fma(r[k], c_expt[3], p[k]);
+#pragma unroll
+   MDB_V p[k] = fma(c_expt[4], r[k], c_expt[5]);
+#pragma unroll
+   MDB_V p[k] = fma(p[k], r[k], c_expt[6]);
+#pragma unroll
+   MDB_V p[k] = fma(p[k], r[k], 0.5);
+#pragma unroll
+   MDB_V p[k] = fma(p[k], r[k], 1.0);
+#pragma unroll
+   MDB_V p[k] = fma(p[k], r[k], 1.0);
+#pragma unroll
+   MDB_V p[k] = p[k] * T[k];
+#pragma unroll
+   MDB_V {
+      int hi;
+      asm("mad.lo.s32 %0, %1, 16384, %2;" : "=r"(hi) : "r"(n[k] & ~63), "r"(__double2hiint(p[k])));
+      out[k] = __hiloint2double(hi, __double2loint(p[k]));
+   }
+}
+
+// dispatch: TAB selects the table-driven exp (tiled pair kernel), otherwise the self-contained one
+template <int NV, bool TAB>
+__device__ __forceinline__ void mdb_exp_sel(const double (&x)[NV], double (&out)[NV], unsigned e2s)
+{
+   if constexpr (TAB) mdb_exp_tab_v<NV>(x, out, e2s);
+   else mdb_exp_v<NV>(x, out);
+}
+
 // ---- pair potentials --------------------------------------------------------
 // -phi'(r)/r and phi(r) for one site pair, the arithmetic of src/kernel.c:182-461
 // (one instantiation per potential type x {Coulomb on, off}; no run-time branch
@@ -140,11 +218,30 @@ enum { PT_LJ = 0, PT_E6 = 1, PT_MCY = 2, PT_GEN = 3, PT_HIW = 4, PT_RSV = 5, PT_
 
 struct PairOut { double fij, phi; };
 
+// A pair-parameter row either behind an ordinary pointer or at a 32-bit shared-memory address
+// (tiled pair kernel: the table lives in shared memory and is read with ld.shared + immediate offset).
+struct MdbSmemRow {
+   unsigned a;
+   __device__ __forceinline__ double operator[](int n) const
+   {
+      double v;
+      asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a + 8u * (unsigned)n));
+      return v;
+   }
+};
+__device__ __forceinline__ double2 mdb_row_ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ double2 mdb_row_ld2(MdbSmemRow r)
+{
+   double2 v;
+   asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(r.a));
+   return v;
+}
+
 // NV pairs at once: r2[k], qq[k] = q_i q_j, p[k] -> parameter row of the (type_i,type_j) entry.
-template <int PT, bool COUL, int NV>
+template <int PT, bool COUL, int NV, bool TAB = false, class ROW = const double *>
 __device__ __forceinline__ void mdb_pair_eval_v(const double (&r2)[NV], const double (&qq)[NV],
-                                                const double *const (&p)[NV], double alpha, double norm,
-                                                double (&fij)[NV], double (&phi)[NV])
+                                                const ROW (&p)[NV], double alpha, double norm,
+                                                double (&fij)[NV], double (&phi)[NV], unsigned e2s = 0)
 {
    double r_r[NV], r[NV], r_sqr_r[NV], erfc_term[NV], t[NV];
    if (COUL || PT != PT_LJ) {
@@ -168,7 +265,7 @@ __device__ __forceinline__ void mdb_pair_eval_v(const double (&r2)[NV], const do
 #pragma unroll
       MDB_V x[k] = na2 * r2[k];
       mdb_rcp_v<NV>(u, tt);
-      mdb_exp_v<NV>(x, e);
+      mdb_exp_sel<NV, TAB>(x, e, e2s);
 #pragma unroll
       MDB_V e[k] = qq[k] * e[k];
 #pragma unroll
@@ -191,7 +288,7 @@ __device__ __forceinline__ void mdb_pair_eval_v(const double (&r2)[NV], const do
       double2 p01[NV];
       double p2[NV];
 #pragma unroll
-      MDB_V { p01[k] = *reinterpret_cast<const double2 *>(p[k]); p2[k] = p[k][2]; }   // rows are 64-byte aligned
+      MDB_V { p01[k] = mdb_row_ld2(p[k]); p2[k] = p[k][2]; }   // rows are 64-byte aligned
 #pragma unroll
       MDB_V r6[k] = p01[k].y * r_sqr_r[k];
 #pragma unroll
@@ -206,7 +303,7 @@ __device__ __forceinline__ void mdb_pair_eval_v(const double (&r2)[NV], const do
       double x[NV], e1[NV], r6[NV];
 #pragma unroll
       MDB_V x[k] = -p[k][2] * r[k];
-      mdb_exp_v<NV>(x, e1);
+      mdb_exp_sel<NV, TAB>(x, e1, e2s);
 #pragma unroll
       MDB_V e1[k] = p[k][1] * e1[k];
 #pragma unroll
@@ -219,8 +316,8 @@ __device__ __forceinline__ void mdb_pair_eval_v(const double (&r2)[NV], const do
       double x1[NV], x2[NV], e1[NV], e2[NV];
 #pragma unroll
       MDB_V { x1[k] = -p[k][1] * r[k]; x2[k] = -p[k][3] * r[k]; }
-      mdb_exp_v<NV>(x1, e1);
-      mdb_exp_v<NV>(x2, e2);
+      mdb_exp_sel<NV, TAB>(x1, e1, e2s);
+      mdb_exp_sel<NV, TAB>(x2, e2, e2s);
 #pragma unroll
       MDB_V { e1[k] = p[k][0] * e1[k]; e2[k] = -p[k][2] * e2[k]; }
 #pragma unroll
@@ -231,7 +328,7 @@ __device__ __forceinline__ void mdb_pair_eval_v(const double (&r2)[NV], const do
       double x[NV], e1[NV];
 #pragma unroll
       MDB_V x[k] = -p[k][1] * r[k];
-      mdb_exp_v<NV>(x, e1);
+      mdb_exp_sel<NV, TAB>(x, e1, e2s);
 #pragma unroll
       MDB_V {
          e1[k] = p[k][0] * e1[k];
@@ -263,9 +360,9 @@ __device__ __forceinline__ void mdb_pair_eval_v(const double (&r2)[NV], const do
          x2[k] = -2.0 * p[k][5] * (r[k] - p[k][6]);
          x3[k] = -p[k][5] * (r[k] - p[k][6]);
       }
-      mdb_exp_v<NV>(x1, e1);
-      mdb_exp_v<NV>(x2, e2);
-      mdb_exp_v<NV>(x3, e3);
+      mdb_exp_sel<NV, TAB>(x1, e1, e2s);
+      mdb_exp_sel<NV, TAB>(x2, e2, e2s);
+      mdb_exp_sel<NV, TAB>(x3, e3, e2s);
 #pragma unroll
       MDB_V {
          e1[k] = p[k][0] * e1[k];

@@ -2,58 +2,85 @@
 //
 // Same pair set and arithmetic as k_pair (mdb_pair.cu), different mapping:
 //   * a WARP owns a batch of <= NI consecutive cell-sorted sites i of one z-column;
-//     their data and force accumulators are warp-uniform registers;
+//     their data sit in shared memory (re-read per use), their force accumulators in registers;
 //   * the 32 LANES own neighbour sites j.  For 64 stencil runs at a time the warp
 //     builds, in shared memory, the list of contiguous j-segments that the union of
 //     the batch's windows covers (cells are sorted z-fastest, so a run is one
 //     contiguous range per periodic piece), prefix-sums their lengths and walks the
 //     flattened list 32 sites per step: lanes are always full, control flow is
 //     warp-uniform, each j is loaded once and reused for the NI sites i;
-//   * a (i,j) visit is masked by the exact window test  dzlo <= cz_j - cz_i <= dzhi
-//     (the batch spans ~2 cells, so ~10 % of the lane-visits are masked off).
+//   * a (i,j) visit is masked by the exact window test  dzlo <= cz_j - cz_i <= dzhi,
+//     one unsigned compare per visit (the batch spans ~2 cells, ~10 % of the visits are masked).
 // mode 3 (full stencil): every reference pair is visited from both ends, forces are
 //   written by their owner only -> no atomics, bit-reproducible.
 // mode 4 (Newton-3): the reference's half list; the lane also accumulates the force
 //   on j over the NI visits and adds it to a cell-sorted accumulator with
-//   red.global.add.f64 (coalesced); results vary in the last bits run to run.
+//   red.global.add.f64 (coalesced); results vary in the last bits run to run.  The
+//   triangular part (own column, central image: j > i) is walked by a short prologue
+//   so that the main loop carries no index test.
+// COUNT instantiations run the same traversal and window tests without the arithmetic and only
+// count the visits: mdb_pair_count() (the number of pairs handed to kernel(), src/force.c:960).
+#include <type_traits>
 #include "mdb_internal.h"
 #include "mdb_math.cuh"
 
 #ifndef MDB_TILED_MINB
 #define MDB_TILED_MINB 3
 #endif
-#ifndef MDB_TILED_NV
-#define MDB_TILED_NV 4                 /* pair evaluations interleaved at a time (<= NI) */
-#endif
 static constexpr int TW = 4;                   // warps per block
 static constexpr int RB = 64;                  // stencil runs per shared-memory pass
 static constexpr int NSLOT = 3 * RB;           // segment slots per pass (3 periodic pieces per run)
 static constexpr int NI = MDB_NI;
 static constexpr int NRED = 8;
+static constexpr int BIGZ = 1 << 20;           // larger than any cell index / window offset
 
-struct SegTable {
-   int jstart[NSLOT];
-   int pre[NSLOT + 1];
-   int colbase[NSLOT];
-   int pack[NSLOT];                            // kimg | zoffidx<<5 | selfcol<<7 | (dzlo+512)<<8 | (dzhi+512)<<18
+// ---- shared-memory layout (dynamic, one block): every access goes through a 32-bit shared
+// address held in a register plus a compile-time offset, so the hot loop never re-derives a base.
+struct WarpSm {                                // per warp
+   int4 q[NSLOT];                              // {jstart - pre, dzlo - zoff, dzhi - dzlo, kimg | selfcol<<5}
+   int pre[NSLOT + 8];                         // running prefix of the segment lengths, INT_MAX sentinels behind
+   double4 ipos[NI];                           // batch sites: x,y,z,q  (warp-uniform, re-read per use to keep
+   int4 iint[NI];                              //   them out of registers): cz, row offset, framework flag, sorted index
 };
+static constexpr int OFF_Q = 0, OFF_PRE = OFF_Q + 16 * NSLOT, OFF_IPOS = OFF_PRE + 4 * (NSLOT + 8),
+                     OFF_IINT = OFF_IPOS + 32 * NI, WARP_SM = OFF_IINT + 16 * NI;
+static_assert(sizeof(WarpSm) == WARP_SM && WARP_SM % 16 == 0, "WarpSm layout");
+static constexpr int OFF_RELOC = TW * WARP_SM;           // double4[27]: image translations
+static constexpr int OFF_E2 = OFF_RELOC + 32 * 28;       // double[64]: 2^(j/64), mdb_exp_tab_v
+static constexpr int OFF_TAB = OFF_E2 + 8 * 64;          // pair-parameter table
+static constexpr size_t TILED_SMEM = OFF_TAB;
 
-// 32-byte / 16-byte shared-memory loads the compiler must re-issue at every use (asm volatile):
-// keeps the warp-uniform batch data out of the register file.
-__device__ __forceinline__ double4 lds_d4(const double4 *p)
+template <int OFF> __device__ __forceinline__ int lds_i(unsigned a)
 {
-   double4 v;
-   const unsigned a = (unsigned)__cvta_generic_to_shared(p);
-   asm volatile("ld.shared.v2.f64 {%0,%1}, [%4];\n\tld.shared.v2.f64 {%2,%3}, [%4+16];"
-                : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "r"(a));
+   int v;
+   asm volatile("ld.shared.s32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
    return v;
 }
-__device__ __forceinline__ int4 lds_i4(const int4 *p)
+template <int OFF> __device__ __forceinline__ int4 lds_i4(unsigned a)
 {
    int4 v;
-   const unsigned a = (unsigned)__cvta_generic_to_shared(p);
-   asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+   asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a), "n"(OFF));
    return v;
+}
+template <int OFF> __device__ __forceinline__ double4 lds_d4(unsigned a)
+{
+   double4 v;
+   asm volatile("ld.shared.v2.f64 {%0,%1}, [%4+%5];\n\tld.shared.v2.f64 {%2,%3}, [%4+%5+16];"
+                : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "r"(a), "n"(OFF));
+   return v;
+}
+template <int OFF> __device__ __forceinline__ void lds_d3(unsigned a, double &x, double &y, double &z)
+{
+   asm volatile("ld.shared.v2.f64 {%0,%1}, [%3+%4];\n\tld.shared.f64 %2, [%3+%4+16];"
+                : "=d"(x), "=d"(y), "=d"(z) : "r"(a), "n"(OFF));
+}
+template <int OFF> __device__ __forceinline__ void sts_i(unsigned a, int v)
+{
+   asm volatile("st.shared.s32 [%0+%1], %2;" :: "r"(a), "n"(OFF), "r"(v) : "memory");
+}
+template <int OFF> __device__ __forceinline__ void sts_i4(unsigned a, int4 v)
+{
+   asm volatile("st.shared.v4.s32 [%0+%1], {%2,%3,%4,%5};" :: "r"(a), "n"(OFF), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 __device__ __forceinline__ double wsum(double v)
@@ -63,67 +90,186 @@ __device__ __forceinline__ double wsum(double v)
    return v;
 }
 
-template <int PT, bool COUL, bool STRICT, bool FW, bool N3>
+struct JBuf {                                  // one lane's neighbour for one step (double-buffered)
+   double4 pj;
+   int2 sj;                                    // {type | framework bit, z index}
+   int j;
+   unsigned qa;                                // shared address of the segment's q entry
+};
+
+template <int PT, bool COUL, bool STRICT, bool FW, bool N3, bool COUNT>
 __global__ void __launch_bounds__(TW * 32, MDB_TILED_MINB)
-k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const int *__restrict__ stype,
-             const int *__restrict__ scell, const int *__restrict__ cstart, const int *__restrict__ order,
+k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const int2 *__restrict__ sinfo,
+             const int *__restrict__ cstart, const int *__restrict__ order,
              const int *__restrict__ mol, const StencilRun *__restrict__ runs, const double *__restrict__ ptab,
              const int2 *__restrict__ batches, const int *__restrict__ nbatch_p, int rank, int nranks,
-             int ptab_in_smem,
              double *__restrict__ out, double *__restrict__ fs, double *__restrict__ partials,
              unsigned long long *__restrict__ counters)
 {
-   __shared__ SegTable s_seg[TW];
-   __shared__ double s_reloc[27][3];
-   __shared__ double4 s_ipos[TW][NI];            // batch sites: x,y,z,q   (warp-uniform, re-read per use to
-   __shared__ int4 s_iint[TW][NI];               //              cz,type,framework,-   keep them out of registers)
-   extern __shared__ double s_ptab[];           // pair-parameter table (when it fits), else read through L1
+   extern __shared__ __align__(16) unsigned char smem_raw[];
    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-   for (int k = threadIdx.x; k < 81; k += TW * 32) s_reloc[k / 3][k % 3] = P.reloc[k / 3][k % 3];
-   const int ntab = P.max_id * P.max_id * MDB_NPOTP;
-   if (ptab_in_smem)
+   {
+      double4 *s_reloc = reinterpret_cast<double4 *>(smem_raw + OFF_RELOC);
+      double *s_e2 = reinterpret_cast<double *>(smem_raw + OFF_E2), *s_ptab = reinterpret_cast<double *>(smem_raw + OFF_TAB);
+      for (int k = threadIdx.x; k < 27; k += TW * 32) s_reloc[k] = make_double4(P.reloc[k][0], P.reloc[k][1], P.reloc[k][2], 0.0);
+      for (int k = threadIdx.x; k < 64; k += TW * 32) s_e2[k] = c_exp2tab[k];
+      const int ntab = P.max_id * P.max_id * MDB_NPOTP;
       for (int k = threadIdx.x; k < ntab; k += TW * 32) s_ptab[k] = ptab[k];
-   const double *__restrict__ tab = ptab_in_smem ? s_ptab : ptab;
+   }
    __syncthreads();
-   SegTable &S = s_seg[w];
+   // the two base addresses of the hot loop; passed through a shuffle so that they stay in registers
+   // (a plain symbol address is re-derived from SR_CgaCtaId at every use under register pressure)
+   const unsigned sb = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared(smem_raw), 0);
+   const unsigned sw = __shfl_sync(0xffffffffu, sb + w * WARP_SM, 0);
 
    const int nbatch = *nbatch_p;
    const long b_lo = (long)nbatch * rank / nranks, b_hi = (long)nbatch * (rank + 1) / nranks;
    const long b = b_lo + (long)blockIdx.x * TW + w;
    const size_t prow_id = (size_t)blockIdx.x * TW + w;
    if (b >= b_hi) {                             // whole warp idle: still publish a zero row
-      if (lane < 7) partials[prow_id * NRED + lane] = 0.0;
+      if (!COUNT && lane < 7) partials[prow_id * NRED + lane] = 0.0;
       return;
    }
-   const int2 bt = batches[b];
-   const int s0 = bt.x, cnt = bt.y;
+   const int2 bt = batches[b];                  // {first sorted site, count | column << 3}
+   const int s0 = bt.x, cnt = bt.y & 7, col = bt.y >> 3;
+   const int cx = col / P.ny, cy = col - cx * P.ny;
+   const int cz_lo = sinfo[s0].y, cz_hi = sinfo[s0 + cnt - 1].y;
 
    // ---- batch (warp-uniform) data
    double fix[NI], fiy[NI], fiz[NI];
-   int cx, cy, cz_lo, cz_hi;
-   {
-      const int c0 = scell[s0];
-      cz_lo = c0 % P.nz;
-      const int t = c0 / P.nz;
-      cy = t % P.ny; cx = t / P.ny;
-      cz_hi = scell[s0 + cnt - 1] % P.nz;
-   }
    if (lane < NI) {
       const int k = lane, sk = s0 + min(k, cnt - 1);
-      s_ipos[w][k] = posq[sk];
-      const int t = stype[sk];
-      // padded entries never pass the window test
-      s_iint[w][k] = make_int4(k < cnt ? scell[sk] % P.nz : (1 << 20), (t & 0x3fffffff) * P.max_id * MDB_NPOTP,
-                               t >> 30, k < cnt ? s0 + k : 0x7fffffff);
+      WarpSm *W = reinterpret_cast<WarpSm *>(smem_raw) + w;
+      W->ipos[k] = posq[sk];
+      const int2 si = sinfo[sk];
+      // padded entries never pass the window test; row offset in bytes from the table start
+      W->iint[k] = make_int4(k < cnt ? si.y : BIGZ, (si.x & 0x3fffffff) * P.max_id * (MDB_NPOTP * 8),
+                             si.x >> 30, k < cnt ? s0 + k : 0x7fffffff);
    }
 #pragma unroll
    for (int k = 0; k < NI; k++) fix[k] = fiy[k] = fiz[k] = 0.0;
    __syncwarp();
-   const double4 *ipos = s_ipos[w];
-   const int4 *iint = s_iint[w];
    double pe = 0, w00 = 0, w01 = 0, w02 = 0, w11 = 0, w12 = 0, w22 = 0;
    unsigned int visits = 0;
    const int nruns = P.nruns;
+
+   // ---- one step: lane's neighbour j against the NI batch sites --------------------------------
+   // u = cz_j - (dzlo - zoff) (or a value no window accepts for padding lanes), wid = dzhi - dzlo:
+   // the visit (i,j) is inside the stencil run iff (unsigned)(u - cz_i) <= wid.
+   auto step = [&](auto selft_tag, const JBuf &J, const bool valid) {
+      constexpr bool SELFT = decltype(selft_tag)::value;
+      const int4 sq = lds_i4<OFF_Q>(J.qa);
+      const int j = J.j, wid = sq.z;
+      const int u = valid ? J.sj.y - sq.y : 3 * BIGZ;
+      const int kimg = sq.w & 31;
+      const int fwj = J.sj.x >> 30;
+      const unsigned tjb = sb + OFF_TAB + (unsigned)(J.sj.x & 0x3fffffff) * (MDB_NPOTP * 8);
+      // mode 3: j == s_i can only happen in the own column's central image
+      const int jself = N3 ? j : (sq.w == (13 | 32) ? j : -1);
+      bool in[NI];
+      if (COUNT) {
+#pragma unroll
+         for (int k = 0; k < NI; k++) {
+            const int4 ik = k == 0 ? lds_i4<OFF_IINT>(sw) : k == 1 ? lds_i4<OFF_IINT + 16>(sw)
+                          : k == 2 ? lds_i4<OFF_IINT + 32>(sw) : lds_i4<OFF_IINT + 48>(sw);
+            in[k] = (unsigned)(u - ik.x) <= (unsigned)wid;
+            if (SELFT) in[k] = in[k] && (N3 ? jself > ik.w : jself != ik.w);
+            if (FW) in[k] = in[k] && !(ik.z & fwj);
+            visits += in[k] ? 1u : 0u;
+         }
+         return;
+      }
+      double4 pj = J.pj;
+      double rlx, rly, rlz;
+      lds_d3<OFF_RELOC>(sb + 32 * kimg, rlx, rly, rlz);
+      pj.x += rlx; pj.y += rly; pj.z += rlz;
+      double gx = 0, gy = 0, gz = 0;
+      double dx[NI], dy[NI], dzz[NI], r2[NI], qq[NI], fij[NI], phi[NI];
+      MdbSmemRow prow[NI];
+#pragma unroll
+      for (int k = 0; k < NI; k++) {
+         const double4 pi = k == 0 ? lds_d4<OFF_IPOS>(sw) : k == 1 ? lds_d4<OFF_IPOS + 32>(sw)
+                          : k == 2 ? lds_d4<OFF_IPOS + 64>(sw) : lds_d4<OFF_IPOS + 96>(sw);
+         const int4 ik = k == 0 ? lds_i4<OFF_IINT>(sw) : k == 1 ? lds_i4<OFF_IINT + 16>(sw)
+                       : k == 2 ? lds_i4<OFF_IINT + 32>(sw) : lds_i4<OFF_IINT + 48>(sw);
+         in[k] = (unsigned)(u - ik.x) <= (unsigned)wid;
+         if (SELFT) in[k] = in[k] && (N3 ? jself > ik.w : jself != ik.w);
+         if (FW) in[k] = in[k] && !(ik.z & fwj);
+         dx[k] = pj.x - pi.x; dy[k] = pj.y - pi.y; dzz[k] = pj.z - pi.z;
+         qq[k] = pi.w * pj.w;
+         prow[k].a = tjb + (unsigned)ik.y;
+      }
+#pragma unroll
+      for (int k = 0; k < NI; k++) r2[k] = fma(dx[k], dx[k], fma(dy[k], dy[k], dzz[k] * dzz[k]));
+      int r2min = __double2hiint(r2[0]);
+#pragma unroll
+      for (int k = 1; k < NI; k++) r2min = min(r2min, __double2hiint(r2[k]));
+      int close = 0;
+      if (r2min < 0x3fd00000) {                 // some r^2 < 0.25 in this step (rare): look closer
+#pragma unroll
+         for (int k = 0; k < NI; k++) close |= (in[k] && r2[k] < MDB_TOO_CLOSE) ? (1 << k) : 0;
+      }
+      if (STRICT) {
+#pragma unroll
+         for (int k = 0; k < NI; k++) r2[k] = r2[k] > P.cutoffsq ? P.cutoff100sq : r2[k];
+      }
+#ifdef MDB_EXP_NOMATH                           /* experiment: traversal + accumulation without the pair arithmetic */
+#pragma unroll
+      for (int k = 0; k < NI; k++) { fij[k] = r2[k] * prow[k][0]; phi[k] = qq[k]; }
+#else
+      mdb_pair_eval_v<PT, COUL, NI, true>(r2, qq, prow, P.alpha, P.norm, fij, phi, sb + OFF_E2);
+#endif
+#pragma unroll
+      for (int k = 0; k < NI; k++) {
+         if (in[k]) {                         // predicated FP64 accumulation, no selects
+            const double f = fij[k];
+            pe += phi[k];
+            fix[k] = fma(-f, dx[k], fix[k]); fiy[k] = fma(-f, dy[k], fiy[k]); fiz[k] = fma(-f, dzz[k], fiz[k]);
+            gx = fma(f, dx[k], gx); gy = fma(f, dy[k], gy); gz = fma(f, dzz[k], gz);
+         }
+      }
+      if (close) {                           // TOO_CLOSE diagnostics, off the hot path (src/force.c:939-949)
+         const int mj = mol[order[j]];
+         for (int k = 0; k < NI; k++)
+            if (((close >> k) & 1) && mol[order[s0 + k]] != mj) {
+               atomicAdd(&counters[1], N3 ? 2ULL : 1ULL);
+               counters[3] = ((unsigned long long)(unsigned)order[s0 + k] << 32) | (unsigned)order[j];
+            }
+      }
+#ifdef MDB_EXP_NORED                            /* experiment: no scatter of the force on j */
+      pe += gx + gy + gz;
+#else
+      if (N3) {
+         if (valid) {
+            atomicAdd(&fs[j], gx);
+            atomicAdd(&fs[(size_t)nsites + j], gy);
+            atomicAdd(&fs[2 * (size_t)nsites + j], gz);
+         }
+      }
+#endif
+      if (kimg != 13) {                      // Bekker image-force virial (src/force.c:983-991)
+         const double sc = N3 ? 1.0 : 0.5;
+         const double rx = sc * rlx, ry = sc * rly, rz = sc * rlz;
+         w00 = fma(rx, gx, w00); w01 = fma(ry, gx, w01); w02 = fma(rz, gx, w02);
+         w11 = fma(ry, gy, w11); w12 = fma(rz, gy, w12); w22 = fma(rz, gz, w22);
+      }
+   };
+
+   // ---- Newton-3 prologue: own column, central image, j > s_i (run 0 of the half list starts at dz = 0)
+   if (N3) {
+      const StencilRun r0 = runs[0];
+      const int jb = s0 + 1, je = cstart[col * P.nz + min(cz_hi + r0.dzhi, P.nz - 1) + 1];
+      if (lane == 0) sts_i4<OFF_Q>(sw, make_int4(0, -BIGZ, r0.dzhi + BIGZ, 13 | 32));
+      __syncwarp();
+      for (int pj = jb + lane; pj - lane < je; pj += 32) {
+         JBuf J;
+         J.j = min(pj, je - 1);
+         J.sj = sinfo[J.j];
+         J.pj = posq[J.j];
+         J.qa = sw;
+         step(std::true_type{}, J, pj < je);
+      }
+   }
 
    for (int rb = 0; rb < nruns; rb += RB) {
       // ---- segment table for runs rb .. rb+RB-1: lane handles runs rb+lane and rb+32+lane
@@ -132,24 +278,25 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
 #pragma unroll
       for (int hh = 0; hh < RB / 32; hh++) {
          const int lr = hh * 32 + lane, r = rb + lr;
-         int cnt3[3] = {0, 0, 0}, js3[3] = {0, 0, 0}, pk3[3] = {0, 0, 0}, colb = 0;
+         int cnt3[3] = {0, 0, 0}, js3[3] = {0, 0, 0}, img3[3] = {0, 0, 0}, dzlo = 0, dzw = 0;
          if (r < nruns) {
             const StencilRun run = runs[r];
             int tx = cx + run.dx, ty = cy + run.dy, ii = 0, jj = 0;
             if (tx < 0) { tx += P.nx; ii = -1; } else if (tx >= P.nx) { tx -= P.nx; ii = 1; }
             if (ty < 0) { ty += P.ny; jj = -1; } else if (ty >= P.ny) { ty -= P.ny; jj = 1; }
-            colb = (tx * P.ny + ty) * P.nz;
+            const int colb = (tx * P.ny + ty) * P.nz;
             const int z0 = cz_lo + run.dzlo, z1 = cz_hi + run.dzhi;
             const int selfcol = (run.dx == 0 && run.dy == 0) ? 1 : 0;
+            dzlo = run.dzlo; dzw = run.dzhi - run.dzlo;
 #pragma unroll
             for (int kk = -1; kk <= 1; kk++) {
                const int zoff = kk * P.nz;
                const int a = max(z0, zoff), bb = min(z1, zoff + P.nz - 1);
-               if (a <= bb) {
+               // Newton-3: the central piece of run 0 is the prologue's
+               if (a <= bb && !(N3 && r == 0 && kk == 0)) {
                   const int jb = cstart[colb + a - zoff], jn = cstart[colb + bb - zoff + 1];
                   js3[kk + 1] = jb; cnt3[kk + 1] = jn - jb;
-                  pk3[kk + 1] = (9 * (ii + 1) + 3 * (jj + 1) + (kk + 1)) | ((kk + 1) << 5) | (selfcol << 7) |
-                                ((run.dzlo + 512) << 8) | ((run.dzhi + 512) << 18);
+                  img3[kk + 1] = (9 * (ii + 1) + 3 * (jj + 1) + (kk + 1)) | (selfcol << 5);
                }
             }
          }
@@ -166,148 +313,55 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
 #pragma unroll
          for (int q = 0; q < 3; q++)
             if (cnt3[q] > 0) {
-               S.jstart[slot] = js3[q]; S.colbase[slot] = colb; S.pack[slot] = pk3[q];
-               S.pre[slot] = base;
+               sts_i4<OFF_Q>(sw + 16 * slot, make_int4(js3[q] - base, dzlo - (q - 1) * P.nz, dzw, img3[q]));
+               sts_i<OFF_PRE>(sw + 4 * slot, base);
                base += cnt3[q];
                slot++;
             }
          total += __shfl_sync(0xffffffffu, inc, 31);
          nseg += __shfl_sync(0xffffffffu, ninc, 31);
       }
-      if (lane == 0) S.pre[nseg] = total;
+      if (lane < 4) sts_i<OFF_PRE>(sw + 4 * (nseg + lane), lane == 0 ? total : 0x7fffffff);
       __syncwarp();
 
-      // ---- walk the flattened j list, 32 sites per step; the loads of step n+1 are
-      // issued before the arithmetic of step n (uniform control flow makes this free)
-      int seg = 0;
-      int n_j = s0, n_pk = 13, n_tj = 0, n_cz = 0;
-      double4 n_pj = make_double4(0, 0, 0, 0);
-      bool n_valid = false;
-      auto fetch = [&](int base) {
-         const int p = base + lane;
-         n_valid = p < total;
-         const int pp = n_valid ? p : total - 1;
-         while (pp >= S.pre[seg + 1]) seg++;
-         n_j = S.jstart[seg] + (pp - S.pre[seg]);
-         n_pk = S.pack[seg];
-         n_pj = posq[n_j];
-         n_tj = stype[n_j];
-         n_cz = scell[n_j] - S.colbase[seg];
+      // ---- walk the flattened j list, 32 sites per step: the loads of step n+1 are issued
+      // before the arithmetic of step n (uniform control flow makes this free)
+      unsigned sega = sw;                       // address of this lane's current segment: pre[seg] at sega + OFF_PRE
+      auto fetch = [&](int p, JBuf &J) {
+         const int pp = min(p, total - 1);
+         const int a1 = lds_i<OFF_PRE + 4>(sega), a2 = lds_i<OFF_PRE + 8>(sega);   // mostly 0..2 boundaries per step
+         sega += (pp >= a1 ? 4u : 0u) + (pp >= a2 ? 4u : 0u);
+         while (pp >= lds_i<OFF_PRE + 4>(sega)) sega += 4;
+         J.qa = sw + 4 * (sega - sw);
+         J.j = lds_i<OFF_Q>(J.qa) + pp;
+#ifdef MDB_EXP_NOFETCH                          /* experiment: no per-step global loads */
+         J.pj = make_double4(0.37 * J.j, 1.1 * lane, 3.0, 0.4); J.sj = make_int2(lane & 3, cz_lo);
+#else
+         J.pj = posq[J.j];
+         J.sj = sinfo[J.j];
+#endif
       };
-      if (total > 0) fetch(0);
-      for (int base = 0; base < total; base += 32) {
-         const bool valid = n_valid;
-         const int j = n_j, pk = n_pk;
-         double4 pj = n_pj;
-         int tj = n_tj;
-         const int kimg = pk & 31;
-         const int dzlo = ((pk >> 8) & 1023) - 512, dzhi = ((pk >> 18) & 1023) - 512;
-         const int zj = n_cz + (((pk >> 5) & 3) - 1) * P.nz;
-         if (base + 32 < total) fetch(base + 32);
-         const int fwj = tj >> 30;
-         tj &= 0x3fffffff;
-         pj.x += s_reloc[kimg][0]; pj.y += s_reloc[kimg][1]; pj.z += s_reloc[kimg][2];
-         const bool central = kimg == 13;
-         const bool samecol = central && ((pk >> 7) & 1);
-         // window test per visit: dzlo_e <= cz_j - cz_i <= dzhi_e  and  jcut > s_i, where
-         //  * invalid (padding) lanes get an empty window,
-         //  * full stencil: jcut = j only in the central image, and j == s_i is the self pair;
-         //    written as (jcut - s_i) != 0 through jself,
-         //  * Newton-3: in the reference cell's own column the window starts at the cell itself
-         //    (dzlo = 0) and "same cell, j <= s_i" is excluded, which is exactly j > s_i.
-         const int dzhi_e = valid ? dzhi : -(1 << 28);
-         const int dzlo_e = (N3 && samecol) ? -(1 << 28) : dzlo;
-         const int jcut = N3 ? (samecol ? j : 0x7fffffff) : (central ? j : -1);
-         const int tjoff = tj * MDB_NPOTP;
-         double gx = 0, gy = 0, gz = 0;
-         double dx[NI], dy[NI], dzz[NI], r2[NI], qq[NI], fij[NI], phi[NI];
-         const double *prow[NI];
-         bool in[NI];
-#pragma unroll
-         for (int k = 0; k < NI; k++) {
-            const double4 pi = lds_d4(&ipos[k]);
-            const int4 ik = lds_i4(&iint[k]);          // cz, type row offset, framework flag, sorted index
-            const int dz = zj - ik.x;
-            in[k] = dz >= dzlo_e && dz <= dzhi_e && (N3 ? jcut > ik.w : jcut != ik.w);
-            if (FW) in[k] = in[k] && !(ik.z & fwj);
-            dx[k] = pj.x - pi.x; dy[k] = pj.y - pi.y; dzz[k] = pj.z - pi.z;
-            qq[k] = pi.w * pj.w;
-#ifdef MDB_EXP_NOPARAM
-            prow[k] = tab;
-#else
-            prow[k] = tab + (ik.y + tjoff);
-#endif
-         }
-#pragma unroll
-         for (int k = 0; k < NI; k++) r2[k] = fma(dx[k], dx[k], fma(dy[k], dy[k], dzz[k] * dzz[k]));
-         int r2min = __double2hiint(r2[0]);
-#pragma unroll
-         for (int k = 1; k < NI; k++) r2min = min(r2min, __double2hiint(r2[k]));
-         int close = 0;
-         if (r2min < 0x3fd00000) {                 // some r^2 < 0.25 in this step (rare): look closer
-#pragma unroll
-            for (int k = 0; k < NI; k++) close |= (in[k] && r2[k] < MDB_TOO_CLOSE) ? (1 << k) : 0;
-         }
-         if (STRICT) {
-#pragma unroll
-            for (int k = 0; k < NI; k++) r2[k] = r2[k] > P.cutoffsq ? P.cutoff100sq : r2[k];
-         }
-#ifdef MDB_EXP_NOMATH
-#pragma unroll
-         for (int k = 0; k < NI; k++) { fij[k] = r2[k] * prow[k][0]; phi[k] = qq[k]; }
-#elif MDB_TILED_NV >= MDB_NI
-         mdb_pair_eval_v<PT, COUL, NI>(r2, qq, prow, P.alpha, P.norm, fij, phi);
-#else
-#pragma unroll
-         for (int g = 0; g < NI; g += MDB_TILED_NV) {          // NV visits in flight at a time
-            double r2g[MDB_TILED_NV], qqg[MDB_TILED_NV], fg[MDB_TILED_NV], pg[MDB_TILED_NV];
-            const double *prg[MDB_TILED_NV];
-#pragma unroll
-            for (int k = 0; k < MDB_TILED_NV; k++) { r2g[k] = r2[g + k]; qqg[k] = qq[g + k]; prg[k] = prow[g + k]; }
-            mdb_pair_eval_v<PT, COUL, MDB_TILED_NV>(r2g, qqg, prg, P.alpha, P.norm, fg, pg);
-#pragma unroll
-            for (int k = 0; k < MDB_TILED_NV; k++) { fij[g + k] = fg[k]; phi[g + k] = pg[k]; }
-         }
-#endif
-#pragma unroll
-         for (int k = 0; k < NI; k++) {
-            if (in[k]) {                         // predicated FP64 accumulation, no selects
-               const double f = fij[k];
-               pe += phi[k];
-               visits++;
-               fix[k] = fma(-f, dx[k], fix[k]); fiy[k] = fma(-f, dy[k], fiy[k]); fiz[k] = fma(-f, dzz[k], fiz[k]);
-               gx = fma(f, dx[k], gx); gy = fma(f, dy[k], gy); gz = fma(f, dzz[k], gz);
-            }
-         }
-         if (close) {                           // TOO_CLOSE diagnostics, off the hot path (src/force.c:939-949)
-            const int mj = mol[order[j]];
-            for (int k = 0; k < NI; k++)
-               if (((close >> k) & 1) && mol[order[s0 + k]] != mj) {
-                  atomicAdd(&counters[1], N3 ? 2ULL : 1ULL);
-                  counters[3] = ((unsigned long long)(unsigned)order[s0 + k] << 32) | (unsigned)order[j];
-               }
-         }
-#ifndef MDB_EXP_NORED
-         if (N3) {
-            if (valid) {
-               atomicAdd(&fs[j], gx);
-               atomicAdd(&fs[(size_t)nsites + j], gy);
-               atomicAdd(&fs[2 * (size_t)nsites + j], gz);
-            }
-         }
-#else
-         pe += gx + gy + gz;
-#endif
-         if (!central) {                        // Bekker image-force virial (src/force.c:983-991)
-            const double sc = N3 ? 1.0 : 0.5;
-            const double rx = sc * s_reloc[kimg][0], ry = sc * s_reloc[kimg][1], rz = sc * s_reloc[kimg][2];
-            w00 = fma(rx, gx, w00); w01 = fma(ry, gx, w01); w02 = fma(rz, gx, w02);
-            w11 = fma(ry, gy, w11); w12 = fma(rz, gy, w12); w22 = fma(rz, gz, w22);
-         }
+      JBuf A, B;
+      int pl = lane;                            // this lane's position in the flattened list (step of A)
+      if (total > 0) fetch(pl, A);
+      // (a two-step unrolled ping-pong of A/B measured 10 % slower: spills and a 17 KB loop body)
+      for (int base = 0; base < total; base += 32, pl += 32) {
+         B = A;
+         if (base + 32 < total) fetch(pl + 32, A);
+         step(std::integral_constant<bool, !N3>{}, B, pl < total);
       }
    }
 
+   if (COUNT) {
+      unsigned int vs = visits;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) vs += __shfl_xor_sync(0xffffffffu, vs, d);
+      if (lane == 0) atomicAdd(&counters[0], (unsigned long long)vs * (N3 ? 2ULL : 1ULL));
+      return;
+   }
+
    // ---- forces on the batch sites: reduce the per-lane partial sums
+   const WarpSm *W = reinterpret_cast<const WarpSm *>(smem_raw) + w;
 #pragma unroll
    for (int k = 0; k < NI; k++) {
       const double fx = wsum(fix[k]), fy = wsum(fiy[k]), fz = wsum(fiz[k]);
@@ -321,7 +375,7 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
             out[o] += fx;
             out[(size_t)nsites + o] += fy;
             out[2 * (size_t)nsites + o] += fz;
-            const double4 pk4 = lds_d4(&ipos[k]);
+            const double4 pk4 = W->ipos[k];
             const double px = pk4.x, py = pk4.y, pz = pk4.z;
             w00 = fma(px, fx, w00); w01 = fma(py, fx, w01); w02 = fma(pz, fx, w02);
             w11 = fma(py, fy, w11); w12 = fma(pz, fy, w12); w22 = fma(pz, fz, w22);
@@ -334,10 +388,6 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
       const double t = wsum(v[k]);
       if (lane == 0) partials[prow_id * NRED + k] = t;
    }
-   unsigned int vs = visits;
-#pragma unroll
-   for (int d = 16; d > 0; d >>= 1) vs += __shfl_xor_sync(0xffffffffu, vs, d);
-   if (lane == 0) atomicAdd(&counters[0], (unsigned long long)vs * (N3 ? 2ULL : 1ULL));
 }
 
 // Newton-3 mode: move the cell-sorted accumulator back to the caller's site order and add the
@@ -419,19 +469,17 @@ __global__ void __launch_bounds__(RS1) k_rows_finish(const double *__restrict__ 
    }
 }
 
-#define TILED_ARGS P, c.nsites, e->d_posq, e->d_stype, e->d_scell, e->d_start, e->d_order, e->d_mol, runs, e->d_ptab, \
-                   e->d_batches, e->d_nbatch, e->ithread, e->nthreads, tab_smem, d_out, e->d_fs, e->d_partials, e->d_counters
+#define TILED_ARGS P, c.nsites, e->d_posq, e->d_sinfo, e->d_start, e->d_order, e->d_mol, runs, e->d_ptab, \
+                   e->d_batches, e->d_nbatch, e->ithread, e->nthreads, d_out, e->d_fs, e->d_partials, e->d_counters
 
-template <int PT, bool COUL>
+template <int PT, bool COUL, bool COUNT>
 static void launch_tiled(bool strict, bool fw, bool n3, dim3 g, cudaStream_t st, PairParams &P, mdb_engine *e,
                          const StencilRun *runs, double *d_out)
 {
    const mdb_config &c = e->cfg;
-   const size_t tab_bytes = sizeof(double) * MDB_NPOTP * (size_t)c.max_id * c.max_id;
-   const int tab_smem = tab_bytes <= 24576 ? 1 : 0;
-   const size_t shm = tab_smem ? tab_bytes : 0;
-#define GO(S, F, N) k_pair_tiled<PT, COUL, S, F, N><<<g, TW * 32, shm, st>>>(TILED_ARGS)
-   if (strict) {
+   const size_t shm = TILED_SMEM + sizeof(double) * MDB_NPOTP * (size_t)c.max_id * c.max_id;
+#define GO(S, F, N) k_pair_tiled<PT, COUL, S, F, N, COUNT><<<g, TW * 32, shm, st>>>(TILED_ARGS)
+   if (strict && !COUNT) {
       if (fw) { if (n3) GO(true, true, true); else GO(true, true, false); }
       else    { if (n3) GO(true, false, true); else GO(true, false, false); }
    } else {
@@ -441,14 +489,12 @@ static void launch_tiled(bool strict, bool fw, bool n3, dim3 g, cudaStream_t st,
 #undef GO
 }
 
-int mdb_launch_pair_tiled(mdb_engine *e, double *d_out, cudaStream_t st)
+static void tiled_params(mdb_engine *e, bool n3, PairParams &P, const StencilRun *&runs, int &nblocks)
 {
    const mdb_config &c = e->cfg;
-   const bool n3 = e->pair_mode == 4;
-   PairParams P;
    P.nx = e->T.nx; P.ny = e->T.ny; P.nz = e->T.nz;
    P.nruns = n3 ? e->nruns_half : e->nruns;
-   const StencilRun *runs = n3 ? e->d_runs_half : e->d_runs;
+   runs = n3 ? e->d_runs_half : e->d_runs;
    for (int k = 0; k < 27; k++)
       for (int a = 0; a < 3; a++) P.reloc[k][a] = e->T.reloc[k][a];
    P.alpha = c.alpha;
@@ -461,7 +507,33 @@ int mdb_launch_pair_tiled(mdb_engine *e, double *d_out, cudaStream_t st)
    // upper bound on this rank's batches (the exact count lives on the device)
    const long nb_max = (long)c.nsites / NI + (long)e->T.nx * e->T.ny + 1;
    const int my_max = (int)((nb_max + e->nthreads - 1) / e->nthreads) + 1;
-   const int nblocks = (my_max + TW - 1) / TW;
+   nblocks = (my_max + TW - 1) / TW;
+}
+
+// pairs handed to kernel() for the current cells: the traversal of the force kernel without its arithmetic
+int mdb_launch_pair_count_tiled(mdb_engine *e, cudaStream_t st)
+{
+   const mdb_config &c = e->cfg;
+   const bool n3 = e->pair_mode == 4, fw = c.nsites_xf < c.nsites;
+   PairParams P;
+   const StencilRun *runs;
+   int nblocks;
+   tiled_params(e, n3, P, runs, nblocks);
+   double *d_out = nullptr;
+   launch_tiled<PT_LJ, false, true>(false, fw, n3, dim3(nblocks), st, P, e, runs, d_out);
+   e->launches += 1;
+   MDB_CUDA(cudaGetLastError());
+   return 0;
+}
+
+int mdb_launch_pair_tiled(mdb_engine *e, double *d_out, cudaStream_t st)
+{
+   const mdb_config &c = e->cfg;
+   const bool n3 = e->pair_mode == 4;
+   PairParams P;
+   const StencilRun *runs;
+   int nblocks;
+   tiled_params(e, n3, P, runs, nblocks);
    const int nrows_pair = nblocks * TW;
    const int nblocks_u = (c.nsites + 255) / 256;
    const int nrows = nrows_pair + (n3 ? nblocks_u : 0);
@@ -473,10 +545,13 @@ int mdb_launch_pair_tiled(mdb_engine *e, double *d_out, cudaStream_t st)
    if (n3) MDB_CUDA(cudaMemsetAsync(e->d_fs, 0, sizeof(double) * 3 * (size_t)c.nsites, st));
    const bool coul = c.alpha > 0.0, strict = c.strict_cutoff != 0 && !c.molpbc, fw = c.nsites_xf < c.nsites;   // src/force.c:951
    dim3 g(nblocks);
-#define PT_CASE(X) case X: if (coul) launch_tiled<X, true>(strict, fw, n3, g, st, P, e, runs, d_out); \
-                           else launch_tiled<X, false>(strict, fw, n3, g, st, P, e, runs, d_out); break
+#define PT_CASE(X) case X: if (coul) launch_tiled<X, true, false>(strict, fw, n3, g, st, P, e, runs, d_out); \
+                           else launch_tiled<X, false, false>(strict, fw, n3, g, st, P, e, runs, d_out); break
    switch (c.ptype) {
-      PT_CASE(PT_LJ); PT_CASE(PT_E6); PT_CASE(PT_MCY); PT_CASE(PT_GEN); PT_CASE(PT_HIW); PT_CASE(PT_MOR);
+      PT_CASE(PT_LJ);
+#ifndef MDB_DEV_LJ_ONLY
+      PT_CASE(PT_E6); PT_CASE(PT_MCY); PT_CASE(PT_GEN); PT_CASE(PT_HIW); PT_CASE(PT_MOR);
+#endif
       default:
          mdb_set_error("KERNEL called with unknown potential type");
          return -1;
