@@ -220,6 +220,15 @@ size_t mdb_recip_sum_doubles(const mdb_engine *e);
 int  mdb_recip_partial(mdb_engine *e, double *d_psum, void *stream);
 int  mdb_recip_finish(mdb_engine *e, const double *d_psum, double *d_out, void *stream);
 
+/* RDF binning pass of force_calc (src/force.c:1302-1313: rdf_inner over the strict neighbour list of
+ * radius `limit`, rdf_accum src/rdf.c:94-108).  h_counts[pair][bin] += number of site pairs (this
+ * rank's share) with bin = (int)(nbins/limit * r) < nbins; pair = (idi <= idj), idi = 1..max_id-1, in
+ * the order init_rdf lays the histograms out (src/rdf.c:82-90); mdb_rdf_size() entries.  force_calc()
+ * of layer (A) adds count/density to the host program's array (rdf_ptr(), src/rdf.c:60-64). */
+size_t mdb_rdf_size(const mdb_engine *e, int nbins);
+int  mdb_rdf_counts(mdb_engine *e, double limit, int nbins, unsigned long long *h_counts, void *stream);
+void mdb_rdf_private_resize(int n);      /* host is not Moldy: size (and clear) the fall-back store rdf_ptr() returns */
+
 /* Device->host copy of a result block (synchronises `stream`). */
 int  mdb_read_out(mdb_engine *e, const double *d_out, double *h_out, void *stream);
 

@@ -49,6 +49,7 @@ static void free_grid(mdb_engine *e)
 {
    FREE(e->d_count); FREE(e->d_start); FREE(e->d_scan_tmp); FREE(e->d_runs); FREE(e->d_runs_half);
    FREE(e->d_batches); FREE(e->d_nbatch); e->batch_cap = 0;
+   FREE(e->d_runs_rdf); e->rdf_limit = -1.0;
    e->cells_cap = 0;
 }
 static void free_recip(mdb_engine *e)
@@ -64,7 +65,7 @@ extern "C" void mdb_destroy(mdb_engine *e)
    if (!e) return;
    cudaSetDevice(e->device);
    free_system(e); free_grid(e); free_recip(e);
-   FREE(e->d_partials); FREE(e->d_counters); FREE(e->d_out_own);
+   FREE(e->d_partials); FREE(e->d_counters); FREE(e->d_out_own); FREE(e->d_rdf);
    if (e->h_stage) cudaFreeHost(e->h_stage);
    delete e;
 }
@@ -349,6 +350,49 @@ extern "C" double mdb_pair_count(mdb_engine *e, void *stream)
    cudaMemcpyAsync(e->d_counters, &z, sizeof z, cudaMemcpyHostToDevice, st);
    cudaStreamSynchronize(st);
    return 0.5 * (double)c[0] / evals;
+}
+
+// RDF binning pass of force_calc (src/force.c:1302-1313, rdf_inner + rdf_accum): h_counts[pair][bin] +=
+// number of site pairs of this rank's share whose distance falls into the bin, pair = (idi <= idj)
+// in the order of init_rdf (src/rdf.c:82-90), nbins bins of width limit/nbins.
+extern "C" size_t mdb_rdf_size(const mdb_engine *e, int nbins)
+{
+   return (size_t)nbins * (e->cfg.max_id * (e->cfg.max_id - 1) / 2);
+}
+extern "C" int mdb_rdf_counts(mdb_engine *e, double limit, int nbins, unsigned long long *h_counts, void *stream)
+{
+   cudaStream_t st = (cudaStream_t)stream;
+   if (!e->configured || !e->sites_set) { mdb_set_error("mdb_rdf_counts: engine not configured / no sites"); return -1; }
+   if (limit <= 0.0 || nbins <= 0) { mdb_set_error("mdb_rdf_counts: bad limit / nbins"); return -1; }
+   for (int i = 0; i < e->cfg.nsites; i++)
+      if (e->h_type[i] < 1) { mdb_set_error("mdb_rdf_counts: site id 0 has no RDF slot (src/rdf.c:78-90)"); return -1; }
+   if (!e->cells_valid && mdb_launch_cells(e, st)) return -1;
+   if (e->pair_mode < 3 && mdb_launch_batches(e, st)) return -1;      // the pass walks the tiled kernel's batches
+   const bool same = e->d_runs_rdf && e->rdf_limit == limit && e->rdf_grid[0] == e->T.nx && e->rdf_grid[1] == e->T.ny &&
+                     e->rdf_grid[2] == e->T.nz && !memcmp(e->rdf_h, e->cfg.h, sizeof e->rdf_h);
+   if (!same) {
+      std::vector<StencilRun> runs;
+      std::string err;
+      if (!mdb_build_rdf_runs(e->cfg, e->T, limit, runs, err)) { mdb_set_error(err); return -1; }
+      if (upload(&e->d_runs_rdf, runs.data(), runs.size())) return -1;
+      e->nruns_rdf = (int)runs.size(); e->rdf_limit = limit;
+      e->rdf_grid[0] = e->T.nx; e->rdf_grid[1] = e->T.ny; e->rdf_grid[2] = e->T.nz;
+      memcpy(e->rdf_h, e->cfg.h, sizeof e->rdf_h);
+   }
+   const size_t nh = mdb_rdf_size(e, nbins);
+   if (nh == 0) return 0;
+   if (nh > e->rdf_cap) {
+      FREE(e->d_rdf);
+      MDB_CUDA(cudaMalloc(&e->d_rdf, sizeof(unsigned long long) * nh));
+      e->rdf_cap = nh;
+   }
+   MDB_CUDA(cudaMemsetAsync(e->d_rdf, 0, sizeof(unsigned long long) * nh, st));
+   if (mdb_launch_rdf_tiled(e, e->d_runs_rdf, e->nruns_rdf, (double)nbins / limit, nbins, e->d_rdf, st)) return -1;
+   std::vector<unsigned long long> tmp(nh);
+   MDB_CUDA(cudaMemcpyAsync(tmp.data(), e->d_rdf, sizeof(unsigned long long) * nh, cudaMemcpyDeviceToHost, st));
+   MDB_CUDA(cudaStreamSynchronize(st));
+   for (size_t k = 0; k < nh; k++) h_counts[k] += tmp[k];
+   return 0;
 }
 
 extern "C" int mdb_too_close(mdb_engine *e, int pair[2], void *stream)

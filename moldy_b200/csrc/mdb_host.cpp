@@ -186,6 +186,22 @@ static bool half_list_strict(const double h[9], double cutoff, int nx, int ny, i
    return true;
 }
 
+static void to_runs(std::map<std::pair<int, int>, std::vector<int>> &m, std::vector<StencilRun> &out)
+{
+   out.clear();
+   for (auto &kv : m) {
+      std::vector<int> &z = kv.second;
+      std::sort(z.begin(), z.end());
+      size_t i = 0;
+      while (i < z.size()) {
+         size_t j = i;
+         while (j + 1 < z.size() && z[j + 1] <= z[j] + 1) j++;
+         out.push_back({kv.first.first, kv.first.second, z[i], z[j]});
+         i = j + 1;
+      }
+   }
+}
+
 bool mdb_build_real_tables(const mdb_config &c, HostTables &T, std::string &err)
 {
    const double *h = c.h;
@@ -221,20 +237,6 @@ bool mdb_build_real_tables(const mdb_config &c, HostTables &T, std::string &err)
    std::map<std::pair<int, int>, std::vector<int>> hcols;
    for (size_t i = 0; i < T.half_list.size(); i += 3)
       hcols[{T.half_list[i], T.half_list[i + 1]}].push_back(T.half_list[i + 2]);
-   auto to_runs = [](std::map<std::pair<int, int>, std::vector<int>> &m, std::vector<StencilRun> &out) {
-      out.clear();
-      for (auto &kv : m) {
-         std::vector<int> &z = kv.second;
-         std::sort(z.begin(), z.end());
-         size_t i = 0;
-         while (i < z.size()) {
-            size_t j = i;
-            while (j + 1 < z.size() && z[j + 1] <= z[j] + 1) j++;
-            out.push_back({kv.first.first, kv.first.second, z[i], z[j]});
-            i = j + 1;
-         }
-      }
-   };
    to_runs(cols, T.runs);
    to_runs(hcols, T.runs_half);
    int k = 0;
@@ -243,6 +245,23 @@ bool mdb_build_real_tables(const mdb_config &c, HostTables &T, std::string &err)
          for (int kk = -1; kk <= 1; kk++, k++)
             for (int a = 0; a < 3; a++)
                T.reloc[k][a] = M(h, a, 0) * ii + M(h, a, 1) * jj + M(h, a, 2) * kk;
+   return true;
+}
+
+// Strict half list of radius `limit` on the current grid as z-runs: the neighbour cells of the RDF
+// pass (src/force.c:1306-1308, strict_neighbour_list with the RDF limit).
+bool mdb_build_rdf_runs(const mdb_config &c, const HostTables &T, double limit, std::vector<StencilRun> &runs,
+                        std::string &err)
+{
+   std::vector<int> half;
+   if (!half_list_strict(c.h, limit, T.nx, T.ny, T.nz, half, err)) return false;
+   if (half.size() < 3 || half[0] != 0 || half[1] != 0 || half[2] != 0) {
+      err = "RDF neighbour list does not start with the reference cell";
+      return false;
+   }
+   std::map<std::pair<int, int>, std::vector<int>> hcols;
+   for (size_t i = 0; i < half.size(); i += 3) hcols[{half[i], half[i + 1]}].push_back(half[i + 2]);
+   to_runs(hcols, runs);
    return true;
 }
 

@@ -99,6 +99,10 @@ struct mdb_engine {
    int2 *d_batches = nullptr; int *d_nbatch = nullptr; int batch_cap = 0;   // i-site batches of the tiled pair kernel
    double *d_fs = nullptr;                // [3N] cell-sorted force accumulator (Newton-3 mode)
    int pair_mode = -1;                    // 2: per-thread full stencil, 3: tiled full stencil, 4: tiled Newton-3
+   // RDF pass: strict stencil of the last (limit, grid) and the device histogram
+   StencilRun *d_runs_rdf = nullptr; int nruns_rdf = 0; double rdf_limit = -1.0; int rdf_grid[3] = {0, 0, 0};
+   double rdf_h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+   unsigned long long *d_rdf = nullptr; size_t rdf_cap = 0;
    // reductions / diagnostics
    double *d_partials = nullptr; int partials_cap = 0;
    long pair_evals = 0;                   // force evaluations since the visit counter was last read (mode 2)
@@ -124,6 +128,8 @@ void mdb_invert3(const double a[9], double b[9]);
 double mdb_det3(const double a[9]);
 bool mdb_build_real_tables(const mdb_config &c, HostTables &T, std::string &err);
 bool mdb_build_recip_tables(const mdb_config &c, HostTables &T, std::string &err);
+bool mdb_build_rdf_runs(const mdb_config &c, const HostTables &T, double limit, std::vector<StencilRun> &runs,
+                        std::string &err);
 double mdb_err_fn(double x);
 void mdb_set_error(const std::string &s);
 
@@ -132,6 +138,8 @@ int mdb_launch_cells(mdb_engine *e, cudaStream_t st);
 int mdb_launch_pair(mdb_engine *e, double *d_out, cudaStream_t st);
 int mdb_launch_pair_tiled(mdb_engine *e, double *d_out, cudaStream_t st);
 int mdb_launch_pair_count_tiled(mdb_engine *e, cudaStream_t st);
+int mdb_launch_rdf_tiled(mdb_engine *e, const StencilRun *d_runs, int nruns, double rbin, int nbins,
+                         unsigned long long *d_counts, cudaStream_t st);
 static constexpr size_t MDB_TILED_TAB_MAX = 28 * 1024;   // pair table of the tiled kernel lives in shared memory
 int mdb_launch_batches(mdb_engine *e, cudaStream_t st);
 static constexpr int MDB_NI = 4;          // i-sites per warp in the tiled pair kernel

@@ -97,15 +97,19 @@ struct JBuf {                                  // one lane's neighbour for one s
    unsigned qa;                                // shared address of the segment's q entry
 };
 
-template <int PT, bool COUL, bool STRICT, bool FW, bool N3, bool COUNT>
+enum { TM_FORCE = 0, TM_COUNT = 1, TM_RDF = 2 };     // what a visit does
+struct RdfParams { double rbin; int nbins, hist_smem; unsigned long long *counts; };
+
+template <int PT, bool COUL, bool STRICT, bool FW, bool N3, int MODE>
 __global__ void __launch_bounds__(TW * 32, MDB_TILED_MINB)
 k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const int2 *__restrict__ sinfo,
              const int *__restrict__ cstart, const int *__restrict__ order,
              const int *__restrict__ mol, const StencilRun *__restrict__ runs, const double *__restrict__ ptab,
              const int2 *__restrict__ batches, const int *__restrict__ nbatch_p, int rank, int nranks,
              double *__restrict__ out, double *__restrict__ fs, double *__restrict__ partials,
-             unsigned long long *__restrict__ counters)
+             unsigned long long *__restrict__ counters, RdfParams R)
 {
+   constexpr bool COUNT = MODE == TM_COUNT;
    extern __shared__ __align__(16) unsigned char smem_raw[];
    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
    {
@@ -113,8 +117,14 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
       double *s_e2 = reinterpret_cast<double *>(smem_raw + OFF_E2), *s_ptab = reinterpret_cast<double *>(smem_raw + OFF_TAB);
       for (int k = threadIdx.x; k < 27; k += TW * 32) s_reloc[k] = make_double4(P.reloc[k][0], P.reloc[k][1], P.reloc[k][2], 0.0);
       for (int k = threadIdx.x; k < 64; k += TW * 32) s_e2[k] = c_exp2tab[k];
-      const int ntab = P.max_id * P.max_id * MDB_NPOTP;
-      for (int k = threadIdx.x; k < ntab; k += TW * 32) s_ptab[k] = ptab[k];
+      if (MODE == TM_RDF) {                      // block-local histogram in place of the pair table
+         unsigned int *hist = reinterpret_cast<unsigned int *>(s_ptab);
+         const int nh = R.hist_smem ? R.nbins * (P.max_id * (P.max_id - 1) / 2) : 0;
+         for (int k = threadIdx.x; k < nh; k += TW * 32) hist[k] = 0u;
+      } else {
+         const int ntab = P.max_id * P.max_id * MDB_NPOTP;
+         for (int k = threadIdx.x; k < ntab; k += TW * 32) s_ptab[k] = ptab[k];
+      }
    }
    __syncthreads();
    // the two base addresses of the hot loop; passed through a shuffle so that they stay in registers
@@ -126,11 +136,12 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
    const long b_lo = (long)nbatch * rank / nranks, b_hi = (long)nbatch * (rank + 1) / nranks;
    const long b = b_lo + (long)blockIdx.x * TW + w;
    const size_t prow_id = (size_t)blockIdx.x * TW + w;
-   if (b >= b_hi) {                             // whole warp idle: still publish a zero row
-      if (!COUNT && lane < 7) partials[prow_id * NRED + lane] = 0.0;
-      return;
+   const bool idle = b >= b_hi;
+   if (idle) {                                  // whole warp idle: still publish a zero row
+      if (MODE == TM_FORCE && lane < 7) partials[prow_id * NRED + lane] = 0.0;
+      if (MODE != TM_RDF) return;               // (the RDF pass ends with a block-wide flush)
    }
-   const int2 bt = batches[b];                  // {first sorted site, count | column << 3}
+   const int2 bt = idle ? make_int2(0, 1) : batches[b];     // {first sorted site, count | column << 3}
    const int s0 = bt.x, cnt = bt.y & 7, col = bt.y >> 3;
    const int cx = col / P.ny, cy = col - cx * P.ny;
    const int cz_lo = sinfo[s0].y, cz_hi = sinfo[s0 + cnt - 1].y;
@@ -143,7 +154,8 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
       W->ipos[k] = posq[sk];
       const int2 si = sinfo[sk];
       // padded entries never pass the window test; row offset in bytes from the table start
-      W->iint[k] = make_int4(k < cnt ? si.y : BIGZ, (si.x & 0x3fffffff) * P.max_id * (MDB_NPOTP * 8),
+      W->iint[k] = make_int4(k < cnt ? si.y : BIGZ,
+                             MODE == TM_RDF ? (si.x & 0x3fffffff) : (si.x & 0x3fffffff) * P.max_id * (MDB_NPOTP * 8),
                              si.x >> 30, k < cnt ? s0 + k : 0x7fffffff);
    }
 #pragma unroll
@@ -151,7 +163,7 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
    __syncwarp();
    double pe = 0, w00 = 0, w01 = 0, w02 = 0, w11 = 0, w12 = 0, w22 = 0;
    unsigned int visits = 0;
-   const int nruns = P.nruns;
+   const int nruns = idle ? 0 : P.nruns;
 
    // ---- one step: lane's neighbour j against the NI batch sites --------------------------------
    // u = cz_j - (dzlo - zoff) (or a value no window accepts for padding lanes), wid = dzhi - dzlo:
@@ -176,6 +188,35 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
             if (SELFT) in[k] = in[k] && (N3 ? jself > ik.w : jself != ik.w);
             if (FW) in[k] = in[k] && !(ik.z & fwj);
             visits += in[k] ? 1u : 0u;
+         }
+         return;
+      }
+      if (MODE == TM_RDF) {
+         // rdf_inner + rdf_accum (src/force.c:1084-1096, src/rdf.c:94-108): the reference's operation
+         // order with explicit roundings so that every pair lands in the same bin, bit for bit
+         double rlx, rly, rlz;
+         lds_d3<OFF_RELOC>(sb + 32 * kimg, rlx, rly, rlz);
+         const int tj = J.sj.x & 0x3fffffff;
+         unsigned int *hist = reinterpret_cast<unsigned int *>(smem_raw + OFF_TAB);
+#pragma unroll
+         for (int k = 0; k < NI; k++) {
+            const double4 pi = k == 0 ? lds_d4<OFF_IPOS>(sw) : k == 1 ? lds_d4<OFF_IPOS + 32>(sw)
+                             : k == 2 ? lds_d4<OFF_IPOS + 64>(sw) : lds_d4<OFF_IPOS + 96>(sw);
+            const int4 ik = k == 0 ? lds_i4<OFF_IINT>(sw) : k == 1 ? lds_i4<OFF_IINT + 16>(sw)
+                          : k == 2 ? lds_i4<OFF_IINT + 32>(sw) : lds_i4<OFF_IINT + 48>(sw);
+            in[k] = (unsigned)(u - ik.x) <= (unsigned)wid;
+            if (SELFT) in[k] = in[k] && (N3 ? jself > ik.w : jself != ik.w);
+            if (FW) in[k] = in[k] && !(ik.z & fwj);
+            const double rx = __dadd_rn(__dsub_rn(J.pj.x, pi.x), rlx), ry = __dadd_rn(__dsub_rn(J.pj.y, pi.y), rly),
+                         rz = __dadd_rn(__dsub_rn(J.pj.z, pi.z), rlz);
+            const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
+            const int bin = (int)__dmul_rn(R.rbin, __dsqrt_rn(rsq));
+            if (in[k] && bin < R.nbins && min(ik.y, tj) >= 1) {
+               const int a = min(ik.y, tj), bb = max(ik.y, tj);          // rdf[idi][idj] = rdf[idj][idi], src/rdf.c:82-90
+               const int slot = ((a - 1) * P.max_id - (a - 1) * a / 2 + (bb - a)) * R.nbins + bin;
+               if (R.hist_smem) atomicAdd(&hist[slot], 1u);
+               else atomicAdd(&R.counts[slot], 1ULL);
+            }
          }
          return;
       }
@@ -256,7 +297,7 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
    };
 
    // ---- Newton-3 prologue: own column, central image, j > s_i (run 0 of the half list starts at dz = 0)
-   if (N3) {
+   if (N3 && !idle) {
       const StencilRun r0 = runs[0];
       const int jb = s0 + 1, je = cstart[col * P.nz + min(cz_hi + r0.dzhi, P.nz - 1) + 1];
       if (lane == 0) sts_i4<OFF_Q>(sw, make_int4(0, -BIGZ, r0.dzhi + BIGZ, 13 | 32));
@@ -352,6 +393,16 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
       }
    }
 
+   if (MODE == TM_RDF) {
+      __syncthreads();
+      if (R.hist_smem) {
+         const unsigned int *hist = reinterpret_cast<const unsigned int *>(smem_raw + OFF_TAB);
+         const int nh = R.nbins * (P.max_id * (P.max_id - 1) / 2);
+         for (int k = threadIdx.x; k < nh; k += TW * 32)
+            if (hist[k]) atomicAdd(&R.counts[k], (unsigned long long)hist[k]);
+      }
+      return;
+   }
    if (COUNT) {
       unsigned int vs = visits;
 #pragma unroll
@@ -470,16 +521,16 @@ __global__ void __launch_bounds__(RS1) k_rows_finish(const double *__restrict__ 
 }
 
 #define TILED_ARGS P, c.nsites, e->d_posq, e->d_sinfo, e->d_start, e->d_order, e->d_mol, runs, e->d_ptab, \
-                   e->d_batches, e->d_nbatch, e->ithread, e->nthreads, d_out, e->d_fs, e->d_partials, e->d_counters
+                   e->d_batches, e->d_nbatch, e->ithread, e->nthreads, d_out, e->d_fs, e->d_partials, e->d_counters, R
 
-template <int PT, bool COUL, bool COUNT>
+template <int PT, bool COUL, int MODE>
 static void launch_tiled(bool strict, bool fw, bool n3, dim3 g, cudaStream_t st, PairParams &P, mdb_engine *e,
-                         const StencilRun *runs, double *d_out)
+                         const StencilRun *runs, double *d_out, RdfParams R = RdfParams{0.0, 0, 0, nullptr}, size_t shm_extra = 0)
 {
    const mdb_config &c = e->cfg;
-   const size_t shm = TILED_SMEM + sizeof(double) * MDB_NPOTP * (size_t)c.max_id * c.max_id;
-#define GO(S, F, N) k_pair_tiled<PT, COUL, S, F, N, COUNT><<<g, TW * 32, shm, st>>>(TILED_ARGS)
-   if (strict && !COUNT) {
+   const size_t shm = TILED_SMEM + (MODE == TM_RDF ? shm_extra : sizeof(double) * MDB_NPOTP * (size_t)c.max_id * c.max_id);
+#define GO(S, F, N) k_pair_tiled<PT, COUL, S, F, N, MODE><<<g, TW * 32, shm, st>>>(TILED_ARGS)
+   if (strict && MODE == TM_FORCE) {
       if (fw) { if (n3) GO(true, true, true); else GO(true, true, false); }
       else    { if (n3) GO(true, false, true); else GO(true, false, false); }
    } else {
@@ -520,7 +571,30 @@ int mdb_launch_pair_count_tiled(mdb_engine *e, cudaStream_t st)
    int nblocks;
    tiled_params(e, n3, P, runs, nblocks);
    double *d_out = nullptr;
-   launch_tiled<PT_LJ, false, true>(false, fw, n3, dim3(nblocks), st, P, e, runs, d_out);
+   launch_tiled<PT_LJ, false, TM_COUNT>(false, fw, n3, dim3(nblocks), st, P, e, runs, d_out);
+   e->launches += 1;
+   MDB_CUDA(cudaGetLastError());
+   return 0;
+}
+
+// RDF binning pass (src/force.c:1302-1313): the Newton-3 traversal over the strict stencil of radius
+// `limit` (runs built by the caller), counts[pair(idi,idj)][bin] += 1 for this rank's batches
+int mdb_launch_rdf_tiled(mdb_engine *e, const StencilRun *d_runs, int nruns, double rbin, int nbins,
+                         unsigned long long *d_counts, cudaStream_t st)
+{
+   const mdb_config &c = e->cfg;
+   const bool fw = c.nsites_xf < c.nsites;
+   PairParams P;
+   const StencilRun *runs;
+   int nblocks;
+   tiled_params(e, true, P, runs, nblocks);
+   runs = d_runs; P.nruns = nruns;
+   RdfParams R;
+   R.rbin = rbin; R.nbins = nbins; R.counts = d_counts;
+   const size_t hbytes = sizeof(unsigned int) * (size_t)nbins * (c.max_id * (c.max_id - 1) / 2);
+   R.hist_smem = hbytes <= MDB_TILED_TAB_MAX ? 1 : 0;
+   double *d_out = nullptr;
+   launch_tiled<PT_LJ, false, TM_RDF>(false, fw, true, dim3(nblocks), st, P, e, runs, d_out, R, R.hist_smem ? hbytes : 0);
    e->launches += 1;
    MDB_CUDA(cudaGetLastError());
    return 0;
@@ -545,8 +619,8 @@ int mdb_launch_pair_tiled(mdb_engine *e, double *d_out, cudaStream_t st)
    if (n3) MDB_CUDA(cudaMemsetAsync(e->d_fs, 0, sizeof(double) * 3 * (size_t)c.nsites, st));
    const bool coul = c.alpha > 0.0, strict = c.strict_cutoff != 0 && !c.molpbc, fw = c.nsites_xf < c.nsites;   // src/force.c:951
    dim3 g(nblocks);
-#define PT_CASE(X) case X: if (coul) launch_tiled<X, true, false>(strict, fw, n3, g, st, P, e, runs, d_out); \
-                           else launch_tiled<X, false, false>(strict, fw, n3, g, st, P, e, runs, d_out); break
+#define PT_CASE(X) case X: if (coul) launch_tiled<X, true, TM_FORCE>(strict, fw, n3, g, st, P, e, runs, d_out); \
+                           else launch_tiled<X, false, TM_FORCE>(strict, fw, n3, g, st, P, e, runs, d_out); break
    switch (c.ptype) {
       PT_CASE(PT_LJ);
 #ifndef MDB_DEV_LJ_ONLY

@@ -32,6 +32,16 @@ __attribute__((weak)) contr_mt control;
 __attribute__((weak)) int ithread = 0;
 __attribute__((weak)) int nthreads = 1;
 
+// Moldy's RDF store (src/rdf.c:60-64): float[nbins * max_id (max_id - 1) / 2].  The weak fall-back keeps a
+// private array so that force_calc's RDF pass can be read back when the host program is not Moldy.
+static std::vector<float> g_rdf_private;
+__attribute__((weak)) void *rdf_ptr(int *size)
+{
+   *size = (int)g_rdf_private.size();
+   return g_rdf_private.data();
+}
+void mdb_rdf_private_resize(int n) { g_rdf_private.assign((size_t)n, 0.0f); }
+
 // Moldy's message()/note() (src/output.c:131,175); weak fall-backs print the same tags.
 __attribute__((weak)) void note(char *text, ...)
 {
@@ -284,11 +294,27 @@ extern "C" void force_calc(real **site, real **site_force, system_mt *system, sp
       message((int *)0, (char *)0, SEV_WARNING, (char *)"Sites %d and %d closer than %fA.", pr[0], pr[1],
               sqrt(MDB_TOO_CLOSE));
 
+   /* Accumulate radial distribution functions, src/force.c:1302-1313 + src/rdf.c:94-108.  The pairs are
+    * binned on the device; count/density is added to the host program's float histograms in one step
+    * (the reference adds 1/density pair by pair in single precision, so it rounds differently). */
    if (control.rdf_interval > 0 && control.istep >= control.begin_rdf &&
-       control.istep % control.rdf_interval == 0 && !G.rdf_warned) {
-      message((int *)0, (char *)0, SEV_WARNING,
-              (char *)"libmoldy_b200: RDF accumulation inside force_calc is not implemented; rdf data will be empty");
-      G.rdf_warned = true;
+       control.istep % control.rdf_interval == 0) {
+      int rsize = 0;
+      float *rdf_base = (float *)rdf_ptr(&rsize);
+      const size_t nh = mdb_rdf_size(G.eng, control.nbins);
+      if (rdf_base && (size_t)rsize >= nh && nh > 0) {
+         std::vector<unsigned long long> cnt(nh, 0ULL);
+         if (mdb_rdf_counts(G.eng, control.limit, control.nbins, cnt.data(), G.stream))
+            FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+         const double hm[9] = {system->h[0][0], system->h[0][1], system->h[0][2], system->h[1][0], system->h[1][1],
+                               system->h[1][2], system->h[2][0], system->h[2][1], system->h[2][2]};
+         const double invrho = 1.0 / (system->nsites / mdb_det3(hm));
+         for (size_t k = 0; k < nh; k++)
+            if (cnt[k]) rdf_base[k] = (float)(rdf_base[k] + (double)cnt[k] * invrho);
+      } else if (!G.rdf_warned) {
+         message((int *)0, (char *)0, SEV_WARNING, (char *)"libmoldy_b200: no RDF store (rdf_ptr) to accumulate into");
+         G.rdf_warned = true;
+      }
    }
 }
 

@@ -75,6 +75,9 @@ def load() -> C.CDLL:
     L.mdb_n_neighbour_cells.argtypes = [C.c_void_p]
     L.mdb_n_kvectors.argtypes = [C.c_void_p]
     L.mdb_get_cell_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mdb_rdf_size.restype = C.c_size_t
+    L.mdb_rdf_size.argtypes = [C.c_void_p, C.c_int]
+    L.mdb_rdf_counts.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
     L.mdb_pair_count.restype = C.c_double
     L.mdb_pair_count.argtypes = [C.c_void_p, C.c_void_p]
     L.mdb_kernel_launches.restype = C.c_long
@@ -156,11 +159,19 @@ def dist_pot(potpar, cutoff, ptype):
     return load().dist_pot(p.ctypes.data_as(DP), cutoff, ptype)
 
 
-def eval_forces(ms: MoldySystem, real=True, recip=True, sites=None, ithread=0, nthreads=1):
+def eval_forces(ms: MoldySystem, real=True, recip=True, sites=None, ithread=0, nthreads=1, rdf=None):
     """The hot-path part of eval_forces() (src/accel.c:488-535) for one
-    configuration through the Moldy-level C ABI with HOST buffers."""
+    configuration through the Moldy-level C ABI with HOST buffers.
+    rdf=(limit, nbins) switches on force_calc's RDF pass for this call (control.rdf_interval = 1) and
+    returns the float histograms the library accumulated (what Moldy's rdf_ptr() store would hold)."""
     L = load()
     ms.control.fill(control())
+    if rdf is not None:
+        c = control()
+        c.rdf_interval, c.begin_rdf, c.istep = 1, 0, 0
+        c.limit, c.nbins = float(rdf[0]), int(rdf[1])
+        mid = ms.sysdef.max_id
+        L.mdb_rdf_private_resize(c.nbins * mid * (mid - 1) // 2)
     set_thread(ithread, nthreads)
     sysm, spec, pot = ms.cstructs()
     n = ms.nsites
@@ -175,7 +186,13 @@ def eval_forces(ms: MoldySystem, real=True, recip=True, sites=None, ithread=0, n
         force_calc(site, force, sysm, spec, chg, pot, pe[0:1], stress)
     if recip and ms.control.alpha > 1e-7:
         ewald(site, force, sysm, spec, chg, pe[1:2], stress)
-    return dict(force=force[:, :n].copy(), pe=pe, stress=stress)
+    out = dict(force=force[:, :n].copy(), pe=pe, stress=stress)
+    if rdf is not None:
+        size = C.c_int(0)
+        L.rdf_ptr.restype = C.POINTER(C.c_float)
+        base = L.rdf_ptr(C.byref(size))
+        out["rdf"] = np.ctypeslib.as_array(base, shape=(size.value,)).copy().reshape(-1, int(rdf[1]))
+    return out
 
 
 def reset():
@@ -301,6 +318,14 @@ class Engine:
         out = np.empty(self.n, dtype=np.int32)
         self._chk(self.L.mdb_get_cell_ids(self.h, out.ctypes.data, stream), "mdb_get_cell_ids")
         return out
+
+    def rdf_counts(self, limit: float, nbins: int, stream=0) -> np.ndarray:
+        """Pair counts per (id pair, bin) of force_calc's RDF pass for the current sites: uint64 [pairs, nbins]."""
+        n = self.L.mdb_rdf_size(self.h, nbins)
+        out = np.zeros(n, dtype=np.uint64)
+        if self.L.mdb_rdf_counts(self.h, limit, nbins, out.ctypes.data, stream):
+            raise RuntimeError(_err(self.L))
+        return out.reshape(-1, nbins)
 
     def pair_count(self, stream=0) -> float:
         return self.L.mdb_pair_count(self.h, stream)

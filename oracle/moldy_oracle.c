@@ -471,6 +471,107 @@ done0:
    return rc;
 }
 
+/* ---- RDF binning pass: force.c:1010-1103 (rdf_inner: same cell walk as the force loop, over the
+ * STRICT neighbour list of radius `limit`, force.c:1306-1308) with rdf.c:94-108 (rdf_accum:
+ * bin = (int)(nbins/limit * sqrt(r^2)), counted when bin < nbins).  counts[pair][bin] += 1 with
+ * pair = (idi <= idj) in the order init_rdf lays the histograms out (rdf.c:82-90). ------------- */
+int orc_rdf(const orc_system *s, const double *x, const double *y, const double *z, double limit, int nbins,
+            double *counts)
+{
+   const int n = s->nsites;
+   int nx, ny, nz, ncells, nhalf, i, c, k;
+   int *cell = (int *)malloc(sizeof(int) * (size_t)n), *start, *members, *half;
+   double reloc[27][3];
+   const double rbin = nbins / limit;
+   int cap, *nab, *img, rc = 0;
+   const int has_fw = s->nsites_xf < n;
+
+   grid_dims(s, &nx, &ny, &nz);
+   ncells = nx * ny * nz;
+   orc_cell_ids(s, x, y, z, cell);
+   start = (int *)calloc((size_t)ncells + 1, sizeof(int));
+   members = (int *)malloc(sizeof(int) * (size_t)n);
+   for (i = 0; i < n; i++) start[cell[i] + 1]++;
+   for (c = 0; c < ncells; c++) start[c + 1] += start[c];
+   {
+      int *cur = (int *)malloc(sizeof(int) * (size_t)ncells);
+      memcpy(cur, start, sizeof(int) * (size_t)ncells);
+      i = n - 1;
+      while (i >= 0) {                                   /* list order as in orc_force_calc */
+         int lo = i, kk;
+         while (lo > 0 && s->site_mol[lo - 1] == s->site_mol[i]) lo--;
+         if (s->molpbc && i < s->nsites_xf)
+            for (kk = lo; kk <= i; kk++) members[cur[cell[kk]]++] = kk;
+         else
+            for (kk = i; kk >= lo; kk--) members[cur[cell[kk]]++] = kk;
+         i = lo - 1;
+      }
+      free(cur);
+   }
+   cap = 3 * 4 * 64 * 64 * 64;
+   half = (int *)malloc(sizeof(int) * (size_t)cap);
+   nhalf = orc_half_list(s->h, limit, 1, nx, ny, nz, half, cap);
+   if (nhalf < 0) { rc = -1; goto done; }
+   k = 0;
+   {
+      int a, b, g;
+      for (a = -1; a <= 1; a++) for (b = -1; b <= 1; b++) for (g = -1; g <= 1; g++, k++) {
+         reloc[k][0] = H(s->h, 0, 0) * a + H(s->h, 0, 1) * b + H(s->h, 0, 2) * g;
+         reloc[k][1] = H(s->h, 1, 0) * a + H(s->h, 1, 1) * b + H(s->h, 1, 2) * g;
+         reloc[k][2] = H(s->h, 2, 0) * a + H(s->h, 2, 1) * b + H(s->h, 2, 2) * g;
+      }
+   }
+   {
+      int maxc = 0;
+      for (c = 0; c < ncells; c++) if (start[c + 1] - start[c] > maxc) maxc = start[c + 1] - start[c];
+      cap = maxc * nhalf * 2 + 8;
+   }
+   nab = (int *)malloc(sizeof(int) * (size_t)cap); img = (int *)malloc(sizeof(int) * (size_t)cap);
+   for (c = s->ithread; c < ncells; c += s->nthreads) {
+      int cx, cy, cz, nnab = 0, nnf = 0, pass, e, m, jmin = 0;
+      if (start[c] == start[c + 1]) continue;
+      cx = c / (ny * nz); cy = c / nz - ny * cx; cz = c - nz * (cy + ny * cx);
+      for (pass = 0; pass < (has_fw ? 2 : 1); pass++) {   /* site_neighbour_list, force.c:521-569 */
+         for (e = (pass == 0 ? 0 : 1); e < nhalf; e++) {
+            int tx = cx + half[3 * e], ty = cy + half[3 * e + 1], tz = cz + half[3 * e + 2];
+            int ia = 1, ib = 1, ig = 1, tc, kimg;
+            if (tx < 0) { tx += nx; ia = 0; } else if (tx >= nx) { tx -= nx; ia = 2; }
+            if (ty < 0) { ty += ny; ib = 0; } else if (ty >= ny) { ty -= ny; ib = 2; }
+            if (tz < 0) { tz += nz; ig = 0; } else if (tz >= nz) { tz -= nz; ig = 2; }
+            tc = tz + nz * (ty + ny * tx);
+            kimg = 9 * ia + 3 * ib + ig;
+            for (m = start[tc]; m < start[tc + 1]; m++) {
+               int j = members[m];
+               if ((j >= s->nsites_xf) == pass) { nab[nnab] = j; img[nnab] = kimg; nnab++; }
+            }
+         }
+         if (pass == 0) nnf = nnab;
+      }
+      if (!has_fw) nnf = nnab;
+      for (m = start[c]; m < start[c + 1]; m++) {
+         const int isite = members[m], idi = s->site_type[isite];
+         const int fw = isite >= s->nsites_xf;
+         int jmax, j;
+         if (fw) { jmin = 0; jmax = nnf; } else { jmax = nnab; jmin++; }
+         for (j = jmin; j < jmax; j++) {
+            const double *rv = reloc[img[j]];
+            const int jj = nab[j], idj = s->site_type[jj];
+            double dx = x[jj] - x[isite] + rv[0], dy = y[jj] - y[isite] + rv[1], dz = z[jj] - z[isite] + rv[2];
+            double rsq = dx * dx + dy * dy + dz * dz;
+            int bin = rbin * sqrt(rsq);
+            if (bin < nbins) {
+               const int a = idi < idj ? idi : idj, b = idi < idj ? idj : idi;
+               counts[(size_t)((a - 1) * s->max_id - (a - 1) * a / 2 + (b - a)) * nbins + bin] += 1.0;
+            }
+         }
+      }
+   }
+   free(nab); free(img);
+done:
+   free(cell); free(start); free(members); free(half);
+   return rc;
+}
+
 /* ---- 4-lane sum of auxil.c:222-256 ----------------------------------------------- */
 static double lane_sum(int n, const double *v)
 {

@@ -60,6 +60,9 @@ int    orc_cell_ids(const orc_system *s, const double *x, const double *y, const
 /* real-space forces: f{x,y,z}[nsites] += ; returns 0 or -1 (cut-off too large) */
 int    orc_force_calc(const orc_system *s, const double *x, const double *y, const double *z,
                       double *fx, double *fy, double *fz, orc_result *res);
+/* RDF binning pass of force_calc: counts[max_id(max_id-1)/2][nbins] += pairs per bin */
+int    orc_rdf(const orc_system *s, const double *x, const double *y, const double *z, double limit, int nbins,
+               double *counts);
 /* reciprocal-space forces */
 int    orc_ewald(const orc_system *s, const double *x, const double *y, const double *z,
                  double *fx, double *fy, double *fz, orc_result *res);

@@ -143,3 +143,18 @@ def run(ms, real=True, recip=True, sites=None, ithread=0, nthreads=1):
         info.update(nhkl=r.nhkl)
     return dict(force=np.stack(fr), pe=pe, stress=stress.reshape(3, 3), eintra=eintra, self_energy=self_e,
                 sheet_energy=sheet_e, **info)
+
+
+def rdf(ms, limit, nbins, sites=None, ithread=0, nthreads=1):
+    """Pair counts per (id pair, bin) of the RDF pass: float64 [max_id (max_id-1)/2, nbins]."""
+    L = load()
+    s, keep = _system(ms, ithread, nthreads)
+    site = np.ascontiguousarray(ms.make_sites(wrap=not ms.control.molpbc) if sites is None else sites)
+    n = ms.nsites
+    x, y, z = (np.ascontiguousarray(site[i, :n]) for i in range(3))
+    mid = ms.sysdef.max_id
+    counts = np.zeros((mid * (mid - 1) // 2, nbins))
+    ptr = lambda a: a.ctypes.data_as(DP)
+    if L.orc_rdf(C.byref(s), ptr(x), ptr(y), ptr(z), C.c_double(limit), C.c_int(nbins), ptr(counts)):
+        raise RuntimeError("RDF limit > cell dimension")
+    return counts

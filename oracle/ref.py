@@ -62,10 +62,16 @@ class RefLib:
     def log(self) -> str:
         return self.lib.mdref_log().decode()
 
-    def run(self, ms, real: bool = True, recip: bool = True, sites=None):
+    def run(self, ms, real: bool = True, recip: bool = True, sites=None, rdf=None):
         """force_calc (+ ewald when alpha > ALPHAMIN) exactly as eval_forces()
-        sequences them (src/accel.c:520-527).  Returns forces[3,N], pe[2], stress[3,3]."""
+        sequences them (src/accel.c:520-527).  Returns forces[3,N], pe[2], stress[3,3].
+        rdf=(limit, nbins): switch on the RDF pass (src/force.c:1302-1313) and return the reference's
+        own float histograms (init_rdf / rdf_accum / rdf_ptr of src/rdf.c, compiled in place)."""
         ms.control.fill(self.control)
+        if rdf is not None:
+            c = self.control
+            c.rdf_interval, c.begin_rdf, c.istep = 1, 0, 0
+            c.limit, c.nbins = float(rdf[0]), int(rdf[1])
         sysm, spec, pot = ms.cstructs()
         n = ms.nsites
         nsa = abi.nsarray(n)
@@ -78,12 +84,20 @@ class RefLib:
         frows = (C.POINTER(C.c_double) * 3)(*[C.cast(force.ctypes.data + 8 * nsa * i, C.POINTER(C.c_double)) for i in range(3)])
         pchg = chg.ctypes.data_as(C.POINTER(C.c_double))
         pstress = stress.ctypes.data_as(C.POINTER(abi.vec_mt))
+        if rdf is not None:
+            self.lib.init_rdf(C.byref(sysm))
         if real:
             self.lib.force_calc(rows, frows, C.byref(sysm), spec, pchg, pot, pe, pstress)
         if recip and ms.control.alpha > 1e-7:
             self.lib.ewald(rows, frows, C.byref(sysm), spec, pchg, C.byref(pe, 8), pstress)
-        return dict(force=force[:, :n].copy(), pe=np.array([pe[0], pe[1]]), stress=stress.copy(),
-                    log=self.log())
+        out = dict(force=force[:, :n].copy(), pe=np.array([pe[0], pe[1]]), stress=stress.copy(),
+                   log=self.log())
+        if rdf is not None:
+            size = C.c_int(0)
+            self.lib.rdf_ptr.restype = C.POINTER(C.c_float)
+            base = self.lib.rdf_ptr(C.byref(size))
+            out["rdf"] = np.ctypeslib.as_array(base, shape=(size.value,)).copy().reshape(-1, int(rdf[1]))
+        return out
 
     def cell_ids(self, ms, sites=None) -> np.ndarray:
         """Per-site link-cell index through the reference's own cellbin()

@@ -9,7 +9,10 @@
  *
  *   control, ithread, nthreads   globals owned by main.c        (src/main.c:83-84)
  *   message(), note()            severity-tagged printing       (src/output.c:131,175)
- *   rdf_accum()                  RDF binning callback           (src/rdf.c:94)
+ *   new_line(), put_line()       output helpers rdf.c imports   (src/output.c)
+ *
+ * rdf.c itself (init_rdf, rdf_accum, rdf_ptr) is compiled in place with the three hot files, so the RDF pass
+ * of force_calc bins into the reference's own float histograms.
  *
  * note()/message() additionally record their text in a ring buffer so tests
  * can read the start-up notes (they are the only goldens the reference's own
@@ -86,10 +89,8 @@ void message(int *nerrs, ...)
    }
 }
 
-void rdf_accum(double density, int lo, int hi, real *rsq, int iid, int *id, int *nab)
-{
-   (void)density; (void)lo; (void)hi; (void)rsq; (void)iid; (void)id; (void)nab;
-}
+void new_line(void) { if (!quiet) putchar('\n'); }
+void put_line(int c) { (void)c; }
 
 /* ---- accessors used by the Python harness ---- */
 contr_mt *mdref_control(void) { return &control; }

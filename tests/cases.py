@@ -150,3 +150,12 @@ EXAMPLE_SYSTEMS = {
 def rel_rms(a, b):
     a, b = np.asarray(a), np.asarray(b)
     return float(np.sqrt(((a - b) ** 2).sum() / max((b ** 2).sum(), 1e-300)))
+
+
+# RDF pass of force_calc (src/force.c:1302-1313): case -> (rdf limit, number of bins).  Covers the lazy and
+# strict force stencils (the RDF stencil is always strict), a triclinic cell, a framework, molecular
+# cut-off binning and a limit larger than half the box (self-image pairs).
+RDF_CASES = {
+    "argon": (7.7, 40), "tip4p": (8.8, 100), "tips2": (5.5, 55), "tips2_tinybox": (8.0, 64), "mgcl2": (8.4, 100),
+    "quartz": (9.0, 90), "slab_framework": (6.3, 63), "tips2_molpbc": (5.5, 50), "tip4p_molpbc_strict": (6.0, 30),
+}

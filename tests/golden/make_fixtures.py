@@ -9,7 +9,11 @@
    for the parity systems of tests/cases.py.  These pin the C restatement
    (oracle/moldy_oracle.c) and, on the GPU box, the CUDA path.
 
-usage: python tests/golden/make_fixtures.py [--eq] [--ref]
+3. ref_rdf.npz : the reference's own RDF histograms (force_calc's RDF pass binning into init_rdf/rdf_accum of
+   src/rdf.c, compiled in place) for tests/cases.py RDF_CASES, stored as pair counts (histogram * density,
+   rounded: the float store holds count/density summed pair by pair).
+
+usage: python tests/golden/make_fixtures.py [--eq] [--ref] [--rdf]
 """
 import os
 import subprocess
@@ -64,8 +68,25 @@ def make_ref():
         print("wrote ref_%s.npz  N=%d pe=%s" % (name, ms.nsites, o["pe"]))
 
 
+def make_rdf():
+    from oracle import ref
+    from tests import cases
+    out = {}
+    for name, (limit, nbins) in cases.RDF_CASES.items():
+        ms = cases.GOLDEN_CASES[name]()
+        r = ref.RefLib().run(ms, recip=False, rdf=(limit, nbins))
+        rho = ms.nsites / float(np.linalg.det(ms.h))
+        cnt = r["rdf"].astype(np.float64) * rho
+        assert np.abs(cnt - np.rint(cnt)).max() < 0.2, name
+        out[name] = np.rint(cnt).astype(np.int64)
+        print("rdf %-20s limit=%g nbins=%d pairs=%d" % (name, limit, nbins, out[name].sum()))
+    np.savez_compressed(os.path.join(GOLD, "ref_rdf.npz"), **out)
+
+
 if __name__ == "__main__":
-    args = sys.argv[1:] or ["--eq", "--ref"]
+    args = sys.argv[1:] or ["--eq", "--ref", "--rdf"]
+    if "--rdf" in args:
+        make_rdf()
     if "--eq" in args:
         make_eq()
     if "--ref" in args:

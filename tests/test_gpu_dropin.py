@@ -39,18 +39,22 @@ begin-average=100000000
 roll-interval=1
 dump-level=0
 backup-interval=0
-rdf-interval=0
+rdf-interval={rdf}
+begin-rdf=0
+rdf-out={rdfout}
+rdf-limit=8.5
+nbins=85
 time-unit=4.8888213e-14
 end
 """
 
 
-def _run(binary, tmp, nsteps, every):
+def _run(binary, tmp, nsteps, every, rdf=0, rdfout=1000000):
     d = os.path.join(tmp, os.path.basename(binary))
     os.makedirs(d, exist_ok=True)
     shutil.copy(os.path.join(ROOT, "tests", "golden", "tip4p_256_eq.txt"), d)
     with open(os.path.join(d, "control"), "w") as f:
-        f.write(CONTROL.format(nsteps=nsteps, every=every))
+        f.write(CONTROL.format(nsteps=nsteps, every=every, rdf=rdf, rdfout=rdfout))
     out = subprocess.run([binary, "control"], cwd=d, capture_output=True, text=True, timeout=3000)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     return out.stdout
@@ -103,3 +107,35 @@ def test_nve_energy_drift_no_worse_than_reference(tmp_path):
     drift_b = np.abs(tot_b - tot_b[0]).max() / ke
     print(f"NVE {nsteps} steps: max |E-E0|/KE  reference {drift_a:.3e}  gpu-linked {drift_b:.3e}")
     assert drift_b <= 1.5 * drift_a + 1e-4
+
+
+def _rdf_tables(text):
+    """{'O-O RDF': [g(r) values]} from print_rdf (src/rdf.c:117-170)."""
+    res, lines, i = {}, text.splitlines(), 0
+    while i < len(lines):
+        m = re.match(r"\s*(\S+-\S+ RDF)\s*$", lines[i])
+        i += 1
+        if not m:
+            continue
+        vals = []
+        while i < len(lines) and re.match(r"^[\s\d.eE+-]+$", lines[i]) and lines[i].strip():
+            vals += [float(t) for t in lines[i].split()]
+            i += 1
+        res.setdefault(m.group(1), []).append(np.array(vals))
+    return res
+
+
+@needs_binaries
+def test_rdf_pass_inside_force_calc_prints_the_same_tables(tmp_path):
+    """rdf-interval > 0: force_calc's RDF pass (src/force.c:1302-1313) feeds the host program's own
+    rdf.c store; the tables print_rdf writes must agree with the all-CPU binary (printed with 6
+    decimals; the reference sums 1/density in single precision, the library adds count/density once)."""
+    a = _rdf_tables(_run(REF, str(tmp_path), 20, 10, rdf=2, rdfout=10))
+    b = _rdf_tables(_run(GPU, str(tmp_path), 20, 10, rdf=2, rdfout=10))
+    assert a and sorted(a) == sorted(b)
+    for key in a:
+        assert len(a[key]) == len(b[key]) == 2
+        for ta, tb in zip(a[key], b[key]):
+            assert ta.shape == tb.shape == (85,)
+            assert ta.max() > 0.5
+            assert np.allclose(ta, tb, rtol=2e-5, atol=2e-6), (key, np.abs(ta - tb).max())

@@ -240,3 +240,48 @@ def test_medium_system_vs_reference_live():
     lib.reset()
     out = lib.eval_forces(ms)
     _check(out, gold, "tip4p_3")
+
+
+@pytest.mark.parametrize("mode", [2, 4])
+@pytest.mark.parametrize("name", list(cases.RDF_CASES))
+def test_rdf_pass_pair_counts_exact(name, mode, golden_dir):
+    """RDF pass of force_calc (src/force.c:1302-1313 + src/rdf.c:94-108) on the device: every pair lands
+    in the reference's bin (integer work: exact), whole and as a 3-way replicated-data split."""
+    import torch
+    limit, nbins = cases.RDF_CASES[name]
+    ms = cases.GOLDEN_CASES[name]()
+    gold = np.load(os.path.join(golden_dir, "ref_rdf.npz"))[name]
+    eng = lib.Engine(0)
+    eng.set_pair_mode(mode)
+    eng.configure(ms)
+    eng.set_sites_host(ms.make_sites(wrap=not ms.control.molpbc))
+    if ms.control.molpbc:
+        eng.set_com_host(ms.c_of_m)
+    st = torch.cuda.current_stream().cuda_stream
+    cnt = eng.rdf_counts(limit, nbins, st)
+    assert cnt.shape == gold.shape
+    assert np.array_equal(cnt.astype(np.int64), gold), int(np.abs(cnt.astype(np.int64) - gold).sum())
+    parts = np.zeros_like(cnt)
+    for r in range(3):
+        eng.set_partition(r, 3)
+        parts += eng.rdf_counts(limit, nbins, st)
+    assert np.array_equal(parts, cnt)
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["tip4p", "slab_framework", "tips2_molpbc"])
+def test_force_calc_accumulates_rdf_store(name, golden_dir):
+    """force_calc() with control.rdf_interval on: the float store behind rdf_ptr() holds count/density
+    (the reference adds 1/density pair by pair in single precision: compare to float accuracy), and the
+    forces are unaffected by the extra pass."""
+    limit, nbins = cases.RDF_CASES[name]
+    ms = cases.GOLDEN_CASES[name]()
+    gold = np.load(os.path.join(golden_dir, "ref_rdf.npz"))[name]
+    ref = np.load(os.path.join(golden_dir, f"ref_{name}.npz"))
+    lib.reset()
+    out = lib.eval_forces(ms, rdf=(limit, nbins))
+    _check(out, ref, name)
+    rho = ms.nsites / float(np.linalg.det(ms.h))
+    assert out["rdf"].shape == gold.shape
+    assert np.allclose(out["rdf"], gold / rho, rtol=1e-6, atol=0)
+    lib.reset()
