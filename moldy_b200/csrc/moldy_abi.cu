@@ -104,6 +104,13 @@ struct AbiState {
    bool sites_fresh = false;
    double *d_out = nullptr; size_t out_cap = 0;
    double *h_out = nullptr; size_t hout_cap = 0;
+   // ewald() results computed ahead of the call, behind force_calc's host-side work (see force_calc)
+   double *d_out2 = nullptr, *h_out2 = nullptr;
+   cudaEvent_t ev_ahead = nullptr;
+   bool ahead_valid = false;
+   const void *ahead_sites = nullptr;
+   long config_epoch = 0, ahead_epoch = -1;
+   int ahead_ithread = 0, ahead_nthreads = 1;
    bool rdf_warned = false;
 };
 static AbiState G;
@@ -179,6 +186,8 @@ static void sync_config(system_mt *system, spec_mt *species, const real *chg, co
    if (!changed) return;
    c.site_type = G.type.data(); c.site_mol = G.mol.data(); c.chg = G.chg.data(); c.potpar = G.potflat.data();
    if (mdb_configure(G.eng, &c)) FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+   G.config_epoch++;
+   G.ahead_valid = false;
    G.cfg = c;
    G.have_cfg = true;
    G.sites_fresh = false;
@@ -186,8 +195,12 @@ static void sync_config(system_mt *system, spec_mt *species, const real *chg, co
    if (need > G.out_cap) {
       if (G.d_out) cudaFree(G.d_out);
       if (G.h_out) cudaFreeHost(G.h_out);
+      if (G.d_out2) cudaFree(G.d_out2);
+      if (G.h_out2) cudaFreeHost(G.h_out2);
       if (cudaMalloc(&G.d_out, sizeof(double) * need) != cudaSuccess ||
-          cudaMallocHost(&G.h_out, sizeof(double) * need) != cudaSuccess)
+          cudaMallocHost(&G.h_out, sizeof(double) * need) != cudaSuccess ||
+          cudaMalloc(&G.d_out2, sizeof(double) * need) != cudaSuccess ||
+          cudaMallocHost(&G.h_out2, sizeof(double) * need) != cudaSuccess)
          FATAL_MSG("libmoldy_b200: out of device/pinned memory for %d sites", n);
       G.out_cap = need;
    }
@@ -208,14 +221,16 @@ static const bool g_timing = getenv("MOLDY_B200_TIMING") != nullptr;
 
 // D2H of the result block into pinned memory, then site_force[a][i] += f (the caller's arrays
 // are only accumulated into, src/accel.c:488-535); the three rows are added by three threads.
-static void pull_and_accumulate(real **site_force, double *pe, real (*stress)[3], int n)
+static void pull_and_accumulate(real **site_force, double *pe, real (*stress)[3], int n, const double *d_src = nullptr,
+                                double *h_dst = nullptr, bool on_host = false)
 {
    const double t0 = now_ms();
-   if (mdb_read_out(G.eng, G.d_out, G.h_out, G.stream)) FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+   if (!d_src) { d_src = G.d_out; h_dst = G.h_out; }
+   if (!on_host && mdb_read_out(G.eng, d_src, h_dst, G.stream)) FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
    const double t1 = now_ms();
    auto add_row = [&](int a) {
       real *dst = site_force[a];
-      const double *src = G.h_out + (size_t)a * n;
+      const double *src = h_dst + (size_t)a * n;
       for (int i = 0; i < n; i++) dst[i] += src[i];
    };
    if (n >= 65536) {
@@ -226,7 +241,7 @@ static void pull_and_accumulate(real **site_force, double *pe, real (*stress)[3]
       for (int a = 0; a < 3; a++) add_row(a);
    }
    if (g_timing) fprintf(stderr, "[moldy_b200] wait+D2H %.2f ms, host += %.2f ms\n", t1 - t0, now_ms() - t1);
-   const double *sc = G.h_out + 3 * (size_t)n;
+   const double *sc = h_dst + 3 * (size_t)n;
    (void)pe;
    stress[0][0] += sc[2]; stress[0][1] += sc[3]; stress[0][2] += sc[4];
    stress[1][1] += sc[6]; stress[1][2] += sc[7]; stress[2][2] += sc[10];
@@ -282,12 +297,29 @@ extern "C" void force_calc(real **site, real **site_force, system_mt *system, sp
    if (mdb_zero_out(G.eng, G.d_out, G.stream) || mdb_build_cells(G.eng, G.stream) ||
        mdb_force_real(G.eng, G.d_out, G.stream))
       FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
-   pull_and_accumulate(site_force, pe, stress, n);
-   *pe += G.h_out[3 * (size_t)n];
+   if (cudaMemcpyAsync(G.h_out, G.d_out, sizeof(double) * mdb_out_doubles(n), cudaMemcpyDeviceToHost, G.stream) != cudaSuccess)
+      FATAL_MSG("libmoldy_b200: D2H copy failed");
+   int pr[2];
+   const int tc = mdb_too_close(G.eng, pr, G.stream);     /* synchronises: the real-space block is on the host now */
    G.sites_fresh = true;
 
-   int pr[2];
-   const int tc = mdb_too_close(G.eng, pr, G.stream);
+   // eval_forces calls ewald() next on the same sites (src/accel.c:520-527): start its kernels now, so
+   // that they run while this thread adds the real-space block into the caller's arrays; ewald() then
+   // only waits for them.  Discarded if the next ewald() comes with other sites, partition or tables.
+   G.ahead_valid = false;
+   if (control.alpha > MDB_ALPHAMIN && !getenv("MOLDY_B200_NO_AHEAD")) {
+      if (!G.ev_ahead) cudaEventCreateWithFlags(&G.ev_ahead, cudaEventDisableTiming);
+      if (mdb_zero_out(G.eng, G.d_out2, G.stream) || mdb_force_recip(G.eng, G.d_out2, G.stream))
+         FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+      cudaMemcpyAsync(G.h_out2, G.d_out2, sizeof(double) * mdb_out_doubles(n), cudaMemcpyDeviceToHost, G.stream);
+      cudaEventRecord(G.ev_ahead, G.stream);
+      G.ahead_valid = true; G.ahead_sites = (const void *)site[0]; G.ahead_epoch = G.config_epoch;
+      G.ahead_ithread = ithread; G.ahead_nthreads = nthreads;
+   }
+
+   pull_and_accumulate(site_force, pe, stress, n, G.d_out, G.h_out, true);
+   *pe += G.h_out[3 * (size_t)n];
+
    if (tc & (1 << 30))
       message((int *)0, (char *)0, SEV_ERROR, (char *)"Co-ordinate out of range in BIN (fill_cells)");
    if (tc & ~(1 << 30))                                  /* src/force.c:944-946 */
@@ -378,6 +410,19 @@ extern "C" void ewald(real **site, real **site_force, system_mp system, spec_mt 
       for (int i = 0; i < 3; i++) stress[i][i] += G.sheet_energy / vol;
    }
 
+   const bool ahead = G.ahead_valid && G.sites_fresh && G.ahead_sites == (const void *)site[0] &&
+                      G.ahead_epoch == G.config_epoch && G.ahead_ithread == ithread && G.ahead_nthreads == nthreads &&
+                      !getenv("MOLDY_B200_ALWAYS_UPLOAD");
+   G.ahead_valid = false;
+   if (ahead) {                                          /* started by force_calc: wait and add */
+      const double t0 = now_ms();
+      if (cudaEventSynchronize(G.ev_ahead) != cudaSuccess) FATAL_MSG("libmoldy_b200: k-space kernels failed");
+      if (g_timing) fprintf(stderr, "[moldy_b200] ewald: waited %.2f ms for the kernels started by force_calc\n", now_ms() - t0);
+      G.sites_fresh = false;
+      pull_and_accumulate(site_force, pe, stress, n, G.d_out2, G.h_out2, true);
+      *pe += G.h_out2[3 * (size_t)n + 1];
+      return;
+   }
    push_sites(site);
    G.sites_fresh = false;
    if (mdb_zero_out(G.eng, G.d_out, G.stream) || mdb_force_recip(G.eng, G.d_out, G.stream))
@@ -447,4 +492,6 @@ extern "C" void mdb_abi_reset(void)
    G.onabor = G.onx = G.ony = G.onz = 0;
    G.type.clear(); G.mol.clear(); G.chg.clear(); G.potflat.clear();
    G.have_cfg = false; G.sites_fresh = false; G.last_sites = nullptr; G.rdf_warned = false;
+   if (G.eng && G.stream) cudaStreamSynchronize(G.stream);
+   G.ahead_valid = false;
 }

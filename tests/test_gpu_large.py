@@ -58,3 +58,22 @@ def test_molecule_relabelling_invariance():
     assert cases.rel_rms(f2, fperm) < 1e-12
     assert np.allclose(pe2, pe, rtol=1e-11)
     assert np.allclose(s2, s, rtol=1e-10, atol=1e-10 * np.abs(s).max())
+
+
+@pytest.mark.parametrize("which", ["mgcl2_7", "quartz_48"])
+def test_other_benchmark_families_at_full_size(which):
+    """BASELINE.json configs[2] (aqueous MgCl2 replicated 7x7x7 = 278 516 sites, MCY + Ewald, automatic
+    cut-offs) and configs[3] (BKS quartz 48x48x48 = 995 328 ions, Buckingham + Ewald, triclinic cell):
+    size-independent properties -- zero net force, and the bit-reproducible owner-computes kernel
+    (full stencil) against the Newton-3 kernel (half stencil + atomics), two different traversals."""
+    ms = systems.mgcl2(7, explicit=False) if which == "mgcl2_7" else systems.quartz(48, pinned_cutoff=False)
+    assert ms.nsites == (278516 if which == "mgcl2_7" else 995328)
+    f4, pe4, s4, pairs, nk = _eval(ms, 4)
+    fmax = np.abs(f4).max()
+    assert np.isfinite(f4).all() and np.abs(f4.sum(1)).max() < 1e-9 * fmax * np.sqrt(ms.nsites)
+    f3, pe3, s3, pairs3, _ = _eval(ms, 3)
+    assert pairs == pairs3 and pairs > 100 * ms.nsites and nk > 1000
+    assert cases.rel_rms(f4, f3) < 1e-12
+    assert np.allclose(pe4, pe3, rtol=1e-11)
+    iu = np.triu_indices(3)
+    assert np.linalg.norm(s4[iu] - s3[iu]) < 1e-11 * np.linalg.norm(s3[iu])
