@@ -110,19 +110,22 @@ def test_nve_energy_drift_no_worse_than_reference(tmp_path):
 
 
 def _rdf_tables(text):
-    """{'O-O RDF': [g(r) values]} from print_rdf (src/rdf.c:117-170)."""
-    res, lines, i = {}, text.splitlines(), 0
-    while i < len(lines):
-        m = re.match(r"\s*(\S+-\S+ RDF)\s*$", lines[i])
-        i += 1
-        if not m:
+    """{'O-O RDF': [g(r) values per print-out]} from print_rdf (src/rdf.c:117-170); page headers and
+    form feeds may interrupt a table."""
+    res, cur = {}, None
+    for ln in text.splitlines():
+        t = ln.strip().strip("\f")
+        m = re.match(r"^(\S+-\S+ RDF)$", t)
+        if m:
+            cur = []
+            res.setdefault(m.group(1), []).append(cur)
+        elif cur is not None and t and re.match(r"^[\d.eE+\-\s]+$", t):
+            cur += [float(x) for x in t.split()]
+        elif cur is not None and (not t or re.search(r"Page \d+$", t)):
             continue
-        vals = []
-        while i < len(lines) and re.match(r"^[\s\d.eE+-]+$", lines[i]) and lines[i].strip():
-            vals += [float(t) for t in lines[i].split()]
-            i += 1
-        res.setdefault(m.group(1), []).append(np.array(vals))
-    return res
+        else:
+            cur = None
+    return {k: [np.array(v) for v in tabs] for k, tabs in res.items()}
 
 
 @needs_binaries
