@@ -388,7 +388,9 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
       // (a two-step unrolled ping-pong of A/B measured 10 % slower: spills and a 17 KB loop body)
       for (int base = 0; base < total; base += 32, pl += 32) {
          B = A;
-         if (base + 32 < total) fetch(pl + 32, A);
+         // unconditional (the position is clamped inside): with the loads under a branch ptxas makes the
+         // first instruction after the join wait for them, which serialises the prefetch with the step
+         fetch(pl + 32, A);
          step(std::integral_constant<bool, !N3>{}, B, pl < total);
       }
    }
