@@ -265,7 +265,9 @@ def run_ours(a):
             pass
         roof = {"bound": "fp64", "kernel": "k_pair_tiled<LJ,coulomb,newton3> (real-space pair kernel, FP64 CUDA cores; no "
                 "tensor-core or HBM roofline applies: ~36 B/site are reused for ~6 300 pair visits; `traffic` is "
-                "dram read+write bytes per launch from the ncu capture in profiles/)",
+                "dram read+write bytes per launch from the ncu capture in profiles/; a DFMA reading three distinct "
+                "registers issues every 3.2 cycles instead of 2.1 on sm_100a, scripts/ubench2.cu, so the DFMA-probe "
+                "peak is not reachable by a*b+c chains on registers)",
                 "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": "FP64 DFMA rate measured in this run by mdb_fp64_peak_probe (MEASURED_PEAKS.json holds "
                                "no FP64 figure; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2)",
@@ -298,7 +300,7 @@ def run_ours(a):
 
 
 # dram__bytes_read+write per k_pair launch from the ncu --set full capture committed under profiles/
-TRAFFIC = {10: 102.4e6}    # bytes per k_pair_tiled launch at n=10 (profiles/r01_final_summary.md)
+TRAFFIC = {10: 104.9e6}    # bytes per k_pair_tiled launch at n=10 (profiles/r01_final_summary.md)
 
 
 def measure_e2e(a, ms, site, world, rank, local):

@@ -370,9 +370,11 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
       unsigned sega = sw;                       // address of this lane's current segment: pre[seg] at sega + OFF_PRE
       auto fetch = [&](int p, JBuf &J) {
          const int pp = min(p, total - 1);
-         const int a1 = lds_i<OFF_PRE + 4>(sega), a2 = lds_i<OFF_PRE + 8>(sega);   // mostly 0..2 boundaries per step
-         sega += (pp >= a1 ? 4u : 0u) + (pp >= a2 ? 4u : 0u);
-         while (pp >= lds_i<OFF_PRE + 4>(sega)) sega += 4;
+         // mostly 0..2 segment boundaries per step: three independent look-ahead loads, a loop only beyond
+         const int a1 = lds_i<OFF_PRE + 4>(sega), a2 = lds_i<OFF_PRE + 8>(sega), a3 = lds_i<OFF_PRE + 12>(sega);
+         sega += (pp >= a1 ? 4u : 0u) + (pp >= a2 ? 4u : 0u) + (pp >= a3 ? 4u : 0u);
+         if (pp >= a3)
+            while (pp >= lds_i<OFF_PRE + 4>(sega)) sega += 4;
          J.qa = sw + 4 * (sega - sw);
          J.j = lds_i<OFF_Q>(J.qa) + pp;
 #ifdef MDB_EXP_NOFETCH                          /* experiment: no per-step global loads */
