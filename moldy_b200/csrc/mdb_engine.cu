@@ -55,7 +55,7 @@ static void free_grid(mdb_engine *e)
 static void free_recip(mdb_engine *e)
 {
    FREE(e->d_hk); FREE(e->d_hk_valid); FREE(e->d_slot_flags); FREE(e->d_ppart);
-   FREE(e->d_coef_tot); FREE(e->d_coef_nf); FREE(e->d_kpartials); FREE(e->d_cidx); FREE(e->d_sfac_blocks);
+   FREE(e->d_coef_tot); FREE(e->d_coef_nf); FREE(e->d_kpartials); FREE(e->d_cidx); FREE(e->d_sfac_blocks); FREE(e->d_kf_groups);
    FREE(e->d_psum);
    e->ppart_cap = 0;
 }
@@ -201,7 +201,7 @@ extern "C" int mdb_configure(mdb_engine *e, const mdb_config *cfg)
       if (upload(&e->d_hk, T.hk.data(), T.hk.size())) return -1;
       if (upload(&e->d_hk_valid, T.hk_valid.data(), T.hk_valid.size())) return -1;
       if (upload(&e->d_slot_flags, slotinfo.data(), slotinfo.size())) return -1;
-      e->sfac_rank = -1;
+      e->sfac_rank = -1; e->kf_rank = -1;
       FREE(e->d_coef_tot); FREE(e->d_coef_nf); FREE(e->d_kpartials);
       MDB_CUDA(cudaMalloc(&e->d_coef_tot, sizeof(double) * 8 * (size_t)std::max(T.nslots, 1)));
       MDB_CUDA(cudaMalloc(&e->d_coef_nf, sizeof(double) * 8 * (size_t)std::max(T.nslots, 1)));

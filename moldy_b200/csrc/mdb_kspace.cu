@@ -23,6 +23,7 @@
 // Framework sites (src/ewald.c:528-579) are handled by keeping their slabs
 // separate in k_sfac and using the non-framework-only coefficient set for them.
 #include <algorithm>
+#include <cstdlib>
 #include "mdb_internal.h"
 
 static constexpr int KT = 256;          // threads per block (k_sfac)
@@ -156,6 +157,194 @@ k_sfac(SfacArgs A, const SfacBlock *__restrict__ blocks, const int *__restrict__
       }
 }
 
+// ---- structure factors on the FP64 tensor pipe (DMMA.8x8x4) -------------------
+// The four sums of a column are one real GEMM over the sites:
+//    [c_hk ; s_hk](2 x sites) . [C_l , S_l](sites x 2)  =  [P1 P4 ; P3 P2].
+// mma.sync.m8n8k4.f64 sustains the nominal FP64 rate on sm_100a (16.3 cycles per warp
+// instruction = 256 FMA, scripts/ubench_dmma.cu) with one issue slot and four operand
+// registers per 256 FMAs, where the register-operand DFMA form above stops at ~60 %.
+// Block = 96 columns x one l-range of <= 32 slots, one block per SM: twelve consumer warps
+// (8 columns each: two 8-row m-tiles of 4 columns x {c,s}, NT n-tiles of 4 slots x {C,S},
+// k = 4 sites per instruction) and four producer warps that build the E_h / E_k / E_l power
+// tables of the NEXT 32-site chunk into the other half of a double buffer, so the serial
+// recurrences never sit between the consumers and a barrier (first version: 34 % of all
+// warp samples waited there).  The A fragment (E_hk of the lane's column and site) is
+// formed in registers from the E_h / E_k tables: no E_hk tile in shared memory.
+static constexpr int MCW = 12;          // consumer warps
+static constexpr int MC = 8 * MCW;      // columns per block
+static constexpr int MSC = 32;          // sites per shared-memory chunk
+static constexpr int MT = 32 * (MCW + 4);
+
+struct SfacMBlock { int e0, ncols, l0, nt; };
+
+struct SfacMArgs {
+   KspaceParams K;
+   int nvalid, rank, nranks;
+   int nslots, slab_sites, n_slabs_nf;
+   int nf_lo, nf_hi, fw_lo, fw_hi;
+   int SB, SH, SK, NLP;                 // row strides: sB in doubles (= 4 mod 16), sH/sK in double2 (odd); padded slot count
+};
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
+{
+   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+       : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double flip_sign(double v, int mask)      // mask = 0 or 0x80000000: no FP64 op
+{
+   return __hiloint2double(__double2hiint(v) ^ mask, __double2loint(v));
+}
+
+// power tables of the three base phase factors for sites [base, base+MSC), one (site,axis) per thread
+__device__ __forceinline__ void sfac_tables(const SfacMArgs &A, int ptid, int base, int s1, const int *__restrict__ cidx,
+                                            const double *__restrict__ x, const double *__restrict__ y,
+                                            const double *__restrict__ z, const double *__restrict__ chg,
+                                            double *sB, double2 *sH, double2 *sK)
+{
+   const KspaceParams &K = A.K;
+   if (ptid >= 3 * MSC) return;
+   const int sl = ptid % MSC, axis = ptid / MSC, gi = base + sl;
+   double q = 0.0, kr = 0.0;
+   const double *ks = axis == 0 ? K.astar : axis == 1 ? K.bstar : K.cstar;
+   if (gi < s1) {
+      const int i = cidx[gi];
+      kr = ks[0] * x[i] + ks[1] * y[i] + ks[2] * z[i];
+      q = chg[i];
+   }
+   double s1v, c1v;
+   sincos(kr, &s1v, &c1v);
+   const double2 e1 = make_double2(c1v, s1v);
+   double2 *tab = axis == 0 ? sH + sl * A.SH : axis == 1 ? sK + sl * A.SK : reinterpret_cast<double2 *>(sB + sl * A.SB);
+   const int nmax = axis == 0 ? K.hmax + 1 : axis == 1 ? K.kmax + 1 : K.nlslots;
+   const double amp = axis == 2 ? q : 1.0;
+   double2 e = make_double2(1.0, 0.0);
+   tab[0] = make_double2(amp, 0.0);
+   for (int m = 1; m < nmax; m++) {
+      e = cmul(e, e1);
+      tab[m] = make_double2(amp * e.x, amp * e.y);
+   }
+   if (axis == 2)
+      for (int m = nmax; m < A.NLP; m++) tab[m] = make_double2(0.0, 0.0);
+}
+
+template <int NT>
+__device__ __forceinline__ void sfac_mma_body(const SfacMArgs &A, const SfacMBlock &B, const int *__restrict__ cidx,
+                                              const double *__restrict__ x, const double *__restrict__ y,
+                                              const double *__restrict__ z, const double *__restrict__ chg,
+                                              const HkDesc *__restrict__ hk, const int *__restrict__ hk_valid,
+                                              double *__restrict__ ppart, double2 *smem)
+{
+   const size_t buf_doubles = (size_t)MSC * A.SB + 2 * (size_t)MSC * (A.SH + A.SK);
+   double *buf0 = reinterpret_cast<double *>(smem);
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   const bool producer = warp >= MCW;
+   const int g = lane >> 2, kq = lane & 3, comp = g & 1;
+
+   const int slab = blockIdx.y;
+   int s0, s1;
+   if (slab < A.n_slabs_nf) {
+      s0 = A.nf_lo + slab * A.slab_sites;
+      s1 = min(s0 + A.slab_sites, A.nf_hi);
+   } else {
+      s0 = A.fw_lo + (slab - A.n_slabs_nf) * A.slab_sites;
+      s1 = min(s0 + A.slab_sites, A.fw_hi);
+   }
+
+   int ch[2] = {0, 0}, ck[2] = {0, 0}, cnl[2] = {0, 0}, cslot[2] = {0, 0}, csign[2] = {0, 0};
+   if (!producer) {
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++) {
+         const int cl = warp * 8 + mt * 4 + (g >> 1);
+         const int v = A.rank + A.nranks * (B.e0 + cl);
+         bool neg = false;
+         if (cl < B.ncols && v < A.nvalid) {
+            const HkDesc d = hk[hk_valid[v]];
+            ch[mt] = d.h; ck[mt] = abs(d.k); neg = d.k < 0; cnl[mt] = d.nl; cslot[mt] = d.slot0;
+         }
+         // c = eh.x ek.x - sg eh.y ek.y    s = eh.y ek.x + sg eh.x ek.y    (sg = -1 for k < 0)
+         csign[mt] = ((comp == 0) != neg) ? (int)0x80000000 : 0;
+      }
+   }
+   const bool warp_on = !producer && warp * 8 < B.ncols;
+
+   double acc[2][NT][2];
+#pragma unroll
+   for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+      for (int n = 0; n < NT; n++) acc[mt][n][0] = acc[mt][n][1] = 0.0;
+
+   auto bufB = [&](int b) { return buf0 + b * buf_doubles; };
+   auto bufH = [&](int b) { return reinterpret_cast<double2 *>(buf0 + b * buf_doubles + (size_t)MSC * A.SB); };
+   auto bufK = [&](int b) { return reinterpret_cast<double2 *>(buf0 + b * buf_doubles + (size_t)MSC * A.SB) + (size_t)MSC * A.SH; };
+
+   if (producer) sfac_tables(A, tid - 32 * MCW, s0, s1, cidx, x, y, z, chg, bufB(0), bufH(0), bufK(0));
+   __syncthreads();
+   int b = 0;
+   for (int base = s0; base < s1; base += MSC, b ^= 1) {
+      if (producer) {
+         if (base + MSC < s1)
+            sfac_tables(A, tid - 32 * MCW, base + MSC, s1, cidx, x, y, z, chg, bufB(b ^ 1), bufH(b ^ 1), bufK(b ^ 1));
+      } else if (warp_on) {
+         const double *sB = bufB(b) + 2 * B.l0 + g;
+         const double2 *sH = bufH(b), *sK = bufK(b);
+#pragma unroll 2
+         for (int t = 0; t < MSC / 4; t++) {
+            const int sl = 4 * t + kq;
+            double a[2];
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) {
+               const double2 eh = sH[sl * A.SH + ch[mt]];
+               const double2 ek = sK[sl * A.SK + ck[mt]];
+               const double p = comp ? eh.y : eh.x, r = comp ? eh.x : eh.y;
+               a[mt] = fma(p, ek.x, flip_sign(r * ek.y, csign[mt]));
+            }
+            const double *bp = sB + sl * A.SB;
+#pragma unroll
+            for (int n = 0; n < NT; n++) {
+               const double bv = bp[8 * n];
+               dmma884(acc[0][n], a[0], bv);
+               dmma884(acc[1][n], a[1], bv);
+            }
+         }
+      }
+      __syncthreads();
+   }
+   // C fragment: row g = (column g/2, c|s), columns 2 kq + e = (slot kq of the n-tile, C|S)
+   if (warp_on)
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+         for (int n = 0; n < NT; n++) {
+            const int l = B.l0 + 4 * n + kq;
+            if (l < cnl[mt]) {
+               double *o = ppart + ((size_t)slab * A.nslots + cslot[mt] + l) * 4;
+               // (c,C) = P1 -> 0   (c,S) = P4 -> 3   (s,C) = P3 -> 2   (s,S) = P2 -> 1
+               o[comp ? 2 : 0] = acc[mt][n][0];
+               o[comp ? 1 : 3] = acc[mt][n][1];
+            }
+         }
+}
+
+__global__ void __launch_bounds__(MT, 1)
+k_sfac_mma(SfacMArgs A, const SfacMBlock *__restrict__ blocks, const int *__restrict__ cidx,
+           const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
+           const double *__restrict__ chg, const HkDesc *__restrict__ hk, const int *__restrict__ hk_valid,
+           double *__restrict__ ppart)
+{
+   extern __shared__ double2 smem[];
+   const SfacMBlock B = blocks[blockIdx.x];
+   switch (B.nt) {          // block-uniform: straight-line DMMA sequences, accumulators in registers
+      case 1: sfac_mma_body<1>(A, B, cidx, x, y, z, chg, hk, hk_valid, ppart, smem); break;
+      case 2: sfac_mma_body<2>(A, B, cidx, x, y, z, chg, hk, hk_valid, ppart, smem); break;
+      case 3: sfac_mma_body<3>(A, B, cidx, x, y, z, chg, hk, hk_valid, ppart, smem); break;
+      case 4: sfac_mma_body<4>(A, B, cidx, x, y, z, chg, hk, hk_valid, ppart, smem); break;
+      case 5: sfac_mma_body<5>(A, B, cidx, x, y, z, chg, hk, hk_valid, ppart, smem); break;
+      case 6: sfac_mma_body<6>(A, B, cidx, x, y, z, chg, hk, hk_valid, ppart, smem); break;
+      case 7: sfac_mma_body<7>(A, B, cidx, x, y, z, chg, hk, hk_valid, ppart, smem); break;
+      default: sfac_mma_body<8>(A, B, cidx, x, y, z, chg, hk, hk_valid, ppart, smem); break;
+   }
+}
+
 // ---- fixed-order sum of the slab partials: psum[0] = non-framework slabs, psum[1] = framework slabs.
 // This 8*nslots block is what ranks all-reduce when k-space is partitioned by sites.
 __global__ void __launch_bounds__(256) k_slab_sum(int nslots, int n_slabs, int n_slabs_nf,
@@ -174,6 +363,7 @@ __global__ void __launch_bounds__(256) k_slab_sum(int nslots, int n_slabs, int n
 struct SfinArgs {
    KspaceParams K;
    int nslots, n_slabs, n_slabs_nf, rank, nranks, framework;
+   int mma;                // coefficient rows in k_kforce_mma's order: {X,Y | el.x, el.y}, {Xz,Yz | el.x, el.y}
 };
 
 __global__ void __launch_bounds__(256)
@@ -223,6 +413,13 @@ k_sfin(SfinArgs A, const HkDesc *__restrict__ hk, const int *__restrict__ slot_h
          ct[4] = fl * ct[2]; ct[5] = fl * ct[1]; ct[6] = fl * ct[0]; ct[7] = fl * ct[3];
          cn[0] = Cn2[0] + Cn2[1]; cn[1] = Sn2[0] + Sn2[1]; cn[2] = Cn2[0] - Cn2[1]; cn[3] = Sn2[0] - Sn2[1];
          cn[4] = fl * cn[2]; cn[5] = fl * cn[1]; cn[6] = fl * cn[0]; cn[7] = fl * cn[3];
+      }
+      if (A.mma) {
+         // X = sum el.x ct0 + el.y ct3   Y = sum -el.x ct1 + el.y ct2   Xz = sum el.x ct4 + el.y ct5   Yz = sum -el.x ct7 + el.y ct6
+         const double mt[8] = {ct[0], -ct[1], ct[3], ct[2], ct[4], -ct[7], ct[5], ct[6]};
+         const double mn[8] = {cn[0], -cn[1], cn[3], cn[2], cn[4], -cn[7], cn[5], cn[6]};
+#pragma unroll
+         for (int k = 0; k < 8; k++) { ct[k] = mt[k]; cn[k] = mn[k]; }
       }
 #pragma unroll
       for (int k = 0; k < 8; k++) coef_tot[(size_t)slot * 8 + k] = ct[k];
@@ -448,6 +645,188 @@ k_kforce(KfArgs A, const int *__restrict__ cidx, const double *__restrict__ x, c
       }
 }
 
+// ---- forces on the FP64 tensor pipe --------------------------------------------------
+// For a site j and a column c the four l-sums of k_kforce are one real GEMM over the slots,
+//    [X Y Xz Yz](j,c) = sum_(l,comp) E_l(j)[l,comp] . coef(c)[l,comp][X Y Xz Yz],
+// m = 8 sites, n = 8 columns, k = 2 slots x {cos,sin} per DMMA.8x8x4, one accumulator tile per
+// quantity.  The C fragment leaves a thread with ONE site and TWO columns, so the back-projection
+//    T = s X + c Y,  Tz = s Xz + c Yz,   Fa += h T,  Fb += k T,  Fc += Tz,   F = a* Fa + b* Fb + c* Fc
+// stays thread-local (k.x = h a*.x + k b*.x, k.z adds l c*.z which is folded into Xz, Yz);
+// lanes are summed once at the end.  Columns come in groups of 8 in descending slot count (the valid
+// list of k_sfac), so a group runs max(nl)/2 steps with 3 % padding; E_hk = E_h E_k is read from per-site
+// power tables in shared memory, which is what limits a block to 128 sites (one block per SM).
+// Warps 0..NSB-1 own 16 sites each and walk the even groups, warps NSB..2NSB-1 the same sites and
+// the odd groups: the coefficient fragments (the same for every site) are then loaded once per 16
+// sites and four warps per scheduler keep the DMMA pipe fed.  Coefficients of the next two groups are
+// staged with cp.async while the current two are consumed.
+struct KfGroup {            // 8 columns, padded with nl = 0
+   int nsteps, pad0, pad1, pad2;
+   int h[8], k[8], nl[8], slot0[8];
+};
+
+struct KfMArgs {
+   KspaceParams K;
+   int c0, c1;              // range in the compacted charged-site list
+   int ngroups, nsb;        // nsb: site-warps per block (block = 2 nsb warps, 16 nsb sites)
+   int SE, SH, SK, LPS;     // table strides: E_l in doubles (= 4 mod 16), E_h/E_k in double2 (odd); stage slots (= 2 mod 4)
+};
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+   const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
+__global__ void __launch_bounds__(512, 1)
+k_kforce_mma(KfMArgs A, const int *__restrict__ cidx, const double *__restrict__ x, const double *__restrict__ y,
+             const double *__restrict__ z, const double *__restrict__ chg, const KfGroup *__restrict__ groups,
+             const double *__restrict__ coef, double *__restrict__ out)
+{
+   extern __shared__ double2 smem[];
+   const KspaceParams &K = A.K;
+   const int nsites_b = 16 * A.nsb, nthreads = 64 * A.nsb;
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   const int g = lane >> 2, kq = lane & 3;
+   const int half = warp / A.nsb, sw = warp % A.nsb;
+   // shared memory: E_l [sites][SE] doubles | E_h [sites][SH] | E_k [sites][SK] | stage [2 bufs][2 halves][2 planes][8][2 LPS] double2 | F [2][sites][3]
+   double *sE = reinterpret_cast<double *>(smem);
+   double2 *sH = reinterpret_cast<double2 *>(sE + (size_t)nsites_b * A.SE);
+   double2 *sK = sH + (size_t)nsites_b * A.SH;
+   double2 *sC = sK + (size_t)nsites_b * A.SK;
+   const int colstride = 2 * A.LPS;                      // double2 per (plane, column)
+   const int stage_half = 2 * 8 * colstride;             // double2 per (buffer, half)
+   double *sF = reinterpret_cast<double *>(sC + 4 * (size_t)stage_half);
+
+   const int site0 = A.c0 + blockIdx.x * nsites_b;
+   // ---- power tables, one (site, axis) per thread
+   for (int job = tid; job < 3 * nsites_b; job += nthreads) {
+      const int sl = job % nsites_b, axis = job / nsites_b, t = site0 + sl;
+      double q = 0.0, kr = 0.0;
+      const double *ks = axis == 0 ? K.astar : axis == 1 ? K.bstar : K.cstar;
+      if (t < A.c1) {
+         const int i = cidx[t];
+         kr = ks[0] * x[i] + ks[1] * y[i] + ks[2] * z[i];
+         q = chg[i];
+      }
+      double s1v, c1v;
+      sincos(kr, &s1v, &c1v);
+      const double2 e1 = make_double2(c1v, s1v);
+      double2 *tab = axis == 0 ? sH + (size_t)sl * A.SH : axis == 1 ? sK + (size_t)sl * A.SK
+                                                                    : reinterpret_cast<double2 *>(sE + (size_t)sl * A.SE);
+      const int nmax = axis == 0 ? K.hmax + 1 : axis == 1 ? K.kmax + 1 : K.nlslots;
+      const double amp = axis == 2 ? q : 1.0;
+      double2 e = make_double2(1.0, 0.0);
+      tab[0] = make_double2(amp, 0.0);
+      for (int m = 1; m < nmax; m++) {
+         e = cmul(e, e1);
+         tab[m] = make_double2(amp * e.x, amp * e.y);
+      }
+      if (axis == 2)
+         for (int m = nmax; m < A.SE / 2; m++) tab[m] = make_double2(0.0, 0.0);
+   }
+
+   // ---- coefficient staging: item = (half, column, slot); real slots by cp.async, padding by zero stores
+   auto stage = [&](int round, int buf) {
+      for (int item = tid; item < 2 * 8 * A.LPS; item += nthreads) {
+         const int hb = item / (8 * A.LPS), rem = item % (8 * A.LPS), c = rem / A.LPS, l = rem % A.LPS;
+         const int gi = 2 * round + hb;
+         if (gi >= A.ngroups) continue;
+         const KfGroup &G = groups[gi];
+         if (l >= 2 * G.nsteps) continue;
+         double2 *d0 = sC + (size_t)(buf * 2 + hb) * stage_half + c * colstride + 2 * l;
+         double2 *d1 = d0 + 8 * colstride;
+         if (l < G.nl[c]) {
+            const double *src = coef + 8 * (size_t)(G.slot0[c] + l);
+            cp_async16(d0, src); cp_async16(d0 + 1, src + 2);
+            cp_async16(d1, src + 4); cp_async16(d1 + 1, src + 6);
+         } else {
+            d0[0] = d0[1] = d1[0] = d1[1] = make_double2(0.0, 0.0);
+         }
+      }
+   };
+
+   const int nrounds = (A.ngroups + 1) / 2;
+   stage(0, 0);
+   cp_async_wait_all();
+   __syncthreads();
+
+   double Fa[2] = {0, 0}, Fb[2] = {0, 0}, Fc[2] = {0, 0};
+   const int sl0 = sw * 16 + g;                          // this thread's site of tile 0 (tile 1: +8)
+   const double *ea0 = sE + (size_t)sl0 * A.SE + kq, *ea1 = ea0 + 8 * (size_t)A.SE;
+   for (int r = 0; r < nrounds; r++) {
+      const int buf = r & 1;
+      if (r + 1 < nrounds) stage(r + 1, buf ^ 1);
+      const int gi = 2 * r + half;
+      if (gi < A.ngroups) {
+         const KfGroup &G = groups[gi];
+         const int nsteps = G.nsteps;
+         const double2 *c0 = sC + (size_t)(buf * 2 + half) * stage_half + g * colstride + kq;
+         const double2 *c1 = c0 + 8 * colstride;
+         double acc[2][4][2];
+#pragma unroll
+         for (int s = 0; s < 2; s++)
+#pragma unroll
+            for (int qn = 0; qn < 4; qn++) acc[s][qn][0] = acc[s][qn][1] = 0.0;
+#pragma unroll 2
+         for (int t = 0; t < nsteps; t++) {
+            const double2 q01 = c0[4 * t], q23 = c1[4 * t];
+            const double a0 = ea0[4 * t], a1 = ea1[4 * t];
+            dmma884(acc[0][0], a0, q01.x); dmma884(acc[0][1], a0, q01.y);
+            dmma884(acc[0][2], a0, q23.x); dmma884(acc[0][3], a0, q23.y);
+            dmma884(acc[1][0], a1, q01.x); dmma884(acc[1][1], a1, q01.y);
+            dmma884(acc[1][2], a1, q23.x); dmma884(acc[1][3], a1, q23.y);
+         }
+         // back-projection: C fragment = (site g of the tile, columns 2 kq + e)
+#pragma unroll
+         for (int e = 0; e < 2; e++) {
+            const int hc = G.h[2 * kq + e], kc = G.k[2 * kq + e];
+            const double fh = (double)hc, fk = (double)kc;
+            const int ka = abs(kc), sg = kc < 0 ? (int)0x80000000 : 0;
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+               const int sl = sl0 + 8 * s;
+               const double2 eh = sH[(size_t)sl * A.SH + hc];
+               double2 ek = sK[(size_t)sl * A.SK + ka];
+               ek.y = flip_sign(ek.y, sg);
+               const double2 ehk = cmul(eh, ek);
+               const double T = fma(ehk.y, acc[s][0][e], ehk.x * acc[s][1][e]);
+               Fa[s] = fma(fh, T, Fa[s]);
+               Fb[s] = fma(fk, T, Fb[s]);
+               Fc[s] = fma(ehk.y, acc[s][2][e], fma(ehk.x, acc[s][3][e], Fc[s]));
+            }
+         }
+      }
+      cp_async_wait_all();
+      __syncthreads();
+   }
+   // ---- sum the four lanes of a site, then the two halves, and add to the caller's force rows
+#pragma unroll
+   for (int s = 0; s < 2; s++) {
+#pragma unroll
+      for (int d = 1; d <= 2; d <<= 1) {
+         Fa[s] += __shfl_xor_sync(0xffffffffu, Fa[s], d);
+         Fb[s] += __shfl_xor_sync(0xffffffffu, Fb[s], d);
+         Fc[s] += __shfl_xor_sync(0xffffffffu, Fc[s], d);
+      }
+      if (kq == 0) {
+         double *f = sF + ((size_t)half * nsites_b + sl0 + 8 * s) * 3;
+         f[0] = Fa[s]; f[1] = Fb[s]; f[2] = Fc[s];
+      }
+   }
+   __syncthreads();
+   for (int sl = tid; sl < nsites_b; sl += nthreads) {
+      const int t = site0 + sl;
+      if (t >= A.c1) continue;
+      const double *f0 = sF + (size_t)sl * 3, *f1 = f0 + (size_t)nsites_b * 3;
+      const double fa = f0[0] + f1[0], fb = f0[1] + f1[1], fc = f0[2] + f1[2];
+      const int i = cidx[t];
+      out[i] += K.astar[0] * fa + K.bstar[0] * fb + K.cstar[0] * fc;
+      out[(size_t)K.nsites + i] += K.astar[1] * fa + K.bstar[1] * fb + K.cstar[1] * fc;
+      out[2 * (size_t)K.nsites + i] += K.astar[2] * fa + K.bstar[2] * fb + K.cstar[2] * fc;
+   }
+}
+
 #ifndef MDB_KF_NS
 #define MDB_KF_NS 2
 #endif
@@ -458,6 +837,18 @@ k_kforce(KfArgs A, const int *__restrict__ cidx, const double *__restrict__ x, c
 //  site mode   (the manual's "RIL" scheme, src/moldy.tex:3441-3466): own sites x all columns; the
 //              8*nslots structure-factor sums are all-reduced between the two passes; both
 //              passes then scale with 1/P.
+// MDB_KSPACE=dfma selects the register-operand DFMA kernels (k_sfac, k_kforce) for A/B timing;
+// the default is the DMMA pair (k_sfac_mma, k_kforce_mma).  Both are device paths.
+static bool kspace_use_mma()
+{
+   static int mode = -1;
+   if (mode < 0) {
+      const char *m = getenv("MDB_KSPACE");
+      mode = (m && std::string(m) == "dfma") ? 0 : 1;
+   }
+   return mode == 1;
+}
+
 struct RecipPlan {
    int col_rank, col_nranks;
    int nf_lo, nf_hi, fw_lo, fw_hi;
@@ -494,12 +885,20 @@ static int make_plan(mdb_engine *e, bool by_sites, RecipPlan &P, cudaStream_t st
       P.add_scalars = true;
    }
    // per-block column table for this column partition
-   if (e->sfac_rank != P.col_rank || e->sfac_nranks != P.col_nranks || !e->d_sfac_blocks) {
-      std::vector<SfacBlock> blocks;
+   const int mode = kspace_use_mma() ? 1 : 0;
+   if (e->sfac_rank != P.col_rank || e->sfac_nranks != P.col_nranks || e->sfac_mode != mode || !e->d_sfac_blocks) {
+      std::vector<SfacBlock> blocks;          // SfacMBlock has the same four ints
       const int my_cols = nvalid > P.col_rank ? (nvalid - P.col_rank + P.col_nranks - 1) / P.col_nranks : 0;
       int e0 = 0;
       while (e0 < my_cols) {
          const int nlmax = T.hk[T.hk_valid[P.col_rank + P.col_nranks * e0]].nl;
+         if (mode == 1) {
+            const int ncols = std::min(MC, my_cols - e0);
+            for (int l0 = 0; l0 < nlmax; l0 += 32)
+               blocks.push_back({e0, ncols, l0, (std::min(32, nlmax - l0) + 3) / 4});
+            e0 += ncols;
+            continue;
+         }
          int nlc = std::max(2, (nlmax + LCH - 1) / LCH);
          if (nlc > 8) { mdb_set_error("k_cutoff gives lmax > 63: not supported by this build of k_sfac"); return -1; }
          const int hkb = KT / nlc;
@@ -514,11 +913,16 @@ static int make_plan(mdb_engine *e, bool by_sites, RecipPlan &P, cudaStream_t st
                                   cudaMemcpyHostToDevice, st));
          MDB_CUDA(cudaStreamSynchronize(st));
       }
-      e->sfac_rank = P.col_rank; e->sfac_nranks = P.col_nranks;
+      e->sfac_rank = P.col_rank; e->sfac_nranks = P.col_nranks; e->sfac_mode = mode;
    }
    // site slabs: enough blocks for about two waves on 148 SMs x 2 resident blocks
    const int own = (P.nf_hi - P.nf_lo) + (P.fw_hi - P.fw_lo);
-   const int want = std::max(1, (4 * 148 + std::max(1, e->n_sfac_blocks) - 1) / std::max(1, e->n_sfac_blocks));
+   int want = std::max(1, (4 * 148 + std::max(1, e->n_sfac_blocks) - 1) / std::max(1, e->n_sfac_blocks));
+   if (mode == 1) {
+      // k_sfac_mma: one block per SM; never a few blocks more than a whole number of waves
+      static int waves = getenv("MDB_SFAC_WAVES") ? atoi(getenv("MDB_SFAC_WAVES")) : 4;
+      want = std::max(1, waves * 148 / std::max(1, e->n_sfac_blocks));
+   }
    int slab = (own + want - 1) / want;
    slab = std::max(SC, ((slab + SC - 1) / SC) * SC);
    P.slab_sites = slab;
@@ -546,7 +950,26 @@ static int recip_partial(mdb_engine *e, const RecipPlan &P, double *d_psum, cuda
    const size_t shm = sizeof(double2) * (size_t)SC * (A.HKB + A.K.nlslots + A.K.hmax + 1 + A.K.kmax + 1);
    if (P.col_nranks > 1)      // slots of other ranks' columns are never written: keep them defined
       MDB_CUDA(cudaMemsetAsync(e->d_ppart, 0, sizeof(double) * (size_t)std::max(1, P.n_slabs) * T.nslots * 4, st));
-   if (e->n_sfac_blocks > 0 && P.n_slabs > 0) {
+   if (e->n_sfac_blocks > 0 && P.n_slabs > 0 && kspace_use_mma()) {
+      SfacMArgs M;
+      M.K = A.K;
+      M.nvalid = A.nvalid; M.rank = A.rank; M.nranks = A.nranks;
+      M.nslots = A.nslots; M.slab_sites = A.slab_sites; M.n_slabs_nf = A.n_slabs_nf;
+      M.nf_lo = A.nf_lo; M.nf_hi = A.nf_hi; M.fw_lo = A.fw_lo; M.fw_hi = A.fw_hi;
+      M.NLP = (A.K.nlslots + 3) / 4 * 4;
+      M.SB = 2 * M.NLP; while (M.SB % 16 != 4) M.SB += 2;
+      M.SH = (A.K.hmax + 1) | 1; M.SK = (A.K.kmax + 1) | 1;
+      const size_t mshm = 2 * (sizeof(double) * (size_t)MSC * M.SB + sizeof(double2) * (size_t)MSC * (M.SH + M.SK));
+      static size_t mshm_set = 0;
+      if (mshm > mshm_set) {
+         MDB_CUDA(cudaFuncSetAttribute(k_sfac_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mshm));
+         mshm_set = mshm;
+      }
+      dim3 g(e->n_sfac_blocks, P.n_slabs);
+      k_sfac_mma<<<g, MT, mshm, st>>>(M, (const SfacMBlock *)e->d_sfac_blocks, e->d_cidx, e->d_x, e->d_y, e->d_z,
+                                       e->d_chg, e->d_hk, e->d_hk_valid, e->d_ppart);
+      e->launches++;
+   } else if (e->n_sfac_blocks > 0 && P.n_slabs > 0) {
       static size_t shm_set = 0;
       if (shm > shm_set) {
          MDB_CUDA(cudaFuncSetAttribute(k_sfac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
@@ -572,6 +995,7 @@ static int recip_finish(mdb_engine *e, const RecipPlan &P, const double *d_psum,
    kspace_params(e, F.K);
    F.nslots = T.nslots; F.n_slabs = 2; F.n_slabs_nf = 1;
    F.rank = P.col_rank; F.nranks = P.col_nranks; F.framework = c.nsites_xf < c.nsites;
+   F.mma = kspace_use_mma() ? 1 : 0;
    const int fb = (T.nslots + 255) / 256;
    k_sfin<<<fb, 256, 0, st>>>(F, e->d_hk, e->d_slot_flags + T.nslots, e->d_slot_flags, d_psum, e->d_coef_tot,
                               e->d_coef_nf, e->d_kpartials);
@@ -579,6 +1003,64 @@ static int recip_finish(mdb_engine *e, const RecipPlan &P, const double *d_psum,
    if (P.add_scalars) {
       k_recip_finish<<<1, 256, 0, st>>>(e->d_kpartials, fb, c.nsites, d_out);
       e->launches++;
+   }
+   if (F.mma) {
+      // groups of 8 columns of this rank's share of the valid list (descending slot count)
+      if (e->kf_rank != P.col_rank || e->kf_nranks != P.col_nranks || !e->d_kf_groups) {
+         std::vector<KfGroup> groups;
+         const int nvalid = (int)T.hk_valid.size();
+         for (int v = P.col_rank; v < nvalid; v += 8 * P.col_nranks) {
+            KfGroup G{};
+            int mx = 0;
+            for (int j = 0; j < 8; j++) {
+               const int vv = v + j * P.col_nranks;
+               if (vv >= nvalid) break;
+               const HkDesc &d = T.hk[T.hk_valid[vv]];
+               G.h[j] = d.h; G.k[j] = d.k; G.nl[j] = d.nl; G.slot0[j] = d.slot0;
+               mx = std::max(mx, d.nl);
+            }
+            G.nsteps = (mx + 1) / 2;
+            groups.push_back(G);
+         }
+         if (e->d_kf_groups) { cudaFree(e->d_kf_groups); e->d_kf_groups = nullptr; }
+         e->n_kf_groups = (int)groups.size();
+         if (!groups.empty()) {
+            MDB_CUDA(cudaMalloc(&e->d_kf_groups, sizeof(KfGroup) * groups.size()));
+            MDB_CUDA(cudaMemcpyAsync(e->d_kf_groups, groups.data(), sizeof(KfGroup) * groups.size(), cudaMemcpyHostToDevice, st));
+            MDB_CUDA(cudaStreamSynchronize(st));
+         }
+         e->kf_rank = P.col_rank; e->kf_nranks = P.col_nranks;
+      }
+      KfMArgs Q;
+      Q.K = F.K; Q.ngroups = e->n_kf_groups;
+      const int nle = (F.K.nlslots + 1) / 2 * 2;
+      Q.SE = 2 * nle; while (Q.SE % 16 != 4) Q.SE += 2;
+      Q.SH = (F.K.hmax + 1) | 1; Q.SK = (F.K.kmax + 1) | 1;
+      Q.LPS = nle; while (Q.LPS % 4 != 2) Q.LPS += 2;
+      const size_t per_site = sizeof(double) * Q.SE + sizeof(double2) * (Q.SH + Q.SK) + 6 * sizeof(double);
+      const size_t stage_bytes = 4 * (size_t)(2 * 8 * 2 * Q.LPS) * sizeof(double2);
+      static int max_smem = 0;
+      if (!max_smem) MDB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
+      Q.nsb = 8;
+      while (Q.nsb > 1 && stage_bytes + 16 * (size_t)Q.nsb * per_site > (size_t)max_smem) Q.nsb--;
+      const size_t kshm = stage_bytes + 16 * (size_t)Q.nsb * per_site;
+      if (kshm > (size_t)max_smem) { mdb_set_error("k_cutoff too large for the shared-memory tables of k_kforce_mma"); return -1; }
+      static size_t kshm_set = 0;
+      if (kshm > kshm_set) {
+         MDB_CUDA(cudaFuncSetAttribute(k_kforce_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kshm));
+         kshm_set = kshm;
+      }
+      for (int part = 0; part < 2; part++) {
+         Q.c0 = part == 0 ? P.nf_lo : P.fw_lo; Q.c1 = part == 0 ? P.nf_hi : P.fw_hi;
+         if (Q.c1 <= Q.c0 || Q.ngroups == 0) continue;
+         const int spb = 16 * Q.nsb;
+         k_kforce_mma<<<(Q.c1 - Q.c0 + spb - 1) / spb, 64 * Q.nsb, kshm, st>>>(
+            Q, e->d_cidx, e->d_x, e->d_y, e->d_z, e->d_chg, (const KfGroup *)e->d_kf_groups,
+            part == 0 ? e->d_coef_tot : e->d_coef_nf, d_out);
+         e->launches++;
+      }
+      MDB_CUDA(cudaGetLastError());
+      return 0;
    }
    KfArgs Q;
    Q.K = F.K; Q.nhk = (int)T.hk.size(); Q.rank = P.col_rank; Q.nranks = P.col_nranks;
