@@ -163,26 +163,43 @@ k_sfac(SfacArgs A, const SfacBlock *__restrict__ blocks, const int *__restrict__
 // mma.sync.m8n8k4.f64 sustains the nominal FP64 rate on sm_100a (16.3 cycles per warp
 // instruction = 256 FMA, scripts/ubench_dmma.cu) with one issue slot and four operand
 // registers per 256 FMAs, where the register-operand DFMA form above stops at ~60 %.
-// Block = 96 columns x one l-range of <= 32 slots, one block per SM: twelve consumer warps
-// (8 columns each: two 8-row m-tiles of 4 columns x {c,s}, NT n-tiles of 4 slots x {C,S},
-// k = 4 sites per instruction) and four producer warps that build the E_h / E_k / E_l power
-// tables of the NEXT 32-site chunk into the other half of a double buffer, so the serial
-// recurrences never sit between the consumers and a barrier (first version: 34 % of all
-// warp samples waited there).  The A fragment (E_hk of the lane's column and site) is
-// formed in registers from the E_h / E_k tables: no E_hk tile in shared memory.
-static constexpr int MCW = 12;          // consumer warps
+//  k_ktables   once per step: per charged site the power tables E_h, E_k (unit modulus) and
+//              q E_l, written to HBM in exactly the padded row layout the GEMM kernel wants in
+//              shared memory (1.4 KB per site; they are re-read once per column block, mostly from L2).
+//  k_sfac_mma  block = 128 columns x one l-range of <= 32 slots, one block per SM, 16 warps of
+//              8 columns each (two 8-row m-tiles of 4 columns x {c,s}, NT n-tiles of 4 slots x {C,S},
+//              k = 4 sites per instruction).  The tables of the next 32-site chunk arrive by cp.async
+//              in the other half of a double buffer while the current chunk is consumed, so no serial
+//              recurrence sits between the DMMA warps and a barrier (versions that built the tables
+//              in the block: 34 % / 21 % of all warp samples waiting at the barrier).  The A fragment
+//              (E_hk of the lane's column and site) is formed in registers from E_h and E_k.
+static constexpr int MCW = 16;          // warps per block
 static constexpr int MC = 8 * MCW;      // columns per block
-static constexpr int MSC = 32;          // sites per shared-memory chunk
-static constexpr int MT = 32 * (MCW + 4);
+#ifndef MDB_MSC
+#define MDB_MSC 32
+#endif
+#ifndef MDB_ABL
+#define MDB_ABL 0
+#endif
+#ifndef MDB_SFAC_PIPE
+#define MDB_SFAC_PIPE 0
+#endif
+static constexpr int MSC = MDB_MSC;      // sites per shared-memory chunk
+static constexpr int MT = 32 * MCW;
 
 struct SfacMBlock { int e0, ncols, l0, nt; };
 
+struct KtabLayout {                     // row strides of the per-site tables
+   int SB, SH, SK, NLP;                 // sB in doubles (= 4 mod 16), sH/sK in double2 (odd); padded slot count
+};
+
 struct SfacMArgs {
    KspaceParams K;
+   KtabLayout L;
    int nvalid, rank, nranks;
    int nslots, slab_sites, n_slabs_nf;
    int nf_lo, nf_hi, fw_lo, fw_hi;
-   int SB, SH, SK, NLP;                 // row strides: sB in doubles (= 4 mod 16), sH/sK in double2 (odd); padded slot count
+   int nrows;                           // rows allocated in the tables (charged sites + MSC of padding)
 };
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
@@ -194,50 +211,66 @@ __device__ __forceinline__ double flip_sign(double v, int mask)      // mask = 0
 {
    return __hiloint2double(__double2hiint(v) ^ mask, __double2loint(v));
 }
-
-// power tables of the three base phase factors for sites [base, base+MSC), one (site,axis) per thread
-__device__ __forceinline__ void sfac_tables(const SfacMArgs &A, int ptid, int base, int s1, const int *__restrict__ cidx,
-                                            const double *__restrict__ x, const double *__restrict__ y,
-                                            const double *__restrict__ z, const double *__restrict__ chg,
-                                            double *sB, double2 *sH, double2 *sK)
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
 {
-   const KspaceParams &K = A.K;
-   if (ptid >= 3 * MSC) return;
-   const int sl = ptid % MSC, axis = ptid / MSC, gi = base + sl;
-   double q = 0.0, kr = 0.0;
-   const double *ks = axis == 0 ? K.astar : axis == 1 ? K.bstar : K.cstar;
-   if (gi < s1) {
-      const int i = cidx[gi];
-      kr = ks[0] * x[i] + ks[1] * y[i] + ks[2] * z[i];
-      q = chg[i];
+   const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
+// power tables of the three base phase factors for rows [g0, g1) of the charged-site list: one (site,axis)
+// per thread builds its row in shared memory by recurrence, then the block writes the 32 rows of each
+// table as one contiguous, coalesced piece (row-at-a-time 16-byte stores ran at 1.1 ms for 1.08 GB)
+static constexpr int KTS = 32;          // sites per block
+__global__ void __launch_bounds__(128)
+k_ktables(KspaceParams K, KtabLayout L, int g0, int g1, const int *__restrict__ cidx, const double *__restrict__ x,
+          const double *__restrict__ y, const double *__restrict__ z, const double *__restrict__ chg,
+          double *__restrict__ tE, double2 *__restrict__ tH, double2 *__restrict__ tK)
+{
+   extern __shared__ double2 smem[];
+   const int vE = L.SB / 2;                                     // double2 per row
+   double2 *sE = smem, *sH = sE + KTS * vE, *sK = sH + KTS * L.SH;
+   const int base = g0 + blockIdx.x * KTS, nv = min(KTS, g1 - base);
+   const int tid = threadIdx.x;
+   if (tid < 3 * KTS) {
+      const int sl = tid % KTS, axis = tid / KTS;
+      if (sl < nv) {
+         const double *ks = axis == 0 ? K.astar : axis == 1 ? K.bstar : K.cstar;
+         const int i = cidx[base + sl];
+         const double kr = ks[0] * x[i] + ks[1] * y[i] + ks[2] * z[i];
+         const double amp = axis == 2 ? chg[i] : 1.0;
+         double s1v, c1v;
+         sincos(kr, &s1v, &c1v);
+         const double2 e1 = make_double2(c1v, s1v);
+         double2 *tab = axis == 0 ? sH + sl * L.SH : axis == 1 ? sK + sl * L.SK : sE + sl * vE;
+         const int nmax = axis == 0 ? K.hmax + 1 : axis == 1 ? K.kmax + 1 : K.nlslots;
+         const int nrow = axis == 0 ? L.SH : axis == 1 ? L.SK : vE;
+         double2 e = make_double2(1.0, 0.0);
+         tab[0] = make_double2(amp, 0.0);
+         for (int m = 1; m < nmax; m++) {
+            e = cmul(e, e1);
+            tab[m] = make_double2(amp * e.x, amp * e.y);
+         }
+         for (int m = nmax; m < nrow; m++) tab[m] = make_double2(0.0, 0.0);
+      }
    }
-   double s1v, c1v;
-   sincos(kr, &s1v, &c1v);
-   const double2 e1 = make_double2(c1v, s1v);
-   double2 *tab = axis == 0 ? sH + sl * A.SH : axis == 1 ? sK + sl * A.SK : reinterpret_cast<double2 *>(sB + sl * A.SB);
-   const int nmax = axis == 0 ? K.hmax + 1 : axis == 1 ? K.kmax + 1 : K.nlslots;
-   const double amp = axis == 2 ? q : 1.0;
-   double2 e = make_double2(1.0, 0.0);
-   tab[0] = make_double2(amp, 0.0);
-   for (int m = 1; m < nmax; m++) {
-      e = cmul(e, e1);
-      tab[m] = make_double2(amp * e.x, amp * e.y);
-   }
-   if (axis == 2)
-      for (int m = nmax; m < A.NLP; m++) tab[m] = make_double2(0.0, 0.0);
+   __syncthreads();
+   double2 *gE = reinterpret_cast<double2 *>(tE + (size_t)base * L.SB), *gH = tH + (size_t)base * L.SH, *gK = tK + (size_t)base * L.SK;
+   for (int u = tid; u < nv * vE; u += 128) gE[u] = sE[u];
+   for (int u = tid; u < nv * L.SH; u += 128) gH[u] = sH[u];
+   for (int u = tid; u < nv * L.SK; u += 128) gK[u] = sK[u];
 }
 
 template <int NT>
-__device__ __forceinline__ void sfac_mma_body(const SfacMArgs &A, const SfacMBlock &B, const int *__restrict__ cidx,
-                                              const double *__restrict__ x, const double *__restrict__ y,
-                                              const double *__restrict__ z, const double *__restrict__ chg,
+__device__ __forceinline__ void sfac_mma_body(const SfacMArgs &A, const SfacMBlock &B, const double *__restrict__ tE,
+                                              const double2 *__restrict__ tH, const double2 *__restrict__ tK,
                                               const HkDesc *__restrict__ hk, const int *__restrict__ hk_valid,
                                               double *__restrict__ ppart, double2 *smem)
 {
-   const size_t buf_doubles = (size_t)MSC * A.SB + 2 * (size_t)MSC * (A.SH + A.SK);
+   const KtabLayout &L = A.L;
+   const size_t buf_doubles = (size_t)MSC * L.SB + 2 * (size_t)MSC * (L.SH + L.SK);
    double *buf0 = reinterpret_cast<double *>(smem);
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-   const bool producer = warp >= MCW;
    const int g = lane >> 2, kq = lane & 3, comp = g & 1;
 
    const int slab = blockIdx.y;
@@ -251,21 +284,19 @@ __device__ __forceinline__ void sfac_mma_body(const SfacMArgs &A, const SfacMBlo
    }
 
    int ch[2] = {0, 0}, ck[2] = {0, 0}, cnl[2] = {0, 0}, cslot[2] = {0, 0}, csign[2] = {0, 0};
-   if (!producer) {
 #pragma unroll
-      for (int mt = 0; mt < 2; mt++) {
-         const int cl = warp * 8 + mt * 4 + (g >> 1);
-         const int v = A.rank + A.nranks * (B.e0 + cl);
-         bool neg = false;
-         if (cl < B.ncols && v < A.nvalid) {
-            const HkDesc d = hk[hk_valid[v]];
-            ch[mt] = d.h; ck[mt] = abs(d.k); neg = d.k < 0; cnl[mt] = d.nl; cslot[mt] = d.slot0;
-         }
-         // c = eh.x ek.x - sg eh.y ek.y    s = eh.y ek.x + sg eh.x ek.y    (sg = -1 for k < 0)
-         csign[mt] = ((comp == 0) != neg) ? (int)0x80000000 : 0;
+   for (int mt = 0; mt < 2; mt++) {
+      const int cl = warp * 8 + mt * 4 + (g >> 1);
+      const int v = A.rank + A.nranks * (B.e0 + cl);
+      bool neg = false;
+      if (cl < B.ncols && v < A.nvalid) {
+         const HkDesc d = hk[hk_valid[v]];
+         ch[mt] = d.h; ck[mt] = abs(d.k); neg = d.k < 0; cnl[mt] = d.nl; cslot[mt] = d.slot0;
       }
+      // c = eh.x ek.x - sg eh.y ek.y    s = eh.y ek.x + sg eh.x ek.y    (sg = -1 for k < 0)
+      csign[mt] = ((comp == 0) != neg) ? (int)0x80000000 : 0;
    }
-   const bool warp_on = !producer && warp * 8 < B.ncols;
+   const bool warp_on = warp * 8 < B.ncols;
 
    double acc[2][NT][2];
 #pragma unroll
@@ -274,31 +305,56 @@ __device__ __forceinline__ void sfac_mma_body(const SfacMArgs &A, const SfacMBlo
       for (int n = 0; n < NT; n++) acc[mt][n][0] = acc[mt][n][1] = 0.0;
 
    auto bufB = [&](int b) { return buf0 + b * buf_doubles; };
-   auto bufH = [&](int b) { return reinterpret_cast<double2 *>(buf0 + b * buf_doubles + (size_t)MSC * A.SB); };
-   auto bufK = [&](int b) { return reinterpret_cast<double2 *>(buf0 + b * buf_doubles + (size_t)MSC * A.SB) + (size_t)MSC * A.SH; };
+   auto bufH = [&](int b) { return reinterpret_cast<double2 *>(buf0 + b * buf_doubles + (size_t)MSC * L.SB); };
+   auto bufK = [&](int b) { return reinterpret_cast<double2 *>(buf0 + b * buf_doubles + (size_t)MSC * L.SB) + (size_t)MSC * L.SH; };
+   // chunk [base, base+MSC) of the table rows -> buffer b.  Rows past the slab end belong to other slabs
+   // (or the zeroed padding): their q E_l row is zeroed, E_h/E_k are copied as they are (finite).
+   auto stage = [&](int base, int b) {
+      const int vE = (L.SB * 8) / 16, vH = L.SH, vK = L.SK;        // 16-byte units per row
+      const int nv = min(MSC, s1 - base);
+      double2 *dE = reinterpret_cast<double2 *>(bufB(b)), *dH = bufH(b), *dK = bufK(b);
+      const double2 *gE = reinterpret_cast<const double2 *>(tE + (size_t)base * L.SB);
+      const double2 *gH = tH + (size_t)base * L.SH, *gK = tK + (size_t)base * L.SK;
+      for (int u = tid; u < MSC * vE; u += MT) {
+         if (u < nv * vE) cp_async16(dE + u, gE + u);
+         else dE[u] = make_double2(0.0, 0.0);
+      }
+      for (int u = tid; u < MSC * vH; u += MT) cp_async16(dH + u, gH + u);
+      for (int u = tid; u < MSC * vK; u += MT) cp_async16(dK + u, gK + u);
+   };
 
-   if (producer) sfac_tables(A, tid - 32 * MCW, s0, s1, cidx, x, y, z, chg, bufB(0), bufH(0), bufK(0));
+   stage(s0, 0);
+   cp_async_wait_all();
    __syncthreads();
    int b = 0;
    for (int base = s0; base < s1; base += MSC, b ^= 1) {
-      if (producer) {
-         if (base + MSC < s1)
-            sfac_tables(A, tid - 32 * MCW, base + MSC, s1, cidx, x, y, z, chg, bufB(b ^ 1), bufH(b ^ 1), bufK(b ^ 1));
-      } else if (warp_on) {
+#if MDB_ABL != 3
+      if (base + MSC < s1) stage(base + MSC, b ^ 1);
+#endif
+      if (warp_on) {
          const double *sB = bufB(b) + 2 * B.l0 + g;
          const double2 *sH = bufH(b), *sK = bufK(b);
-#pragma unroll 2
-         for (int t = 0; t < MSC / 4; t++) {
+         auto make_a = [&](int t, double (&a)[2]) {
             const int sl = 4 * t + kq;
-            double a[2];
+#if MDB_ABL == 1
+            a[0] = sB[sl * L.SB + 3]; a[1] = sB[sl * L.SB + 5]; return;
+#endif
 #pragma unroll
             for (int mt = 0; mt < 2; mt++) {
-               const double2 eh = sH[sl * A.SH + ch[mt]];
-               const double2 ek = sK[sl * A.SK + ck[mt]];
+               const double2 eh = sH[sl * L.SH + ch[mt]];
+               const double2 ek = sK[sl * L.SK + ck[mt]];
                const double p = comp ? eh.y : eh.x, r = comp ? eh.x : eh.y;
                a[mt] = fma(p, ek.x, flip_sign(r * ek.y, csign[mt]));
             }
-            const double *bp = sB + sl * A.SB;
+         };
+#if MDB_SFAC_PIPE
+         double an[2];
+         make_a(0, an);
+#pragma unroll
+         for (int t = 0; t < MSC / 4; t++) {
+            double a[2] = {an[0], an[1]};
+            if (t + 1 < MSC / 4) make_a(t + 1, an);      // next step's A fragments ahead of this step's DMMAs
+            const double *bp = sB + (4 * t + kq) * L.SB;
 #pragma unroll
             for (int n = 0; n < NT; n++) {
                const double bv = bp[8 * n];
@@ -306,7 +362,26 @@ __device__ __forceinline__ void sfac_mma_body(const SfacMArgs &A, const SfacMBlo
                dmma884(acc[1][n], a[1], bv);
             }
          }
+#else
+#pragma unroll 2
+         for (int t = 0; t < MSC / 4; t++) {
+            double a[2];
+            make_a(t, a);
+            const double *bp = sB + (4 * t + kq) * L.SB;
+#pragma unroll
+            for (int n = 0; n < NT; n++) {
+#if MDB_ABL == 2
+               const double bv = a[0] + n;
+#else
+               const double bv = bp[8 * n];
+#endif
+               dmma884(acc[0][n], a[0], bv);
+               dmma884(acc[1][n], a[1], bv);
+            }
+         }
+#endif
       }
+      cp_async_wait_all();
       __syncthreads();
    }
    // C fragment: row g = (column g/2, c|s), columns 2 kq + e = (slot kq of the n-tile, C|S)
@@ -326,22 +401,21 @@ __device__ __forceinline__ void sfac_mma_body(const SfacMArgs &A, const SfacMBlo
 }
 
 __global__ void __launch_bounds__(MT, 1)
-k_sfac_mma(SfacMArgs A, const SfacMBlock *__restrict__ blocks, const int *__restrict__ cidx,
-           const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
-           const double *__restrict__ chg, const HkDesc *__restrict__ hk, const int *__restrict__ hk_valid,
-           double *__restrict__ ppart)
+k_sfac_mma(SfacMArgs A, const SfacMBlock *__restrict__ blocks, const double *__restrict__ tE,
+           const double2 *__restrict__ tH, const double2 *__restrict__ tK, const HkDesc *__restrict__ hk,
+           const int *__restrict__ hk_valid, double *__restrict__ ppart)
 {
    extern __shared__ double2 smem[];
    const SfacMBlock B = blocks[blockIdx.x];
    switch (B.nt) {          // block-uniform: straight-line DMMA sequences, accumulators in registers
-      case 1: sfac_mma_body<1>(A, B, cidx, x, y, z, chg, hk, hk_valid, ppart, smem); break;
-      case 2: sfac_mma_body<2>(A, B, cidx, x, y, z, chg, hk, hk_valid, ppart, smem); break;
-      case 3: sfac_mma_body<3>(A, B, cidx, x, y, z, chg, hk, hk_valid, ppart, smem); break;
-      case 4: sfac_mma_body<4>(A, B, cidx, x, y, z, chg, hk, hk_valid, ppart, smem); break;
-      case 5: sfac_mma_body<5>(A, B, cidx, x, y, z, chg, hk, hk_valid, ppart, smem); break;
-      case 6: sfac_mma_body<6>(A, B, cidx, x, y, z, chg, hk, hk_valid, ppart, smem); break;
-      case 7: sfac_mma_body<7>(A, B, cidx, x, y, z, chg, hk, hk_valid, ppart, smem); break;
-      default: sfac_mma_body<8>(A, B, cidx, x, y, z, chg, hk, hk_valid, ppart, smem); break;
+      case 1: sfac_mma_body<1>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem); break;
+      case 2: sfac_mma_body<2>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem); break;
+      case 3: sfac_mma_body<3>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem); break;
+      case 4: sfac_mma_body<4>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem); break;
+      case 5: sfac_mma_body<5>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem); break;
+      case 6: sfac_mma_body<6>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem); break;
+      case 7: sfac_mma_body<7>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem); break;
+      default: sfac_mma_body<8>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem); break;
    }
 }
 
@@ -671,12 +745,6 @@ struct KfMArgs {
    int SE, SH, SK, LPS;     // table strides: E_l in doubles (= 4 mod 16), E_h/E_k in double2 (odd); stage slots (= 2 mod 4)
 };
 
-__device__ __forceinline__ void cp_async16(void *dst, const void *src)
-{
-   const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src));
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
 __global__ void __launch_bounds__(512, 1)
 k_kforce_mma(KfMArgs A, const int *__restrict__ cidx, const double *__restrict__ x, const double *__restrict__ y,
@@ -726,40 +794,73 @@ k_kforce_mma(KfMArgs A, const int *__restrict__ cidx, const double *__restrict__
          for (int m = nmax; m < A.SE / 2; m++) tab[m] = make_double2(0.0, 0.0);
    }
 
-   // ---- coefficient staging: item = (half, column, slot); real slots by cp.async, padding by zero stores
-   auto stage = [&](int round, int buf) {
-      for (int item = tid; item < 2 * 8 * A.LPS; item += nthreads) {
-         const int hb = item / (8 * A.LPS), rem = item % (8 * A.LPS), c = rem / A.LPS, l = rem % A.LPS;
-         const int gi = 2 * round + hb;
-         if (gi >= A.ngroups) continue;
+   // ---- coefficient staging, per half: item = (column, slot); real slots by cp.async, padding by zero
+   // stores; the group descriptor travels with them (nine 16-byte pieces).  The two halves run on their
+   // own named barriers, so neither waits for the other's group.
+   KfGroup *sG = reinterpret_cast<KfGroup *>(sF + 2 * (size_t)nsites_b * 3);       // [2 bufs][2 halves]
+   const int hthreads = 32 * A.nsb, htid = tid - half * hthreads;
+   // The fields a thread needs to stage its (column, slot) item are fetched one round ahead into registers
+   // (pf_*): read at the point of use they cost every warp an L2 round trip right after the barrier, with
+   // the DMMA pipe idle (12 % of all stall samples in the first version).
+   const bool one_item = 8 * A.LPS <= hthreads;
+   const int it_c = htid / A.LPS, it_l = htid % A.LPS;
+   int pf_ns = 0, pf_nl = 0, pf_s0 = 0;
+   auto prefetch = [&](int round) {
+      const int gi = 2 * round + half;
+      pf_ns = 0;
+      if (one_item && gi < A.ngroups && it_c < 8) {
          const KfGroup &G = groups[gi];
-         if (l >= 2 * G.nsteps) continue;
-         double2 *d0 = sC + (size_t)(buf * 2 + hb) * stage_half + c * colstride + 2 * l;
-         double2 *d1 = d0 + 8 * colstride;
-         if (l < G.nl[c]) {
-            const double *src = coef + 8 * (size_t)(G.slot0[c] + l);
-            cp_async16(d0, src); cp_async16(d0 + 1, src + 2);
-            cp_async16(d1, src + 4); cp_async16(d1 + 1, src + 6);
-         } else {
-            d0[0] = d0[1] = d1[0] = d1[1] = make_double2(0.0, 0.0);
-         }
+         pf_ns = __ldg(&G.nsteps); pf_nl = __ldg(&G.nl[it_c]); pf_s0 = __ldg(&G.slot0[it_c]);
       }
    };
+   auto put = [&](int buf, int c, int l, int nl, int s0) {
+      double2 *d0 = sC + (size_t)(buf * 2 + half) * stage_half + c * colstride + 2 * l;
+      double2 *d1 = d0 + 8 * colstride;
+      if (l < nl) {
+         const double *src = coef + 8 * (size_t)(s0 + l);
+         cp_async16(d0, src); cp_async16(d0 + 1, src + 2);
+         cp_async16(d1, src + 4); cp_async16(d1 + 1, src + 6);
+      } else {
+         d0[0] = d0[1] = d1[0] = d1[1] = make_double2(0.0, 0.0);
+      }
+   };
+   auto stage = [&](int round, int buf) {
+      const int gi = 2 * round + half;
+      if (gi >= A.ngroups) return;
+      const KfGroup &G = groups[gi];
+      if (htid < (int)(sizeof(KfGroup) / 16))
+         cp_async16(reinterpret_cast<double2 *>(sG + buf * 2 + half) + htid, reinterpret_cast<const double2 *>(&G) + htid);
+      if (one_item) {
+         if (it_c < 8 && it_l < 2 * pf_ns) put(buf, it_c, it_l, pf_nl, pf_s0);
+         return;
+      }
+      const int nslot = 2 * __ldg(&G.nsteps);
+      for (int item = htid; item < 8 * nslot; item += hthreads) {
+         const int c = item / nslot, l = item % nslot;
+         put(buf, c, l, __ldg(&G.nl[c]), __ldg(&G.slot0[c]));
+      }
+   };
+   auto half_barrier = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(hthreads) : "memory"); };
 
    const int nrounds = (A.ngroups + 1) / 2;
+   prefetch(0);
    stage(0, 0);
+   prefetch(1);
    cp_async_wait_all();
-   __syncthreads();
+   __syncthreads();                                      // tables + first stage
 
    double Fa[2] = {0, 0}, Fb[2] = {0, 0}, Fc[2] = {0, 0};
    const int sl0 = sw * 16 + g;                          // this thread's site of tile 0 (tile 1: +8)
    const double *ea0 = sE + (size_t)sl0 * A.SE + kq, *ea1 = ea0 + 8 * (size_t)A.SE;
    for (int r = 0; r < nrounds; r++) {
       const int buf = r & 1;
-      if (r + 1 < nrounds) stage(r + 1, buf ^ 1);
+      if (r + 1 < nrounds) {
+         stage(r + 1, buf ^ 1);
+         prefetch(r + 2);
+      }
       const int gi = 2 * r + half;
       if (gi < A.ngroups) {
-         const KfGroup &G = groups[gi];
+         const KfGroup &G = sG[buf * 2 + half];
          const int nsteps = G.nsteps;
          const double2 *c0 = sC + (size_t)(buf * 2 + half) * stage_half + g * colstride + kq;
          const double2 *c1 = c0 + 8 * colstride;
@@ -798,7 +899,7 @@ k_kforce_mma(KfMArgs A, const int *__restrict__ cidx, const double *__restrict__
          }
       }
       cp_async_wait_all();
-      __syncthreads();
+      half_barrier();
    }
    // ---- sum the four lanes of a site, then the two halves, and add to the caller's force rows
 #pragma unroll
@@ -920,7 +1021,7 @@ static int make_plan(mdb_engine *e, bool by_sites, RecipPlan &P, cudaStream_t st
    int want = std::max(1, (4 * 148 + std::max(1, e->n_sfac_blocks) - 1) / std::max(1, e->n_sfac_blocks));
    if (mode == 1) {
       // k_sfac_mma: one block per SM; never a few blocks more than a whole number of waves
-      static int waves = getenv("MDB_SFAC_WAVES") ? atoi(getenv("MDB_SFAC_WAVES")) : 4;
+      static int waves = getenv("MDB_SFAC_WAVES") ? atoi(getenv("MDB_SFAC_WAVES")) : 8;
       want = std::max(1, waves * 148 / std::max(1, e->n_sfac_blocks));
    }
    int slab = (own + want - 1) / want;
@@ -956,18 +1057,44 @@ static int recip_partial(mdb_engine *e, const RecipPlan &P, double *d_psum, cuda
       M.nvalid = A.nvalid; M.rank = A.rank; M.nranks = A.nranks;
       M.nslots = A.nslots; M.slab_sites = A.slab_sites; M.n_slabs_nf = A.n_slabs_nf;
       M.nf_lo = A.nf_lo; M.nf_hi = A.nf_hi; M.fw_lo = A.fw_lo; M.fw_hi = A.fw_hi;
-      M.NLP = (A.K.nlslots + 3) / 4 * 4;
-      M.SB = 2 * M.NLP; while (M.SB % 16 != 4) M.SB += 2;
-      M.SH = (A.K.hmax + 1) | 1; M.SK = (A.K.kmax + 1) | 1;
-      const size_t mshm = 2 * (sizeof(double) * (size_t)MSC * M.SB + sizeof(double2) * (size_t)MSC * (M.SH + M.SK));
+      M.L.NLP = (A.K.nlslots + 3) / 4 * 4;
+      M.L.SB = 2 * M.L.NLP; while (M.L.SB % 16 != 4) M.L.SB += 2;
+      M.L.SH = (A.K.hmax + 1) | 1; M.L.SK = (A.K.kmax + 1) | 1;
+      M.nrows = e->n_charged + MSC;
+      // per-site power tables (zeroed once: rows a rank never computes must stay finite)
+      const size_t row_bytes = sizeof(double) * M.L.SB + sizeof(double2) * (M.L.SH + M.L.SK);
+      const size_t need = row_bytes * (size_t)M.nrows;
+      if (need > e->ktab_cap) {
+         if (e->d_ktab) cudaFree(e->d_ktab);
+         e->d_ktab = nullptr; e->ktab_cap = 0;
+         MDB_CUDA(cudaMalloc(&e->d_ktab, need));
+         MDB_CUDA(cudaMemsetAsync(e->d_ktab, 0, need, st));
+         e->ktab_cap = need;
+      }
+      double *tE = reinterpret_cast<double *>(e->d_ktab);
+      double2 *tH = reinterpret_cast<double2 *>(tE + (size_t)M.nrows * M.L.SB);
+      double2 *tK = tH + (size_t)M.nrows * M.L.SH;
+      static size_t tshm_set = 48 * 1024;
+      if (KTS * row_bytes > tshm_set) {
+         MDB_CUDA(cudaFuncSetAttribute(k_ktables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KTS * row_bytes)));
+         tshm_set = KTS * row_bytes;
+      }
+      for (int part = 0; part < 2; part++) {
+         const int g0 = part == 0 ? P.nf_lo : P.fw_lo, g1 = part == 0 ? P.nf_hi : P.fw_hi;
+         if (g1 <= g0) continue;
+         k_ktables<<<(g1 - g0 + KTS - 1) / KTS, 128, KTS * row_bytes, st>>>(M.K, M.L, g0, g1, e->d_cidx, e->d_x, e->d_y, e->d_z,
+                                                                        e->d_chg, tE, tH, tK);
+         e->launches++;
+      }
+      const size_t mshm = 2 * (size_t)MSC * row_bytes;
       static size_t mshm_set = 0;
       if (mshm > mshm_set) {
          MDB_CUDA(cudaFuncSetAttribute(k_sfac_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mshm));
          mshm_set = mshm;
       }
       dim3 g(e->n_sfac_blocks, P.n_slabs);
-      k_sfac_mma<<<g, MT, mshm, st>>>(M, (const SfacMBlock *)e->d_sfac_blocks, e->d_cidx, e->d_x, e->d_y, e->d_z,
-                                       e->d_chg, e->d_hk, e->d_hk_valid, e->d_ppart);
+      k_sfac_mma<<<g, MT, mshm, st>>>(M, (const SfacMBlock *)e->d_sfac_blocks, tE, tH, tK, e->d_hk, e->d_hk_valid,
+                                      e->d_ppart);
       e->launches++;
    } else if (e->n_sfac_blocks > 0 && P.n_slabs > 0) {
       static size_t shm_set = 0;
@@ -1038,7 +1165,7 @@ static int recip_finish(mdb_engine *e, const RecipPlan &P, const double *d_psum,
       Q.SH = (F.K.hmax + 1) | 1; Q.SK = (F.K.kmax + 1) | 1;
       Q.LPS = nle; while (Q.LPS % 4 != 2) Q.LPS += 2;
       const size_t per_site = sizeof(double) * Q.SE + sizeof(double2) * (Q.SH + Q.SK) + 6 * sizeof(double);
-      const size_t stage_bytes = 4 * (size_t)(2 * 8 * 2 * Q.LPS) * sizeof(double2);
+      const size_t stage_bytes = 4 * (size_t)(2 * 8 * 2 * Q.LPS) * sizeof(double2) + 4 * sizeof(KfGroup);
       static int max_smem = 0;
       if (!max_smem) MDB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
       Q.nsb = 8;
