@@ -201,18 +201,120 @@ __global__ void __launch_bounds__(CB) k_fill_batches(int ncols, int nz, int ni, 
    if (col == ncols - 1) *nbatch = off[ncols];
 }
 
+static int launch_batches(mdb_engine *e, const int *start, int *scratch, int *scan_tmp, int2 *batches, int *nbatch,
+                          cudaStream_t st)
+{
+   const int ncols = e->T.nx * e->T.ny;
+   int *nb = scratch, *off = scratch + ncols + 1;
+   const int ntiles = (ncols + SCAN_TILE - 1) / SCAN_TILE;
+   k_col_batches<<<(ncols + CB - 1) / CB, CB, 0, st>>>(ncols, e->T.nz, MDB_NI, start, nb);
+   k_scan_tiles<<<ntiles, SCAN_T, 0, st>>>(nb, ncols, scan_tmp);
+   k_scan_sums<<<1, SCAN_T, 0, st>>>(scan_tmp, ntiles);
+   k_scan_apply<<<ntiles, SCAN_T, 0, st>>>(nb, ncols, scan_tmp, off);
+   k_fill_batches<<<(ncols + CB - 1) / CB, CB, 0, st>>>(ncols, e->T.nz, MDB_NI, start, off, batches, nbatch);
+   e->launches += 5;
+   MDB_CUDA(cudaGetLastError());
+   return 0;
+}
+
 int mdb_launch_batches(mdb_engine *e, cudaStream_t st)
 {
    const int ncols = e->T.nx * e->T.ny;
-   int *nb = e->d_count, *off = e->d_count + ncols + 1;        // the cell-count array is free after the fill
    if (2 * (ncols + 1) > e->cells_cap) { mdb_set_error("batch scratch too small"); return -1; }
-   const int ntiles = (ncols + SCAN_TILE - 1) / SCAN_TILE;
-   k_col_batches<<<(ncols + CB - 1) / CB, CB, 0, st>>>(ncols, e->T.nz, MDB_NI, e->d_start, nb);
-   k_scan_tiles<<<ntiles, SCAN_T, 0, st>>>(nb, ncols, e->d_scan_tmp);
-   k_scan_sums<<<1, SCAN_T, 0, st>>>(e->d_scan_tmp, ntiles);
-   k_scan_apply<<<ntiles, SCAN_T, 0, st>>>(nb, ncols, e->d_scan_tmp, off);
-   k_fill_batches<<<(ncols + CB - 1) / CB, CB, 0, st>>>(ncols, e->T.nz, MDB_NI, e->d_start, off, e->d_batches, e->d_nbatch);
-   e->launches += 5;
+   // the cell-count array is free after the fill
+   return launch_batches(e, e->d_start, e->d_count, e->d_scan_tmp, e->d_batches, e->d_nbatch, st);
+}
+
+// ---- site-class sublists: stream compaction of the cell-sorted list (order within a cell is kept, so a
+// cell's members stay contiguous and start_K[c] is the scanned flag count at start[c])
+__global__ void __launch_bounds__(CB) k_sub_flags(int n, const int *__restrict__ order, const unsigned char *__restrict__ cls,
+                                                  int bit, int *__restrict__ flag)
+{
+   const int s = blockIdx.x * CB + threadIdx.x;
+   if (s < n) flag[s] = (cls[order[s]] >> bit) & 1;
+}
+__global__ void __launch_bounds__(CB) k_sub_scatter(int n, const int *__restrict__ flag, const int *__restrict__ pos,
+                                                    const double4 *__restrict__ posq, const int2 *__restrict__ sinfo,
+                                                    const int *__restrict__ order, double4 *__restrict__ posq_k,
+                                                    int2 *__restrict__ sinfo_k, int *__restrict__ order_k)
+{
+   const int s = blockIdx.x * CB + threadIdx.x;
+   if (s >= n || !flag[s]) return;
+   const int d = pos[s];
+   posq_k[d] = posq[s]; sinfo_k[d] = sinfo[s]; order_k[d] = order[s];
+}
+__global__ void __launch_bounds__(CB) k_sub_start(int ncells, const int *__restrict__ start, const int *__restrict__ pos,
+                                                  int *__restrict__ start_k)
+{
+   const int c = blockIdx.x * CB + threadIdx.x;
+   if (c <= ncells) start_k[c] = pos[start[c]];          // pos[n] = class size
+}
+
+int mdb_build_sublist(mdb_engine *e, int k, cudaStream_t st)
+{
+   SubList &S = e->sub[k];
+   if (S.valid) return 0;
+   const int n = e->cfg.nsites, nc = e->ncells;
+   const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+   k_sub_flags<<<(n + CB - 1) / CB, CB, 0, st>>>(n, e->d_order, e->d_cls, k, e->d_sub_flag);
+   k_scan_tiles<<<ntiles, SCAN_T, 0, st>>>(e->d_sub_flag, n, e->d_sub_scan);
+   k_scan_sums<<<1, SCAN_T, 0, st>>>(e->d_sub_scan, ntiles);
+   k_scan_apply<<<ntiles, SCAN_T, 0, st>>>(e->d_sub_flag, n, e->d_sub_scan, e->d_sub_pos);
+   k_sub_scatter<<<(n + CB - 1) / CB, CB, 0, st>>>(n, e->d_sub_flag, e->d_sub_pos, e->d_posq, e->d_sinfo, e->d_order,
+                                                   S.posq, S.sinfo, S.order);
+   k_sub_start<<<(nc + 1 + CB - 1) / CB, CB, 0, st>>>(nc, e->d_start, e->d_sub_pos, S.start);
+   e->launches += 6;
+   MDB_CUDA(cudaGetLastError());
+   if (launch_batches(e, S.start, e->d_sub_cols, e->d_sub_scan, S.batches, S.nbatch, st)) return -1;
+   S.valid = true;
+   return 0;
+}
+
+// ---- TOO_CLOSE diagnostics for the pairs the split passes never visit (src/force.c:939-949 looks at every
+// pair of the stencil).  Two sites closer than 0.5 A sit in the same or in adjacent cells (mdb_configure
+// refuses the split for cells thinner than that), so 27 cells per site are enough.
+struct CloseParams { int nx, ny, nz; double reloc[27][3]; };
+__global__ void __launch_bounds__(CB) k_too_close_scan(CloseParams P, int n, const double4 *__restrict__ posq,
+                                                       const int *__restrict__ scell, const int *__restrict__ start,
+                                                       const int *__restrict__ order, const int *__restrict__ mol,
+                                                       const unsigned char *__restrict__ cls,
+                                                       unsigned long long *__restrict__ counters)
+{
+   const int s = blockIdx.x * CB + threadIdx.x;
+   if (s >= n) return;
+   const int c = scell[s], cz = c % P.nz, cy = (c / P.nz) % P.ny, cx = c / (P.nz * P.ny);
+   const double4 pi = posq[s];
+   const int oi = order[s], mi = mol[oi], ci = cls[oi];
+   for (int d = 0; d < 27; d++) {
+      int tx = cx + d / 9 - 1, ty = cy + (d / 3) % 3 - 1, tz = cz + d % 3 - 1, ii = 0, jj = 0, kk = 0;
+      if (tx < 0) { tx += P.nx; ii = -1; } else if (tx >= P.nx) { tx -= P.nx; ii = 1; }
+      if (ty < 0) { ty += P.ny; jj = -1; } else if (ty >= P.ny) { ty -= P.ny; jj = 1; }
+      if (tz < 0) { tz += P.nz; kk = -1; } else if (tz >= P.nz) { tz -= P.nz; kk = 1; }
+      const int img = 9 * (ii + 1) + 3 * (jj + 1) + (kk + 1), cc = tz + P.nz * (ty + P.ny * tx);
+      for (int t = max(start[cc], s + 1); t < start[cc + 1]; t++) {
+         const double4 pj = posq[t];
+         const double dx = pj.x + P.reloc[img][0] - pi.x, dy = pj.y + P.reloc[img][1] - pi.y, dz = pj.z + P.reloc[img][2] - pi.z;
+         if (dx * dx + dy * dy + dz * dz < MDB_TOO_CLOSE) {
+            const int oj = order[t], both = ci & cls[oj];
+            if (!both && mol[oj] != mi) {             // not seen by the charged or the potential pass
+               atomicAdd(&counters[1], 2ULL);
+               counters[3] = ((unsigned long long)(unsigned)oi << 32) | (unsigned)oj;
+            }
+         }
+      }
+   }
+}
+
+int mdb_launch_too_close_scan(mdb_engine *e, cudaStream_t st)
+{
+   CloseParams P;
+   P.nx = e->T.nx; P.ny = e->T.ny; P.nz = e->T.nz;
+   for (int k = 0; k < 27; k++)
+      for (int a = 0; a < 3; a++) P.reloc[k][a] = e->T.reloc[k][a];
+   const int n = e->cfg.nsites;
+   k_too_close_scan<<<(n + CB - 1) / CB, CB, 0, st>>>(P, n, e->d_posq, e->d_scell, e->d_start, e->d_order, e->d_mol,
+                                                      e->d_cls, e->d_counters);
+   e->launches += 1;
    MDB_CUDA(cudaGetLastError());
    return 0;
 }
@@ -242,6 +344,7 @@ int mdb_launch_cells(mdb_engine *e, cudaStream_t st)
    e->launches += 6;
    MDB_CUDA(cudaGetLastError());
    if (e->pair_mode >= 3 && mdb_launch_batches(e, st)) return -1;
+   e->sub[0].valid = e->sub[1].valid = false;
    e->cells_valid = true;
    return 0;
 }

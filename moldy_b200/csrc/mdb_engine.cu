@@ -45,6 +45,16 @@ static void free_system(mdb_engine *e)
    FREE(e->d_stype); FREE(e->d_scell); FREE(e->d_sinfo); FREE(e->d_fs); FREE(e->d_com); e->com_cap = 0; e->com_set = false;
    e->d_x = e->d_y = e->d_z = nullptr;
 }
+static void free_sublists(mdb_engine *e)
+{
+   for (int k = 0; k < 2; k++) {
+      SubList &S = e->sub[k];
+      FREE(S.posq); FREE(S.sinfo); FREE(S.order); FREE(S.start); FREE(S.batches); FREE(S.nbatch); FREE(S.fs);
+      S.n = 0; S.batch_cap = 0; S.valid = false;
+   }
+   FREE(e->d_cls); FREE(e->d_sub_flag); FREE(e->d_sub_pos); FREE(e->d_sub_scan); FREE(e->d_sub_cols);
+   e->sub_cap = 0;
+}
 static void free_grid(mdb_engine *e)
 {
    FREE(e->d_count); FREE(e->d_start); FREE(e->d_scan_tmp); FREE(e->d_runs); FREE(e->d_runs_half);
@@ -64,7 +74,7 @@ extern "C" void mdb_destroy(mdb_engine *e)
 {
    if (!e) return;
    cudaSetDevice(e->device);
-   free_system(e); free_grid(e); free_recip(e);
+   free_system(e); free_grid(e); free_recip(e); free_sublists(e);
    FREE(e->d_partials); FREE(e->d_counters); FREE(e->d_out_own); FREE(e->d_rdf);
    if (e->h_stage) cudaFreeHost(e->h_stage);
    delete e;
@@ -73,6 +83,7 @@ extern "C" void mdb_destroy(mdb_engine *e)
 extern "C" void mdb_set_pair_mode(mdb_engine *e, int mode)
 {
    e->pair_mode = (mode == 2 || mode == 3) ? mode : 4;
+   if (e->pair_mode == 2) e->pair_split = 0;
    if (e->configured && sizeof(double) * e->h_potpar.size() > MDB_TILED_TAB_MAX) e->pair_mode = 2;
    e->cells_valid = false;
 }
@@ -178,6 +189,75 @@ extern "C" int mdb_configure(mdb_engine *e, const mdb_config *cfg)
       if (!e->d_fs) MDB_CUDA(cudaMalloc(&e->d_fs, sizeof(double) * 3 * (size_t)n));
       for (auto &r : e->T.runs)
          if (r.dzlo < -500 || r.dzhi > 500) { mdb_set_error("stencil z extent > 500 cells"); return -1; }
+   }
+   // ---- site classes for the split pair passes.  A pair whose charge product is zero gets an exact
+   // zero from the Coulomb term, one whose potential parameters all vanish an exact zero from kernel()'s
+   // potential (src/kernel.c:182-461), so charged x charged pairs with the Coulomb term alone plus
+   // potential x potential pairs with the potential alone give the reference's sums term for term.
+   {
+      const int id = cfg->max_id;
+      auto amp_zero = [&](const double *p) {          // amplitudes of the potential, by type
+         switch (cfg->ptype) {
+            case 0: return p[0] == 0.0;                                              // eps
+            case 1: return p[0] == 0.0 && p[1] == 0.0;                               // -A/r^6 + B exp(-C r)
+            case 2: return p[0] == 0.0 && p[2] == 0.0;                               // A exp(-B r) - C exp(-D r)
+            case 3: return p[0] == 0.0 && p[2] == 0.0 && p[3] == 0.0 && p[4] == 0.0 && p[5] == 0.0;
+            case 4: return p[0] == 0.0 && p[1] == 0.0 && p[2] == 0.0;
+            default: return p[0] == 0.0 && p[3] == 0.0 && p[4] == 0.0;               // Morse / BIG
+         }
+      };
+      std::vector<char> active(id, 0);
+      for (int a = 0; a < id; a++)
+         for (int b = 0; b < id; b++)
+            if (!amp_zero(&e->h_potpar[((size_t)a * id + b) * MDB_NPOTP])) active[a] = 1;
+      std::vector<unsigned char> cls(n);
+      long nc = 0, np2 = 0;
+      for (int i = 0; i < n; i++) {
+         cls[i] = (e->h_chg[i] != 0.0 ? 1 : 0) | (active[e->h_type[i]] ? 2 : 0);
+         nc += cls[i] & 1; np2 += (cls[i] >> 1) & 1;
+      }
+      // FP64 instructions per visit (profiles/): 22 shared (r^2, 1/r, accumulation), 23 Coulomb, 9..30 potential
+      static const double ptc[7] = {9, 19, 27, 30, 12, 0, 40};
+      const bool coul = cfg->alpha > 0.0;
+      const double fused = (double)n * n * (22 + (coul ? 23 : 0) + ptc[cfg->ptype]);
+      const double split = (double)nc * nc * (22 + 23) + (double)np2 * np2 * (22 + ptc[cfg->ptype]);
+      const char *sp = getenv("MDB_PAIR_SPLIT");
+      e->pair_split = coul && e->pair_mode >= 3 && (sp ? atoi(sp) != 0 : split < 0.85 * fused);
+      // the TOO_CLOSE scan of the unvisited pairs looks at adjacent cells only: cells must be >= 0.5 A thick
+      const int ng[3] = {e->T.nx, e->T.ny, e->T.nz};
+      for (int d = 0; d < 3; d++) {
+         const double *r = &e->T.hinv[3 * d];
+         if (1.0 / sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]) / ng[d] < 0.5) e->pair_split = 0;
+      }
+      for (int k = 0; k < 2; k++) e->sub[k].valid = false;
+      if (e->pair_split) {
+         if (upload(&e->d_cls, cls.data(), n)) return -1;
+         const int ncols = e->T.nx * e->T.ny;
+         if (n + 1 > e->sub_cap || new_system) {
+            FREE(e->d_sub_flag); FREE(e->d_sub_pos); FREE(e->d_sub_scan);
+            MDB_CUDA(cudaMalloc(&e->d_sub_flag, sizeof(int) * (size_t)(n + 1)));
+            MDB_CUDA(cudaMalloc(&e->d_sub_pos, sizeof(int) * (size_t)(n + 1)));
+            MDB_CUDA(cudaMalloc(&e->d_sub_scan, sizeof(int) * (size_t)(n / 2048 + ncols / 2048 + 4)));
+            e->sub_cap = n + 1;
+         }
+         FREE(e->d_sub_cols);
+         MDB_CUDA(cudaMalloc(&e->d_sub_cols, sizeof(int) * 2 * (size_t)(ncols + 1)));
+         const long cnt[2] = {nc, np2};
+         for (int k = 0; k < 2; k++) {
+            SubList &S = e->sub[k];
+            FREE(S.posq); FREE(S.sinfo); FREE(S.order); FREE(S.start); FREE(S.batches); FREE(S.nbatch); FREE(S.fs);
+            S.n = (int)cnt[k];
+            const size_t m = (size_t)std::max(S.n, 1);
+            MDB_CUDA(cudaMalloc(&S.posq, sizeof(double4) * m));
+            MDB_CUDA(cudaMalloc(&S.sinfo, sizeof(int2) * m));
+            MDB_CUDA(cudaMalloc(&S.order, sizeof(int) * m));
+            MDB_CUDA(cudaMalloc(&S.start, sizeof(int) * (size_t)(e->ncells + 1)));
+            S.batch_cap = S.n / MDB_NI + ncols + 8;
+            MDB_CUDA(cudaMalloc(&S.batches, sizeof(int2) * (size_t)S.batch_cap));
+            MDB_CUDA(cudaMalloc(&S.nbatch, sizeof(int)));
+            MDB_CUDA(cudaMalloc(&S.fs, sizeof(double) * 3 * m));
+         }
+      }
    }
 
    // ---- reciprocal space ----

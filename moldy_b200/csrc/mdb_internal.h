@@ -69,6 +69,20 @@ struct KspaceParams {
    int nsites, nsites_xf;
 };
 
+// A class of sites (charged / with a non-zero pair potential) as its own cell-sorted list: the tiled
+// pair kernel then visits charged x charged pairs with the Coulomb term only and potential x potential
+// pairs with the pair potential only, instead of every pair with both (TIP4P: 27 of 54 FP64
+// instructions per reference pair).  Compacted from the full cell-sorted list after every cell build.
+struct SubList {
+   int n = 0;                             // sites in the class (static per system)
+   double4 *posq = nullptr; int2 *sinfo = nullptr;
+   int *order = nullptr;                  // compacted sorted index -> original site index
+   int *start = nullptr;                  // [ncells+1]
+   int2 *batches = nullptr; int *nbatch = nullptr; int batch_cap = 0;
+   double *fs = nullptr;                  // [3 n] cell-sorted force accumulator
+   bool valid = false;
+};
+
 struct mdb_engine {
    int device = 0;
    bool configured = false;
@@ -99,6 +113,10 @@ struct mdb_engine {
    int2 *d_batches = nullptr; int *d_nbatch = nullptr; int batch_cap = 0;   // i-site batches of the tiled pair kernel
    double *d_fs = nullptr;                // [3N] cell-sorted force accumulator (Newton-3 mode)
    int pair_mode = -1;                    // 2: per-thread full stencil, 3: tiled full stencil, 4: tiled Newton-3
+   int pair_split = 0;                    // tiled kernel: one pass per site class (sub[0] charged, sub[1] potential)
+   SubList sub[2];
+   unsigned char *d_cls = nullptr;        // per original site: bit 0 charged, bit 1 has a non-zero pair potential
+   int *d_sub_flag = nullptr, *d_sub_pos = nullptr, *d_sub_scan = nullptr, *d_sub_cols = nullptr; int sub_cap = 0;
    // RDF pass: strict stencil of the last (limit, grid) and the device histogram
    StencilRun *d_runs_rdf = nullptr; int nruns_rdf = 0; double rdf_limit = -1.0; int rdf_grid[3] = {0, 0, 0};
    double rdf_h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -144,6 +162,8 @@ int mdb_launch_rdf_tiled(mdb_engine *e, const StencilRun *d_runs, int nruns, dou
                          unsigned long long *d_counts, cudaStream_t st);
 static constexpr size_t MDB_TILED_TAB_MAX = 28 * 1024;   // pair table of the tiled kernel lives in shared memory
 int mdb_launch_batches(mdb_engine *e, cudaStream_t st);
+int mdb_build_sublist(mdb_engine *e, int k, cudaStream_t st);
+int mdb_launch_too_close_scan(mdb_engine *e, cudaStream_t st);
 static constexpr int MDB_NI = 4;          // i-sites per warp in the tiled pair kernel
 int mdb_launch_recip(mdb_engine *e, double *d_out, cudaStream_t st);
 int mdb_launch_recip_partial(mdb_engine *e, double *d_psum, cudaStream_t st);

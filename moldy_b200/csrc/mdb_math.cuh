@@ -214,7 +214,8 @@ __device__ __forceinline__ void mdb_exp_sel(const double (&x)[NV], double (&out)
 // Moldy stores them in pot_mt.p (LJ: derived values, see PairTable).  The
 // Coulomb part is the reference's erfc-screened term with its own A&S 7.1.26
 // polynomial (src/kernel.c:88-96,195-201) -- NOT erfc().
-enum { PT_LJ = 0, PT_E6 = 1, PT_MCY = 2, PT_GEN = 3, PT_HIW = 4, PT_RSV = 5, PT_MOR = 6 };
+enum { PT_LJ = 0, PT_E6 = 1, PT_MCY = 2, PT_GEN = 3, PT_HIW = 4, PT_RSV = 5, PT_MOR = 6,
+       PT_NONE = 7 };   // PT_NONE: Coulomb term only (charged-site pass of the split pair kernel)
 
 struct PairOut { double fij, phi; };
 
@@ -283,7 +284,10 @@ __device__ __forceinline__ void mdb_pair_eval_v(const double (&r2)[NV], const do
 #pragma unroll
       MDB_V erfc_term[k] = fma(norm, e[k], t[k]);
    }
-   if (PT == PT_LJ) {                       // p[0]=eps, p[1]=sigma^2, p[2]=6 eps
+   if (PT == PT_NONE) {                     // what every potential below gives with all-zero parameters
+#pragma unroll
+      MDB_V { phi[k] = t[k]; fij[k] = r_sqr_r[k] * erfc_term[k]; }
+   } else if (PT == PT_LJ) {                // p[0]=eps, p[1]=sigma^2, p[2]=6 eps
       double r6[NV], r12[NV];
       double2 p01[NV];
       double p2[NV];

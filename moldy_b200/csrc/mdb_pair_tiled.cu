@@ -102,7 +102,7 @@ struct RdfParams { double rbin; int nbins, hist_smem; unsigned long long *counts
 
 template <int PT, bool COUL, bool STRICT, bool FW, bool N3, int MODE>
 __global__ void __launch_bounds__(TW * 32, MDB_TILED_MINB)
-k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const int2 *__restrict__ sinfo,
+k_pair_tiled(PairParams P, int nsites, int nout, const double4 *__restrict__ posq, const int2 *__restrict__ sinfo,
              const int *__restrict__ cstart, const int *__restrict__ order,
              const int *__restrict__ mol, const StencilRun *__restrict__ runs, const double *__restrict__ ptab,
              const int2 *__restrict__ batches, const int *__restrict__ nbatch_p, int rank, int nranks,
@@ -426,10 +426,10 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
             atomicAdd(&fs[(size_t)nsites + s0 + k], fy);
             atomicAdd(&fs[2 * (size_t)nsites + s0 + k], fz);
          } else {
-            const int o = order[s0 + k];
+            const int o = order[s0 + k];          // nsites = length of this pass's site list, nout = all sites
             out[o] += fx;
-            out[(size_t)nsites + o] += fy;
-            out[2 * (size_t)nsites + o] += fz;
+            out[(size_t)nout + o] += fy;
+            out[2 * (size_t)nout + o] += fz;
             const double4 pk4 = W->ipos[k];
             const double px = pk4.x, py = pk4.y, pz = pk4.z;
             w00 = fma(px, fx, w00); w01 = fma(py, fx, w01); w02 = fma(pz, fx, w02);
@@ -447,7 +447,7 @@ k_pair_tiled(PairParams P, int nsites, const double4 *__restrict__ posq, const i
 
 // Newton-3 mode: move the cell-sorted accumulator back to the caller's site order and add the
 // site virial sum_i r_i (x) F_i (src/force.c:973-982), one row of partial sums per block.
-__global__ void __launch_bounds__(256) k_unsort_virial(int n, const double4 *__restrict__ posq,
+__global__ void __launch_bounds__(256) k_unsort_virial(int n, int nout, const double4 *__restrict__ posq,
                                                        const int *__restrict__ order, const double *__restrict__ fs,
                                                        double *__restrict__ out, double *__restrict__ partials)
 {
@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(256) k_unsort_virial(int n, const double4 *__r
       const double fx = fs[s], fy = fs[(size_t)n + s], fz = fs[2 * (size_t)n + s];
       const double4 p = posq[s];
       const int o = order[s];
-      out[o] += fx; out[(size_t)n + o] += fy; out[2 * (size_t)n + o] += fz;
+      out[o] += fx; out[(size_t)nout + o] += fy; out[2 * (size_t)nout + o] += fz;
       v[0] = p.x * fx; v[1] = p.y * fx; v[2] = p.z * fx; v[3] = p.y * fy; v[4] = p.z * fy; v[5] = p.z * fz;
    }
    __shared__ double red[8][6];
@@ -524,11 +524,26 @@ __global__ void __launch_bounds__(RS1) k_rows_finish(const double *__restrict__ 
    }
 }
 
-#define TILED_ARGS P, c.nsites, e->d_posq, e->d_sinfo, e->d_start, e->d_order, e->d_mol, runs, e->d_ptab, \
-                   e->d_batches, e->d_nbatch, e->ithread, e->nthreads, d_out, e->d_fs, e->d_partials, e->d_counters, R
+// the cell-sorted site list a pass runs on: all sites, or one site class (SubList)
+struct SiteList {
+   int n; const double4 *posq; const int2 *sinfo; const int *start; const int *order; const int2 *batches; const int *nbatch;
+   double *fs;
+};
+static SiteList full_list(const mdb_engine *e)
+{
+   return SiteList{e->cfg.nsites, e->d_posq, e->d_sinfo, e->d_start, e->d_order, e->d_batches, e->d_nbatch, e->d_fs};
+}
+static SiteList sub_list(const mdb_engine *e, int k)
+{
+   const SubList &S = e->sub[k];
+   return SiteList{S.n, S.posq, S.sinfo, S.start, S.order, S.batches, S.nbatch, S.fs};
+}
+
+#define TILED_ARGS P, L.n, c.nsites, L.posq, L.sinfo, L.start, L.order, e->d_mol, runs, e->d_ptab, \
+                   L.batches, L.nbatch, e->ithread, e->nthreads, d_out, L.fs, e->d_partials, e->d_counters, R
 
 template <int PT, bool COUL, int MODE>
-static void launch_tiled(bool strict, bool fw, bool n3, dim3 g, cudaStream_t st, PairParams &P, mdb_engine *e,
+static void launch_tiled(bool strict, bool fw, bool n3, dim3 g, cudaStream_t st, PairParams &P, mdb_engine *e, const SiteList &L,
                          const StencilRun *runs, double *d_out, RdfParams R = RdfParams{0.0, 0, 0, nullptr}, size_t shm_extra = 0)
 {
    const mdb_config &c = e->cfg;
@@ -544,7 +559,7 @@ static void launch_tiled(bool strict, bool fw, bool n3, dim3 g, cudaStream_t st,
 #undef GO
 }
 
-static void tiled_params(mdb_engine *e, bool n3, PairParams &P, const StencilRun *&runs, int &nblocks)
+static void tiled_params(mdb_engine *e, bool n3, int nlist, PairParams &P, const StencilRun *&runs, int &nblocks)
 {
    const mdb_config &c = e->cfg;
    P.nx = e->T.nx; P.ny = e->T.ny; P.nz = e->T.nz;
@@ -558,9 +573,9 @@ static void tiled_params(mdb_engine *e, bool n3, PairParams &P, const StencilRun
    P.cutoff100sq = 10000.0 * P.cutoffsq;
    P.max_id = c.max_id;
    P.strict = c.strict_cutoff;
-   P.s_lo = 0; P.s_hi = c.nsites;
+   P.s_lo = 0; P.s_hi = nlist;
    // upper bound on this rank's batches (the exact count lives on the device)
-   const long nb_max = (long)c.nsites / NI + (long)e->T.nx * e->T.ny + 1;
+   const long nb_max = (long)nlist / NI + (long)e->T.nx * e->T.ny + 1;
    const int my_max = (int)((nb_max + e->nthreads - 1) / e->nthreads) + 1;
    nblocks = (my_max + TW - 1) / TW;
 }
@@ -573,9 +588,10 @@ int mdb_launch_pair_count_tiled(mdb_engine *e, cudaStream_t st)
    PairParams P;
    const StencilRun *runs;
    int nblocks;
-   tiled_params(e, n3, P, runs, nblocks);
+   tiled_params(e, n3, c.nsites, P, runs, nblocks);
    double *d_out = nullptr;
-   launch_tiled<PT_LJ, false, TM_COUNT>(false, fw, n3, dim3(nblocks), st, P, e, runs, d_out);
+   const SiteList L = full_list(e);
+   launch_tiled<PT_LJ, false, TM_COUNT>(false, fw, n3, dim3(nblocks), st, P, e, L, runs, d_out);
    e->launches += 1;
    MDB_CUDA(cudaGetLastError());
    return 0;
@@ -591,45 +607,49 @@ int mdb_launch_rdf_tiled(mdb_engine *e, const StencilRun *d_runs, int nruns, dou
    PairParams P;
    const StencilRun *runs;
    int nblocks;
-   tiled_params(e, true, P, runs, nblocks);
+   tiled_params(e, true, c.nsites, P, runs, nblocks);
    runs = d_runs; P.nruns = nruns;
+   const SiteList L = full_list(e);
    RdfParams R;
    R.rbin = rbin; R.nbins = nbins; R.counts = d_counts;
    const size_t hbytes = sizeof(unsigned int) * (size_t)nbins * (c.max_id * (c.max_id - 1) / 2);
    R.hist_smem = hbytes <= MDB_TILED_TAB_MAX ? 1 : 0;
    double *d_out = nullptr;
-   launch_tiled<PT_LJ, false, TM_RDF>(false, fw, true, dim3(nblocks), st, P, e, runs, d_out, R, R.hist_smem ? hbytes : 0);
+   launch_tiled<PT_LJ, false, TM_RDF>(false, fw, true, dim3(nblocks), st, P, e, L, runs, d_out, R, R.hist_smem ? hbytes : 0);
    e->launches += 1;
    MDB_CUDA(cudaGetLastError());
    return 0;
 }
 
-int mdb_launch_pair_tiled(mdb_engine *e, double *d_out, cudaStream_t st)
+// one pass of the force kernel over a site list: pair potential `ptype` (PT_NONE: none) and/or the Coulomb term
+static int pair_pass(mdb_engine *e, const SiteList &L, int ptype, bool coul, double *d_out, cudaStream_t st)
 {
    const mdb_config &c = e->cfg;
+   if (L.n <= 0) return 0;
    const bool n3 = e->pair_mode == 4;
    PairParams P;
    const StencilRun *runs;
    int nblocks;
-   tiled_params(e, n3, P, runs, nblocks);
+   tiled_params(e, n3, L.n, P, runs, nblocks);
    const int nrows_pair = nblocks * TW;
-   const int nblocks_u = (c.nsites + 255) / 256;
+   const int nblocks_u = (L.n + 255) / 256;
    const int nrows = nrows_pair + (n3 ? nblocks_u : 0);
    if (nrows + RS1 > e->partials_cap) {
       if (e->d_partials) cudaFree(e->d_partials);
       MDB_CUDA(cudaMalloc(&e->d_partials, sizeof(double) * NRED * (size_t)(nrows + RS1)));
       e->partials_cap = nrows + RS1;
    }
-   if (n3) MDB_CUDA(cudaMemsetAsync(e->d_fs, 0, sizeof(double) * 3 * (size_t)c.nsites, st));
-   const bool coul = c.alpha > 0.0, strict = c.strict_cutoff != 0 && !c.molpbc, fw = c.nsites_xf < c.nsites;   // src/force.c:951
+   if (n3) MDB_CUDA(cudaMemsetAsync(L.fs, 0, sizeof(double) * 3 * (size_t)L.n, st));
+   const bool strict = c.strict_cutoff != 0 && !c.molpbc, fw = c.nsites_xf < c.nsites;   // src/force.c:951
    dim3 g(nblocks);
-#define PT_CASE(X) case X: if (coul) launch_tiled<X, true, TM_FORCE>(strict, fw, n3, g, st, P, e, runs, d_out); \
-                           else launch_tiled<X, false, TM_FORCE>(strict, fw, n3, g, st, P, e, runs, d_out); break
-   switch (c.ptype) {
+#define PT_CASE(X) case X: if (coul) launch_tiled<X, true, TM_FORCE>(strict, fw, n3, g, st, P, e, L, runs, d_out); \
+                           else launch_tiled<X, false, TM_FORCE>(strict, fw, n3, g, st, P, e, L, runs, d_out); break
+   switch (ptype) {
       PT_CASE(PT_LJ);
 #ifndef MDB_DEV_LJ_ONLY
       PT_CASE(PT_E6); PT_CASE(PT_MCY); PT_CASE(PT_GEN); PT_CASE(PT_HIW); PT_CASE(PT_MOR);
 #endif
+      case PT_NONE: launch_tiled<PT_NONE, true, TM_FORCE>(strict, fw, n3, g, st, P, e, L, runs, d_out); break;
       default:
          mdb_set_error("KERNEL called with unknown potential type");
          return -1;
@@ -637,7 +657,7 @@ int mdb_launch_pair_tiled(mdb_engine *e, double *d_out, cudaStream_t st)
 #undef PT_CASE
    e->launches += 1;
    if (n3) {
-      k_unsort_virial<<<nblocks_u, 256, 0, st>>>(c.nsites, e->d_posq, e->d_order, e->d_fs, d_out,
+      k_unsort_virial<<<nblocks_u, 256, 0, st>>>(L.n, c.nsites, L.posq, L.order, L.fs, d_out,
                                                  e->d_partials + (size_t)nrows_pair * NRED);
       e->launches += 1;
    }
@@ -647,6 +667,18 @@ int mdb_launch_pair_tiled(mdb_engine *e, double *d_out, cudaStream_t st)
    e->launches += 2;
    MDB_CUDA(cudaGetLastError());
    return 0;
+}
+
+int mdb_launch_pair_tiled(mdb_engine *e, double *d_out, cudaStream_t st)
+{
+   const mdb_config &c = e->cfg;
+   const bool coul = c.alpha > 0.0;
+   if (!e->pair_split) return pair_pass(e, full_list(e), c.ptype, coul, d_out, st);
+   // split passes: charged x charged with the Coulomb term only, potential x potential with the potential only
+   if (mdb_build_sublist(e, 0, st) || mdb_build_sublist(e, 1, st)) return -1;
+   if (pair_pass(e, sub_list(e, 0), PT_NONE, true, d_out, st)) return -1;
+   if (pair_pass(e, sub_list(e, 1), c.ptype, false, d_out, st)) return -1;
+   return mdb_launch_too_close_scan(e, st);
 }
 
 // ---- micro-benchmark: throughput of the pair arithmetic alone (no memory traffic) -----------------
