@@ -263,16 +263,23 @@ def run_ours(a):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        roof = {"bound": "fp64", "kernel": "k_pair_tiled<LJ,coulomb,newton3> (real-space pair kernel, FP64 CUDA cores; no "
-                "tensor-core or HBM roofline applies: ~36 B/site are reused for ~6 300 pair visits; `traffic` is "
-                "dram read+write bytes per launch from the ncu capture in profiles/; a DFMA reading three distinct "
-                "registers issues every 3.2 cycles instead of 2.1 on sm_100a, scripts/ubench2.cu, so the DFMA-probe "
-                "peak is not reachable by a*b+c chains on registers)",
+        split = eng.pair_split()
+        roof = {"bound": "fp64",
+                "kernel": ("real-space phase = k_pair_tiled<none,coulomb,newton3> over the charged sites + "
+                           "k_pair_tiled<LJ,no-coulomb,newton3> over the Lennard-Jones sites (+ sublist compaction): "
+                           "the reference's pair set, with the pairs whose charge product / epsilon is exactly zero "
+                           "skipped term by term" if split else
+                           "k_pair_tiled<LJ,coulomb,newton3> (one fused pass over all sites)") +
+                          "; FP64 CUDA cores, no tensor-core or HBM roofline applies (~36 B/site are reused for ~6 300 "
+                          "pair visits; `traffic` is dram read+write bytes of the phase from the ncu capture in profiles/). "
+                          "`achieved` counts SURVEY 8d's 59 flop for every pair the reference hands to kernel() "
+                          "(pairs_per_launch, counted on the device), so skipped zero terms raise it: it is the "
+                          "algorithmic rate of the phase, not the FP64 pipe utilisation (profiles/ has that)",
                 "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": "FP64 DFMA rate measured in this run by mdb_fp64_peak_probe (MEASURED_PEAKS.json holds "
                                "no FP64 figure; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2)",
                 "algorithmic_flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs / world,
-                "avg_launch_ms": pair_ms, "traffic": TRAFFIC.get(a.n),
+                "avg_launch_ms": pair_ms, "split_passes": bool(split), "traffic": TRAFFIC.get(a.n),
                 "hbm_peak_gbs_measured": peaks.get("hbm_gbs")}
         line = {"metric": "md_force_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -282,7 +289,7 @@ def run_ours(a):
                 "k_vectors": nhkl, "site_k_terms_per_s": N * nhkl / (ms_step * 1e-3),
                 "phase_ms": {"cells": float(ph[:, 0].mean()), "pair": pair_ms, "recip": float(ph[:, 2].mean()),
                              "allreduce": float(ph[:, 3].mean())},
-                "recip_roofline": {"bound": "fp64", "achieved": FLOP_PER_SITEK * N * nhkl / world / (ph[:, 2].mean() * 1e-3) / 1e12,
+                "recip_roofline": {"bound": "fp64", "kernel": "k_ktables + k_sfac_mma + k_kforce_mma (DMMA.8x8x4, FP64 tensor pipe)", "achieved": FLOP_PER_SITEK * N * nhkl / world / (ph[:, 2].mean() * 1e-3) / 1e12,
                                    "peak": peak / 1e12, "unit": "TFLOP/s",
                                    "frac": FLOP_PER_SITEK * N * nhkl / world / (ph[:, 2].mean() * 1e-3) / peak},
                 "roofline": roof, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),

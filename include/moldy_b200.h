@@ -236,6 +236,7 @@ int  mdb_read_out(mdb_engine *e, const double *d_out, double *h_out, void *strea
 int    mdb_grid(const mdb_engine *e, int nxyz[3]);           /* link-cell grid          */
 int    mdb_n_neighbour_cells(const mdb_engine *e);            /* half list, as NABORS/2  */
 int    mdb_n_kvectors(const mdb_engine *e);                   /* nhkl                    */
+int    mdb_pair_split(const mdb_engine *e);                   /* 1: real space runs as one pass per site class (charged / pair potential) */
 int    mdb_get_cell_ids(mdb_engine *e, int *h_cell, void *stream);   /* [nsites], NCELL()  */
 double mdb_pair_count(mdb_engine *e, void *stream);           /* pairs handed to kernel() per force evaluation
                                                                   (src/force.c:960) for the current sites */

@@ -390,6 +390,7 @@ extern "C" int mdb_grid(const mdb_engine *e, int nxyz[3])
 }
 extern "C" int mdb_n_neighbour_cells(const mdb_engine *e) { return (int)e->T.half_list.size() / 3; }
 extern "C" int mdb_n_kvectors(const mdb_engine *e) { return e->T.nhkl; }
+extern "C" int mdb_pair_split(const mdb_engine *e) { return e->pair_split; }
 extern "C" long mdb_kernel_launches(const mdb_engine *e) { return e->launches; }
 
 extern "C" int mdb_get_cell_ids(mdb_engine *e, int *h_cell, void *stream)

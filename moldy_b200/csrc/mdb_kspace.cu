@@ -942,12 +942,8 @@ k_kforce_mma(KfMArgs A, const int *__restrict__ cidx, const double *__restrict__
 // the default is the DMMA pair (k_sfac_mma, k_kforce_mma).  Both are device paths.
 static bool kspace_use_mma()
 {
-   static int mode = -1;
-   if (mode < 0) {
-      const char *m = getenv("MDB_KSPACE");
-      mode = (m && std::string(m) == "dfma") ? 0 : 1;
-   }
-   return mode == 1;
+   const char *m = getenv("MDB_KSPACE");           // read per call: the tests switch it between engines
+   return !(m && std::string(m) == "dfma");
 }
 
 struct RecipPlan {

@@ -74,6 +74,7 @@ def load() -> C.CDLL:
     L.mdb_grid.argtypes = [C.c_void_p, IP]
     L.mdb_n_neighbour_cells.argtypes = [C.c_void_p]
     L.mdb_n_kvectors.argtypes = [C.c_void_p]
+    L.mdb_pair_split.argtypes = [C.c_void_p]
     L.mdb_get_cell_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.mdb_rdf_size.restype = C.c_size_t
     L.mdb_rdf_size.argtypes = [C.c_void_p, C.c_int]
@@ -329,6 +330,10 @@ class Engine:
 
     def pair_count(self, stream=0) -> float:
         return self.L.mdb_pair_count(self.h, stream)
+
+    def pair_split(self) -> int:
+        """1 when the real-space sum runs as two passes by site class (charged / with a pair potential)."""
+        return self.L.mdb_pair_split(self.h)
 
     def launches(self) -> int:
         return self.L.mdb_kernel_launches(self.h)

@@ -285,3 +285,105 @@ def test_force_calc_accumulates_rdf_store(name, golden_dir):
     assert out["rdf"].shape == gold.shape
     assert np.allclose(out["rdf"], gold / rho, rtol=1e-6, atol=0)
     lib.reset()
+
+
+def _real_space(ms, mode, env):
+    """force_real through the engine API under the given environment switches"""
+    import torch
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        eng = lib.Engine(0)
+        eng.set_pair_mode(mode)
+        eng.configure(ms)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return eng
+
+
+@pytest.mark.parametrize("split", [0, 1])
+@pytest.mark.parametrize("mode", [3, 4])
+@pytest.mark.parametrize("name", list(cases.GOLDEN_CASES))
+def test_split_pair_passes_vs_golden(name, mode, split, golden_dir):
+    """The real-space sum as one fused pass and as two passes by site class (charged x charged with the
+    Coulomb term only + potential x potential with the potential only), both forced, against force_calc()."""
+    import torch
+    from oracle import port
+    ms = cases.GOLDEN_CASES[name]()
+    n = ms.nsites
+    eng = _real_space(ms, mode, {"MDB_PAIR_SPLIT": str(split)})
+    eng.set_sites_host(ms.make_sites(wrap=not ms.control.molpbc))
+    if ms.control.molpbc:
+        eng.set_com_host(ms.c_of_m)
+    st = torch.cuda.current_stream().cuda_stream
+    out = torch.zeros(eng.out_doubles(), dtype=torch.float64, device="cuda")
+    eng.build_cells(st)
+    eng.force_real(out.data_ptr(), st)
+    torch.cuda.synchronize()
+    f, pe, s = lib.unpack(out.cpu().numpy(), n)
+    gold = port.run(ms, recip=False)
+    assert cases.rel_rms(f, gold["force"]) <= F_TOL
+    ref_pe = gold["pe"][0] + gold["eintra"]
+    assert abs(pe[0] - ref_pe) <= E_TOL * abs(ref_pe)
+    iu = np.triu_indices(3)
+    assert np.linalg.norm(s[iu] - gold["stress"][iu]) <= E_TOL * np.linalg.norm(gold["stress"][iu])
+    assert abs(eng.pair_count(st) - gold["npairs"]) < 0.5     # the reference's pair count, whatever the passes visit
+    eng.close()
+
+
+@pytest.mark.parametrize("name", [k for k in cases.GOLDEN_CASES if cases.GOLDEN_CASES[k]().control.alpha > 0])
+def test_kspace_dmma_and_dfma_kernels_agree(name, golden_dir):
+    """Reciprocal space on the FP64 tensor pipe (k_ktables/k_sfac_mma/k_kforce_mma, the default) and with the
+    register-operand DFMA kernels (MDB_KSPACE=dfma): same sums, different order."""
+    import torch
+    ms = cases.GOLDEN_CASES[name]()
+    n = ms.nsites
+    res = {}
+    for kind in ("mma", "dfma"):
+        os.environ["MDB_KSPACE"] = kind
+        try:
+            eng = lib.Engine(0)
+            eng.configure(ms)
+            eng.set_sites_host(ms.make_sites(wrap=not ms.control.molpbc))
+            st = torch.cuda.current_stream().cuda_stream
+            out = torch.zeros(eng.out_doubles(), dtype=torch.float64, device="cuda")
+            eng.force_recip(out.data_ptr(), st)
+            torch.cuda.synchronize()
+            res[kind] = lib.unpack(out.cpu().numpy(), n)
+            eng.close()
+        finally:
+            os.environ.pop("MDB_KSPACE", None)
+    (f1, pe1, s1), (f2, pe2, s2) = res["mma"], res["dfma"]
+    assert cases.rel_rms(f1, f2) <= 1e-12
+    assert abs(pe1[1] - pe2[1]) <= 1e-12 * abs(pe2[1])
+    assert np.linalg.norm(s1 - s2) <= 1e-12 * np.linalg.norm(s2)
+
+
+def test_too_close_pairs_counted_alike_by_fused_and_split_passes(golden_dir):
+    """src/force.c:939-949 warns about every inter-molecular pair closer than 0.5 A, whatever its types.  A
+    hydrogen pushed onto a foreign oxygen (a pair neither split pass visits: O carries no charge, H no
+    Lennard-Jones term) must be reported the same by the fused pass and by the split passes + cell scan."""
+    import torch
+    ms = cases.GOLDEN_CASES["tip4p"]()
+    site = ms.make_sites(wrap=True)
+    nsm = ms.sysdef.species[0].nsites
+    # sites of a TIP4P molecule: O, H, H, M; put an H of molecule 1 next to the O of molecule 0
+    site[:, nsm + 1] = site[:, 0] + np.array([0.05, 0.03, 0.02])
+    counts = []
+    for split in (0, 1):
+        eng = _real_space(ms, 4, {"MDB_PAIR_SPLIT": str(split)})
+        eng.set_sites_host(site)
+        st = torch.cuda.current_stream().cuda_stream
+        out = torch.zeros(eng.out_doubles(), dtype=torch.float64, device="cuda")
+        eng.build_cells(st)
+        eng.force_real(out.data_ptr(), st)
+        torch.cuda.synchronize()
+        ntc, pair = eng.too_close(st)
+        counts.append(ntc)
+        assert ntc > 0 and pair[0] // nsm != pair[1] // nsm
+        eng.close()
+    assert counts[0] == counts[1]
