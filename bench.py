@@ -331,7 +331,7 @@ def measure_e2e(a, ms, site, world, rank, local):
         stress = np.zeros((3, 3))
 
         def one():
-            f_np[:] = 0.0
+            hf.zero_()                    # the caller's zero_real(site_force), src/accel.c:470-472
             pe[:] = 0.0
             stress[:] = 0.0
             lib.force_calc(s_np, f_np, sysm, spec, chg, pot, pe[0:1], stress)

@@ -218,6 +218,27 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
+// ---- 1-D bulk copies (TMA unit, UBLKCP) completing on an mbarrier
+__device__ __forceinline__ void mbar_init(unsigned mb, int count)
+{
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mb, unsigned bytes)
+{
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned mb)
+{
+   const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                ::"r"(d), "l"(src), "r"(bytes), "r"(mb) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mb, unsigned parity)
+{
+   asm volatile("{\n\t.reg .pred p;\n\tMBAR_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                "@p bra MBAR_DONE;\n\tbra MBAR_WAIT;\n\tMBAR_DONE:\n\t}" ::"r"(mb), "r"(parity) : "memory");
+}
+
 // power tables of the three base phase factors for rows [g0, g1) of the charged-site list: one (site,axis)
 // per thread builds its row in shared memory by recurrence, then the block writes the 32 rows of each
 // table as one contiguous, coalesced piece (row-at-a-time 16-byte stores ran at 1.1 ms for 1.08 GB)
@@ -307,30 +328,41 @@ __device__ __forceinline__ void sfac_mma_body(const SfacMArgs &A, const SfacMBlo
    auto bufB = [&](int b) { return buf0 + b * buf_doubles; };
    auto bufH = [&](int b) { return reinterpret_cast<double2 *>(buf0 + b * buf_doubles + (size_t)MSC * L.SB); };
    auto bufK = [&](int b) { return reinterpret_cast<double2 *>(buf0 + b * buf_doubles + (size_t)MSC * L.SB) + (size_t)MSC * L.SH; };
-   // chunk [base, base+MSC) of the table rows -> buffer b.  Rows past the slab end belong to other slabs
-   // (or the zeroed padding): their q E_l row is zeroed, E_h/E_k are copied as they are (finite).
+   // chunk [base, base+MSC) of the table rows -> buffer b: three bulk copies issued by one thread, completing on
+   // the buffer's mbarrier (as 16-byte cp.async pieces the staging cost 0.5 ms of LSU time per launch).  Rows past
+   // the slab end belong to other slabs (or the zeroed padding): their q E_l row is zeroed instead of copied,
+   // E_h/E_k are copied as they are (finite).
+   __shared__ __align__(8) unsigned long long mbar_store[2];
+   const unsigned mb0 = (unsigned)__cvta_generic_to_shared(mbar_store);
+   if (tid == 0) {
+      mbar_init(mb0, 1); mbar_init(mb0 + 8, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+   }
+   __syncthreads();
    auto stage = [&](int base, int b) {
-      const int vE = (L.SB * 8) / 16, vH = L.SH, vK = L.SK;        // 16-byte units per row
+      const int vE = L.SB / 2;                                        // 16-byte units per E row
       const int nv = min(MSC, s1 - base);
-      double2 *dE = reinterpret_cast<double2 *>(bufB(b)), *dH = bufH(b), *dK = bufK(b);
-      const double2 *gE = reinterpret_cast<const double2 *>(tE + (size_t)base * L.SB);
-      const double2 *gH = tH + (size_t)base * L.SH, *gK = tK + (size_t)base * L.SK;
-      for (int u = tid; u < MSC * vE; u += MT) {
-         if (u < nv * vE) cp_async16(dE + u, gE + u);
-         else dE[u] = make_double2(0.0, 0.0);
+      double2 *dE = reinterpret_cast<double2 *>(bufB(b));
+      if (tid == 0) {
+         const unsigned bE = (unsigned)nv * L.SB * 8u, bH = (unsigned)MSC * L.SH * 16u, bK = (unsigned)MSC * L.SK * 16u;
+         const unsigned mb = mb0 + 8u * b;
+         mbar_expect_tx(mb, bE + bH + bK);
+         bulk_g2s(dE, tE + (size_t)base * L.SB, bE, mb);
+         bulk_g2s(bufH(b), tH + (size_t)base * L.SH, bH, mb);
+         bulk_g2s(bufK(b), tK + (size_t)base * L.SK, bK, mb);
       }
-      for (int u = tid; u < MSC * vH; u += MT) cp_async16(dH + u, gH + u);
-      for (int u = tid; u < MSC * vK; u += MT) cp_async16(dK + u, gK + u);
+      for (int u = nv * vE + tid; u < MSC * vE; u += MT) dE[u] = make_double2(0.0, 0.0);
    };
 
+   unsigned phase[2] = {0u, 0u};
    stage(s0, 0);
-   cp_async_wait_all();
-   __syncthreads();
    int b = 0;
    for (int base = s0; base < s1; base += MSC, b ^= 1) {
 #if MDB_ABL != 3
       if (base + MSC < s1) stage(base + MSC, b ^ 1);
 #endif
+      mbar_wait(mb0 + 8u * b, phase[b]);
+      phase[b] ^= 1u;
       if (warp_on) {
          const double *sB = bufB(b) + 2 * B.l0 + g;
          const double2 *sH = bufH(b), *sK = bufK(b);
@@ -381,8 +413,7 @@ __device__ __forceinline__ void sfac_mma_body(const SfacMArgs &A, const SfacMBlo
          }
 #endif
       }
-      cp_async_wait_all();
-      __syncthreads();
+      __syncthreads();          // everyone is done with buffer b before the next bulk copy lands in it
    }
    // C fragment: row g = (column g/2, c|s), columns 2 kq + e = (slot kq of the n-tile, C|S)
    if (warp_on)

@@ -92,7 +92,9 @@ const dim_mt pot_dim[][MDB_NPOTP] = {
 // ---- process-wide state (the reference keeps the same in function statics) -----
 struct AbiState {
    mdb_engine *eng = nullptr;
-   cudaStream_t stream = nullptr;
+   cudaStream_t stream = nullptr, copy_stream = nullptr;   // copy_stream: D2H of the real-space block beside the k-space kernels
+   cudaEvent_t ev_real = nullptr, ev_copied = nullptr;
+   bool chg_unchecked = false;                              // sync_config(defer_chg): contents of chg[] still to be compared
    bool real_init = false, recip_init = false;
    double eintra = 0, self_energy = 0, sheet_energy = 0;
    int onabor = 0, onx = 0, ony = 0, onz = 0;
@@ -124,7 +126,10 @@ static void ensure_engine()
    if (s) dev = atoi(s);
    G.eng = mdb_create(dev);
    if (!G.eng) FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
-   if (cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking) != cudaSuccess)
+   if (cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking) != cudaSuccess ||
+       cudaStreamCreateWithFlags(&G.copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+       cudaEventCreateWithFlags(&G.ev_real, cudaEventDisableTiming) != cudaSuccess ||
+       cudaEventCreateWithFlags(&G.ev_copied, cudaEventDisableTiming) != cudaSuccess)
       FATAL_MSG("libmoldy_b200: cannot create CUDA stream");
 }
 
@@ -139,7 +144,9 @@ static int count_xf_sites(const system_mt *system, const spec_mt *species)
 // Flatten system/species/potpar/control into mdb_config and (re)configure the engine
 // when anything that shapes the tables changed (cell matrix changes every step under
 // constant-stress dynamics; everything else is constant in a Moldy run).
-static void sync_config(system_mt *system, spec_mt *species, const real *chg, const pot_mt *potpar)
+// defer_chg: do not compare the N charges now (8 MB, 0.6 ms at 10^6 sites); the caller does it with
+// chg_changed_late() once its kernels are running and repeats the call if they differ.
+static void sync_config(system_mt *system, spec_mt *species, const real *chg, const pot_mt *potpar, bool defer_chg = false)
 {
    ensure_engine();
    const int n = system->nsites, max_id = system->max_id;
@@ -171,7 +178,10 @@ static void sync_config(system_mt *system, spec_mt *species, const real *chg, co
             for (int is = 0; is < sp->nsites; is++, js++) { G.type[js] = sp->site_id[is]; G.mol[js] = jm; }
       changed = true;
    }
-   if ((int)G.chg.size() != n || memcmp(G.chg.data(), chg, sizeof(double) * n)) {
+   G.chg_unchecked = false;
+   if (defer_chg && !changed && (int)G.chg.size() == n) {
+      G.chg_unchecked = true;
+   } else if ((int)G.chg.size() != n || memcmp(G.chg.data(), chg, sizeof(double) * n)) {
       G.chg.assign(chg, chg + n);
       changed = true;
    }
@@ -204,6 +214,13 @@ static void sync_config(system_mt *system, spec_mt *species, const real *chg, co
          FATAL_MSG("libmoldy_b200: out of device/pinned memory for %d sites", n);
       G.out_cap = need;
    }
+}
+
+static bool chg_changed_late(const real *chg, int n)
+{
+   if (!G.chg_unchecked) return false;
+   G.chg_unchecked = false;
+   return memcmp(G.chg.data(), chg, sizeof(double) * n) != 0;
 }
 
 static void push_sites(real **site)
@@ -254,7 +271,7 @@ extern "C" void force_calc(real **site, real **site_force, system_mt *system, sp
                            pot_mt *potpar, double *pe, mat_mt stress)
 {
    const double tc0 = now_ms();
-   sync_config(system, species, chg, potpar);
+   sync_config(system, species, chg, potpar, true);
    if (g_timing) fprintf(stderr, "[moldy_b200] force_calc: sync_config %.2f ms\n", now_ms() - tc0);
    mdb_set_partition(G.eng, ithread, nthreads);
    const int n = system->nsites;
@@ -293,17 +310,30 @@ extern "C" void force_calc(real **site, real **site_force, system_mt *system, sp
       G.onx = g[0]; G.ony = g[1]; G.onz = g[2];
    }
 
-   G.sites_fresh = false;
-   push_sites(site);
-   if (control.molpbc && mdb_set_com_host(G.eng, &system->c_of_m[0][0], G.stream))
-      FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
-   if (mdb_zero_out(G.eng, G.d_out, G.stream) || mdb_build_cells(G.eng, G.stream) ||
-       mdb_force_real(G.eng, G.d_out, G.stream))
-      FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
-   if (cudaMemcpyAsync(G.h_out, G.d_out, sizeof(double) * mdb_out_doubles(n), cudaMemcpyDeviceToHost, G.stream) != cudaSuccess)
-      FATAL_MSG("libmoldy_b200: D2H copy failed");
+   auto launch_real = [&]() {
+      G.sites_fresh = false;
+      push_sites(site);
+      if (control.molpbc && mdb_set_com_host(G.eng, &system->c_of_m[0][0], G.stream))
+         FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+      if (mdb_zero_out(G.eng, G.d_out, G.stream) || mdb_build_cells(G.eng, G.stream) ||
+          mdb_force_real(G.eng, G.d_out, G.stream))
+         FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+      // the result block goes home on the copy stream, so that the k-space kernels started below do not queue behind it
+      cudaEventRecord(G.ev_real, G.stream);
+      cudaStreamWaitEvent(G.copy_stream, G.ev_real, 0);
+      if (cudaMemcpyAsync(G.h_out, G.d_out, sizeof(double) * mdb_out_doubles(n), cudaMemcpyDeviceToHost, G.copy_stream) != cudaSuccess)
+         FATAL_MSG("libmoldy_b200: D2H copy failed");
+      cudaEventRecord(G.ev_copied, G.copy_stream);
+   };
+   launch_real();
+   if (chg_changed_late(chg, n)) {                       /* compared while the kernels run; never in a Moldy run */
+      cudaStreamSynchronize(G.stream);
+      cudaStreamSynchronize(G.copy_stream);
+      sync_config(system, species, chg, potpar);
+      launch_real();
+   }
    int pr[2];
-   const int tc = mdb_too_close(G.eng, pr, G.stream);     /* synchronises: the real-space block is on the host now */
+   const int tc = mdb_too_close(G.eng, pr, G.stream);     /* synchronises G.stream: the real-space kernels are done */
    G.sites_fresh = true;
 
    // eval_forces calls ewald() next on the same sites (src/accel.c:520-527): start its kernels now, so
@@ -320,6 +350,7 @@ extern "C" void force_calc(real **site, real **site_force, system_mt *system, sp
       G.ahead_ithread = ithread; G.ahead_nthreads = nthreads;
    }
 
+   if (cudaEventSynchronize(G.ev_copied) != cudaSuccess) FATAL_MSG("libmoldy_b200: D2H copy failed");
    pull_and_accumulate(site_force, pe, stress, n, G.d_out, G.h_out, true);
    *pe += G.h_out[3 * (size_t)n];
 
