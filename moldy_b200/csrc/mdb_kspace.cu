@@ -877,6 +877,9 @@ k_kforce_mma(KfMArgs A, const int *__restrict__ cidx, const double *__restrict__
    prefetch(0);
    stage(0, 0);
    prefetch(1);
+#if MDB_ABL == 5 || MDB_ABL == 7
+   if (nrounds > 1) stage(1, 1);
+#endif
    cp_async_wait_all();
    __syncthreads();                                      // tables + first stage
 
@@ -885,10 +888,12 @@ k_kforce_mma(KfMArgs A, const int *__restrict__ cidx, const double *__restrict__
    const double *ea0 = sE + (size_t)sl0 * A.SE + kq, *ea1 = ea0 + 8 * (size_t)A.SE;
    for (int r = 0; r < nrounds; r++) {
       const int buf = r & 1;
+#if MDB_ABL != 5 && MDB_ABL != 7
       if (r + 1 < nrounds) {
          stage(r + 1, buf ^ 1);
          prefetch(r + 2);
       }
+#endif
       const int gi = 2 * r + half;
       if (gi < A.ngroups) {
          const KfGroup &G = sG[buf * 2 + half];
@@ -910,6 +915,9 @@ k_kforce_mma(KfMArgs A, const int *__restrict__ cidx, const double *__restrict__
             dmma884(acc[1][2], a1, q23.x); dmma884(acc[1][3], a1, q23.y);
          }
          // back-projection: C fragment = (site g of the tile, columns 2 kq + e)
+#if MDB_ABL == 4 || MDB_ABL == 7
+         Fa[0] += acc[0][0][0] + acc[0][1][1] + acc[0][2][0] + acc[0][3][1]; Fa[1] += acc[1][0][0] + acc[1][1][1] + acc[1][2][0] + acc[1][3][1];
+#else
 #pragma unroll
          for (int e = 0; e < 2; e++) {
             const int hc = G.h[2 * kq + e], kc = G.k[2 * kq + e];
@@ -928,9 +936,12 @@ k_kforce_mma(KfMArgs A, const int *__restrict__ cidx, const double *__restrict__
                Fc[s] = fma(ehk.y, acc[s][2][e], fma(ehk.x, acc[s][3][e], Fc[s]));
             }
          }
+#endif
       }
       cp_async_wait_all();
+#if MDB_ABL != 6 && MDB_ABL != 7
       half_barrier();
+#endif
    }
    // ---- sum the four lanes of a site, then the two halves, and add to the caller's force rows
 #pragma unroll
