@@ -274,13 +274,13 @@ int mdb_build_sublist(mdb_engine *e, int k, cudaStream_t st)
 // pair of the stencil).  Two sites closer than 0.5 A sit in the same or in adjacent cells (mdb_configure
 // refuses the split for cells thinner than that), so 27 cells per site are enough.
 struct CloseParams { int nx, ny, nz; double reloc[27][3]; };
-__global__ void __launch_bounds__(CB) k_too_close_scan(CloseParams P, int n, const double4 *__restrict__ posq,
+__global__ void __launch_bounds__(CB) k_too_close_scan(CloseParams P, int s_lo, int n, const double4 *__restrict__ posq,
                                                        const int *__restrict__ scell, const int *__restrict__ start,
                                                        const int *__restrict__ order, const int *__restrict__ mol,
                                                        const unsigned char *__restrict__ cls,
                                                        unsigned long long *__restrict__ counters)
 {
-   const int s = blockIdx.x * CB + threadIdx.x;
+   const int s = s_lo + blockIdx.x * CB + threadIdx.x;      // this rank's slice of the sorted sites; partners t > s anywhere
    if (s >= n) return;
    const int c = scell[s], cz = c % P.nz, cy = (c / P.nz) % P.ny, cx = c / (P.nz * P.ny);
    const double4 pi = posq[s];
@@ -311,8 +311,10 @@ int mdb_launch_too_close_scan(mdb_engine *e, cudaStream_t st)
    P.nx = e->T.nx; P.ny = e->T.ny; P.nz = e->T.nz;
    for (int k = 0; k < 27; k++)
       for (int a = 0; a < 3; a++) P.reloc[k][a] = e->T.reloc[k][a];
-   const int n = e->cfg.nsites;
-   k_too_close_scan<<<(n + CB - 1) / CB, CB, 0, st>>>(P, n, e->d_posq, e->d_scell, e->d_start, e->d_order, e->d_mol,
+   const long nall = e->cfg.nsites;
+   const int s_lo = (int)(nall * e->ithread / e->nthreads), n = (int)(nall * (e->ithread + 1) / e->nthreads);
+   if (n <= s_lo) return 0;
+   k_too_close_scan<<<(n - s_lo + CB - 1) / CB, CB, 0, st>>>(P, s_lo, n, e->d_posq, e->d_scell, e->d_start, e->d_order, e->d_mol,
                                                       e->d_cls, e->d_counters);
    e->launches += 1;
    MDB_CUDA(cudaGetLastError());
