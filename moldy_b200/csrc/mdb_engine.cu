@@ -65,7 +65,7 @@ static void free_grid(mdb_engine *e)
 static void free_recip(mdb_engine *e)
 {
    FREE(e->d_hk); FREE(e->d_hk_valid); FREE(e->d_slot_flags); FREE(e->d_ppart);
-   FREE(e->d_coef_tot); FREE(e->d_coef_nf); FREE(e->d_kpartials); FREE(e->d_cidx); FREE(e->d_sfac_blocks); FREE(e->d_kf_groups); FREE(e->d_ktab); e->ktab_cap = 0;
+   FREE(e->d_coef_tot); FREE(e->d_coef_nf); FREE(e->d_kpartials); FREE(e->d_cidx); FREE(e->d_sfac_blocks); FREE(e->d_kf_groups); FREE(e->d_kf_slot_dst); FREE(e->d_ktab); e->ktab_cap = 0;
    FREE(e->d_psum);
    e->ppart_cap = 0;
 }

@@ -132,7 +132,8 @@ struct mdb_engine {
    int *d_cidx = nullptr;                 // charged sites (non-framework first), original indices
    int n_charged = 0, n_charged_nf = 0;
    void *d_sfac_blocks = nullptr; int n_sfac_blocks = 0, sfac_rank = -1, sfac_nranks = -1, sfac_mode = -1;
-   void *d_kf_groups = nullptr; int n_kf_groups = 0, kf_rank = -1, kf_nranks = -1;   // column groups of k_kforce_mma
+   void *d_kf_groups = nullptr; int n_kf_groups = 0, kf_rank = -1, kf_nranks = -1;   // k_kforce_mma: coefficient blocks (descriptor + planes) of the column groups, total | non-framework
+   int *d_kf_slot_dst = nullptr;          // slot -> entry of its block (k_sfin writes through it)
    void *d_ktab = nullptr; size_t ktab_cap = 0;      // per-site power tables E_l | E_h | E_k of the DMMA kernels
    double *d_kpartials = nullptr;
    double *d_psum = nullptr;              // [2][nslots][4] structure-factor sums (non-framework, framework)

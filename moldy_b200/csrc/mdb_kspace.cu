@@ -468,13 +468,16 @@ __global__ void __launch_bounds__(256) k_slab_sum(int nslots, int n_slabs, int n
 struct SfinArgs {
    KspaceParams K;
    int nslots, n_slabs, n_slabs_nf, rank, nranks, framework;
-   int mma;                // coefficient rows in k_kforce_mma's order: {X,Y | el.x, el.y}, {Xz,Yz | el.x, el.y}
+   int mma;                // coefficients go to k_kforce_mma's padded group blocks (slot_dst), in its order:
+                           // plane 0 {X,Y} x {el.x, el.y}, plane 1 {Xz,Yz} x {el.x, el.y}
+   int plane;              // double2 between the two planes of a block
 };
 
 __global__ void __launch_bounds__(256)
 k_sfin(SfinArgs A, const HkDesc *__restrict__ hk, const int *__restrict__ slot_hk,
        const int *__restrict__ slot_flags, const double *__restrict__ ppart, double *__restrict__ coef_tot,
-       double *__restrict__ coef_nf, double *__restrict__ kpartials)
+       double *__restrict__ coef_nf, double *__restrict__ kpartials, const int *__restrict__ slot_dst,
+       double2 *__restrict__ blk_tot, double2 *__restrict__ blk_nf)
 {
    const KspaceParams &K = A.K;
    const int slot = blockIdx.x * 256 + threadIdx.x;
@@ -521,16 +524,22 @@ k_sfin(SfinArgs A, const HkDesc *__restrict__ hk, const int *__restrict__ slot_h
       }
       if (A.mma) {
          // X = sum el.x ct0 + el.y ct3   Y = sum -el.x ct1 + el.y ct2   Xz = sum el.x ct4 + el.y ct5   Yz = sum -el.x ct7 + el.y ct6
-         const double mt[8] = {ct[0], -ct[1], ct[3], ct[2], ct[4], -ct[7], ct[5], ct[6]};
-         const double mn[8] = {cn[0], -cn[1], cn[3], cn[2], cn[4], -cn[7], cn[5], cn[6]};
+         const int dst = slot_dst[slot];
+         if (dst >= 0) {
+            blk_tot[dst] = make_double2(ct[0], -ct[1]); blk_tot[dst + 1] = make_double2(ct[3], ct[2]);
+            blk_tot[dst + A.plane] = make_double2(ct[4], -ct[7]); blk_tot[dst + A.plane + 1] = make_double2(ct[5], ct[6]);
+            if (A.framework) {
+               blk_nf[dst] = make_double2(cn[0], -cn[1]); blk_nf[dst + 1] = make_double2(cn[3], cn[2]);
+               blk_nf[dst + A.plane] = make_double2(cn[4], -cn[7]); blk_nf[dst + A.plane + 1] = make_double2(cn[5], cn[6]);
+            }
+         }
+      } else {
 #pragma unroll
-         for (int k = 0; k < 8; k++) { ct[k] = mt[k]; cn[k] = mn[k]; }
+         for (int k = 0; k < 8; k++) coef_tot[(size_t)slot * 8 + k] = ct[k];
+         if (A.framework)
+#pragma unroll
+            for (int k = 0; k < 8; k++) coef_nf[(size_t)slot * 8 + k] = cn[k];
       }
-#pragma unroll
-      for (int k = 0; k < 8; k++) coef_tot[(size_t)slot * 8 + k] = ct[k];
-      if (A.framework)
-#pragma unroll
-         for (int k = 0; k < 8; k++) coef_nf[(size_t)slot * 8 + k] = cn[k];
    }
    __shared__ double sm[8][7];
    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -762,40 +771,52 @@ k_kforce(KfArgs A, const int *__restrict__ cidx, const double *__restrict__ x, c
 // power tables in shared memory, which is what limits a block to 128 sites (one block per SM).
 // Warps 0..NSB-1 own 16 sites each and walk the even groups, warps NSB..2NSB-1 the same sites and
 // the odd groups: the coefficient fragments (the same for every site) are then loaded once per 16
-// sites and four warps per scheduler keep the DMMA pipe fed.  Coefficients of the next two groups are
-// staged with cp.async while the current two are consumed.
+// sites and four warps per scheduler keep the DMMA pipe fed.
+// k_sfin stores the coefficients group-major and zero-padded ("blocks": descriptor + two planes of 8
+// columns), so a group arrives by ONE TMA bulk copy issued by a producer warp into a two-deep ring per
+// half; consumers wait on the stage's `full` mbarrier and release it (`empty`) after their DMMA loop,
+// before the back-projection.  No block-wide barrier in the loop: the warps of a scheduler drift apart
+// and one warp's epilogue overlaps the others' DMMAs (with a barrier per round and cp.async staging by the
+// consumers the kernel lost ~2 200 of ~7 100 cycles per round: 9.72 ms).
 struct KfGroup {            // 8 columns, padded with nl = 0
    int nsteps, pad0, pad1, pad2;
    int h[8], k[8], nl[8], slot0[8];
 };
+static constexpr int KFB_HDR = 16;      // double2 units in front of the planes (descriptor, 256 bytes)
 
 struct KfMArgs {
    KspaceParams K;
    int c0, c1;              // range in the compacted charged-site list
-   int ngroups, nsb;        // nsb: site-warps per block (block = 2 nsb warps, 16 nsb sites)
+   int ngroups, nsb;        // nsb: site-warps per block (block = 2 nsb consumer warps + 1 producer warp, 16 nsb sites)
    int SE, SH, SK, LPS;     // table strides: E_l in doubles (= 4 mod 16), E_h/E_k in double2 (odd); stage slots (= 2 mod 4)
+   int blk2;                // double2 per coefficient block: KFB_HDR + 2 planes x 8 columns x 2 LPS
 };
 
-
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(544, 1)
 k_kforce_mma(KfMArgs A, const int *__restrict__ cidx, const double *__restrict__ x, const double *__restrict__ y,
-             const double *__restrict__ z, const double *__restrict__ chg, const KfGroup *__restrict__ groups,
-             const double *__restrict__ coef, double *__restrict__ out)
+             const double *__restrict__ z, const double *__restrict__ chg, const double2 *__restrict__ blocks,
+             double *__restrict__ out)
 {
    extern __shared__ double2 smem[];
    const KspaceParams &K = A.K;
-   const int nsites_b = 16 * A.nsb, nthreads = 64 * A.nsb;
+   const int nsites_b = 16 * A.nsb, ncons = 64 * A.nsb, nthreads = ncons + 32;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    const int g = lane >> 2, kq = lane & 3;
-   const int half = warp / A.nsb, sw = warp % A.nsb;
-   // shared memory: E_l [sites][SE] doubles | E_h [sites][SH] | E_k [sites][SK] | stage [2 bufs][2 halves][2 planes][8][2 LPS] double2 | F [2][sites][3]
+   const bool producer = warp >= 2 * A.nsb;
+   const int half = producer ? 0 : warp / A.nsb, sw = warp % A.nsb;
+   // shared memory: E_l [sites][SE] doubles | E_h [sites][SH] | E_k [sites][SK] | ring [2 halves][2 stages][blk2] double2 | F [2][sites][3] | mbarriers
    double *sE = reinterpret_cast<double *>(smem);
    double2 *sH = reinterpret_cast<double2 *>(sE + (size_t)nsites_b * A.SE);
    double2 *sK = sH + (size_t)nsites_b * A.SH;
    double2 *sC = sK + (size_t)nsites_b * A.SK;
    const int colstride = 2 * A.LPS;                      // double2 per (plane, column)
-   const int stage_half = 2 * 8 * colstride;             // double2 per (buffer, half)
-   double *sF = reinterpret_cast<double *>(sC + 4 * (size_t)stage_half);
+   double *sF = reinterpret_cast<double *>(sC + 4 * (size_t)A.blk2);
+   const unsigned mb0 = (unsigned)__cvta_generic_to_shared(sF + 2 * (size_t)nsites_b * 3);
+   // full[half][stage] at mb0 + 8 (2 half + stage), empty[half][stage] 32 bytes further
+   if (tid == 0) {
+      for (int k = 0; k < 4; k++) { mbar_init(mb0 + 8 * k, 1); mbar_init(mb0 + 32 + 8 * k, A.nsb); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+   }
 
    const int site0 = A.c0 + blockIdx.x * nsites_b;
    // ---- power tables, one (site, axis) per thread
@@ -824,81 +845,34 @@ k_kforce_mma(KfMArgs A, const int *__restrict__ cidx, const double *__restrict__
       if (axis == 2)
          for (int m = nmax; m < A.SE / 2; m++) tab[m] = make_double2(0.0, 0.0);
    }
-
-   // ---- coefficient staging, per half: item = (column, slot); real slots by cp.async, padding by zero
-   // stores; the group descriptor travels with them (nine 16-byte pieces).  The two halves run on their
-   // own named barriers, so neither waits for the other's group.
-   KfGroup *sG = reinterpret_cast<KfGroup *>(sF + 2 * (size_t)nsites_b * 3);       // [2 bufs][2 halves]
-   const int hthreads = 32 * A.nsb, htid = tid - half * hthreads;
-   // The fields a thread needs to stage its (column, slot) item are fetched one round ahead into registers
-   // (pf_*): read at the point of use they cost every warp an L2 round trip right after the barrier, with
-   // the DMMA pipe idle (12 % of all stall samples in the first version).
-   const bool one_item = 8 * A.LPS <= hthreads;
-   const int it_c = htid / A.LPS, it_l = htid % A.LPS;
-   int pf_ns = 0, pf_nl = 0, pf_s0 = 0;
-   auto prefetch = [&](int round) {
-      const int gi = 2 * round + half;
-      pf_ns = 0;
-      if (one_item && gi < A.ngroups && it_c < 8) {
-         const KfGroup &G = groups[gi];
-         pf_ns = __ldg(&G.nsteps); pf_nl = __ldg(&G.nl[it_c]); pf_s0 = __ldg(&G.slot0[it_c]);
-      }
-   };
-   auto put = [&](int buf, int c, int l, int nl, int s0) {
-      double2 *d0 = sC + (size_t)(buf * 2 + half) * stage_half + c * colstride + 2 * l;
-      double2 *d1 = d0 + 8 * colstride;
-      if (l < nl) {
-         const double *src = coef + 8 * (size_t)(s0 + l);
-         cp_async16(d0, src); cp_async16(d0 + 1, src + 2);
-         cp_async16(d1, src + 4); cp_async16(d1 + 1, src + 6);
-      } else {
-         d0[0] = d0[1] = d1[0] = d1[1] = make_double2(0.0, 0.0);
-      }
-   };
-   auto stage = [&](int round, int buf) {
-      const int gi = 2 * round + half;
-      if (gi >= A.ngroups) return;
-      const KfGroup &G = groups[gi];
-      if (htid < (int)(sizeof(KfGroup) / 16))
-         cp_async16(reinterpret_cast<double2 *>(sG + buf * 2 + half) + htid, reinterpret_cast<const double2 *>(&G) + htid);
-      if (one_item) {
-         if (it_c < 8 && it_l < 2 * pf_ns) put(buf, it_c, it_l, pf_nl, pf_s0);
-         return;
-      }
-      const int nslot = 2 * __ldg(&G.nsteps);
-      for (int item = htid; item < 8 * nslot; item += hthreads) {
-         const int c = item / nslot, l = item % nslot;
-         put(buf, c, l, __ldg(&G.nl[c]), __ldg(&G.slot0[c]));
-      }
-   };
-   auto half_barrier = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(hthreads) : "memory"); };
+   __syncthreads();                                      // tables and mbarriers are ready
 
    const int nrounds = (A.ngroups + 1) / 2;
-   prefetch(0);
-   stage(0, 0);
-   prefetch(1);
-#if MDB_ABL == 5 || MDB_ABL == 7
-   if (nrounds > 1) stage(1, 1);
-#endif
-   cp_async_wait_all();
-   __syncthreads();                                      // tables + first stage
-
    double Fa[2] = {0, 0}, Fb[2] = {0, 0}, Fc[2] = {0, 0};
    const int sl0 = sw * 16 + g;                          // this thread's site of tile 0 (tile 1: +8)
-   const double *ea0 = sE + (size_t)sl0 * A.SE + kq, *ea1 = ea0 + 8 * (size_t)A.SE;
-   for (int r = 0; r < nrounds; r++) {
-      const int buf = r & 1;
-#if MDB_ABL != 5 && MDB_ABL != 7
-      if (r + 1 < nrounds) {
-         stage(r + 1, buf ^ 1);
-         prefetch(r + 2);
+   if (producer) {
+      if (lane == 0) {
+         const unsigned bytes = (unsigned)A.blk2 * 16u;
+         for (int r = 0; r < nrounds; r++)
+            for (int hf = 0; hf < 2; hf++) {
+               const int gi = 2 * r + hf, st = r & 1, slot = 2 * hf + st;
+               if (gi >= A.ngroups) continue;
+               mbar_wait(mb0 + 32 + 8 * slot, ((r >> 1) & 1) ^ 1);     // stage free (passes at once the first time round)
+               mbar_expect_tx(mb0 + 8 * slot, bytes);
+               bulk_g2s(sC + (size_t)slot * A.blk2, blocks + (size_t)gi * A.blk2, bytes, mb0 + 8 * slot);
+            }
       }
-#endif
-      const int gi = 2 * r + half;
-      if (gi < A.ngroups) {
-         const KfGroup &G = sG[buf * 2 + half];
+   } else {
+      const double *ea0 = sE + (size_t)sl0 * A.SE + kq, *ea1 = ea0 + 8 * (size_t)A.SE;
+      for (int r = 0; r < nrounds; r++) {
+         const int gi = 2 * r + half, st = r & 1, slot = 2 * half + st;
+         if (gi >= A.ngroups) break;
+         mbar_wait(mb0 + 8 * slot, (r >> 1) & 1);
+         const double2 *blk = sC + (size_t)slot * A.blk2;
+         const KfGroup &G = *reinterpret_cast<const KfGroup *>(blk);
          const int nsteps = G.nsteps;
-         const double2 *c0 = sC + (size_t)(buf * 2 + half) * stage_half + g * colstride + kq;
+         const int hc0 = G.h[2 * kq], kc0 = G.k[2 * kq], hc1 = G.h[2 * kq + 1], kc1 = G.k[2 * kq + 1];
+         const double2 *c0 = blk + KFB_HDR + g * colstride + kq;
          const double2 *c1 = c0 + 8 * colstride;
          double acc[2][4][2];
 #pragma unroll
@@ -914,13 +888,12 @@ k_kforce_mma(KfMArgs A, const int *__restrict__ cidx, const double *__restrict__
             dmma884(acc[1][0], a1, q01.x); dmma884(acc[1][1], a1, q01.y);
             dmma884(acc[1][2], a1, q23.x); dmma884(acc[1][3], a1, q23.y);
          }
+         __syncwarp();
+         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb0 + 32 + 8 * slot) : "memory");
          // back-projection: C fragment = (site g of the tile, columns 2 kq + e)
-#if MDB_ABL == 4 || MDB_ABL == 7
-         Fa[0] += acc[0][0][0] + acc[0][1][1] + acc[0][2][0] + acc[0][3][1]; Fa[1] += acc[1][0][0] + acc[1][1][1] + acc[1][2][0] + acc[1][3][1];
-#else
 #pragma unroll
          for (int e = 0; e < 2; e++) {
-            const int hc = G.h[2 * kq + e], kc = G.k[2 * kq + e];
+            const int hc = e ? hc1 : hc0, kc = e ? kc1 : kc0;
             const double fh = (double)hc, fk = (double)kc;
             const int ka = abs(kc), sg = kc < 0 ? (int)0x80000000 : 0;
 #pragma unroll
@@ -936,27 +909,23 @@ k_kforce_mma(KfMArgs A, const int *__restrict__ cidx, const double *__restrict__
                Fc[s] = fma(ehk.y, acc[s][2][e], fma(ehk.x, acc[s][3][e], Fc[s]));
             }
          }
-#endif
       }
-      cp_async_wait_all();
-#if MDB_ABL != 6 && MDB_ABL != 7
-      half_barrier();
-#endif
    }
    // ---- sum the four lanes of a site, then the two halves, and add to the caller's force rows
+   if (!producer)
 #pragma unroll
-   for (int s = 0; s < 2; s++) {
+      for (int s = 0; s < 2; s++) {
 #pragma unroll
-      for (int d = 1; d <= 2; d <<= 1) {
-         Fa[s] += __shfl_xor_sync(0xffffffffu, Fa[s], d);
-         Fb[s] += __shfl_xor_sync(0xffffffffu, Fb[s], d);
-         Fc[s] += __shfl_xor_sync(0xffffffffu, Fc[s], d);
+         for (int d = 1; d <= 2; d <<= 1) {
+            Fa[s] += __shfl_xor_sync(0xffffffffu, Fa[s], d);
+            Fb[s] += __shfl_xor_sync(0xffffffffu, Fb[s], d);
+            Fc[s] += __shfl_xor_sync(0xffffffffu, Fc[s], d);
+         }
+         if (kq == 0) {
+            double *f = sF + ((size_t)half * nsites_b + sl0 + 8 * s) * 3;
+            f[0] = Fa[s]; f[1] = Fb[s]; f[2] = Fc[s];
+         }
       }
-      if (kq == 0) {
-         double *f = sF + ((size_t)half * nsites_b + sl0 + 8 * s) * 3;
-         f[0] = Fa[s]; f[1] = Fb[s]; f[2] = Fc[s];
-      }
-   }
    __syncthreads();
    for (int sl = tid; sl < nsites_b; sl += nthreads) {
       const int t = site0 + sl;
@@ -1162,53 +1131,72 @@ static int recip_finish(mdb_engine *e, const RecipPlan &P, const double *d_psum,
    F.rank = P.col_rank; F.nranks = P.col_nranks; F.framework = c.nsites_xf < c.nsites;
    F.mma = kspace_use_mma() ? 1 : 0;
    const int fb = (T.nslots + 255) / 256;
-   k_sfin<<<fb, 256, 0, st>>>(F, e->d_hk, e->d_slot_flags + T.nslots, e->d_slot_flags, d_psum, e->d_coef_tot,
-                              e->d_coef_nf, e->d_kpartials);
-   e->launches++;
-   if (P.add_scalars) {
-      k_recip_finish<<<1, 256, 0, st>>>(e->d_kpartials, fb, c.nsites, d_out);
-      e->launches++;
-   }
+   KfMArgs Q{};
+   size_t kshm = 0;
    if (F.mma) {
-      // groups of 8 columns of this rank's share of the valid list (descending slot count)
+      // groups of 8 columns of this rank's share of the valid list (descending slot count); their coefficient
+      // blocks [descriptor | plane 0 | plane 1], zero-padded, and the slot -> block entry map k_sfin writes through
+      Q.K = F.K;
+      const int nle = (F.K.nlslots + 1) / 2 * 2;
+      Q.SE = 2 * nle; while (Q.SE % 16 != 4) Q.SE += 2;
+      Q.SH = (F.K.hmax + 1) | 1; Q.SK = (F.K.kmax + 1) | 1;
+      Q.LPS = nle; while (Q.LPS % 4 != 2) Q.LPS += 2;
+      const int colstride = 2 * Q.LPS;
+      Q.blk2 = KFB_HDR + 2 * 8 * colstride;
+      F.plane = 8 * colstride;
       if (e->kf_rank != P.col_rank || e->kf_nranks != P.col_nranks || !e->d_kf_groups) {
-         std::vector<KfGroup> groups;
          const int nvalid = (int)T.hk_valid.size();
+         std::vector<KfGroup> groups;
+         std::vector<int> slot_dst((size_t)std::max(T.nslots, 1), -1);
          for (int v = P.col_rank; v < nvalid; v += 8 * P.col_nranks) {
             KfGroup G{};
             int mx = 0;
+            const size_t base = groups.size() * (size_t)Q.blk2 + KFB_HDR;
             for (int j = 0; j < 8; j++) {
                const int vv = v + j * P.col_nranks;
                if (vv >= nvalid) break;
                const HkDesc &d = T.hk[T.hk_valid[vv]];
                G.h[j] = d.h; G.k[j] = d.k; G.nl[j] = d.nl; G.slot0[j] = d.slot0;
                mx = std::max(mx, d.nl);
+               for (int l = 0; l < d.nl; l++) slot_dst[d.slot0 + l] = (int)(base + (size_t)j * colstride + 2 * l);
             }
             G.nsteps = (mx + 1) / 2;
             groups.push_back(G);
          }
          if (e->d_kf_groups) { cudaFree(e->d_kf_groups); e->d_kf_groups = nullptr; }
+         if (e->d_kf_slot_dst) { cudaFree(e->d_kf_slot_dst); e->d_kf_slot_dst = nullptr; }
          e->n_kf_groups = (int)groups.size();
-         if (!groups.empty()) {
-            MDB_CUDA(cudaMalloc(&e->d_kf_groups, sizeof(KfGroup) * groups.size()));
-            MDB_CUDA(cudaMemcpyAsync(e->d_kf_groups, groups.data(), sizeof(KfGroup) * groups.size(), cudaMemcpyHostToDevice, st));
-            MDB_CUDA(cudaStreamSynchronize(st));
-         }
+         const size_t nb2 = (size_t)std::max(e->n_kf_groups, 1) * Q.blk2;
+         // both coefficient sets (total | non-framework) in one allocation, zeroed once; headers = descriptors
+         MDB_CUDA(cudaMalloc(&e->d_kf_groups, sizeof(double2) * 2 * nb2));
+         MDB_CUDA(cudaMemsetAsync(e->d_kf_groups, 0, sizeof(double2) * 2 * nb2, st));
+         for (int set = 0; set < 2 && !groups.empty(); set++)
+            MDB_CUDA(cudaMemcpy2DAsync((double2 *)e->d_kf_groups + set * nb2, sizeof(double2) * Q.blk2, groups.data(), sizeof(KfGroup),
+                                       sizeof(KfGroup), groups.size(), cudaMemcpyHostToDevice, st));
+         MDB_CUDA(cudaMalloc(&e->d_kf_slot_dst, sizeof(int) * slot_dst.size()));
+         MDB_CUDA(cudaMemcpyAsync(e->d_kf_slot_dst, slot_dst.data(), sizeof(int) * slot_dst.size(), cudaMemcpyHostToDevice, st));
+         MDB_CUDA(cudaStreamSynchronize(st));
          e->kf_rank = P.col_rank; e->kf_nranks = P.col_nranks;
       }
-      KfMArgs Q;
-      Q.K = F.K; Q.ngroups = e->n_kf_groups;
-      const int nle = (F.K.nlslots + 1) / 2 * 2;
-      Q.SE = 2 * nle; while (Q.SE % 16 != 4) Q.SE += 2;
-      Q.SH = (F.K.hmax + 1) | 1; Q.SK = (F.K.kmax + 1) | 1;
-      Q.LPS = nle; while (Q.LPS % 4 != 2) Q.LPS += 2;
+      Q.ngroups = e->n_kf_groups;
+   }
+   const size_t nb2 = (size_t)std::max(e->n_kf_groups, 1) * (size_t)Q.blk2;
+   double2 *blk_tot = (double2 *)e->d_kf_groups, *blk_nf = blk_tot ? blk_tot + nb2 : nullptr;
+   k_sfin<<<fb, 256, 0, st>>>(F, e->d_hk, e->d_slot_flags + T.nslots, e->d_slot_flags, d_psum, e->d_coef_tot,
+                              e->d_coef_nf, e->d_kpartials, e->d_kf_slot_dst, blk_tot, blk_nf);
+   e->launches++;
+   if (P.add_scalars) {
+      k_recip_finish<<<1, 256, 0, st>>>(e->d_kpartials, fb, c.nsites, d_out);
+      e->launches++;
+   }
+   if (F.mma) {
       const size_t per_site = sizeof(double) * Q.SE + sizeof(double2) * (Q.SH + Q.SK) + 6 * sizeof(double);
-      const size_t stage_bytes = 4 * (size_t)(2 * 8 * 2 * Q.LPS) * sizeof(double2) + 4 * sizeof(KfGroup);
+      const size_t stage_bytes = 4 * (size_t)Q.blk2 * sizeof(double2) + 64;
       static int max_smem = 0;
       if (!max_smem) MDB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
       Q.nsb = 8;
       while (Q.nsb > 1 && stage_bytes + 16 * (size_t)Q.nsb * per_site > (size_t)max_smem) Q.nsb--;
-      const size_t kshm = stage_bytes + 16 * (size_t)Q.nsb * per_site;
+      kshm = stage_bytes + 16 * (size_t)Q.nsb * per_site;
       if (kshm > (size_t)max_smem) { mdb_set_error("k_cutoff too large for the shared-memory tables of k_kforce_mma"); return -1; }
       static size_t kshm_set = 0;
       if (kshm > kshm_set) {
@@ -1219,29 +1207,28 @@ static int recip_finish(mdb_engine *e, const RecipPlan &P, const double *d_psum,
          Q.c0 = part == 0 ? P.nf_lo : P.fw_lo; Q.c1 = part == 0 ? P.nf_hi : P.fw_hi;
          if (Q.c1 <= Q.c0 || Q.ngroups == 0) continue;
          const int spb = 16 * Q.nsb;
-         k_kforce_mma<<<(Q.c1 - Q.c0 + spb - 1) / spb, 64 * Q.nsb, kshm, st>>>(
-            Q, e->d_cidx, e->d_x, e->d_y, e->d_z, e->d_chg, (const KfGroup *)e->d_kf_groups,
-            part == 0 ? e->d_coef_tot : e->d_coef_nf, d_out);
+         k_kforce_mma<<<(Q.c1 - Q.c0 + spb - 1) / spb, 64 * Q.nsb + 32, kshm, st>>>(
+            Q, e->d_cidx, e->d_x, e->d_y, e->d_z, e->d_chg, part == 0 ? blk_tot : blk_nf, d_out);
          e->launches++;
       }
       MDB_CUDA(cudaGetLastError());
       return 0;
    }
-   KfArgs Q;
-   Q.K = F.K; Q.nhk = (int)T.hk.size(); Q.rank = P.col_rank; Q.nranks = P.col_nranks;
-   Q.hb = std::max(1, std::min(16, 512 / F.K.nlslots));
-   Q.max_slots = Q.hb * F.K.nlslots;
-   const size_t kshm = sizeof(double4) * 2 * (size_t)Q.max_slots + sizeof(HkDesc) * (size_t)Q.hb;
+   KfArgs Qd;
+   Qd.K = F.K; Qd.nhk = (int)T.hk.size(); Qd.rank = P.col_rank; Qd.nranks = P.col_nranks;
+   Qd.hb = std::max(1, std::min(16, 512 / F.K.nlslots));
+   Qd.max_slots = Qd.hb * F.K.nlslots;
+   kshm = sizeof(double4) * 2 * (size_t)Qd.max_slots + sizeof(HkDesc) * (size_t)Qd.hb;
    if (P.nf_hi > P.nf_lo) {
-      Q.c0 = P.nf_lo; Q.c1 = P.nf_hi;
-      k_kforce<MDB_KF_NS><<<(Q.c1 - Q.c0 + KF * MDB_KF_NS - 1) / (KF * MDB_KF_NS), KF, kshm, st>>>(
-         Q, e->d_cidx, e->d_x, e->d_y, e->d_z, e->d_chg, e->d_hk, e->d_coef_tot, d_out);
+      Qd.c0 = P.nf_lo; Qd.c1 = P.nf_hi;
+      k_kforce<MDB_KF_NS><<<(Qd.c1 - Qd.c0 + KF * MDB_KF_NS - 1) / (KF * MDB_KF_NS), KF, kshm, st>>>(
+         Qd, e->d_cidx, e->d_x, e->d_y, e->d_z, e->d_chg, e->d_hk, e->d_coef_tot, d_out);
       e->launches++;
    }
    if (P.fw_hi > P.fw_lo) {
-      Q.c0 = P.fw_lo; Q.c1 = P.fw_hi;
-      k_kforce<MDB_KF_NS><<<(Q.c1 - Q.c0 + KF * MDB_KF_NS - 1) / (KF * MDB_KF_NS), KF, kshm, st>>>(
-         Q, e->d_cidx, e->d_x, e->d_y, e->d_z, e->d_chg, e->d_hk, e->d_coef_nf, d_out);
+      Qd.c0 = P.fw_lo; Qd.c1 = P.fw_hi;
+      k_kforce<MDB_KF_NS><<<(Qd.c1 - Qd.c0 + KF * MDB_KF_NS - 1) / (KF * MDB_KF_NS), KF, kshm, st>>>(
+         Qd, e->d_cidx, e->d_x, e->d_y, e->d_z, e->d_chg, e->d_hk, e->d_coef_nf, d_out);
       e->launches++;
    }
    MDB_CUDA(cudaGetLastError());
