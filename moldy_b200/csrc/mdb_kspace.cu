@@ -173,7 +173,10 @@ k_sfac(SfacArgs A, const SfacBlock *__restrict__ blocks, const int *__restrict__
 //              recurrence sits between the DMMA warps and a barrier (versions that built the tables
 //              in the block: 34 % / 21 % of all warp samples waiting at the barrier).  The A fragment
 //              (E_hk of the lane's column and site) is formed in registers from E_h and E_k.
-static constexpr int MCW = 16;          // warps per block
+#ifndef MDB_MCW
+#define MDB_MCW 16
+#endif
+static constexpr int MCW = MDB_MCW;      // consumer warps per block
 static constexpr int MC = 8 * MCW;      // columns per block
 #ifndef MDB_MSC
 #define MDB_MSC 32
@@ -185,7 +188,7 @@ static constexpr int MC = 8 * MCW;      // columns per block
 #define MDB_SFAC_PIPE 0
 #endif
 static constexpr int MSC = MDB_MSC;      // sites per shared-memory chunk
-static constexpr int MT = 32 * MCW;
+static constexpr int MT = 32 * MCW + 32;  // + one producer warp
 
 struct SfacMBlock { int e0, ncols, l0, nt; };
 
@@ -332,45 +335,44 @@ __device__ __forceinline__ void sfac_mma_body(const SfacMArgs &A, const SfacMBlo
    // the buffer's mbarrier (as 16-byte cp.async pieces the staging cost 0.5 ms of LSU time per launch).  Rows past
    // the slab end belong to other slabs (or the zeroed padding): their q E_l row is zeroed instead of copied,
    // E_h/E_k are copied as they are (finite).
-   __shared__ __align__(8) unsigned long long mbar_store[2];
+   __shared__ __align__(8) unsigned long long mbar_store[4];         // full[2], empty[2]
    const unsigned mb0 = (unsigned)__cvta_generic_to_shared(mbar_store);
    if (tid == 0) {
       mbar_init(mb0, 1); mbar_init(mb0 + 8, 1);
+      mbar_init(mb0 + 16, MCW); mbar_init(mb0 + 24, MCW);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
    __syncthreads();
-   auto stage = [&](int base, int b) {
+   const int nchunks = (s1 - s0 + MSC - 1) / MSC;
+   if (warp == MCW) {
+      // producer warp: chunk c -> buffer c & 1 once every consumer warp has released it
       const int vE = L.SB / 2;                                        // 16-byte units per E row
-      const int nv = min(MSC, s1 - base);
-      double2 *dE = reinterpret_cast<double2 *>(bufB(b));
-      if (tid == 0) {
-         const unsigned bE = (unsigned)nv * L.SB * 8u, bH = (unsigned)MSC * L.SH * 16u, bK = (unsigned)MSC * L.SK * 16u;
-         const unsigned mb = mb0 + 8u * b;
-         mbar_expect_tx(mb, bE + bH + bK);
-         bulk_g2s(dE, tE + (size_t)base * L.SB, bE, mb);
-         bulk_g2s(bufH(b), tH + (size_t)base * L.SH, bH, mb);
-         bulk_g2s(bufK(b), tK + (size_t)base * L.SK, bK, mb);
+      for (int c = 0; c < nchunks; c++) {
+         const int b = c & 1, base = s0 + c * MSC, nv = min(MSC, s1 - base);
+         if (lane == 0) mbar_wait(mb0 + 16 + 8 * b, ((c >> 1) & 1) ^ 1);
+         __syncwarp();
+         double2 *dE = reinterpret_cast<double2 *>(bufB(b));
+         for (int u = nv * vE + lane; u < MSC * vE; u += 32) dE[u] = make_double2(0.0, 0.0);
+         __syncwarp();
+         if (lane == 0) {
+            const unsigned bE = (unsigned)nv * L.SB * 8u, bH = (unsigned)MSC * L.SH * 16u, bK = (unsigned)MSC * L.SK * 16u;
+            const unsigned mb = mb0 + 8u * b;
+            mbar_expect_tx(mb, bE + bH + bK);                         // (an arrive: releases the zero stores above)
+            bulk_g2s(dE, tE + (size_t)base * L.SB, bE, mb);
+            bulk_g2s(bufH(b), tH + (size_t)base * L.SH, bH, mb);
+            bulk_g2s(bufK(b), tK + (size_t)base * L.SK, bK, mb);
+         }
       }
-      for (int u = nv * vE + tid; u < MSC * vE; u += MT) dE[u] = make_double2(0.0, 0.0);
-   };
-
-   unsigned phase[2] = {0u, 0u};
-   stage(s0, 0);
-   int b = 0;
-   for (int base = s0; base < s1; base += MSC, b ^= 1) {
-#if MDB_ABL != 3
-      if (base + MSC < s1) stage(base + MSC, b ^ 1);
-#endif
-      mbar_wait(mb0 + 8u * b, phase[b]);
-      phase[b] ^= 1u;
+      return;
+   }
+   for (int c = 0; c < nchunks; c++) {
+      const int b = c & 1;
+      mbar_wait(mb0 + 8u * b, (c >> 1) & 1);
       if (warp_on) {
          const double *sB = bufB(b) + 2 * B.l0 + g;
          const double2 *sH = bufH(b), *sK = bufK(b);
          auto make_a = [&](int t, double (&a)[2]) {
             const int sl = 4 * t + kq;
-#if MDB_ABL == 1
-            a[0] = sB[sl * L.SB + 3]; a[1] = sB[sl * L.SB + 5]; return;
-#endif
 #pragma unroll
             for (int mt = 0; mt < 2; mt++) {
                const double2 eh = sH[sl * L.SH + ch[mt]];
@@ -379,22 +381,6 @@ __device__ __forceinline__ void sfac_mma_body(const SfacMArgs &A, const SfacMBlo
                a[mt] = fma(p, ek.x, flip_sign(r * ek.y, csign[mt]));
             }
          };
-#if MDB_SFAC_PIPE
-         double an[2];
-         make_a(0, an);
-#pragma unroll
-         for (int t = 0; t < MSC / 4; t++) {
-            double a[2] = {an[0], an[1]};
-            if (t + 1 < MSC / 4) make_a(t + 1, an);      // next step's A fragments ahead of this step's DMMAs
-            const double *bp = sB + (4 * t + kq) * L.SB;
-#pragma unroll
-            for (int n = 0; n < NT; n++) {
-               const double bv = bp[8 * n];
-               dmma884(acc[0][n], a[0], bv);
-               dmma884(acc[1][n], a[1], bv);
-            }
-         }
-#else
 #pragma unroll 2
          for (int t = 0; t < MSC / 4; t++) {
             double a[2];
@@ -402,18 +388,14 @@ __device__ __forceinline__ void sfac_mma_body(const SfacMArgs &A, const SfacMBlo
             const double *bp = sB + (4 * t + kq) * L.SB;
 #pragma unroll
             for (int n = 0; n < NT; n++) {
-#if MDB_ABL == 2
-               const double bv = a[0] + n;
-#else
                const double bv = bp[8 * n];
-#endif
                dmma884(acc[0][n], a[0], bv);
                dmma884(acc[1][n], a[1], bv);
             }
          }
-#endif
       }
-      __syncthreads();          // everyone is done with buffer b before the next bulk copy lands in it
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb0 + 16 + 8 * b) : "memory");
    }
    // C fragment: row g = (column g/2, c|s), columns 2 kq + e = (slot kq of the n-tile, C|S)
    if (warp_on)
