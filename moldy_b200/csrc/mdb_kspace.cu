@@ -166,15 +166,15 @@ k_sfac(SfacArgs A, const SfacBlock *__restrict__ blocks, const int *__restrict__
 //  k_ktables   once per step: per charged site the power tables E_h, E_k (unit modulus) and
 //              q E_l, written to HBM in exactly the padded row layout the GEMM kernel wants in
 //              shared memory (1.4 KB per site; they are re-read once per column block, mostly from L2).
-//  k_sfac_mma  block = 128 columns x one l-range of <= 32 slots, one block per SM, 16 warps of
+//  k_sfac_mma  block = 96 columns x one l-range of <= 32 slots, one block per SM: 12 consumer warps of
 //              8 columns each (two 8-row m-tiles of 4 columns x {c,s}, NT n-tiles of 4 slots x {C,S},
-//              k = 4 sites per instruction).  The tables of the next 32-site chunk arrive by cp.async
-//              in the other half of a double buffer while the current chunk is consumed, so no serial
-//              recurrence sits between the DMMA warps and a barrier (versions that built the tables
-//              in the block: 34 % / 21 % of all warp samples waiting at the barrier).  The A fragment
-//              (E_hk of the lane's column and site) is formed in registers from E_h and E_k.
+//              k = 4 sites per instruction) and one producer warp that brings the tables of the next
+//              32-site chunk in by three TMA bulk copies (full / empty mbarriers on a double buffer; no
+//              block barrier in the loop).  Versions that built the tables in the block had 34 % / 21 % of
+//              all warp samples waiting at a barrier.  The A fragment (E_hk of the lane's column and site)
+//              is formed in registers from E_h and E_k.  12 warps measured faster than 8, 10, 14, 15, 16.
 #ifndef MDB_MCW
-#define MDB_MCW 16
+#define MDB_MCW 12
 #endif
 static constexpr int MCW = MDB_MCW;      // consumer warps per block
 static constexpr int MC = 8 * MCW;      // columns per block
@@ -1010,7 +1010,7 @@ static int make_plan(mdb_engine *e, bool by_sites, RecipPlan &P, cudaStream_t st
    int want = std::max(1, (4 * 148 + std::max(1, e->n_sfac_blocks) - 1) / std::max(1, e->n_sfac_blocks));
    if (mode == 1) {
       // k_sfac_mma: one block per SM; never a few blocks more than a whole number of waves
-      static int waves = getenv("MDB_SFAC_WAVES") ? atoi(getenv("MDB_SFAC_WAVES")) : 8;
+      static int waves = getenv("MDB_SFAC_WAVES") ? atoi(getenv("MDB_SFAC_WAVES")) : 12;
       want = std::max(1, waves * 148 / std::max(1, e->n_sfac_blocks));
    }
    int slab = (own + want - 1) / want;
