@@ -1178,6 +1178,22 @@ static int recip_finish(mdb_engine *e, const RecipPlan &P, const double *d_psum,
       if (!max_smem) MDB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
       Q.nsb = 8;
       while (Q.nsb > 1 && stage_bytes + 16 * (size_t)Q.nsb * per_site > (size_t)max_smem) Q.nsb--;
+      {
+         // few waves (a rank's share of the sites at 8 GPUs: 750 blocks = 5.07 waves of 148): pick the block
+         // size whose last wave is fullest, cost = waves x sites per block
+         int nsm = 148;
+         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, e->device);
+         const long nown = std::max(P.nf_hi - P.nf_lo, P.fw_hi - P.fw_lo);
+         long best = -1;
+         int best_nsb = Q.nsb;
+         for (int nb = Q.nsb; nb >= std::max(4, Q.nsb - 3) && nown > 0; nb--) {
+            const long blocks = (nown + 16 * nb - 1) / (16 * nb), waves = (blocks + nsm - 1) / nsm;
+            if (waves > 16) break;                         // many waves: the tail does not matter
+            const long cost = waves * nb;
+            if (best < 0 || cost < best) { best = cost; best_nsb = nb; }
+         }
+         Q.nsb = best_nsb;
+      }
       kshm = stage_bytes + 16 * (size_t)Q.nsb * per_site;
       if (kshm > (size_t)max_smem) { mdb_set_error("k_cutoff too large for the shared-memory tables of k_kforce_mma"); return -1; }
       static size_t kshm_set = 0;
