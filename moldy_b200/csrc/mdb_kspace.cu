@@ -181,12 +181,6 @@ static constexpr int MC = 8 * MCW;      // columns per block
 #ifndef MDB_MSC
 #define MDB_MSC 32
 #endif
-#ifndef MDB_ABL
-#define MDB_ABL 0
-#endif
-#ifndef MDB_SFAC_PIPE
-#define MDB_SFAC_PIPE 0
-#endif
 static constexpr int MSC = MDB_MSC;      // sites per shared-memory chunk
 static constexpr int MT = 32 * MCW + 32;  // + one producer warp
 
@@ -214,13 +208,6 @@ __device__ __forceinline__ double flip_sign(double v, int mask)      // mask = 0
 {
    return __hiloint2double(__double2hiint(v) ^ mask, __double2loint(v));
 }
-__device__ __forceinline__ void cp_async16(void *dst, const void *src)
-{
-   const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src));
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
-
 // ---- 1-D bulk copies (TMA unit, UBLKCP) completing on an mbarrier
 __device__ __forceinline__ void mbar_init(unsigned mb, int count)
 {
