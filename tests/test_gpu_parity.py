@@ -387,3 +387,36 @@ def test_too_close_pairs_counted_alike_by_fused_and_split_passes(golden_dir):
         assert ntc > 0 and pair[0] // nsm != pair[1] // nsm
         eng.close()
     assert counts[0] == counts[1]
+
+
+@pytest.mark.parametrize("kind", ["mma", "dfma"])
+def test_many_l_slots_are_split_into_l_ranges(kind, golden_dir):
+    """k_cutoff large enough for lmax > 32: the structure-factor GEMM then runs a column block over two l-ranges
+    of <= 32 slots, the back-projection shrinks its site block to fit the longer tables into shared memory.
+    Reciprocal space only, against the oracle (bit-identical to the compiled reference, test_oracle.py)."""
+    import torch
+    from oracle import port
+    ms = cases.GOLDEN_CASES["tip4p"]()
+    ms.control.k_cutoff = 2 * np.pi * 34.5 / np.linalg.norm(ms.h[:, 2])        # lmax = 34
+    n = ms.nsites
+    os.environ["MDB_KSPACE"] = kind
+    try:
+        eng = lib.Engine(0)
+        eng.configure(ms)
+        eng.set_sites_host(ms.make_sites(wrap=True))
+        st = torch.cuda.current_stream().cuda_stream
+        out = torch.zeros(eng.out_doubles(), dtype=torch.float64, device="cuda")
+        eng.force_recip(out.data_ptr(), st)
+        torch.cuda.synchronize()
+        f, pe, s = lib.unpack(out.cpu().numpy(), n)
+        nk = eng.n_kvectors()
+        eng.close()
+    finally:
+        os.environ.pop("MDB_KSPACE", None)
+    gold = port.run(ms, real=False)
+    assert nk == gold["nhkl"] and nk > 70000
+    assert cases.rel_rms(f, gold["force"]) <= F_TOL
+    ref_pe = gold["pe"][1] + gold["self_energy"] - gold["sheet_energy"] / float(np.linalg.det(ms.h))
+    assert abs(pe[1] - ref_pe) <= E_TOL * abs(ref_pe)
+    iu = np.triu_indices(3)
+    assert np.linalg.norm(s[iu] - gold["stress"][iu]) <= E_TOL * np.linalg.norm(gold["stress"][iu])
