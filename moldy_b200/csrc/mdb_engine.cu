@@ -50,10 +50,10 @@ static void free_sublists(mdb_engine *e)
    for (int k = 0; k < 2; k++) {
       SubList &S = e->sub[k];
       FREE(S.posq); FREE(S.sinfo); FREE(S.order); FREE(S.start); FREE(S.batches); FREE(S.nbatch); FREE(S.fs);
-      S.n = 0; S.batch_cap = 0; S.valid = false;
+      S.n = 0; S.batch_cap = 0; S.cap_n = 0; S.cap_cells = 0; S.valid = false;
    }
    FREE(e->d_cls); FREE(e->d_sub_flag); FREE(e->d_sub_pos); FREE(e->d_sub_scan); FREE(e->d_sub_cols);
-   e->sub_cap = 0;
+   e->sub_cap = 0; e->sub_cols_cap = 0;
 }
 static void free_grid(mdb_engine *e)
 {
@@ -231,31 +231,39 @@ extern "C" int mdb_configure(mdb_engine *e, const mdb_config *cfg)
       }
       for (int k = 0; k < 2; k++) e->sub[k].valid = false;
       if (e->pair_split) {
-         if (upload(&e->d_cls, cls.data(), n)) return -1;
+         if (new_system || !e->d_cls) { if (upload(&e->d_cls, cls.data(), n)) return -1; }
+         else MDB_CUDA(cudaMemcpy(e->d_cls, cls.data(), n, cudaMemcpyHostToDevice));
          const int ncols = e->T.nx * e->T.ny;
-         if (n + 1 > e->sub_cap || new_system) {
+         if (n + 1 > e->sub_cap || new_system || n / 2048 + ncols / 2048 + 4 > e->sub_scan_cap) {
             FREE(e->d_sub_flag); FREE(e->d_sub_pos); FREE(e->d_sub_scan);
             MDB_CUDA(cudaMalloc(&e->d_sub_flag, sizeof(int) * (size_t)(n + 1)));
             MDB_CUDA(cudaMalloc(&e->d_sub_pos, sizeof(int) * (size_t)(n + 1)));
             MDB_CUDA(cudaMalloc(&e->d_sub_scan, sizeof(int) * (size_t)(n / 2048 + ncols / 2048 + 4)));
-            e->sub_cap = n + 1;
+            e->sub_cap = n + 1; e->sub_scan_cap = n / 2048 + ncols / 2048 + 4;
          }
-         FREE(e->d_sub_cols);
-         MDB_CUDA(cudaMalloc(&e->d_sub_cols, sizeof(int) * 2 * (size_t)(ncols + 1)));
+         if (2 * (ncols + 1) > e->sub_cols_cap) {
+            FREE(e->d_sub_cols);
+            MDB_CUDA(cudaMalloc(&e->d_sub_cols, sizeof(int) * 2 * (size_t)(ncols + 1)));
+            e->sub_cols_cap = 2 * (ncols + 1);
+         }
          const long cnt[2] = {nc, np2};
          for (int k = 0; k < 2; k++) {
+            // (re)allocate only when the class or the grid grew: constant-stress runs reconfigure every step
             SubList &S = e->sub[k];
-            FREE(S.posq); FREE(S.sinfo); FREE(S.order); FREE(S.start); FREE(S.batches); FREE(S.nbatch); FREE(S.fs);
+            const int need_b = (int)cnt[k] / MDB_NI + ncols + 8;
+            if ((int)cnt[k] > S.cap_n || e->ncells + 1 > S.cap_cells || need_b > S.batch_cap) {
+               FREE(S.posq); FREE(S.sinfo); FREE(S.order); FREE(S.start); FREE(S.batches); FREE(S.nbatch); FREE(S.fs);
+               const size_t m = (size_t)std::max((int)cnt[k], 1);
+               MDB_CUDA(cudaMalloc(&S.posq, sizeof(double4) * m));
+               MDB_CUDA(cudaMalloc(&S.sinfo, sizeof(int2) * m));
+               MDB_CUDA(cudaMalloc(&S.order, sizeof(int) * m));
+               MDB_CUDA(cudaMalloc(&S.start, sizeof(int) * (size_t)(e->ncells + 1)));
+               MDB_CUDA(cudaMalloc(&S.batches, sizeof(int2) * (size_t)need_b));
+               MDB_CUDA(cudaMalloc(&S.nbatch, sizeof(int)));
+               MDB_CUDA(cudaMalloc(&S.fs, sizeof(double) * 3 * m));
+               S.cap_n = (int)cnt[k]; S.cap_cells = e->ncells + 1; S.batch_cap = need_b;
+            }
             S.n = (int)cnt[k];
-            const size_t m = (size_t)std::max(S.n, 1);
-            MDB_CUDA(cudaMalloc(&S.posq, sizeof(double4) * m));
-            MDB_CUDA(cudaMalloc(&S.sinfo, sizeof(int2) * m));
-            MDB_CUDA(cudaMalloc(&S.order, sizeof(int) * m));
-            MDB_CUDA(cudaMalloc(&S.start, sizeof(int) * (size_t)(e->ncells + 1)));
-            S.batch_cap = S.n / MDB_NI + ncols + 8;
-            MDB_CUDA(cudaMalloc(&S.batches, sizeof(int2) * (size_t)S.batch_cap));
-            MDB_CUDA(cudaMalloc(&S.nbatch, sizeof(int)));
-            MDB_CUDA(cudaMalloc(&S.fs, sizeof(double) * 3 * m));
          }
       }
    }

@@ -80,6 +80,7 @@ struct SubList {
    int *start = nullptr;                  // [ncells+1]
    int2 *batches = nullptr; int *nbatch = nullptr; int batch_cap = 0;
    double *fs = nullptr;                  // [3 n] cell-sorted force accumulator
+   int cap_n = 0, cap_cells = 0;          // allocated sizes
    bool valid = false;
 };
 
@@ -116,7 +117,8 @@ struct mdb_engine {
    int pair_split = 0;                    // tiled kernel: one pass per site class (sub[0] charged, sub[1] potential)
    SubList sub[2];
    unsigned char *d_cls = nullptr;        // per original site: bit 0 charged, bit 1 has a non-zero pair potential
-   int *d_sub_flag = nullptr, *d_sub_pos = nullptr, *d_sub_scan = nullptr, *d_sub_cols = nullptr; int sub_cap = 0;
+   int *d_sub_flag = nullptr, *d_sub_pos = nullptr, *d_sub_scan = nullptr, *d_sub_cols = nullptr;
+   int sub_cap = 0, sub_cols_cap = 0, sub_scan_cap = 0;
    // RDF pass: strict stencil of the last (limit, grid) and the device histogram
    StencilRun *d_runs_rdf = nullptr; int nruns_rdf = 0; double rdf_limit = -1.0; int rdf_grid[3] = {0, 0, 0};
    double rdf_h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
