@@ -217,6 +217,14 @@ static int launch_batches(mdb_engine *e, const int *start, int *scratch, int *sc
    return 0;
 }
 
+int mdb_need_batches(mdb_engine *e, cudaStream_t st)
+{
+   if (e->batches_valid) return 0;
+   if (mdb_launch_batches(e, st)) return -1;
+   e->batches_valid = true;
+   return 0;
+}
+
 int mdb_launch_batches(mdb_engine *e, cudaStream_t st)
 {
    const int ncols = e->T.nx * e->T.ny;
@@ -254,18 +262,20 @@ int mdb_build_sublist(mdb_engine *e, int k, cudaStream_t st)
 {
    SubList &S = e->sub[k];
    if (S.valid) return 0;
-   const int n = e->cfg.nsites, nc = e->ncells;
+   const int n = e->cfg.nsites, nc = e->ncells, ncols = e->T.nx * e->T.ny;
    const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-   k_sub_flags<<<(n + CB - 1) / CB, CB, 0, st>>>(n, e->d_order, e->d_cls, k, e->d_sub_flag);
-   k_scan_tiles<<<ntiles, SCAN_T, 0, st>>>(e->d_sub_flag, n, e->d_sub_scan);
-   k_scan_sums<<<1, SCAN_T, 0, st>>>(e->d_sub_scan, ntiles);
-   k_scan_apply<<<ntiles, SCAN_T, 0, st>>>(e->d_sub_flag, n, e->d_sub_scan, e->d_sub_pos);
-   k_sub_scatter<<<(n + CB - 1) / CB, CB, 0, st>>>(n, e->d_sub_flag, e->d_sub_pos, e->d_posq, e->d_sinfo, e->d_order,
-                                                   S.posq, S.sinfo, S.order);
-   k_sub_start<<<(nc + 1 + CB - 1) / CB, CB, 0, st>>>(nc, e->d_start, e->d_sub_pos, S.start);
+   // each class has its own scratch: class 1 is compacted on a second stream beside the class-0 pair pass
+   int *flag = e->d_sub_flag + (size_t)k * (n + 1), *pos = e->d_sub_pos + (size_t)k * (n + 1);
+   int *scan = e->d_sub_scan + (size_t)k * e->sub_scan_cap, *cols = e->d_sub_cols + (size_t)k * 2 * (ncols + 1);
+   k_sub_flags<<<(n + CB - 1) / CB, CB, 0, st>>>(n, e->d_order, e->d_cls, k, flag);
+   k_scan_tiles<<<ntiles, SCAN_T, 0, st>>>(flag, n, scan);
+   k_scan_sums<<<1, SCAN_T, 0, st>>>(scan, ntiles);
+   k_scan_apply<<<ntiles, SCAN_T, 0, st>>>(flag, n, scan, pos);
+   k_sub_scatter<<<(n + CB - 1) / CB, CB, 0, st>>>(n, flag, pos, e->d_posq, e->d_sinfo, e->d_order, S.posq, S.sinfo, S.order);
+   k_sub_start<<<(nc + 1 + CB - 1) / CB, CB, 0, st>>>(nc, e->d_start, pos, S.start);
    e->launches += 6;
    MDB_CUDA(cudaGetLastError());
-   if (launch_batches(e, S.start, e->d_sub_cols, e->d_sub_scan, S.batches, S.nbatch, st)) return -1;
+   if (launch_batches(e, S.start, cols, scan, S.batches, S.nbatch, st)) return -1;
    S.valid = true;
    return 0;
 }
@@ -345,7 +355,10 @@ int mdb_launch_cells(mdb_engine *e, cudaStream_t st)
                                                    e->T.nz);
    e->launches += 6;
    MDB_CUDA(cudaGetLastError());
-   if (e->pair_mode >= 3 && mdb_launch_batches(e, st)) return -1;
+   // batches of the full list: the fused pass, the counting pass and the RDF pass want them; with split
+   // passes they are built on demand (mdb_need_batches)
+   e->batches_valid = false;
+   if (e->pair_mode >= 3 && !e->pair_split && mdb_need_batches(e, st)) return -1;
    e->sub[0].valid = e->sub[1].valid = false;
    e->cells_valid = true;
    return 0;

@@ -54,6 +54,9 @@ static void free_sublists(mdb_engine *e)
    }
    FREE(e->d_cls); FREE(e->d_sub_flag); FREE(e->d_sub_pos); FREE(e->d_sub_scan); FREE(e->d_sub_cols);
    e->sub_cap = 0; e->sub_cols_cap = 0;
+   if (e->aux_stream) { cudaStreamDestroy(e->aux_stream); e->aux_stream = nullptr; }
+   if (e->ev_cells) { cudaEventDestroy(e->ev_cells); e->ev_cells = nullptr; }
+   if (e->ev_sub1) { cudaEventDestroy(e->ev_sub1); e->ev_sub1 = nullptr; }
 }
 static void free_grid(mdb_engine *e)
 {
@@ -236,14 +239,14 @@ extern "C" int mdb_configure(mdb_engine *e, const mdb_config *cfg)
          const int ncols = e->T.nx * e->T.ny;
          if (n + 1 > e->sub_cap || new_system || n / 2048 + ncols / 2048 + 4 > e->sub_scan_cap) {
             FREE(e->d_sub_flag); FREE(e->d_sub_pos); FREE(e->d_sub_scan);
-            MDB_CUDA(cudaMalloc(&e->d_sub_flag, sizeof(int) * (size_t)(n + 1)));
-            MDB_CUDA(cudaMalloc(&e->d_sub_pos, sizeof(int) * (size_t)(n + 1)));
-            MDB_CUDA(cudaMalloc(&e->d_sub_scan, sizeof(int) * (size_t)(n / 2048 + ncols / 2048 + 4)));
+            MDB_CUDA(cudaMalloc(&e->d_sub_flag, sizeof(int) * 2 * (size_t)(n + 1)));
+            MDB_CUDA(cudaMalloc(&e->d_sub_pos, sizeof(int) * 2 * (size_t)(n + 1)));
+            MDB_CUDA(cudaMalloc(&e->d_sub_scan, sizeof(int) * 2 * (size_t)(n / 2048 + ncols / 2048 + 4)));
             e->sub_cap = n + 1; e->sub_scan_cap = n / 2048 + ncols / 2048 + 4;
          }
          if (2 * (ncols + 1) > e->sub_cols_cap) {
             FREE(e->d_sub_cols);
-            MDB_CUDA(cudaMalloc(&e->d_sub_cols, sizeof(int) * 2 * (size_t)(ncols + 1)));
+            MDB_CUDA(cudaMalloc(&e->d_sub_cols, sizeof(int) * 4 * (size_t)(ncols + 1)));
             e->sub_cols_cap = 2 * (ncols + 1);
          }
          const long cnt[2] = {nc, np2};

@@ -114,11 +114,13 @@ struct mdb_engine {
    int2 *d_batches = nullptr; int *d_nbatch = nullptr; int batch_cap = 0;   // i-site batches of the tiled pair kernel
    double *d_fs = nullptr;                // [3N] cell-sorted force accumulator (Newton-3 mode)
    int pair_mode = -1;                    // 2: per-thread full stencil, 3: tiled full stencil, 4: tiled Newton-3
+   bool batches_valid = false;
    int pair_split = 0;                    // tiled kernel: one pass per site class (sub[0] charged, sub[1] potential)
    SubList sub[2];
    unsigned char *d_cls = nullptr;        // per original site: bit 0 charged, bit 1 has a non-zero pair potential
    int *d_sub_flag = nullptr, *d_sub_pos = nullptr, *d_sub_scan = nullptr, *d_sub_cols = nullptr;
    int sub_cap = 0, sub_cols_cap = 0, sub_scan_cap = 0;
+   cudaStream_t aux_stream = nullptr; cudaEvent_t ev_cells = nullptr, ev_sub1 = nullptr;   // class-1 compaction beside the class-0 pass
    // RDF pass: strict stencil of the last (limit, grid) and the device histogram
    StencilRun *d_runs_rdf = nullptr; int nruns_rdf = 0; double rdf_limit = -1.0; int rdf_grid[3] = {0, 0, 0};
    double rdf_h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -165,6 +167,7 @@ int mdb_launch_rdf_tiled(mdb_engine *e, const StencilRun *d_runs, int nruns, dou
                          unsigned long long *d_counts, cudaStream_t st);
 static constexpr size_t MDB_TILED_TAB_MAX = 28 * 1024;   // pair table of the tiled kernel lives in shared memory
 int mdb_launch_batches(mdb_engine *e, cudaStream_t st);
+int mdb_need_batches(mdb_engine *e, cudaStream_t st);     // batches of the full cell-sorted list, built once per cell build
 int mdb_build_sublist(mdb_engine *e, int k, cudaStream_t st);
 int mdb_launch_too_close_scan(mdb_engine *e, cudaStream_t st);
 static constexpr int MDB_NI = 4;          // i-sites per warp in the tiled pair kernel

@@ -590,6 +590,7 @@ int mdb_launch_pair_count_tiled(mdb_engine *e, cudaStream_t st)
    PairParams P;
    const StencilRun *runs;
    int nblocks;
+   if (mdb_need_batches(e, st)) return -1;
    tiled_params(e, n3, c.nsites, P, runs, nblocks);
    double *d_out = nullptr;
    const SiteList L = full_list(e);
@@ -609,6 +610,7 @@ int mdb_launch_rdf_tiled(mdb_engine *e, const StencilRun *d_runs, int nruns, dou
    PairParams P;
    const StencilRun *runs;
    int nblocks;
+   if (mdb_need_batches(e, st)) return -1;
    tiled_params(e, true, c.nsites, P, runs, nblocks);
    runs = d_runs; P.nruns = nruns;
    const SiteList L = full_list(e);
@@ -675,10 +677,28 @@ int mdb_launch_pair_tiled(mdb_engine *e, double *d_out, cudaStream_t st)
 {
    const mdb_config &c = e->cfg;
    const bool coul = c.alpha > 0.0;
-   if (!e->pair_split) return pair_pass(e, full_list(e), c.ptype, coul, d_out, st);
+   if (!e->pair_split) {
+      if (mdb_need_batches(e, st)) return -1;
+      return pair_pass(e, full_list(e), c.ptype, coul, d_out, st);
+   }
    // split passes: charged x charged with the Coulomb term only, potential x potential with the potential only
-   if (mdb_build_sublist(e, 0, st) || mdb_build_sublist(e, 1, st)) return -1;
+   // the potential-site list is compacted on a second stream while the Coulomb pass runs
+   bool wait_sub1 = false;
+   if (!e->sub[1].valid) {
+      if (!e->aux_stream) {
+         MDB_CUDA(cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking));
+         MDB_CUDA(cudaEventCreateWithFlags(&e->ev_cells, cudaEventDisableTiming));
+         MDB_CUDA(cudaEventCreateWithFlags(&e->ev_sub1, cudaEventDisableTiming));
+      }
+      MDB_CUDA(cudaEventRecord(e->ev_cells, st));
+      MDB_CUDA(cudaStreamWaitEvent(e->aux_stream, e->ev_cells, 0));
+      if (mdb_build_sublist(e, 1, e->aux_stream)) return -1;
+      MDB_CUDA(cudaEventRecord(e->ev_sub1, e->aux_stream));
+      wait_sub1 = true;
+   }
+   if (mdb_build_sublist(e, 0, st)) return -1;
    if (pair_pass(e, sub_list(e, 0), PT_NONE, true, d_out, st)) return -1;
+   if (wait_sub1) MDB_CUDA(cudaStreamWaitEvent(st, e->ev_sub1, 0));
    if (pair_pass(e, sub_list(e, 1), c.ptype, false, d_out, st)) return -1;
    return mdb_launch_too_close_scan(e, st);
 }
