@@ -197,6 +197,7 @@ struct SfacMArgs {
    int nslots, slab_sites, n_slabs_nf;
    int nf_lo, nf_hi, fw_lo, fw_hi;
    int nrows;                           // rows allocated in the tables (charged sites + MSC of padding)
+   int n_slabs, nblk, sgroup;           // 1-D grid order: slab groups of `sgroup` slabs; inside a group column blocks, heaviest first
 };
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
@@ -276,7 +277,7 @@ template <int NT>
 __device__ __forceinline__ void sfac_mma_body(const SfacMArgs &A, const SfacMBlock &B, const double *__restrict__ tE,
                                               const double2 *__restrict__ tH, const double2 *__restrict__ tK,
                                               const HkDesc *__restrict__ hk, const int *__restrict__ hk_valid,
-                                              double *__restrict__ ppart, double2 *smem)
+                                              double *__restrict__ ppart, double2 *smem, const int slab)
 {
    const KtabLayout &L = A.L;
    const size_t buf_doubles = (size_t)MSC * L.SB + 2 * (size_t)MSC * (L.SH + L.SK);
@@ -284,7 +285,6 @@ __device__ __forceinline__ void sfac_mma_body(const SfacMArgs &A, const SfacMBlo
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    const int g = lane >> 2, kq = lane & 3, comp = g & 1;
 
-   const int slab = blockIdx.x;
    int s0, s1;
    if (slab < A.n_slabs_nf) {
       s0 = A.nf_lo + slab * A.slab_sites;
@@ -406,18 +406,26 @@ k_sfac_mma(SfacMArgs A, const SfacMBlock *__restrict__ blocks, const double *__r
            const int *__restrict__ hk_valid, double *__restrict__ ppart)
 {
    extern __shared__ double2 smem[];
-   // grid = (slabs, column blocks): the blocks of the column block with the most slots (the list is sorted) are
-   // scheduled first, the tail of the grid is made of the cheapest blocks (4.79 -> 4.57 ms against column-block-fastest order)
-   const SfacMBlock B = blocks[blockIdx.y];
+   // 1-D grid, ordered [slab group][column block][slab of the group]: inside a group of `sgroup` slabs the column
+   // blocks with the most slots (the list is sorted) come first, so the tail of the grid is made of the cheapest
+   // blocks, and the blocks that run at the same time share the table chunks of one or two slab groups through L2.
+   // Measured (1.024 M sites, MDB_SFAC_GROUP): groups of 4 / 8 / 16 / 32 / all slabs = 4.87 / 4.88 / 4.71 / 4.69 / 4.57 ms
+   // with 1.3 / 1.8 / 3.3 / 6.0 / 10.2 GB read from HBM (one global heavy-first order re-reads the 1 GB of tables once
+   // per column block); column-block-fastest order: 4.79 ms, 1.1 GB.  Default 16.
+   const int per_group = A.sgroup * A.nblk, sg = blockIdx.x / per_group, rem = blockIdx.x - sg * per_group;
+   const int gsz = min(A.sgroup, A.n_slabs - sg * A.sgroup);
+   const int cb = rem / gsz, slab = sg * A.sgroup + rem - cb * gsz;
+   if (cb >= A.nblk) return;                                      // (short last group)
+   const SfacMBlock B = blocks[cb];
    switch (B.nt) {          // block-uniform: straight-line DMMA sequences, accumulators in registers
-      case 1: sfac_mma_body<1>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem); break;
-      case 2: sfac_mma_body<2>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem); break;
-      case 3: sfac_mma_body<3>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem); break;
-      case 4: sfac_mma_body<4>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem); break;
-      case 5: sfac_mma_body<5>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem); break;
-      case 6: sfac_mma_body<6>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem); break;
-      case 7: sfac_mma_body<7>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem); break;
-      default: sfac_mma_body<8>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem); break;
+      case 1: sfac_mma_body<1>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem, slab); break;
+      case 2: sfac_mma_body<2>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem, slab); break;
+      case 3: sfac_mma_body<3>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem, slab); break;
+      case 4: sfac_mma_body<4>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem, slab); break;
+      case 5: sfac_mma_body<5>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem, slab); break;
+      case 6: sfac_mma_body<6>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem, slab); break;
+      case 7: sfac_mma_body<7>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem, slab); break;
+      default: sfac_mma_body<8>(A, B, tE, tH, tK, hk, hk_valid, ppart, smem, slab); break;
    }
 }
 
@@ -1070,7 +1078,10 @@ static int recip_partial(mdb_engine *e, const RecipPlan &P, double *d_psum, cuda
          MDB_CUDA(cudaFuncSetAttribute(k_sfac_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mshm));
          mshm_set = mshm;
       }
-      dim3 g(P.n_slabs, e->n_sfac_blocks);
+      static const int sgroup = getenv("MDB_SFAC_GROUP") ? std::max(1, atoi(getenv("MDB_SFAC_GROUP"))) : 16;
+      M.n_slabs = P.n_slabs; M.nblk = e->n_sfac_blocks; M.sgroup = std::min(sgroup, P.n_slabs);
+      const int ngrp = (P.n_slabs + M.sgroup - 1) / M.sgroup;
+      dim3 g(ngrp * M.sgroup * M.nblk);
       k_sfac_mma<<<g, MT, mshm, st>>>(M, (const SfacMBlock *)e->d_sfac_blocks, tE, tH, tK, e->d_hk, e->d_hk_valid,
                                       e->d_ppart);
       e->launches++;
