@@ -9,6 +9,10 @@
 //        P1 = sum c_hk C_l   P2 = sum s_hk S_l   P3 = sum s_hk C_l   P4 = sum c_hk S_l
 // (C_l = q cos(l c*.r), S_l = q sin(l c*.r)):  C(+-l) = P1 -+ P2,  S(+-l) = P3 +- P4.
 //
+// Default path (FP64 tensor pipe, further down): k_ktables -> k_sfac_mma -> k_slab_sum -> k_sfin -> k_kforce_mma,
+// both heavy kernels as DMMA.8x8x4 GEMMs fed by TMA bulk copies.  The register-operand DFMA kernels below
+// (k_sfac, k_kforce) are the earlier formulation, kept selectable with MDB_KSPACE=dfma for A/B timing:
+//
 //  k_sfac    structure factors: thread owns one (h,k) column and up to 8 l-slots
 //            (32 FP64 accumulators), sites stream through shared memory in
 //            chunks with their E_h/E_k/E_l power tables built by recurrence.
