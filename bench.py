@@ -289,7 +289,11 @@ def run_ours(a):
                 "k_vectors": nhkl, "site_k_terms_per_s": N * nhkl / (ms_step * 1e-3),
                 "phase_ms": {"cells": float(ph[:, 0].mean()), "pair": pair_ms, "recip": float(ph[:, 2].mean()),
                              "allreduce": float(ph[:, 3].mean())},
-                "recip_roofline": {"bound": "fp64", "kernel": "k_ktables + k_sfac_mma + k_kforce_mma (DMMA.8x8x4, FP64 tensor pipe)", "achieved": FLOP_PER_SITEK * N * nhkl / world / (ph[:, 2].mean() * 1e-3) / 1e12,
+                "recip_roofline": {"bound": "fp64", "kernel": "k_ktables + k_sfac_mma + k_kforce_mma (DMMA.8x8x4, FP64 tensor pipe)",
+                                   "note": "SURVEY 8d's algorithmic 18 flop per (site, k-vector) of the reference's loops over the time of the "
+                                           "factorised GEMMs, which need ~6: a frac above 1 is not a pipe utilisation (DMMA sub-pipe active "
+                                           "74 % / 78 % in k_sfac_mma / k_kforce_mma, profiles/r01_s3_summary.md)",
+                                   "achieved": FLOP_PER_SITEK * N * nhkl / world / (ph[:, 2].mean() * 1e-3) / 1e12,
                                    "peak": peak / 1e12, "unit": "TFLOP/s",
                                    "frac": FLOP_PER_SITEK * N * nhkl / world / (ph[:, 2].mean() * 1e-3) / peak},
                 "roofline": roof, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
