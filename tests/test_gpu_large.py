@@ -77,3 +77,24 @@ def test_other_benchmark_families_at_full_size(which):
     assert np.allclose(pe4, pe3, rtol=1e-11)
     iu = np.triu_indices(3)
     assert np.linalg.norm(s4[iu] - s3[iu]) < 1e-11 * np.linalg.norm(s3[iu])
+
+
+def test_kspace_gemm_kernels_are_bit_reproducible():
+    """k_sfac_mma / k_kforce_mma stream their operands through mbarrier-guarded TMA rings with warps drifting
+    apart; the sums themselves have a fixed order, so three evaluations at 128 000 sites must agree bit for bit
+    (a stage overwritten too early or read too early would show up here)."""
+    import torch
+    ms = systems.tip4p(5)
+    eng = lib.Engine(0)
+    eng.configure(ms)
+    eng.set_sites_host(ms.make_sites())
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for _ in range(3):
+        out = torch.zeros(eng.out_doubles(), dtype=torch.float64, device="cuda")
+        eng.force_recip(out.data_ptr(), st)
+        torch.cuda.synchronize()
+        outs.append(out.cpu().numpy())
+    eng.close()
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    assert np.abs(outs[0][:3 * ms.nsites]).max() > 0
