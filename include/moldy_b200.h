@@ -229,6 +229,21 @@ size_t mdb_rdf_size(const mdb_engine *e, int nbins);
 int  mdb_rdf_counts(mdb_engine *e, double limit, int nbins, unsigned long long *h_counts, void *stream);
 void mdb_rdf_private_resize(int n);      /* host is not Moldy: size (and clear) the fall-back store rdf_ptr() returns */
 
+/* Molecular-frame steps of eval_forces() around force_calc()/ewald() (src/accel.c:497-560), as
+ * device-level building blocks; one call per species, all pointers are DEVICE pointers.
+ * mdb_make_sites: make_sites() (src/algorith.c:169-217) into the engine's own position rows [site_offset,
+ *   site_offset + nmols*nsites): site = h.com_s + R(quat).p_f_site, brought into the cell site by site when sitepbc != 0
+ *   (SITEPBC), whole molecules otherwise (MOLPBC); d_quat NULL for species without rotational freedom.  Bit-identical
+ *   to the reference's sites (the cell assignment depends on them).  The engine then uses its own rows as the sites.
+ * mdb_mol_forces: mol_force() + mol_torque() (src/algorith.c:111-163) of one species from the site forces of a result
+ *   block: d_force[nmols][3], d_torque[nmols][3] (NULL: no torques).
+ * mdb_get_sites: the engine's current sites to host rows (synchronises). */
+int  mdb_make_sites(mdb_engine *e, const double h[9], const double *d_com_s, const double *d_quat, const double *d_pfs,
+                    int nmols, int nsites, int site_offset, int sitepbc, void *stream);
+int  mdb_mol_forces(mdb_engine *e, const double *d_out, const double *d_quat, const double *d_pfs, int nmols, int nsites,
+                    int site_offset, double *d_force, double *d_torque, void *stream);
+int  mdb_get_sites(mdb_engine *e, double *hx, double *hy, double *hz, void *stream);
+
 /* Device->host copy of a result block (synchronises `stream`). */
 int  mdb_read_out(mdb_engine *e, const double *d_out, double *h_out, void *stream);
 

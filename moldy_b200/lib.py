@@ -75,6 +75,9 @@ def load() -> C.CDLL:
     L.mdb_n_neighbour_cells.argtypes = [C.c_void_p]
     L.mdb_n_kvectors.argtypes = [C.c_void_p]
     L.mdb_pair_split.argtypes = [C.c_void_p]
+    L.mdb_make_sites.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.mdb_mol_forces.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mdb_get_sites.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mdb_get_cell_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.mdb_rdf_size.restype = C.c_size_t
     L.mdb_rdf_size.argtypes = [C.c_void_p, C.c_int]
@@ -330,6 +333,24 @@ class Engine:
 
     def pair_count(self, stream=0) -> float:
         return self.L.mdb_pair_count(self.h, stream)
+
+    def make_sites(self, h: np.ndarray, d_com_s: int, d_quat: int, d_pfs: int, nmols: int, nsites: int, site_offset: int,
+                   sitepbc: bool, stream=0):
+        """make_sites() of one species on the device (device pointers; d_quat 0 for species without quaternions)."""
+        hh = np.ascontiguousarray(h, dtype=np.float64)
+        self._chk(self.L.mdb_make_sites(self.h, hh.ctypes.data, d_com_s, d_quat or None, d_pfs, nmols, nsites, site_offset,
+                                        1 if sitepbc else 0, stream), "mdb_make_sites")
+
+    def mol_forces(self, d_out: int, d_quat: int, d_pfs: int, nmols: int, nsites: int, site_offset: int, d_force: int,
+                   d_torque: int, stream=0):
+        """mol_force() + mol_torque() of one species from a result block (device pointers; d_torque 0: forces only)."""
+        self._chk(self.L.mdb_mol_forces(self.h, d_out, d_quat or None, d_pfs, nmols, nsites, site_offset, d_force,
+                                        d_torque or None, stream), "mdb_mol_forces")
+
+    def get_sites(self, stream=0) -> np.ndarray:
+        out = np.empty((3, self.n))
+        self._chk(self.L.mdb_get_sites(self.h, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data, stream), "mdb_get_sites")
+        return out
 
     def pair_split(self) -> int:
         """1 when the real-space sum runs as two passes by site class (charged / with a pair potential)."""
