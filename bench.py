@@ -253,6 +253,7 @@ def run_ours(a):
 
     # ---- end-to-end through the public host-buffer API --------------------------------
     e2e = measure_e2e(a, ms, site, world, rank, local)
+    e2e_mol = measure_e2e_eval_forces(a, ms) if world == 1 else None
 
     if rank == 0:
         pair_ms = float(ph[:, 1].mean())
@@ -296,7 +297,7 @@ def run_ours(a):
                                    "achieved": FLOP_PER_SITEK * N * nhkl / world / (ph[:, 2].mean() * 1e-3) / 1e12,
                                    "peak": peak / 1e12, "unit": "TFLOP/s",
                                    "frac": FLOP_PER_SITEK * N * nhkl / world / (ph[:, 2].mean() * 1e-3) / peak},
-                "roofline": roof, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roof, "clocks": clocks, "e2e": e2e, "e2e_eval_forces": e2e_mol, "gpu_launches": int(launches),
                 "wall_s_timed_region": t_wall}
         if world == 1 and not a.no_cpu_baseline:
             from oracle import ref
@@ -367,6 +368,33 @@ def measure_e2e(a, ms, site, world, rank, local):
     return {"value": 1.0 / dt, "unit": "steps/s", "ms_per_step": 1e3 * dt,
             "h2d_bytes_per_step": 3 * N * 8 * world, "d2h_bytes_per_step": (3 * N + 16) * 8 * world,
             "api": "moldy_b200.spmd.SpmdForces.step(pinned host sites) -> host [forces|pe|stress] on every rank"}
+
+
+def measure_e2e_eval_forces(a, ms):
+    """The same step one level up: Moldy's eval_forces() of libmoldy_b200.so -- scaled centres of
+    mass and quaternions in, molecular forces/torques, pe, stress and dipole moment out; sites and site forces stay in
+    HBM.  An auxiliary figure next to `e2e` (which stays force_calc()+ewald(), the north_star's boundary)."""
+    from moldy_b200 import lib
+    steps = max(2, min(a.steps, 5))
+    try:
+        L = lib.load()
+        ms.control.fill(lib.control())
+        lib.set_thread(0, 1)
+        args, out = ms.eval_forces_args()
+        lib.reset()
+        L.eval_forces(*args); L.eval_forces(*args)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            L.eval_forces(*args)
+        dt = (time.perf_counter() - t0) / steps
+        nq = sum(s.nmols for s in ms.sysdef.species if s.rdof)
+        return {"value": 1.0 / dt, "unit": "steps/s", "ms_per_step": 1e3 * dt,
+                "h2d_bytes_per_step": (3 * ms.nmols + 4 * nq) * 8,
+                "d2h_bytes_per_step": int(L.mdb_eval_result_doubles(L.mdb_abi_engine())) * 8,
+                "pe": [float(out["pe"][0]), float(out["pe"][1])],
+                "api": "eval_forces() of libmoldy_b200.so (src/accel.c:398 prototype), pageable host c_of_m/quat"}
+    except Exception as exc:      # auxiliary measurement only: never take the bench line down with it
+        return {"value": None, "error": repr(exc)}
 
 
 def emit(line: dict):

@@ -244,6 +244,44 @@ int  mdb_mol_forces(mdb_engine *e, const double *d_out, const double *d_quat, co
                     int site_offset, double *d_force, double *d_torque, void *stream);
 int  mdb_get_sites(mdb_engine *e, double *hx, double *hy, double *hz, void *stream);
 
+/* The whole of eval_forces() (src/accel.c:398-617) on the device: only the scaled centres of mass
+ * and quaternions go in and molecular forces, torques and 23 scalars come out; site positions and site forces never
+ * leave HBM.  Sequence, all on `stream`: make_sites per species (SITEPBC, or MOLPBC under molecular-cutoff) -> cell
+ * build -> real-space sum -> reciprocal-space sum (do_recip) -> make_sites again (MOLPBC, frameworks SITEPBC;
+ * src/accel.c:537-542) -> dipole moment sum chg*site (:550) -> surface-dipole force term (:551-558) folded into ->
+ * mol_force/mol_torque (:564-571) and the site->molecular virial sum_sites f_i (r_j - R_j) (:576-601, evaluated per
+ * molecule, which is the same sum without the reference's cancellation of two O(N L) terms).
+ * mdb_set_species: the species table in system order (frameworks last) and every species' principal-frame sites,
+ *   concatenated [sum nsites][3] (HOST).  Call after mdb_configure.
+ * mdb_eval_forces_host: com[ispec] = spec->c_of_m (HOST [nmols][3] scaled), quat[ispec] = spec->quat (HOST [nmols][4])
+ *   or NULL for a species whose sites are not rotated.  h_result (HOST, mdb_eval_result_doubles() doubles) =
+ *   [force 3*nmols | torque 3*nmols_r (species with rdof > 0, in order) | MDB_EVAL_SCALARS scalars]; scalars:
+ *   [0..2] dipole moment, [3..11] virial correction V[i][j] (subtract from the symmetrised stress), [12] real-space
+ *   energy, [13] reciprocal-space energy (without the surface term), [14..22] stress[3][3] as force_calc+ewald leave it
+ *   (upper triangle).  The constants of the first call (intramolecular, self and sheet energies, distant-potential
+ *   terms) and the surface-dipole energy are the host program's: eval_forces() of layer (A) adds them.
+ *   Synchronises `stream`. */
+typedef struct {
+   int nmols, nsites;      /* spec->nmols, spec->nsites                          */
+   int framework;          /* spec->framework                                    */
+   int rotates;            /* spec->quat != NULL: make_sites rotates the sites   */
+   int rdof;               /* spec->rdof: torques are returned when > 0          */
+} mdb_species;
+#define MDB_EVAL_SCALARS 32
+int    mdb_set_species(mdb_engine *e, int nspecies, const mdb_species *sp, const double *pfs);
+size_t mdb_eval_result_doubles(const mdb_engine *e);
+int    mdb_eval_forces_host(mdb_engine *e, const double h[9], const double *const *com, const double *const *quat,
+                            int surface_dipole, int do_recip, double *h_result, void *stream);
+/* The library's own pinned copy of the last result (valid until the next call); pass h_result = NULL above to skip
+ * the copy into caller memory. */
+const double *mdb_eval_result(const mdb_engine *e);
+
+/* Moldy's eval_forces() itself (src/accel.c:398-617) on top of mdb_eval_forces_host: same prototype, same outputs
+ * (pe[NPE], dip_mom[3], the full symmetric virial stress, force[ispec][imol], torque[ispec][imol]), same first-call
+ * notes.  Linking it in place of accel.c's definition is described in INTEGRATION.md section 5. */
+void eval_forces(system_mp sys, spec_mt *species, site_mt *site_info, pot_mt *potpar, double *pe, real *dip_mom,
+                 mat_mt stress, vec_mp *force, vec_mp *torque);
+
 /* Device->host copy of a result block (synchronises `stream`). */
 int  mdb_read_out(mdb_engine *e, const double *d_out, double *h_out, void *stream);
 

@@ -80,6 +80,9 @@ extern "C" void mdb_destroy(mdb_engine *e)
    free_system(e); free_grid(e); free_recip(e); free_sublists(e);
    FREE(e->d_partials); FREE(e->d_counters); FREE(e->d_out_own); FREE(e->d_rdf);
    if (e->h_stage) cudaFreeHost(e->h_stage);
+   FREE(e->mf.d_pfs); FREE(e->mf.d_in); FREE(e->mf.d_res); FREE(e->mf.d_vpart); FREE(e->mf.d_dpart);
+   if (e->mf.h_in) cudaFreeHost(e->mf.h_in);
+   if (e->mf.h_res) cudaFreeHost(e->mf.h_res);
    delete e;
 }
 

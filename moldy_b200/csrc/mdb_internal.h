@@ -143,6 +143,16 @@ struct mdb_engine {
    double *d_psum = nullptr;              // [2][nslots][4] structure-factor sums (non-framework, framework)
    int n_slabs = 0, n_slabs_nf = 0, slab_sites = 0;
 
+   // eval_forces() on the device (mdb_molframe.cu): species table and molecular-frame buffers
+   struct MolFrame {
+      std::vector<mdb_species> sp;
+      std::vector<int> site_off, mol_off, quat_off, torq_off, pfs_off, blk_off;   // per species; quat_off/torq_off -1: none
+      int nmols = 0, nmols_q = 0, nmols_r = 0, npfs = 0, nblocks = 0;
+      double *d_pfs = nullptr, *d_in = nullptr, *d_res = nullptr, *d_vpart = nullptr, *d_dpart = nullptr;
+      double *h_in = nullptr, *h_res = nullptr;                                   // pinned
+      size_t in_cap = 0, res_cap = 0;
+   } mf;
+
    // pinned staging for host-facing calls
    double *h_stage = nullptr; size_t stage_cap = 0;
    double *d_out_own = nullptr; size_t out_cap = 0;

@@ -111,7 +111,7 @@ struct AbiState {
    cudaEvent_t ev_ahead = nullptr;
    bool ahead_valid = false;
    const void *ahead_sites = nullptr;
-   long config_epoch = 0, ahead_epoch = -1;
+   long config_epoch = 0, ahead_epoch = -1, chg_epoch = 0;     // chg_epoch: bumped whenever G.chg is replaced
    int ahead_ithread = 0, ahead_nthreads = 1;
    bool rdf_warned = false;
 };
@@ -146,7 +146,8 @@ static int count_xf_sites(const system_mt *system, const spec_mt *species)
 // constant-stress dynamics; everything else is constant in a Moldy run).
 // defer_chg: do not compare the N charges now (8 MB, 0.6 ms at 10^6 sites); the caller does it with
 // chg_changed_late() once its kernels are running and repeats the call if they differ.
-static void sync_config(system_mt *system, spec_mt *species, const real *chg, const pot_mt *potpar, bool defer_chg = false)
+static void sync_config(system_mt *system, spec_mt *species, const real *chg, const pot_mt *potpar, bool defer_chg = false,
+                        bool chg_known = false)      // chg_known: chg IS G.chg's content (eval_forces' cached array)
 {
    ensure_engine();
    const int n = system->nsites, max_id = system->max_id;
@@ -179,10 +180,13 @@ static void sync_config(system_mt *system, spec_mt *species, const real *chg, co
       changed = true;
    }
    G.chg_unchecked = false;
-   if (defer_chg && !changed && (int)G.chg.size() == n) {
+   if (chg_known && (int)G.chg.size() == n) {
+      /* nothing to compare */
+   } else if (defer_chg && !changed && (int)G.chg.size() == n) {
       G.chg_unchecked = true;
    } else if ((int)G.chg.size() != n || memcmp(G.chg.data(), chg, sizeof(double) * n)) {
       G.chg.assign(chg, chg + n);
+      G.chg_epoch++;
       changed = true;
    }
    if (potpar) {
@@ -267,15 +271,9 @@ static void pull_and_accumulate(real **site_force, double *pe, real (*stress)[3]
    stress[1][1] += sc[6]; stress[1][2] += sc[7]; stress[2][2] += sc[10];
 }
 
-extern "C" void force_calc(real **site, real **site_force, system_mt *system, spec_mt *species, real *chg,
-                           pot_mt *potpar, double *pe, mat_mt stress)
+// First-call constant and notes of force_calc (src/force.c:1158-1169, 218-223, 1240-1243)
+static void real_first_call(system_mt *system, spec_mt *species, const real *chg, pot_mt *potpar)
 {
-   const double tc0 = now_ms();
-   sync_config(system, species, chg, potpar, true);
-   if (g_timing) fprintf(stderr, "[moldy_b200] force_calc: sync_config %.2f ms\n", now_ms() - tc0);
-   mdb_set_partition(G.eng, ithread, nthreads);
-   const int n = system->nsites;
-
    if (!G.real_init) {                                   /* src/force.c:1158-1169 */
       int isite = 0;
       for (spec_mt *sp = species; sp < species + system->nspecies; sp++) {
@@ -296,8 +294,6 @@ extern "C" void force_calc(real **site, real **site_force, system_mt *system, sp
       note((char *)"Intramolecular potential energy correction = %g", G.eintra * CONV_E_KJ);
       G.real_init = true;
    }
-   if (ithread == 0) *pe -= G.eintra;
-
    const int nhalf = mdb_n_neighbour_cells(G.eng);
    if (nhalf != G.onabor) {                              /* src/force.c:218-223 */
       note((char *)"Neighbour list contains %d cells", 2 * nhalf);
@@ -309,6 +305,19 @@ extern "C" void force_calc(real **site, real **site_force, system_mt *system, sp
       note((char *)"MD cell divided into %d subcells (%dx%dx%d)", ncells, g[0], g[1], g[2]);
       G.onx = g[0]; G.ony = g[1]; G.onz = g[2];
    }
+}
+
+extern "C" void force_calc(real **site, real **site_force, system_mt *system, spec_mt *species, real *chg,
+                           pot_mt *potpar, double *pe, mat_mt stress)
+{
+   const double tc0 = now_ms();
+   sync_config(system, species, chg, potpar, true);
+   if (g_timing) fprintf(stderr, "[moldy_b200] force_calc: sync_config %.2f ms\n", now_ms() - tc0);
+   mdb_set_partition(G.eng, ithread, nthreads);
+   const int n = system->nsites;
+
+   real_first_call(system, species, chg, potpar);
+   if (ithread == 0) *pe -= G.eintra;
 
    auto launch_real = [&]() {
       G.sites_fresh = false;
@@ -384,19 +393,10 @@ extern "C" void force_calc(real **site, real **site_force, system_mt *system, sp
    }
 }
 
-extern "C" void ewald(real **site, real **site_force, system_mp system, spec_mt *species, real *chg, double *pe,
-                      real (*stress)[3])
+// First-call constants and notes of ewald (src/ewald.c:367-425)
+static void recip_first_call(system_mp system, spec_mt *species, const real *chg, double vol)
 {
-   const double tc0 = now_ms();
-   sync_config(system, species, chg, nullptr);
-   if (g_timing) fprintf(stderr, "[moldy_b200] ewald: sync_config %.2f ms\n", now_ms() - tc0);
-   mdb_set_partition(G.eng, ithread, nthreads);
    const int n = system->nsites;
-   double h9[9];
-   for (int i = 0; i < 3; i++)
-      for (int j = 0; j < 3; j++) h9[3 * i + j] = system->h[i][j];
-   const double vol = mdb_det3(h9);
-
    if (!G.recip_init) {                                  /* src/ewald.c:367-425 */
       double sqsq = 0, sq = 0, last_intra = 0;
       int ssite = 0;
@@ -438,6 +438,22 @@ extern "C" void ewald(real **site, real **site_force, system_mp system, spec_mt 
       note((char *)"%d K-vectors included in reciprocal-space sum", mdb_n_kvectors(G.eng));
       G.recip_init = true;
    }
+}
+
+extern "C" void ewald(real **site, real **site_force, system_mp system, spec_mt *species, real *chg, double *pe,
+                      real (*stress)[3])
+{
+   const double tc0 = now_ms();
+   sync_config(system, species, chg, nullptr);
+   if (g_timing) fprintf(stderr, "[moldy_b200] ewald: sync_config %.2f ms\n", now_ms() - tc0);
+   mdb_set_partition(G.eng, ithread, nthreads);
+   const int n = system->nsites;
+   double h9[9];
+   for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) h9[3 * i + j] = system->h[i][j];
+   const double vol = mdb_det3(h9);
+
+   recip_first_call(system, species, chg, vol);
    if (ithread == 0) {                                   /* src/ewald.c:427-433 */
       *pe -= G.self_energy;
       *pe += G.sheet_energy / vol;
@@ -514,6 +530,157 @@ extern "C" double dist_pot(real *p, double rc, int ptype)
    }
 }
 
+// ---- eval_forces(): the whole of src/accel.c:398-617 with the sites and site forces resident in HBM -------------
+// distant_const (src/accel.c:293-326): -2 pi sum_ij Ni Nj A_ij(rc) [+ 2/3 pi Ni Nj rc^3 U_ij(rc) for the pressure term]
+static double distant_const_abi(system_mp system, spec_mt *species, pot_mt *potpar, double cutoff, int iflag)
+{
+   std::vector<int> count(system->max_id, 0);
+   for (spec_mt *sp = species; sp < species + system->nspecies; sp++)
+      for (int is = 0; is < sp->nsites; is++) count[sp->site_id[is]] += sp->nmols;
+   double c = 0.0;
+   for (int id = 1; id < system->max_id; id++)
+      for (int jd = 1; jd < system->max_id; jd++) {
+         c -= 2 * MDB_PI * count[id] * count[jd] * dist_pot(potpar[id + system->max_id * jd].p, cutoff, system->ptype);
+         if (iflag)
+            c += 2.0 / 3.0 * MDB_PI * count[id] * count[jd] * (cutoff * cutoff * cutoff) *
+                 poteval(potpar[id + system->max_id * jd].p, cutoff, system->ptype, 0.0);
+      }
+   return c;
+}
+
+struct EvalState {
+   bool init = false;
+   double dist = 0, distp = 0;
+   std::vector<double> chg, pfs, site_charge;     // site_charge: site_info[].charge the chg array was expanded from
+   std::vector<int> layout;                        // nmols, nsites and site ids of every species, ditto
+   std::vector<mdb_species> sp;
+   long species_epoch = -1, chg_epoch = -1;
+};
+static EvalState E;
+
+#define CONV_P_MPA (1.6605402e-27 / (1.0e-10 * 1.0e-12 * 1.0e-12) / 1.0e6)   /* src/defs.h:231 CONV_P */
+
+extern "C" void eval_forces(system_mp sys, spec_mt *species, site_mt *site_info, pot_mt *potpar, double *pe,
+                            real *dip_mom, mat_mt stress, vec_mp *force, vec_mp *torque)
+{
+   const int n = sys->nsites, nspecies = sys->nspecies;
+   double h9[9];
+   for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) h9[3 * i + j] = sys->h[i][j];
+   const double vol = mdb_det3(h9);
+
+   /* site charges, src/accel.c:473-480; expanded again only when site_info or the species layout changed */
+   const double tc0 = now_ms();
+   bool chg_cached = (int)E.chg.size() == n && (int)E.site_charge.size() == sys->max_id;
+   {
+      std::vector<int> layout;
+      for (spec_mt *sp = species; sp < species + nspecies; sp++) {
+         layout.push_back(sp->nmols); layout.push_back(sp->nsites);
+         for (int is = 0; is < sp->nsites; is++) layout.push_back(sp->site_id[is]);
+      }
+      for (int id = 0; chg_cached && id < sys->max_id; id++) chg_cached = site_info[id].charge == E.site_charge[id];
+      chg_cached = chg_cached && layout == E.layout;
+      if (!chg_cached) {
+         E.chg.resize(n);
+         double *c = E.chg.data();
+         for (spec_mt *sp = species; sp < species + nspecies; sp++)
+            for (int im = 0; im < sp->nmols; im++)
+               for (int is = 0; is < sp->nsites; is++) *c++ = site_info[sp->site_id[is]].charge;
+         E.site_charge.resize(sys->max_id);
+         for (int id = 0; id < sys->max_id; id++) E.site_charge[id] = site_info[id].charge;
+         E.layout.swap(layout);
+      }
+   }
+   sync_config(sys, species, E.chg.data(), potpar, false, chg_cached && E.chg_epoch == G.chg_epoch);
+   E.chg_epoch = G.chg_epoch;
+   const double tc1 = now_ms();
+   mdb_set_partition(G.eng, 0, 1);            /* complete sums: the library stands for all of the SPMD ranks */
+
+   if (!E.init) {                             /* src/accel.c:444-453 */
+      E.dist = distant_const_abi(sys, species, potpar, control.cutoff, 0);
+      E.distp = distant_const_abi(sys, species, potpar, control.cutoff, 1);
+      note((char *)"Distant potential correction = %f, Pressure correction = %f", CONV_E_KJ * E.dist / vol,
+           CONV_P_MPA * E.distp / (vol * vol));
+      E.init = true;
+   }
+   const bool do_recip = control.alpha > MDB_ALPHAMIN;
+   real_first_call(sys, species, E.chg.data(), potpar);
+   if (do_recip) recip_first_call(sys, species, E.chg.data(), vol);
+
+   if (E.species_epoch != G.config_epoch || (int)E.sp.size() != nspecies) {
+      E.sp.resize(nspecies);
+      E.pfs.clear();
+      for (int i = 0; i < nspecies; i++) {
+         const spec_mt &sp = species[i];
+         E.sp[i] = mdb_species{sp.nmols, sp.nsites, sp.framework ? 1 : 0, sp.quat ? 1 : 0, sp.rdof};
+         for (int is = 0; is < sp.nsites; is++)
+            for (int k = 0; k < 3; k++) E.pfs.push_back(sp.p_f_sites[is][k]);
+      }
+      if (mdb_set_species(G.eng, nspecies, E.sp.data(), E.pfs.data())) FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+      E.species_epoch = G.config_epoch;
+   }
+   std::vector<const double *> com(nspecies), quat(nspecies);
+   for (int i = 0; i < nspecies; i++) {
+      com[i] = &species[i].c_of_m[0][0];
+      quat[i] = species[i].quat ? &species[i].quat[0][0] : nullptr;
+   }
+   G.sites_fresh = false; G.ahead_valid = false;          /* the engine's sites are no longer the ones force_calc uploaded */
+   if (mdb_eval_forces_host(G.eng, h9, com.data(), quat.data(), control.surface_dipole ? 1 : 0, do_recip ? 1 : 0,
+                            nullptr, G.stream))
+      FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+   const double tc2 = now_ms();
+
+   int pr[2];
+   const int tc = mdb_too_close(G.eng, pr, G.stream);
+   if (tc & (1 << 30))
+      message((int *)0, (char *)0, SEV_ERROR, (char *)"Co-ordinate out of range in BIN (fill_cells)");
+   if (tc & ~(1 << 30))                                  /* src/force.c:944-946 */
+      message((int *)0, (char *)0, SEV_WARNING, (char *)"Sites %d and %d closer than %fA.", pr[0], pr[1],
+              sqrt(MDB_TOO_CLOSE));
+
+   /* molecular forces and torques, src/accel.c:564-571 */
+   const double *res = mdb_eval_result(G.eng);            /* pinned: copied straight into the caller's arrays */
+   int nmols = 0, nmols_r = 0;
+   for (int i = 0; i < nspecies; i++) nmols += species[i].nmols;
+   for (int i = 0; i < nspecies; i++) nmols_r += species[i].rdof > 0 ? species[i].nmols : 0;
+   {
+      const double *f = res, *t = res + 3 * (size_t)nmols;
+      for (int i = 0; i < nspecies; i++) {
+         memcpy(&force[i][0][0], f, sizeof(double) * 3 * (size_t)species[i].nmols);
+         f += 3 * (size_t)species[i].nmols;
+         if (species[i].rdof > 0) {
+            memcpy(&torque[i][0][0], t, sizeof(double) * 3 * (size_t)species[i].nmols);
+            t += 3 * (size_t)species[i].nmols;
+         }
+      }
+   }
+   const double *sc = res + 3 * (size_t)nmols + 3 * (size_t)nmols_r;
+   /* energies: force_calc's and ewald's constants (src/force.c:1170, src/ewald.c:427-433), surface dipole
+    * (src/accel.c:557), distant potential (:606) */
+   pe[0] = sc[12] - G.eintra + E.dist / vol;
+   pe[1] = 0.0;
+   for (int i = 0; i < 3; i++) dip_mom[i] = 0.0;
+   memset(&stress[0][0], 0, sizeof(double) * 9);
+   stress[0][0] = sc[14]; stress[0][1] = sc[15]; stress[0][2] = sc[16];
+   stress[1][1] = sc[18]; stress[1][2] = sc[19]; stress[2][2] = sc[22];
+   if (do_recip) {
+      pe[1] = sc[13] - G.self_energy + G.sheet_energy / vol;
+      for (int i = 0; i < 3; i++) stress[i][i] += G.sheet_energy / vol;
+      for (int i = 0; i < 3; i++) dip_mom[i] = sc[i];
+      if (control.surface_dipole)
+         pe[1] += 2.0 * MDB_PI / (3.0 * vol) * (sc[0] * sc[0] + sc[1] * sc[1] + sc[2] * sc[2]);
+   }
+   /* site -> molecular virial (src/accel.c:576-601) and distant pressure term (:607-608) */
+   for (int i = 0; i < 3; i++)
+      for (int j = i + 1; j < 3; j++) stress[j][i] = stress[i][j];
+   for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) stress[i][j] -= sc[3 + 3 * i + j];
+   for (int i = 0; i < 3; i++) stress[i][i] += E.distp / vol;
+   if (g_timing)
+      fprintf(stderr, "[moldy_b200] eval_forces: config %.2f ms, device (H2D .. D2H) %.2f ms, results %.2f ms\n", tc1 - tc0,
+              tc2 - tc1, now_ms() - tc2);
+}
+
 // ---- test/bench accessors ------------------------------------------------------
 extern "C" mdb_engine *mdb_abi_engine(void) { ensure_engine(); return G.eng; }
 extern "C" void *mdb_abi_stream(void) { ensure_engine(); return (void *)G.stream; }
@@ -528,4 +695,5 @@ extern "C" void mdb_abi_reset(void)
    G.have_cfg = false; G.sites_fresh = false; G.last_sites = nullptr; G.rdf_warned = false;
    if (G.eng && G.stream) cudaStreamSynchronize(G.stream);
    G.ahead_valid = false;
+   E.init = false; E.species_epoch = -1; E.sp.clear(); E.chg.clear(); E.site_charge.clear(); E.layout.clear();
 }

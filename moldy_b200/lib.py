@@ -99,6 +99,11 @@ def load() -> C.CDLL:
     L.poteval.argtypes = [DP, C.c_double, C.c_int, C.c_double]
     L.dist_pot.restype = C.c_double
     L.dist_pot.argtypes = [DP, C.c_double, C.c_int]
+    L.mdb_set_species.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.mdb_eval_result_doubles.restype = C.c_size_t
+    L.mdb_eval_result_doubles.argtypes = [C.c_void_p]
+    L.mdb_eval_forces_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.eval_forces.restype = None
     L.kernel.argtypes = [C.c_int, C.c_int, DP, DP, DP, DP, C.c_double, C.c_double, C.c_double, C.c_int,
                          C.POINTER(DP)]
     _LIB = L
@@ -196,6 +201,18 @@ def eval_forces(ms: MoldySystem, real=True, recip=True, sites=None, ithread=0, n
         L.rdf_ptr.restype = C.POINTER(C.c_float)
         base = L.rdf_ptr(C.byref(size))
         out["rdf"] = np.ctypeslib.as_array(base, shape=(size.value,)).copy().reshape(-1, int(rdf[1]))
+    return out
+
+
+def eval_forces_mol(ms: MoldySystem):
+    """Moldy's eval_forces() itself (src/accel.c:398-617) through the library's drop-in symbol: scaled centres of mass
+    and quaternions in; pe[2], dip_mom[3], the full virial stress[3,3], molecular force[nmols,3] and
+    torque[nmols_r,3] out.  Sites and site forces stay in HBM."""
+    L = load()
+    ms.control.fill(control())
+    set_thread(0, 1)
+    args, out = ms.eval_forces_args()
+    L.eval_forces(*args)
     return out
 
 

@@ -478,6 +478,40 @@ class MoldySystem:
         self._keep = keep + [spec_arr, pot]
         return sysm, spec_arr, pot
 
+    def eval_forces_args(self):
+        """Argument list of eval_forces() (src/accel.c:398-407) for this configuration, laid out as Moldy's
+        allocate_dynamics does: spec->quat is NULL for species without rotational freedom (src/startup.c:560),
+        force[ispec] / torque[ispec] point into one contiguous [nmols][3] / [nmols_r][3] block.
+        Returns (args tuple for the C call, dict of the numpy outputs)."""
+        sysm, spec, pot = self.cstructs()
+        sd = self.sysdef
+        nsp = len(sd.species)
+        site_info = (abi.site_mt * sd.max_id)()
+        for i in range(sd.max_id):
+            site_info[i].mass, site_info[i].charge = float(sd.site_mass[i]), float(sd.site_charge[i])
+        nmols_r = sum(s.nmols for s in sd.species if s.rdof)
+        force = np.zeros((self.nmols, 3))
+        torque = np.zeros((max(nmols_r, 1), 3))
+        fptr = (C.POINTER(abi.vec_mt) * nsp)()
+        tptr = (C.POINTER(abi.vec_mt) * nsp)()
+        m0 = r0 = 0
+        for i, s in enumerate(sd.species):
+            fptr[i] = C.cast(force.ctypes.data + 24 * m0, C.POINTER(abi.vec_mt))
+            if s.rdof:
+                tptr[i] = C.cast(torque.ctypes.data + 24 * r0, C.POINTER(abi.vec_mt))
+                r0 += s.nmols
+            else:
+                spec[i].quat = C.POINTER(abi.quat_mt)()
+            m0 += s.nmols
+        pe = np.zeros(abi.NPE)
+        dip = np.zeros(3)
+        stress = np.zeros((3, 3))
+        DP = C.POINTER(C.c_double)
+        args = (C.byref(sysm), spec, site_info, pot, pe.ctypes.data_as(DP), dip.ctypes.data_as(DP),
+                stress.ctypes.data_as(C.POINTER(abi.vec_mt)), fptr, tptr)
+        self._keep += [sysm, site_info, fptr, tptr]
+        return args, dict(pe=pe, dip_mom=dip, stress=stress, force=force, torque=torque[:nmols_r])
+
     # ---- replication ----
     def replicate(self, nx, ny=None, nz=None, jitter=0.0, seed=0) -> "MoldySystem":
         """Periodic replication nx*ny*nz with optional rigid-molecule jitter (A)."""

@@ -26,13 +26,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
 
 
-def available(fast: bool = False) -> bool:
-    return os.path.exists(os.path.join(REF_DIR, "libmoldyref_fast.so" if fast else "libmoldyref.so"))
+def available(fast: bool = False, evalf: bool = False) -> bool:
+    return os.path.exists(os.path.join(REF_DIR, "libmoldyref_evalf.so" if evalf else
+                                       "libmoldyref_fast.so" if fast else "libmoldyref.so"))
 
 
 class RefLib:
-    def __init__(self, fast: bool = False):
-        src = os.path.join(REF_DIR, "libmoldyref_fast.so" if fast else "libmoldyref.so")
+    def __init__(self, fast: bool = False, evalf: bool = False):
+        """evalf: load libmoldyref_evalf.so instead -- the same hot-path files plus the reference's accel.c, algorith.c,
+        quaterns.c and leapfrog.c compiled in place, for eval_forces() (src/accel.c:398-617)."""
+        src = os.path.join(REF_DIR, "libmoldyref_evalf.so" if evalf else
+                           "libmoldyref_fast.so" if fast else "libmoldyref.so")
         if not os.path.exists(src):
             raise FileNotFoundError(f"{src} missing: run `make -C oracle ref` where /root/reference exists")
         fd, self._tmp = tempfile.mkstemp(suffix=".so", prefix="moldyref_")
@@ -97,6 +101,16 @@ class RefLib:
             self.lib.rdf_ptr.restype = C.POINTER(C.c_float)
             base = self.lib.rdf_ptr(C.byref(size))
             out["rdf"] = np.ctypeslib.as_array(base, shape=(size.value,)).copy().reshape(-1, int(rdf[1]))
+        return out
+
+    def eval_forces(self, ms):
+        """The reference's own eval_forces() on the configuration (needs RefLib(evalf=True)): pe[2], dip_mom[3],
+        stress[3,3], molecular force[nmols,3], torque[nmols_r,3]."""
+        ms.control.fill(self.control)
+        args, out = ms.eval_forces_args()
+        self.lib.eval_forces.restype = None
+        self.lib.eval_forces(*args)
+        out["log"] = self.log()
         return out
 
     def cell_ids(self, ms, sites=None) -> np.ndarray:

@@ -1,0 +1,41 @@
+"""Oracle of SURVEY 8f rank 1 (the whole of eval_forces): the restatement oracle/evalf.py -- the reference's own
+force_calc/ewald plus the molecular-frame steps written the way the device path evaluates them -- against the
+reference's eval_forces() (src/accel.c:398-617) compiled in place into oracle/_ref/libmoldyref_evalf.so.  Pins the
+per-molecule form of the site->molecular virial, the dipole/surface-dipole term and the distant-potential constants."""
+import numpy as np
+import pytest
+
+from oracle import ref as refmod
+from tests import cases
+
+pytestmark = pytest.mark.skipif(not refmod.available(evalf=True), reason="oracle/_ref/libmoldyref_evalf.so not built")
+
+
+def _rel(a, b):
+    s = max(float(np.abs(b).max()), 1e-300)
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max()) / s
+
+
+@pytest.mark.parametrize("surface_dipole", [0, 1])
+@pytest.mark.parametrize("name", ["argon", "tip4p", "mgcl2", "quartz", "slab_framework"])
+def test_restated_eval_forces_matches_reference(name, surface_dipole):
+    from oracle import evalf
+    ms = cases.GOLDEN_CASES[name]()
+    ms.control.surface_dipole = surface_dipole
+    want = refmod.RefLib(evalf=True).eval_forces(ms)
+    got = evalf.eval_forces(ms)
+    assert _rel(got["force"], want["force"]) < 1e-12
+    if want["torque"].size:
+        assert _rel(got["torque"], want["torque"]) < 1e-12
+    assert _rel(got["pe"], want["pe"]) < 1e-12
+    # the reference subtracts two O(N L f) sums; the per-molecule form has no such cancellation
+    assert _rel(got["stress"], want["stress"]) < 1e-10
+    assert np.abs(got["dip_mom"] - want["dip_mom"]).max() < 1e-9 * max(1.0, np.abs(want["dip_mom"]).max())
+
+
+def test_reference_eval_forces_notes_tip4p():
+    """The first call prints the distant-potential note before force_calc's own notes (src/accel.c:449-451)."""
+    ms = cases.GOLDEN_CASES["tip4p"]()
+    log = refmod.RefLib(evalf=True).eval_forces(ms)["log"]
+    assert "Distant potential correction" in log
+    assert log.index("Distant potential correction") < log.index("Ewald self-energy")
