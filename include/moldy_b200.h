@@ -272,6 +272,12 @@ int    mdb_set_species(mdb_engine *e, int nspecies, const mdb_species *sp, const
 size_t mdb_eval_result_doubles(const mdb_engine *e);
 int    mdb_eval_forces_host(mdb_engine *e, const double h[9], const double *const *com, const double *const *quat,
                             int surface_dipole, int do_recip, double *h_result, void *stream);
+/* One-shot: the next mdb_eval_forces_host also runs the RDF pass (mdb_rdf_counts) on its cell lists, between the force
+ * sums and the second make_sites, into h_counts (HOST, mdb_rdf_size() entries). */
+void   mdb_eval_request_rdf(mdb_engine *e, double limit, int nbins, unsigned long long *h_counts);
+/* eval_forces() under a name of the library's own (for a trampoline object). */
+void   mdb_eval_forces_moldy(system_mp sys, spec_mt *species, site_mt *site_info, pot_mt *potpar, double *pe, real *dip_mom,
+                             mat_mt stress, vec_mp *force, vec_mp *torque);
 /* The library's own pinned copy of the last result (valid until the next call); pass h_result = NULL above to skip
  * the copy into caller memory. */
 const double *mdb_eval_result(const mdb_engine *e);

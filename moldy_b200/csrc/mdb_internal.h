@@ -151,6 +151,7 @@ struct mdb_engine {
       double *d_pfs = nullptr, *d_in = nullptr, *d_res = nullptr, *d_vpart = nullptr, *d_dpart = nullptr;
       double *h_in = nullptr, *h_res = nullptr;                                   // pinned
       size_t in_cap = 0, res_cap = 0;
+      double rdf_limit = 0.0; int rdf_nbins = 0; unsigned long long *rdf_counts = nullptr;   // one-shot RDF request
    } mf;
 
    // pinned staging for host-facing calls

@@ -200,12 +200,11 @@ __global__ void __launch_bounds__(MB)
 k_dipole_finish(const double *__restrict__ part, int nb, double *__restrict__ scal)
 {
    __shared__ double sh[MB / 32];
-   for (int c = 0; c < 3; c++) {
-      double v = 0.0;
-      for (int k = threadIdx.x; k < nb; k += MB) v += part[3 * k + c];
-      v = block_sum(v, sh);
-      if (threadIdx.x == 0) scal[c] = v;
-   }
+   const int c = blockIdx.x;                       // one block per component
+   double v = 0.0;
+   for (int k = threadIdx.x; k < nb; k += MB) v += part[3 * k + c];
+   v = block_sum(v, sh);
+   if (threadIdx.x == 0) scal[c] = v;
 }
 
 // One thread per molecule of one species.  f' = f - (coef dip_i) chg (surface-dipole term, src/accel.c:553-555);
@@ -261,18 +260,18 @@ k_mol_frame(const double *__restrict__ fx, const double *__restrict__ fy, const 
    }
 }
 
-// scal[3..11] = sum of the virial partials; scal[12..22] = pe_real, pe_recip, stress[9] of the result block
+// scal[3..11] = sum of the virial partials (one block per component); scal[12..22] = pe_real, pe_recip, stress[9] of the
+// result block
 __global__ void __launch_bounds__(MB)
 k_eval_finish(const double *__restrict__ vpart, int nb, const double *__restrict__ out_scal, double *__restrict__ scal)
 {
    __shared__ double sh[MB / 32];
-   for (int c = 0; c < 9; c++) {
-      double v = 0.0;
-      for (int k = threadIdx.x; k < nb; k += MB) v += vpart[9 * (size_t)k + c];
-      v = block_sum(v, sh);
-      if (threadIdx.x == 0) scal[3 + c] = v;
-   }
-   if (threadIdx.x < 11) scal[12 + threadIdx.x] = out_scal[threadIdx.x];
+   const int c = blockIdx.x;
+   double v = 0.0;
+   for (int k = threadIdx.x; k < nb; k += MB) v += vpart[9 * (size_t)k + c];
+   v = block_sum(v, sh);
+   if (threadIdx.x == 0) scal[3 + c] = v;
+   if (c == 0 && threadIdx.x < 11) scal[12 + threadIdx.x] = out_scal[threadIdx.x];
 }
 
 extern "C" int mdb_set_species(mdb_engine *e, int nspecies, const mdb_species *sp, const double *pfs)
@@ -324,6 +323,11 @@ extern "C" int mdb_set_species(mdb_engine *e, int nspecies, const mdb_species *s
       e->out_cap = need_out;
    }
    return 0;
+}
+
+extern "C" void mdb_eval_request_rdf(mdb_engine *e, double limit, int nbins, unsigned long long *h_counts)
+{
+   e->mf.rdf_limit = limit; e->mf.rdf_nbins = nbins; e->mf.rdf_counts = h_counts;
 }
 
 extern "C" size_t mdb_eval_result_doubles(const mdb_engine *e)
@@ -399,6 +403,11 @@ extern "C" int mdb_eval_forces_host(mdb_engine *e, const double h[9], const doub
    double *d_out = e->d_out_own;
    if (mdb_zero_out(e, d_out, stream) || mdb_build_cells(e, stream) || mdb_force_real(e, d_out, stream)) return -1;
    if (do_recip && mdb_force_recip(e, d_out, stream)) return -1;
+   if (M.rdf_counts) {                         // RDF pass of force_calc on this step's cell lists (synchronises)
+      unsigned long long *dst = M.rdf_counts;
+      M.rdf_counts = nullptr;
+      if (mdb_rdf_counts(e, M.rdf_limit, M.rdf_nbins, dst, stream)) return -1;
+   }
 
    double *scal = M.d_res + 3 * (size_t)M.nmols + 3 * (size_t)M.nmols_r;
    MDB_CUDA(cudaMemsetAsync(scal, 0, sizeof(double) * MDB_EVAL_SCALARS, st));
@@ -406,7 +415,7 @@ extern "C" int mdb_eval_forces_host(mdb_engine *e, const double h[9], const doub
    if (do_recip) {
       if (make_all_sites(e, h, true, st)) return -1;
       k_dipole_partial<<<DIP_BLOCKS, MB, 0, st>>>(e->d_x, e->d_y, e->d_z, e->d_chg, (int)n, M.d_dpart);
-      k_dipole_finish<<<1, MB, 0, st>>>(M.d_dpart, DIP_BLOCKS, scal);
+      k_dipole_finish<<<3, MB, 0, st>>>(M.d_dpart, DIP_BLOCKS, scal);
       e->launches += 2;
       if (surface_dipole) coef = 4.0 * MDB_PI / (3.0 * mdb_det3(h));
    }
@@ -422,7 +431,7 @@ extern "C" int mdb_eval_forces_host(mdb_engine *e, const double h[9], const doub
          M.d_vpart + 9 * (size_t)M.blk_off[i]);
       e->launches++;
    }
-   k_eval_finish<<<1, MB, 0, st>>>(M.d_vpart, M.nblocks, d_out + 3 * n, scal);
+   k_eval_finish<<<9, MB, 0, st>>>(M.d_vpart, M.nblocks, d_out + 3 * n, scal);
    e->launches++;
    MDB_CUDA(cudaGetLastError());
    const size_t nres = mdb_eval_result_doubles(e);

@@ -1,6 +1,6 @@
 // moldy_abi.cu -- layer (A) of include/moldy_b200.h: Moldy's own entry points
-// (force_calc, ewald, kernel, poteval, dist_pot, potspec, pot_dim) on top of the
-// device engine.  Linked in place of force.o / kernel.o / ewald.o the rest of
+// (force_calc, ewald, kernel, poteval, dist_pot, potspec, pot_dim, and eval_forces
+// one level up) on top of the device engine.  Linked in place of force.o / kernel.o / ewald.o the rest of
 // Moldy is unchanged.  There is no CPU path: if no CUDA device
 // can be opened every entry point reports FATAL through Moldy's message().
 //
@@ -271,6 +271,33 @@ static void pull_and_accumulate(real **site_force, double *pe, real (*stress)[3]
    stress[1][1] += sc[6]; stress[1][2] += sc[7]; stress[2][2] += sc[10];
 }
 
+/* Radial distribution functions, src/force.c:1302-1313 + src/rdf.c:94-108.  The pairs are binned on the device;
+ * count/density is added to the host program's float histograms in one step (the reference adds 1/density pair by
+ * pair in single precision, so it rounds differently). */
+static bool rdf_due()
+{
+   return control.rdf_interval > 0 && control.istep >= control.begin_rdf && control.istep % control.rdf_interval == 0;
+}
+static float *rdf_store(size_t nh)
+{
+   int rsize = 0;
+   float *rdf_base = (float *)rdf_ptr(&rsize);
+   if (rdf_base && (size_t)rsize >= nh && nh > 0) return rdf_base;
+   if (!G.rdf_warned) {
+      message((int *)0, (char *)0, SEV_WARNING, (char *)"libmoldy_b200: no RDF store (rdf_ptr) to accumulate into");
+      G.rdf_warned = true;
+   }
+   return nullptr;
+}
+static void rdf_add_counts(system_mt *system, float *rdf_base, const std::vector<unsigned long long> &cnt)
+{
+   const double hm[9] = {system->h[0][0], system->h[0][1], system->h[0][2], system->h[1][0], system->h[1][1],
+                         system->h[1][2], system->h[2][0], system->h[2][1], system->h[2][2]};
+   const double invrho = 1.0 / (system->nsites / mdb_det3(hm));
+   for (size_t k = 0; k < cnt.size(); k++)
+      if (cnt[k]) rdf_base[k] = (float)(rdf_base[k] + (double)cnt[k] * invrho);
+}
+
 // First-call constant and notes of force_calc (src/force.c:1158-1169, 218-223, 1240-1243)
 static void real_first_call(system_mt *system, spec_mt *species, const real *chg, pot_mt *potpar)
 {
@@ -369,26 +396,13 @@ extern "C" void force_calc(real **site, real **site_force, system_mt *system, sp
       message((int *)0, (char *)0, SEV_WARNING, (char *)"Sites %d and %d closer than %fA.", pr[0], pr[1],
               sqrt(MDB_TOO_CLOSE));
 
-   /* Accumulate radial distribution functions, src/force.c:1302-1313 + src/rdf.c:94-108.  The pairs are
-    * binned on the device; count/density is added to the host program's float histograms in one step
-    * (the reference adds 1/density pair by pair in single precision, so it rounds differently). */
-   if (control.rdf_interval > 0 && control.istep >= control.begin_rdf &&
-       control.istep % control.rdf_interval == 0) {
-      int rsize = 0;
-      float *rdf_base = (float *)rdf_ptr(&rsize);
-      const size_t nh = mdb_rdf_size(G.eng, control.nbins);
-      if (rdf_base && (size_t)rsize >= nh && nh > 0) {
-         std::vector<unsigned long long> cnt(nh, 0ULL);
+   if (rdf_due()) {
+      float *rdf_base = rdf_store(mdb_rdf_size(G.eng, control.nbins));
+      if (rdf_base) {
+         std::vector<unsigned long long> cnt(mdb_rdf_size(G.eng, control.nbins), 0ULL);
          if (mdb_rdf_counts(G.eng, control.limit, control.nbins, cnt.data(), G.stream))
             FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
-         const double hm[9] = {system->h[0][0], system->h[0][1], system->h[0][2], system->h[1][0], system->h[1][1],
-                               system->h[1][2], system->h[2][0], system->h[2][1], system->h[2][2]};
-         const double invrho = 1.0 / (system->nsites / mdb_det3(hm));
-         for (size_t k = 0; k < nh; k++)
-            if (cnt[k]) rdf_base[k] = (float)(rdf_base[k] + (double)cnt[k] * invrho);
-      } else if (!G.rdf_warned) {
-         message((int *)0, (char *)0, SEV_WARNING, (char *)"libmoldy_b200: no RDF store (rdf_ptr) to accumulate into");
-         G.rdf_warned = true;
+         rdf_add_counts(system, rdf_base, cnt);
       }
    }
 }
@@ -560,8 +574,11 @@ static EvalState E;
 
 #define CONV_P_MPA (1.6605402e-27 / (1.0e-10 * 1.0e-12 * 1.0e-12) / 1.0e6)   /* src/defs.h:231 CONV_P */
 
-extern "C" void eval_forces(system_mp sys, spec_mt *species, site_mt *site_info, pot_mt *potpar, double *pe,
-                            real *dip_mom, mat_mt stress, vec_mp *force, vec_mp *torque)
+// Internal linkage on purpose: when the host program carries its own `eval_forces` symbol (the trampoline of
+// evalf_tramp.c), a call to the exported name from inside the library would bind to the program's definition and
+// recurse; both exported names below call this function directly.
+static void eval_forces_impl(system_mp sys, spec_mt *species, site_mt *site_info, pot_mt *potpar, double *pe,
+                             real *dip_mom, mat_mt stress, vec_mp *force, vec_mp *torque)
 {
    const int n = sys->nsites, nspecies = sys->nspecies;
    double h9[9];
@@ -625,10 +642,17 @@ extern "C" void eval_forces(system_mp sys, spec_mt *species, site_mt *site_info,
       quat[i] = species[i].quat ? &species[i].quat[0][0] : nullptr;
    }
    G.sites_fresh = false; G.ahead_valid = false;          /* the engine's sites are no longer the ones force_calc uploaded */
+   std::vector<unsigned long long> rdf_cnt;
+   float *rdf_base = nullptr;
+   if (rdf_due() && (rdf_base = rdf_store(mdb_rdf_size(G.eng, control.nbins))) != nullptr) {
+      rdf_cnt.assign(mdb_rdf_size(G.eng, control.nbins), 0ULL);   /* binned between the force sums and the second make_sites */
+      mdb_eval_request_rdf(G.eng, control.limit, control.nbins, rdf_cnt.data());
+   }
    if (mdb_eval_forces_host(G.eng, h9, com.data(), quat.data(), control.surface_dipole ? 1 : 0, do_recip ? 1 : 0,
                             nullptr, G.stream))
       FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
    const double tc2 = now_ms();
+   if (rdf_base) rdf_add_counts(sys, rdf_base, rdf_cnt);
 
    int pr[2];
    const int tc = mdb_too_close(G.eng, pr, G.stream);
@@ -644,14 +668,30 @@ extern "C" void eval_forces(system_mp sys, spec_mt *species, site_mt *site_info,
    for (int i = 0; i < nspecies; i++) nmols += species[i].nmols;
    for (int i = 0; i < nspecies; i++) nmols_r += species[i].rdof > 0 ? species[i].nmols : 0;
    {
+      struct Job { double *dst; const double *src; size_t n; };
+      std::vector<Job> jobs;
       const double *f = res, *t = res + 3 * (size_t)nmols;
       for (int i = 0; i < nspecies; i++) {
-         memcpy(&force[i][0][0], f, sizeof(double) * 3 * (size_t)species[i].nmols);
+         jobs.push_back({&force[i][0][0], f, 3 * (size_t)species[i].nmols});
          f += 3 * (size_t)species[i].nmols;
          if (species[i].rdof > 0) {
-            memcpy(&torque[i][0][0], t, sizeof(double) * 3 * (size_t)species[i].nmols);
+            jobs.push_back({&torque[i][0][0], t, 3 * (size_t)species[i].nmols});
             t += 3 * (size_t)species[i].nmols;
          }
+      }
+      auto run = [&](int part, int nparts) {
+         for (auto &j : jobs) {
+            const size_t lo = j.n * part / nparts, hi = j.n * (part + 1) / nparts;
+            memcpy(j.dst + lo, j.src + lo, sizeof(double) * (hi - lo));
+         }
+      };
+      if (nmols >= 65536) {                   /* 12 MB at 10^6 sites: four threads */
+         std::thread th[3];
+         for (int k = 1; k < 4; k++) th[k - 1] = std::thread(run, k, 4);
+         run(0, 4);
+         for (auto &th_k : th) th_k.join();
+      } else {
+         run(0, 1);
       }
    }
    const double *sc = res + 3 * (size_t)nmols + 3 * (size_t)nmols_r;
@@ -679,6 +719,20 @@ extern "C" void eval_forces(system_mp sys, spec_mt *species, site_mt *site_info,
    if (g_timing)
       fprintf(stderr, "[moldy_b200] eval_forces: config %.2f ms, device (H2D .. D2H) %.2f ms, results %.2f ms\n", tc1 - tc0,
               tc2 - tc1, now_ms() - tc2);
+}
+
+// The same function under a name of the library's own: a host program that keeps its own (weakened) eval_forces can
+// still reach this one through a one-line trampoline object (moldy_b200/csrc/evalf_tramp.c).
+extern "C" void mdb_eval_forces_moldy(system_mp sys, spec_mt *species, site_mt *site_info, pot_mt *potpar, double *pe,
+                                      real *dip_mom, mat_mt stress, vec_mp *force, vec_mp *torque)
+{
+   eval_forces_impl(sys, species, site_info, potpar, pe, dip_mom, stress, force, torque);
+}
+
+extern "C" void eval_forces(system_mp sys, spec_mt *species, site_mt *site_info, pot_mt *potpar, double *pe,
+                            real *dip_mom, mat_mt stress, vec_mp *force, vec_mp *torque)
+{
+   eval_forces_impl(sys, species, site_info, potpar, pe, dip_mom, stress, force, torque);
 }
 
 // ---- test/bench accessors ------------------------------------------------------

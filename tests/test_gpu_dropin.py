@@ -4,6 +4,11 @@ against libmoldy_b200.so INSTEAD of force.o / kernel.o / ewald.o (oracle/Makefil
 section 2).  It is run next to the all-CPU reference binary oracle/_ref/moldy on the same control
 and sys-spec files:
 
+oracle/_ref/moldy_gpu_evalf goes one level up: the same unmodified
+sources, but eval_forces() itself (src/accel.c:398-617) is the library's -- accel.c's own definition is weakened with
+objcopy and a one-function trampoline object forwards to libmoldy_b200.so, so only centres of mass and quaternions
+go to the device and molecular forces and torques come back.  Every test below runs for both programs.
+
   * short run: every number both programs print (energies, temperatures, stress) must agree;
   * NVE run: total-energy drift of the GPU-linked program no worse than the reference's
     (north_star: "10k-step NVE energy drift no worse than the reference's"; the step count is
@@ -22,6 +27,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "oracle", "_ref", "moldy")
 GPU = os.path.join(ROOT, "oracle", "_ref", "moldy_gpu")
+GPU_EVALF = os.path.join(ROOT, "oracle", "_ref", "moldy_gpu_evalf")
 
 CONTROL = """title=drop-in test
 surface-dipole=1
@@ -55,7 +61,7 @@ def _run(binary, tmp, nsteps, every, rdf=0, rdfout=1000000):
     shutil.copy(os.path.join(ROOT, "tests", "golden", "tip4p_256_eq.txt"), d)
     with open(os.path.join(d, "control"), "w") as f:
         f.write(CONTROL.format(nsteps=nsteps, every=every, rdf=rdf, rdfout=rdfout))
-    out = subprocess.run([binary, "control"], cwd=d, capture_output=True, text=True, timeout=3000)
+    out = subprocess.run([binary, "control"], cwd=d, capture_output=True, text=True, timeout=240 + nsteps // 4)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     return out.stdout
 
@@ -73,14 +79,16 @@ def _current_values(text):
     return res
 
 
-needs_binaries = pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(GPU)),
-                                    reason="oracle/_ref/moldy{,_gpu} not built (make -C oracle ref)")
+needs_binaries = pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(GPU) and os.path.exists(GPU_EVALF)),
+                                    reason="oracle/_ref/moldy{,_gpu,_gpu_evalf} not built (make -C oracle ref)")
+both = pytest.mark.parametrize("gpu_binary", [GPU, GPU_EVALF], ids=["force_calc+ewald", "eval_forces"])
 
 
 @needs_binaries
-def test_unmodified_moldy_linked_against_the_library_prints_the_same_run(tmp_path):
+@both
+def test_unmodified_moldy_linked_against_the_library_prints_the_same_run(tmp_path, gpu_binary):
     a = _run(REF, str(tmp_path), 40, 10)
-    b = _run(GPU, str(tmp_path), 40, 10)
+    b = _run(gpu_binary, str(tmp_path), 40, 10)
     va, vb = _current_values(a), _current_values(b)
     assert sorted(va) == sorted(vb) == [10, 20, 30, 40]
     for step in va:
@@ -94,11 +102,12 @@ def test_unmodified_moldy_linked_against_the_library_prints_the_same_run(tmp_pat
 
 
 @needs_binaries
-def test_nve_energy_drift_no_worse_than_reference(tmp_path):
+@both
+def test_nve_energy_drift_no_worse_than_reference(tmp_path, gpu_binary):
     nsteps = int(os.environ.get("MOLDY_B200_NVE_STEPS", "2000"))
     every = max(1, nsteps // 20)
     ea = _current_values(_run(REF, str(tmp_path), nsteps, every))
-    eb = _current_values(_run(GPU, str(tmp_path), nsteps, every))
+    eb = _current_values(_run(gpu_binary, str(tmp_path), nsteps, every))
     steps = sorted(ea)
     tot_a = np.array([ea[s][3] for s in steps])           # "Energy E" column, kJ/mol
     tot_b = np.array([eb[s][3] for s in steps])
@@ -129,14 +138,15 @@ def _rdf_tables(text):
 
 
 @needs_binaries
-def test_rdf_pass_inside_force_calc_prints_the_same_tables(tmp_path):
+@both
+def test_rdf_pass_inside_force_calc_prints_the_same_tables(tmp_path, gpu_binary):
     """rdf-interval > 0: force_calc's RDF pass (src/force.c:1302-1313) feeds the host program's own
     rdf.c store; the tables print_rdf writes must agree with the all-CPU binary.  The reference adds
     1/density to a float histogram pair by pair (bins of ~1e4 pairs carry ~1e-5 relative rounding
     noise), the library adds count/density once: compare to 3e-4; the pair COUNTS are compared exactly
     in test_gpu_parity.py::test_rdf_pass_pair_counts_exact."""
     a = _rdf_tables(_run(REF, str(tmp_path), 20, 10, rdf=2, rdfout=10))
-    b = _rdf_tables(_run(GPU, str(tmp_path), 20, 10, rdf=2, rdfout=10))
+    b = _rdf_tables(_run(gpu_binary, str(tmp_path), 20, 10, rdf=2, rdfout=10))
     assert a and sorted(a) == sorted(b)
     for key in a:
         assert len(a[key]) == len(b[key]) == 2
