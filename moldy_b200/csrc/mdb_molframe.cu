@@ -296,6 +296,7 @@ extern "C" int mdb_set_species(mdb_engine *e, int nspecies, const mdb_species *s
    M.nmols = mo; M.nmols_q = qo; M.nmols_r = to; M.npfs = po; M.nblocks = bo;
    if (M.d_pfs) cudaFree(M.d_pfs);
    if (M.d_vpart) cudaFree(M.d_vpart);
+   M.d_pfs = M.d_vpart = nullptr;
    if (!M.d_dpart) MDB_CUDA(cudaMalloc(&M.d_dpart, sizeof(double) * 3 * DIP_BLOCKS));
    MDB_CUDA(cudaMalloc(&M.d_pfs, sizeof(double) * 3 * (size_t)std::max(po, 1)));
    MDB_CUDA(cudaMalloc(&M.d_vpart, sizeof(double) * 9 * (size_t)std::max(bo, 1)));
@@ -304,6 +305,7 @@ extern "C" int mdb_set_species(mdb_engine *e, int nspecies, const mdb_species *s
    if (need_in > M.in_cap) {
       if (M.d_in) cudaFree(M.d_in);
       if (M.h_in) cudaFreeHost(M.h_in);
+      M.d_in = M.h_in = nullptr; M.in_cap = 0;
       MDB_CUDA(cudaMalloc(&M.d_in, sizeof(double) * need_in));
       MDB_CUDA(cudaMallocHost(&M.h_in, sizeof(double) * need_in));
       M.in_cap = need_in;
@@ -311,6 +313,7 @@ extern "C" int mdb_set_species(mdb_engine *e, int nspecies, const mdb_species *s
    if (need_res > M.res_cap) {
       if (M.d_res) cudaFree(M.d_res);
       if (M.h_res) cudaFreeHost(M.h_res);
+      M.d_res = M.h_res = nullptr; M.res_cap = 0;
       MDB_CUDA(cudaMalloc(&M.d_res, sizeof(double) * need_res));
       MDB_CUDA(cudaMallocHost(&M.h_res, sizeof(double) * need_res));
       M.res_cap = need_res;
@@ -318,7 +321,7 @@ extern "C" int mdb_set_species(mdb_engine *e, int nspecies, const mdb_species *s
    const size_t need_out = mdb_out_doubles(e->cfg.nsites);
    if (need_out > e->out_cap) {
       if (e->d_out_own) cudaFree(e->d_out_own);
-      e->d_out_own = nullptr;
+      e->d_out_own = nullptr; e->out_cap = 0;
       MDB_CUDA(cudaMalloc(&e->d_out_own, sizeof(double) * need_out));
       e->out_cap = need_out;
    }

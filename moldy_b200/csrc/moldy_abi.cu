@@ -625,15 +625,22 @@ static void eval_forces_impl(system_mp sys, spec_mt *species, site_mt *site_info
    if (do_recip) recip_first_call(sys, species, E.chg.data(), vol);
 
    if (E.species_epoch != G.config_epoch || (int)E.sp.size() != nspecies) {
-      E.sp.resize(nspecies);
-      E.pfs.clear();
+      // the engine was reconfigured (every step under constant-stress dynamics: the cell matrix changes); the species table
+      // and its device buffers depend on the system definition only and are rebuilt only when that changed
+      std::vector<mdb_species> sp_new(nspecies);
+      std::vector<double> pfs_new;
       for (int i = 0; i < nspecies; i++) {
          const spec_mt &sp = species[i];
-         E.sp[i] = mdb_species{sp.nmols, sp.nsites, sp.framework ? 1 : 0, sp.quat ? 1 : 0, sp.rdof};
+         sp_new[i] = mdb_species{sp.nmols, sp.nsites, sp.framework ? 1 : 0, sp.quat ? 1 : 0, sp.rdof};
          for (int is = 0; is < sp.nsites; is++)
-            for (int k = 0; k < 3; k++) E.pfs.push_back(sp.p_f_sites[is][k]);
+            for (int k = 0; k < 3; k++) pfs_new.push_back(sp.p_f_sites[is][k]);
       }
-      if (mdb_set_species(G.eng, nspecies, E.sp.data(), E.pfs.data())) FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+      const bool same = sp_new.size() == E.sp.size() && pfs_new == E.pfs &&
+                        !memcmp(sp_new.data(), E.sp.data(), sizeof(mdb_species) * sp_new.size());
+      if (!same) {
+         E.sp.swap(sp_new); E.pfs.swap(pfs_new);
+         if (mdb_set_species(G.eng, nspecies, E.sp.data(), E.pfs.data())) FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+      }
       E.species_epoch = G.config_epoch;
    }
    std::vector<const double *> com(nspecies), quat(nspecies);
