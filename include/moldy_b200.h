@@ -7,6 +7,9 @@
  *  (A) Moldy's own symbols.  Linking libmoldy_b200.so in place of force.o,
  *      kernel.o and ewald.o (moldy_SOURCES, src/Makefile.am:17) leaves the rest
  *      of Moldy unchanged.  Each prototype cites the definition it replaces.
+ *      One level up, eval_forces() (src/accel.c:398) is exported as well: with
+ *      it the sites and site forces stay in HBM and only molecular data cross
+ *      PCIe (declared after the mdb_ building blocks it is made of).
  *  (B) mdb_* : the device-resident engine underneath (A), for callers that keep
  *      positions and forces in HBM (bench.py `value`, multi-GPU ranks that
  *      all-reduce the packed result with NCCL).

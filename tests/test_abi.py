@@ -25,7 +25,8 @@ def test_library_exports_every_declared_symbol():
     L = lib.load()
     syms = _declared_symbols()
     for must in ("force_calc", "ewald", "kernel", "poteval", "dist_pot", "potspec", "pot_dim",
-                 "mdb_create", "mdb_configure", "mdb_force_real", "mdb_force_recip"):
+                 "mdb_create", "mdb_configure", "mdb_force_real", "mdb_force_recip",
+                 "eval_forces", "mdb_eval_forces_moldy", "mdb_set_species", "mdb_eval_forces_host", "mdb_eval_result"):
         assert must in syms, f"{must} not parsed from the header"
     for s in syms:
         assert hasattr(L, s), f"libmoldy_b200.so does not export {s}"
