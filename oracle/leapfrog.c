@@ -156,3 +156,53 @@ int orc_leapf_quat(double step, double *quat, double *amom, const double *inerti
    }
    return bad;
 }
+
+/* ---- kinetic-energy reductions the step needs from the momenta (values()/do_step: tot_ke, stress_kin, src/accel.c:330-357)
+ *   orc_trans_ke     trans_ke    src/algorith.c:221-239   p = (h^-1)' mom (mat_vec_mul src/matrix.c:46-90), sum p.p / (2 m s^2)
+ *   orc_rot_ke       rot_ke      src/algorith.c:244-257
+ *   orc_energy_dyad  energy_dyad src/algorith.c:261-284   ke_dyad[i][j] += sum p_i p_j / (m s^2)
+ * Sequential sums in the reference's order (vdot, src/auxil.c: generic version); a device reduction is compared with
+ * these to a tolerance, not bit for bit. */
+static void lf_real_mom(const double *h9, const double *mom, int m, double p[3])
+{
+   double h[3][3], hi[3][3];
+   for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) h[i][j] = h9[3 * i + j];
+   lf_invert(h, hi);
+   const double *x = mom + 3 * m;
+   for (int i = 0; i < 3; i++) p[i] = hi[0][i] * x[0] + hi[1][i] * x[1] + hi[2][i] * x[2];     /* transposed inverse */
+}
+
+double orc_trans_ke(const double *h9, const double *mom, double s, double mass, int nmols)
+{
+   double ke = 0.0, p[3];
+   for (int m = 0; m < nmols; m++) {
+      lf_real_mom(h9, mom, m, p);
+      ke += p[0] * p[0]; ke += p[1] * p[1]; ke += p[2] * p[2];
+   }
+   return ke / (2.0 * mass * (s * s));
+}
+
+double orc_rot_ke(const double *amom, double s, const double *inertia, int nmols)
+{
+   double ke = 0.0;
+   for (int i = 0; i < 3; i++)
+      if (inertia[i] > INERTIA_MIN) {
+         double dot = 0.0;
+         for (int m = 0; m < nmols; m++) dot += amom[4 * m + i + 1] * amom[4 * m + i + 1];
+         ke += dot / inertia[i];
+      }
+   return 0.5 * ke / (s * s);
+}
+
+void orc_energy_dyad(double *ke_dyad9, const double *h9, double s, const double *mom, double mass, int nmols)
+{
+   double dot[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, p[3];
+   for (int m = 0; m < nmols; m++) {
+      lf_real_mom(h9, mom, m, p);
+      for (int i = 0; i < 3; i++)
+         for (int j = 0; j < 3; j++) dot[i][j] += p[i] * p[j];
+   }
+   for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) ke_dyad9[3 * i + j] += dot[i][j] / (mass * (s * s));
+}

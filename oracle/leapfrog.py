@@ -92,3 +92,45 @@ def leapf_quat(step, quat, amom, inertia, ts, symmetric=True, saxis=None):
         saxis = symmetry_axis(inertia)
     bad = _port().orc_leapf_quat(step, _p(quat), _p(amom), _p(_c(inertia)), ts, len(quat), 1 if symmetric else 0, saxis)
     return quat, amom, bad
+
+
+# ---- kinetic-energy reductions (trans_ke, rot_ke, energy_dyad: src/algorith.c:221-284) ----
+def trans_ke(h, mom, s, mass, impl="port", ref=None):
+    h, mom = _c(h), _c(mom)
+    if impl == "port":
+        L = _port()
+        L.orc_trans_ke.restype = C.c_double
+        L.orc_trans_ke.argtypes = [DP, DP, C.c_double, C.c_double, C.c_int]
+        return L.orc_trans_ke(_p(h), _p(mom), s, mass, len(mom))
+    L = (ref or Ref()).R.lib
+    L.trans_ke.restype = C.c_double
+    L.trans_ke.argtypes = [DP, DP, C.c_double, C.c_double, C.c_int]
+    return L.trans_ke(_p(h), _p(mom), s, mass, len(mom))
+
+
+def rot_ke(amom, s, inertia, impl="port", ref=None):
+    amom, inertia = _c(amom), _c(inertia)
+    if impl == "port":
+        L = _port()
+        L.orc_rot_ke.restype = C.c_double
+        L.orc_rot_ke.argtypes = [DP, C.c_double, DP, C.c_int]
+        return L.orc_rot_ke(_p(amom), s, _p(inertia), len(amom))
+    L = (ref or Ref()).R.lib
+    L.rot_ke.restype = C.c_double
+    L.rot_ke.argtypes = [DP, C.c_double, DP, C.c_int]
+    return L.rot_ke(_p(amom), s, _p(inertia), len(amom))
+
+
+def energy_dyad(h, s, mom, mass, impl="port", ref=None):
+    h, mom = _c(h), _c(mom)
+    out = np.zeros((3, 3))
+    if impl == "port":
+        L = _port()
+        L.orc_energy_dyad.argtypes = [DP, DP, C.c_double, DP, C.c_double, C.c_int]
+        L.orc_energy_dyad(_p(out), _p(h), s, _p(mom), mass, len(mom))
+    else:
+        L = (ref or Ref()).R.lib
+        L.energy_dyad.restype = None
+        L.energy_dyad.argtypes = [DP, DP, C.c_double, DP, C.c_double, C.c_int]
+        L.energy_dyad(_p(out), _p(h), s, _p(mom), mass, len(mom))
+    return out

@@ -73,3 +73,19 @@ def test_symmetry_axis_is_chosen_once_from_the_first_species():
     assert np.array_equal(q, q_ref) and np.array_equal(a, a_ref)
     q2, a2, _ = lf.leapf_quat(0.00025, quat, amom, second, 1.0)           # its own axis: a different splitting
     assert not np.array_equal(a2, a_ref)
+
+
+@pytest.mark.parametrize("h", [H_CUBIC, H_TRICLINIC], ids=["cubic", "triclinic"])
+def test_kinetic_energy_reductions_bit_identical(h):
+    """trans_ke / rot_ke / energy_dyad (src/algorith.c:221-284): what tot_ke() and stress_kin() of do_step need from the
+    momenta every step."""
+    from oracle import leapfrog as lf
+    com, mom, force, torque, quat, amom = _state(1001, 4)
+    R = lf.Ref()
+    for s, mass in [(1.0, 18.0154), (1.21, 35.453)]:
+        assert lf.trans_ke(h, mom, s, mass) == lf.trans_ke(h, mom, s, mass, impl="ref", ref=R)
+        assert np.array_equal(lf.energy_dyad(h, s, mom, mass), lf.energy_dyad(h, s, mom, mass, impl="ref", ref=R))
+    for inertia in (TIP4P_INERTIA, LINEAR):
+        assert lf.rot_ke(amom, 1.1, inertia) == lf.rot_ke(amom, 1.1, inertia, impl="ref", ref=R)
+    # trace of the dyad is twice the kinetic energy
+    assert abs(np.trace(lf.energy_dyad(h, 1.0, mom, 18.0)) - 2 * lf.trans_ke(h, mom, 1.0, 18.0)) < 1e-9 * lf.trans_ke(h, mom, 1.0, 18.0)
