@@ -30,34 +30,36 @@ def _distant_const(R, ms, iflag):
     return c
 
 
-def eval_forces(ms):
-    """pe[2], dip_mom[3], stress[3,3], force[nmols,3], torque[nmols_r,3] from the reference's force_calc/ewald
-    site forces plus the restated molecular-frame steps."""
+def _sites(ms, second):
+    """make_sites per species with the reference's own routine: first pass (control.molpbc ? MOLPBC : SITEPBC,
+    src/accel.c:500-504) or second pass (framework ? SITEPBC : MOLPBC, :537-542)."""
     from moldy_b200 import abi
-    R = refmod.RefLib()
+    out = np.zeros((3, abi.nsarray(ms.nsites)))
+    m0 = s0 = 0
+    for sp in ms.sysdef.species:
+        q = ms.quat[m0:m0 + sp.nmols] if sp.rdof else None
+        pbc = bool(sp.framework) if second else not ms.control.molpbc
+        blk = molframe.make_sites(ms.h, ms.c_of_m[m0:m0 + sp.nmols], q, sp.p_f_sites, pbc, impl="ref")
+        out[:, s0:s0 + sp.nmols * sp.nsites] = blk
+        m0 += sp.nmols
+        s0 += sp.nmols * sp.nsites
+    return out
+
+
+def tail(ms, f, pe, stress, R=None):
+    """Everything eval_forces() does after the global sums of the site forces (src/accel.c:537-608), in the device path's
+    formulation.  f[3,N], pe[2], stress[3,3] (upper triangle) are the COMPLETE sums of force_calc + ewald -- under SPMD
+    the all-reduced block -- so every rank that runs this gets the same molecular forces, torques, energies and stress."""
+    from moldy_b200.systems import quat_to_rot
+    R = R or refmod.RefLib()
     sd = ms.sysdef
-    n, nsa = ms.nsites, abi.nsarray(ms.nsites)
+    n = ms.nsites
+    f, pe, stress = np.array(f, dtype=np.float64), np.array(pe, dtype=np.float64), np.array(stress, dtype=np.float64)
     vol = abs(np.linalg.det(ms.h))
-    recip = ms.control.alpha > 1e-7
-
-    def sites(second):
-        out = np.zeros((3, nsa))
-        m0 = s0 = 0
-        for sp in sd.species:
-            q = ms.quat[m0:m0 + sp.nmols] if sp.rdof else None
-            pbc = bool(sp.framework) if second else not ms.control.molpbc
-            blk = molframe.make_sites(ms.h, ms.c_of_m[m0:m0 + sp.nmols], q, sp.p_f_sites, pbc, impl="ref")
-            out[:, s0:s0 + sp.nmols * sp.nsites] = blk
-            m0 += sp.nmols
-            s0 += sp.nmols * sp.nsites
-        return out
-
-    r = R.run(ms, sites=sites(False))
-    f, pe, stress = r["force"].copy(), r["pe"].copy(), r["stress"].copy()
     chg = ms.charges()
     dip = np.zeros(3)
-    if recip:
-        s2 = sites(True)[:, :n]
+    if ms.control.alpha > 1e-7:
+        s2 = _sites(ms, True)[:, :n]
         dip = (s2 * chg).sum(axis=1)
         if ms.control.surface_dipole:
             f -= (4.0 * np.pi / (3.0 * vol) * dip)[:, None] * chg[None, :]
@@ -75,7 +77,6 @@ def eval_forces(ms):
             torque.append(molframe.mol_torque(fs, pfs, q, impl="ref"))
         # d = site - centre of mass of the MOLPBC sites (non-framework) or the principal-frame site (framework)
         if sp.rdof and not sp.framework:
-            from moldy_b200.systems import quat_to_rot
             d = np.einsum("mij,sj->msi", quat_to_rot(q), pfs)
         else:
             d = np.broadcast_to(pfs[None], (sp.nmols, sp.nsites, 3))
@@ -88,3 +89,11 @@ def eval_forces(ms):
     stress += np.eye(3) * _distant_const(R, ms, 1) / vol
     return dict(pe=pe, dip_mom=dip, stress=stress, force=np.concatenate(force),
                 torque=np.concatenate(torque) if torque else np.zeros((0, 3)))
+
+
+def eval_forces(ms):
+    """pe[2], dip_mom[3], stress[3,3], force[nmols,3], torque[nmols_r,3] from the reference's force_calc/ewald
+    site forces plus the restated molecular-frame steps."""
+    R = refmod.RefLib()
+    r = R.run(ms, sites=_sites(ms, False))
+    return tail(ms, r["force"], r["pe"], r["stress"], R)

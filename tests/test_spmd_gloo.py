@@ -73,6 +73,65 @@ def test_two_rank_allreduce_reproduces_single_rank():
     assert np.allclose(block[3 * n + 2:3 * n + 11].reshape(3, 3), whole["stress"], rtol=1e-11, atol=1e-9)
 
 
+def _worker_evalf(rank, world, port_no, q):
+    """eval_forces under SPMD: partial site forces -> combine() -> the molecular-frame tail on EVERY rank."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from moldy_b200 import spmd
+    from oracle import evalf, port
+    from tests import cases
+    ms = cases.GOLDEN_CASES["mgcl2"]()
+    ms.control.surface_dipole = 1
+    n = ms.nsites
+    part = port.run(ms, ithread=rank, nthreads=world)
+    block = torch.zeros(3 * n + 16, dtype=torch.float64)
+    block[:3 * n] = torch.from_numpy(part["force"].reshape(-1))
+    block[3 * n:3 * n + 2] = torch.from_numpy(part["pe"])
+    block[3 * n + 2:3 * n + 11] = torch.from_numpy(part["stress"].reshape(-1))
+    spmd.combine(block)
+    b = block.numpy()
+    out = evalf.tail(ms, b[:3 * n].reshape(3, n), b[3 * n:3 * n + 2], b[3 * n + 2:3 * n + 11].reshape(3, 3))
+    flat = torch.from_numpy(np.concatenate([out[k].reshape(-1) for k in ("force", "torque", "pe", "stress", "dip_mom")]))
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    same = all(torch.equal(gathered[0], g) for g in gathered)
+    if rank == 0:
+        q.put(({k: np.array(v) for k, v in out.items()}, same))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_eval_forces_tail_after_the_allreduce():
+    """SURVEY 8f rank 1 under the replicated-data scheme: the molecular-frame steps of eval_forces (surface dipole,
+    mol_force/mol_torque, site->molecular virial, distant terms) run after the packed all-reduce, identically on every
+    rank, and reproduce the reference's single-process eval_forces()."""
+    from oracle import ref as refmod
+    from tests import cases
+    if not refmod.available(evalf=True):
+        pytest.skip("oracle/_ref/libmoldyref_evalf.so not built")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = _free_port()
+    procs = [ctx.Process(target=_worker_evalf, args=(r, world, port_no, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out, same = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert same, "ranks disagree on the molecular forces after the all-reduce"
+    ms = cases.GOLDEN_CASES["mgcl2"]()
+    ms.control.surface_dipole = 1
+    want = refmod.RefLib(evalf=True).eval_forces(ms)
+    assert cases.rel_rms(out["force"], want["force"]) < 1e-12
+    assert cases.rel_rms(out["torque"], want["torque"]) < 1e-12
+    assert np.allclose(out["pe"], want["pe"], rtol=1e-12)
+    assert np.linalg.norm(out["stress"] - want["stress"]) / np.linalg.norm(want["stress"]) < 1e-11
+    assert np.allclose(out["dip_mom"], want["dip_mom"], rtol=1e-10, atol=1e-8)
+
+
 def test_partition_helpers_cover_everything_once():
     from moldy_b200 import spmd
     for n, w in ((1024000, 8), (1000, 3), (7, 8)):
