@@ -291,6 +291,11 @@ const double *mdb_eval_result(const mdb_engine *e);
 void eval_forces(system_mp sys, spec_mt *species, site_mt *site_info, pot_mt *potpar, double *pe, real *dip_mom,
                  mat_mt stress, vec_mp *force, vec_mp *torque);
 
+/* Number of values in which three HOST rows differ (bit for bit) from the sites the engine currently holds; the rows are
+ * staged in `d_scratch` (DEVICE, 3*nsites doubles).  Synchronises `stream`; -1 on error.  ewald() of layer (A) validates
+ * the k-space sums that force_calc() started ahead of it with this. */
+long mdb_sites_differ_host(mdb_engine *e, const double *x, const double *y, const double *z, double *d_scratch, void *stream);
+
 /* Device->host copy of a result block (synchronises `stream`). */
 int  mdb_read_out(mdb_engine *e, const double *d_out, double *h_out, void *stream);
 

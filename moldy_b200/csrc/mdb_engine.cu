@@ -229,6 +229,9 @@ extern "C" int mdb_configure(mdb_engine *e, const mdb_config *cfg)
       const double split = (double)nc * nc * (22 + 23) + (double)np2 * np2 * (22 + ptc[cfg->ptype]);
       const char *sp = getenv("MDB_PAIR_SPLIT");
       e->pair_split = coul && e->pair_mode >= 3 && (sp ? atoi(sp) != 0 : split < 0.85 * fused);
+      // molecular cut-off: whole molecules are binned by their centre of mass, so two close sites of different molecules
+      // can lie more than one cell apart and the adjacent-cell TOO_CLOSE scan of the unvisited pairs would miss them
+      if (cfg->molpbc) e->pair_split = 0;
       // the TOO_CLOSE scan of the unvisited pairs looks at adjacent cells only: cells must be >= 0.5 A thick
       const int ng[3] = {e->T.nx, e->T.ny, e->T.nz};
       for (int d = 0; d < 3; d++) {
@@ -341,6 +344,36 @@ extern "C" int mdb_set_sites_device(mdb_engine *e, const double *dx, const doubl
    e->d_x = const_cast<double *>(dx); e->d_y = const_cast<double *>(dy); e->d_z = const_cast<double *>(dz);
    e->sites_set = true; e->cells_valid = false;
    return 0;
+}
+
+// Are the engine's current sites bit-identical to three HOST rows?  The rows are copied H2D into `d_scratch` (3 N
+// doubles of device memory) on `stream` and compared there; returns the number of differing values (synchronises
+// `stream`), or -1.  moldy_abi.cu uses it to validate the k-space sums it started ahead of ewald().
+__global__ void __launch_bounds__(256) k_sites_differ(const unsigned long long *__restrict__ a, const unsigned long long *__restrict__ b,
+                                                      size_t n, unsigned int *__restrict__ ndiff)
+{
+   unsigned int d = 0;
+   for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) d += a[i] != b[i];
+   if (__syncthreads_or(d != 0) && d) atomicAdd(ndiff, d);
+}
+extern "C" long mdb_sites_differ_host(mdb_engine *e, const double *x, const double *y, const double *z, double *d_scratch,
+                                      void *stream)
+{
+   cudaStream_t st = (cudaStream_t)stream;
+   const size_t n = e->cfg.nsites;
+   if (!e->sites_set || e->d_x != e->own_xyz) return -1;
+   MDB_CUDA(cudaMemcpyAsync(d_scratch, x, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+   MDB_CUDA(cudaMemcpyAsync(d_scratch + n, y, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+   MDB_CUDA(cudaMemcpyAsync(d_scratch + 2 * n, z, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+   unsigned int *d_nd = reinterpret_cast<unsigned int *>(e->d_counters + 7);
+   MDB_CUDA(cudaMemsetAsync(d_nd, 0, sizeof(unsigned int), st));
+   k_sites_differ<<<592, 256, 0, st>>>(reinterpret_cast<const unsigned long long *>(d_scratch),
+                                       reinterpret_cast<const unsigned long long *>(e->own_xyz), 3 * n, d_nd);
+   e->launches++;
+   unsigned int nd = 0;
+   MDB_CUDA(cudaMemcpyAsync(&nd, d_nd, sizeof nd, cudaMemcpyDeviceToHost, st));
+   MDB_CUDA(cudaStreamSynchronize(st));
+   return (long)nd;
 }
 
 extern "C" int mdb_zero_out(mdb_engine *e, double *d_out, void *stream)

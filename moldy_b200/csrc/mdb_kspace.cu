@@ -30,6 +30,11 @@
 #include <cstdlib>
 #include "mdb_internal.h"
 
+// dynamic shared-memory sizes already granted to the kernels, PER DEVICE (cudaFuncSetAttribute acts on the current
+// device only, and a later smaller request must not shrink an earlier grant)
+static size_t g_shm_set[64][4];
+static int g_max_smem[64];
+
 static constexpr int KT = 256;          // threads per block (k_sfac)
 static constexpr int SC = 32;           // sites per shared-memory chunk
 static constexpr int LCH = 8;           // l-slots per thread
@@ -1064,8 +1069,8 @@ static int recip_partial(mdb_engine *e, const RecipPlan &P, double *d_psum, cuda
       double *tE = reinterpret_cast<double *>(e->d_ktab);
       double2 *tH = reinterpret_cast<double2 *>(tE + (size_t)M.nrows * M.L.SB);
       double2 *tK = tH + (size_t)M.nrows * M.L.SH;
-      static size_t tshm_set = 48 * 1024;
-      if (KTS * row_bytes > tshm_set) {
+      size_t &tshm_set = g_shm_set[e->device & 63][0];
+      if (KTS * row_bytes > 48 * 1024 && KTS * row_bytes > tshm_set) {
          MDB_CUDA(cudaFuncSetAttribute(k_ktables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KTS * row_bytes)));
          tshm_set = KTS * row_bytes;
       }
@@ -1077,7 +1082,7 @@ static int recip_partial(mdb_engine *e, const RecipPlan &P, double *d_psum, cuda
          e->launches++;
       }
       const size_t mshm = 2 * (size_t)MSC * row_bytes;
-      static size_t mshm_set = 0;
+      size_t &mshm_set = g_shm_set[e->device & 63][1];
       if (mshm > mshm_set) {
          MDB_CUDA(cudaFuncSetAttribute(k_sfac_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mshm));
          mshm_set = mshm;
@@ -1090,7 +1095,7 @@ static int recip_partial(mdb_engine *e, const RecipPlan &P, double *d_psum, cuda
                                       e->d_ppart);
       e->launches++;
    } else if (e->n_sfac_blocks > 0 && P.n_slabs > 0) {
-      static size_t shm_set = 0;
+      size_t &shm_set = g_shm_set[e->device & 63][2];
       if (shm > shm_set) {
          MDB_CUDA(cudaFuncSetAttribute(k_sfac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
          shm_set = shm;
@@ -1178,7 +1183,7 @@ static int recip_finish(mdb_engine *e, const RecipPlan &P, const double *d_psum,
    if (F.mma) {
       const size_t per_site = sizeof(double) * Q.SE + sizeof(double2) * (Q.SH + Q.SK) + 6 * sizeof(double);
       const size_t stage_bytes = 4 * (size_t)Q.blk2 * sizeof(double2) + 64;
-      static int max_smem = 0;
+      int &max_smem = g_max_smem[e->device & 63];
       if (!max_smem) MDB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
       Q.nsb = 8;
       while (Q.nsb > 1 && stage_bytes + 16 * (size_t)Q.nsb * per_site > (size_t)max_smem) Q.nsb--;
@@ -1200,7 +1205,7 @@ static int recip_finish(mdb_engine *e, const RecipPlan &P, const double *d_psum,
       }
       kshm = stage_bytes + 16 * (size_t)Q.nsb * per_site;
       if (kshm > (size_t)max_smem) { mdb_set_error("k_cutoff too large for the shared-memory tables of k_kforce_mma"); return -1; }
-      static size_t kshm_set = 0;
+      size_t &kshm_set = g_shm_set[e->device & 63][3];
       if (kshm > kshm_set) {
          MDB_CUDA(cudaFuncSetAttribute(k_kforce_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kshm));
          kshm_set = kshm;

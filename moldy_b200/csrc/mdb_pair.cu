@@ -327,9 +327,13 @@ int mdb_launch_kernel_vec(int jmin, int nnab, double *forceij, double *pe, const
       return -1;
    }
    const int nb = (cnt + 255) / 256;
-   double *d = nullptr;
    const size_t n = (size_t)nnab;
-   MDB_CUDA(cudaMalloc(&d, sizeof(double) * (n * (3 + rows) + nb)));
+   struct Scratch {                             // freed on every return path
+      double *p = nullptr;
+      ~Scratch() { if (p) cudaFree(p); }
+   } scratch;
+   MDB_CUDA(cudaMalloc(&scratch.p, sizeof(double) * (n * (3 + rows) + nb)));
+   double *d = scratch.p;
    double *d_f = d, *d_r2 = d + n, *d_q = d + 2 * n, *d_pot = d + 3 * n, *d_peb = d + (3 + rows) * n;
    MDB_CUDA(cudaMemcpy(d_r2, r_sqr, sizeof(double) * n, cudaMemcpyHostToDevice));
    MDB_CUDA(cudaMemcpy(d_q, nab_chg, sizeof(double) * n, cudaMemcpyHostToDevice));
@@ -351,6 +355,5 @@ int mdb_launch_kernel_vec(int jmin, int nnab, double *forceij, double *pe, const
    double s = 0;
    for (int k = 0; k < nb; k++) s += peb[k];
    *pe += s;
-   cudaFree(d);
    return 0;
 }

@@ -229,7 +229,6 @@ static bool chg_changed_late(const real *chg, int n)
 
 static void push_sites(real **site)
 {
-   if (G.sites_fresh && G.last_sites == (const void *)site[0] && !getenv("MOLDY_B200_ALWAYS_UPLOAD")) return;
    if (mdb_set_sites_host(G.eng, site[0], site[1], site[2], G.stream)) FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
    G.last_sites = site[0];
 }
@@ -474,10 +473,20 @@ extern "C" void ewald(real **site, real **site_force, system_mp system, spec_mt 
       for (int i = 0; i < 3; i++) stress[i][i] += G.sheet_energy / vol;
    }
 
-   const bool ahead = G.ahead_valid && G.sites_fresh && G.ahead_sites == (const void *)site[0] &&
-                      G.ahead_epoch == G.config_epoch && G.ahead_ithread == ithread && G.ahead_nthreads == nthreads &&
-                      !getenv("MOLDY_B200_ALWAYS_UPLOAD");
+   bool ahead = G.ahead_valid && G.sites_fresh && G.ahead_sites == (const void *)site[0] &&
+                G.ahead_epoch == G.config_epoch && G.ahead_ithread == ithread && G.ahead_nthreads == nthreads;
    G.ahead_valid = false;
+   if (ahead) {
+      /* ewald(site,...) must compute from the sites it is passed (src/ewald.c:280): the rows go up again on the copy
+       * stream while the kernels started by force_calc run (G.d_out is free by now) and are compared bit for bit on
+       * the device with the sites those kernels used; any difference discards the look-ahead result. */
+      const long nd = mdb_sites_differ_host(G.eng, site[0], site[1], site[2], G.d_out, G.copy_stream);
+      if (nd != 0) {
+         if (g_timing) fprintf(stderr, "[moldy_b200] ewald: sites changed since force_calc (%ld values), recomputing\n", nd);
+         cudaEventSynchronize(G.ev_ahead);
+         ahead = false;
+      }
+   }
    if (ahead) {                                          /* started by force_calc: wait and add */
       const double t0 = now_ms();
       if (cudaEventSynchronize(G.ev_ahead) != cudaSuccess) FATAL_MSG("libmoldy_b200: k-space kernels failed");

@@ -159,3 +159,15 @@ RDF_CASES = {
     "argon": (7.7, 40), "tip4p": (8.8, 100), "tips2": (5.5, 55), "tips2_tinybox": (8.0, 64), "mgcl2": (8.4, 100),
     "quartz": (9.0, 90), "slab_framework": (6.3, 63), "tips2_molpbc": (5.5, 50), "tip4p_molpbc_strict": (6.0, 30),
 }
+
+
+# BASELINE.json configs[1..4] at full size: checked on the GPU against reduced records of the compiled
+# reference (tests/golden/large_*.npz, written by tests/golden/make_large_fixtures.py).
+LARGE_CASES = {
+    "tip4p_5": lambda: systems.tip4p(5),                               # configs[1]: 128 000 sites
+    "mgcl2_7": lambda: systems.mgcl2(7, explicit=False),               # configs[2]: 278 516 sites, MCY
+    "quartz_48": lambda: systems.quartz(48, pinned_cutoff=False),      # configs[3]: 995 328 ions, Buckingham, triclinic
+    "tip4p_10": lambda: systems.tip4p(10),                             # configs[4] / bench workload: 1 024 000 sites
+    "tip4p_13": lambda: systems.tip4p(13),                             # configs[4] sweep: 2 249 728 sites
+    "tip4p_16": lambda: systems.tip4p(16),                             # configs[4] sweep: 4 194 304 sites
+}

@@ -389,6 +389,76 @@ def test_too_close_pairs_counted_alike_by_fused_and_split_passes(golden_dir):
     assert counts[0] == counts[1]
 
 
+@pytest.mark.parametrize("split", [0, 1])
+def test_too_close_count_equals_the_references_warnings(split, golden_dir):
+    """The reference prints one TOOCLS warning per inter-molecular pair of its half list closer than 0.5 A
+    (src/force.c:939-949).  Three displaced sites -- H on a foreign O (visited by neither split pass), H on a foreign
+    H (Coulomb pass), O on a foreign O (Lennard-Jones pass) -- and one intra-molecular contact that must NOT count:
+    the library's count through mdb_too_close equals the number of warnings the compiled reference issues."""
+    import torch
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    ms = cases.GOLDEN_CASES["tip4p"]()
+    site = ms.make_sites(wrap=True)
+    nsm = ms.sysdef.species[0].nsites
+    d = np.array([0.05, 0.03, 0.02])
+    site[:, 1 * nsm + 1] = site[:, 0 * nsm + 0] + d          # H(1) on O(0)
+    site[:, 3 * nsm + 2] = site[:, 2 * nsm + 1] + d          # H(3) on H(2)
+    site[:, 5 * nsm + 0] = site[:, 4 * nsm + 0] - d          # O(5) on O(4)
+    site[:, 6 * nsm + 3] = site[:, 6 * nsm + 0] + d          # M(6) on its own O: same molecule, no warning
+    r = ref.RefLib()
+    w0 = r.lib.mdref_warnings()
+    r.run(ms, recip=False, sites=site)
+    nref = r.lib.mdref_warnings() - w0
+    assert nref >= 3
+    eng = _real_space(ms, 4, {"MDB_PAIR_SPLIT": str(split)})
+    eng.set_sites_host(site)
+    st = torch.cuda.current_stream().cuda_stream
+    out = torch.zeros(eng.out_doubles(), dtype=torch.float64, device="cuda")
+    eng.build_cells(st)
+    eng.force_real(out.data_ptr(), st)
+    torch.cuda.synchronize()
+    ntc, pair = eng.too_close(st)
+    eng.close()
+    assert ntc == nref, (ntc, nref)
+
+
+def test_ewald_recomputes_when_the_sites_changed_after_force_calc(golden_dir):
+    """force_calc() starts the k-space kernels ahead of ewald(); ewald(site, ...) must still compute from the sites it
+    is passed (src/ewald.c:280).  The caller rewrites its site array IN PLACE between the two calls: the result must be
+    the reciprocal-space sum of the new sites, not the look-ahead result for the old ones."""
+    from moldy_b200 import abi
+    ms = cases.GOLDEN_CASES["tip4p_2"]()
+    n, nsa = ms.nsites, abi.nsarray(ms.nsites)
+    ms.control.fill(lib.control())
+    lib.set_thread(0, 1)
+    lib.reset()
+    sysm, spec, pot = ms.cstructs()
+    chg = ms.charges()
+    site = np.ascontiguousarray(ms.make_sites())
+    rng = np.random.default_rng(3)
+    moved = site.copy()
+    moved[:, :n] += 0.05 * rng.standard_normal((3, n))
+
+    def recip_only(s):
+        f, pe, stress = np.zeros((3, nsa)), np.zeros(2), np.zeros((3, 3))
+        lib.ewald(s, f, sysm, spec, chg, pe[1:2], stress)
+        return f[:, :n].copy(), pe[1], stress.copy()
+
+    f_new, pe_new, s_new = recip_only(moved)                 # no look-ahead: plain ewald() on the moved sites
+    f, pe, stress = np.zeros((3, nsa)), np.zeros(2), np.zeros((3, 3))
+    buf = site.copy()
+    lib.force_calc(buf, f, sysm, spec, chg, pot, pe[0:1], stress)     # starts the k-space kernels for `site`
+    buf[:] = moved                                                      # same array, new contents
+    f2, stress2 = np.zeros((3, nsa)), np.zeros((3, 3))
+    lib.ewald(buf, f2, sysm, spec, chg, pe[1:2], stress2)
+    lib.reset()
+    assert cases.rel_rms(f2[:, :n], f_new) < 1e-13
+    assert abs(pe[1] - pe_new) <= 1e-13 * abs(pe_new)
+    assert np.linalg.norm(stress2 - s_new) <= 1e-13 * np.linalg.norm(s_new)
+
+
 @pytest.mark.parametrize("kind", ["mma", "dfma"])
 def test_many_l_slots_are_split_into_l_ranges(kind, golden_dir):
     """k_cutoff large enough for lmax > 32: the structure-factor GEMM then runs a column block over two l-ranges
