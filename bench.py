@@ -1,26 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- Moldy force-evaluation hot path on B200 (contract: see DESIGN.md section 7).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n REPL]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-A "step" is one full force evaluation of the synthetic TIP4P system (256-molecule
-equilibrated cell replicated n^3 with jitter; n=10 -> 1 024 000 sites, the ~10^6-site
-configuration BASELINE.json's metric is quoted on): link-cell build + real-space pair
-kernel + reciprocal-space Ewald (structure factors, energy/stress, forces), i.e. what
-force_calc() + ewald() do per MD step.
+A "step" is one full force evaluation of a synthetic replicated-lattice system: link-cell build + real-space pair
+kernel + reciprocal-space Ewald (structure factors, energy/stress, forces), i.e. what force_calc() + ewald() do per
+MD step.  Workloads (BASELINE.json configs): tip4p10 (default; TIP4P 10x10x10 = 1 024 000 sites, the ~10^6-site
+configuration the metric is quoted on), tip4p5, mgcl2_7, quartz48, tip4p13, tip4p16.
 
-`value`   steps/s with positions already resident in HBM (CUDA events per step, max
-          over ranks; for N>1 the system is the same -- strong scaling -- each rank owns
-          a slice of the cell-sorted sites and of the (h,k) columns and the packed
-          [forces|pe|stress] block is all-reduced with NCCL inside the timed step).
-`e2e`     the same metric through Moldy's own entry points force_calc()+ewald() of
-          libmoldy_b200.so with HOST (pinned) buffers: H2D of the site rows and D2H of
-          the force rows inside the timed region (N=1), or through
-          moldy_b200.spmd.SpmdForces (N>1).
-`--impl reference` times the reference's own CPU code (oracle/_ref, built from
-          /root/reference with its own flags) on all host cores, replicated-data SPMD
-          exactly as parallel.c runs it (rank p of P evaluates cells p mod P and its
-          block of k-vectors), on a bounded 1/S sample of the ranks.
+`value`   steps/s with the sites resident in HBM (CUDA events per step, max over ranks).  N>1: the same system
+          (strong scaling), rank r owns a slice of the site batches and of the charged sites; the partial
+          [forces|pe|stress] blocks are summed by the library's own peer-memory kernels over NVLink (mdb_peer.cu:
+          structure-factor all-reduce, force reduce-scatter + all-gather = par_rsum's all-reduce) inside the timed step
+          (`--collective nccl` selects the torch.distributed/NCCL all-reduce of round 1 instead).
+`e2e`     the same metric through the host-buffer API: N=1 Moldy's own entry points force_calc()+ewald() of
+          libmoldy_b200.so with pinned host rows; N>1 moldy_b200.spmd.SpmdForces (every rank uploads its slice of the
+          site rows and downloads its slice of the summed forces).  H2D/D2H inside the timed region.
+`check`   energies, stress norm, force rms and a weighted force checksum of the last step, on every line and for
+          every N: the N-GPU result must agree with the 1-GPU result to ~1e-12 (visible in SCALE_*.json).
+`--impl reference` times the reference's own CPU code (oracle/_ref, built from /root/reference with its own flags) on
+          all host cores as the replicated-data SPMD step parallel.c runs (rank p of P evaluates cells p mod P and its
+          block of k-vectors).  Each of the W+K "steps" is a bounded sample: all P cores run ranks p*S of a P*S-way
+          split (1/S of every core's share); `ms_per_step` is the measured sample time, `value` the full-step rate
+          extrapolated from it (`extrapolated`, `sample_fraction` say so).  Also reported: the serial rate, and the
+          whole reference program -- serial build and the unchanged parallel.c (-DSPMD -DMPI over oracle/mpi_shim) on
+          all cores -- on a smaller replica.
 """
 from __future__ import annotations
 
@@ -30,14 +34,21 @@ import os
 import statistics
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOP_PER_PAIR = 59          # LJ + erfc-Coulomb pair, mk_r_sqr + kernel + mk_forces
+# SURVEY.md 8d, algorithmic flop per site pair handed to kernel(): mk_r_sqr 11 + kernel + mk_forces 9
+FLOP_PER_PAIR = {"lennard-jones": 59, "buckingham": 59, "mcy": 59, "generic": 73}
 FLOP_PER_SITEK = 18         # qsincos + sum + force per (site, k-vector)
+
+WORKLOADS = {
+    "tip4p10": ("tip4p", 10), "tip4p5": ("tip4p", 5), "tip4p13": ("tip4p", 13), "tip4p16": ("tip4p", 16),
+    "mgcl2_7": ("mgcl2", 7), "quartz48": ("quartz", 48),
+}
 
 
 def parse():
@@ -46,10 +57,41 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=10, help="replication factor of the 256-water cell (10 -> 1.024M sites)")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the bounded reference sample")
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=None, help="TIP4P replication factor (same as --workload tip4p<n>)")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"])
+    ap.add_argument("--cpu-seconds", type=float, default=5.0, help="target wall time of one bounded reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-programs", action="store_true", help="reference arm: skip the whole-program (serial / MPI) runs")
+    a = ap.parse_args()
+    if a.workload is None:
+        a.workload = f"tip4p{a.n}" if a.n else "tip4p10"
+    if a.workload not in WORKLOADS:
+        WORKLOADS[a.workload] = ("tip4p", a.n)
+    return a
+
+
+def build_system(workload):
+    from moldy_b200 import systems
+    fam, n = WORKLOADS[workload]
+    if fam == "tip4p":
+        return systems.tip4p(n)
+    if fam == "mgcl2":
+        return systems.mgcl2(n, explicit=False)
+    return systems.quartz(n, pinned_cutoff=False)
+
+
+def workload_config(workload, ms):
+    fam, n = WORKLOADS[workload]
+    what = {"tip4p": f"TIP4P water, 256-molecule equilibrated cell replicated {n}x{n}x{n}",
+            "mgcl2": f"aqueous MgCl2 (200 MCY waters + 4 Mg + 8 Cl), equilibrated cell replicated {n}x{n}x{n}",
+            "quartz": f"BKS alpha-quartz (Buckingham), {n}x{n}x{n} triclinic unit cells"}[fam]
+    return {"workload": f"{what} = {ms.nsites} sites, real-space link-cell + reciprocal-space Ewald (force_calc + ewald), "
+                        "Ewald parameters from the reference's init_cutoffs formulas",
+            "name": workload,
+            "l2_flush": "256 MiB device memset between steps, outside the per-step CUDA-event brackets",
+            "cutoff_A": ms.control.cutoff, "alpha": ms.control.alpha, "k_cutoff": ms.control.k_cutoff,
+            "subcell_A": ms.control.subcell}
 
 
 # --------------------------------------------------------------------------- clocks
@@ -63,7 +105,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -95,54 +137,140 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- reference arm
-def _ref_worker(args):
-    """One SPMD rank of the reference (runs in its own process: function statics)."""
-    n, ithread, nthreads, fast = args
+_W = {}
+
+
+def _ref_init(workload):
+    """Pool initialiser: every worker builds the system once."""
     sys.path.insert(0, ROOT)
-    from moldy_b200 import systems
+    ms = build_system(workload)
+    _W["ms"], _W["site"] = ms, ms.make_sites()
+
+
+def _ref_rank(args):
+    """One SPMD rank of the reference: a fresh private copy of the shared object per call (function statics)."""
+    ithread, nthreads = args
     from oracle import ref
-    ms = systems.tip4p(n)
-    r = ref.RefLib(fast=fast)
+    r = ref.RefLib(fast=True)
     r.set_thread(ithread, nthreads)
-    site = ms.make_sites()
     t0 = time.perf_counter()
-    r.run(ms, sites=site)
+    r.run(_W["ms"], sites=_W["site"])
     return time.perf_counter() - t0
 
 
-def reference_sample(n: int, target_s: float, steps: int = 1):
-    """Time the reference's replicated-data SPMD step on all usable host cores on a
-    bounded sample.  Full step on P cores = every rank p<P does cells p mod P and
-    k-block p.  We run P processes as ranks p of P*S (each does 1/(P*S) of the work),
-    plus one calibration with (almost) no work to separate the non-partitioned
-    overhead (trig tables, cell lists, potp expansion), and extrapolate
-        t_step(P cores) = t_over + S * (t_sample - t_over)."""
-    import multiprocessing as mp
-    from moldy_b200 import systems
+def _usable_cores(nsites):
     ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    nsites = 1024 * n ** 3
-    mem_per_rank = 1.7e9 * nsites / 1.024e6 + 0.4e9
+    mem_per_rank = 1.7e9 * nsites / 1.024e6 + 0.5e9         # trig tables of ewald(), SURVEY 8a row a18
     try:
         avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
     except (ValueError, OSError):
         avail = 32e9
-    P = int(max(1, min(ncpu, 64, 0.6 * avail // mem_per_rank)))
-    # serial cost model from the survey probe (541 s at 1.024M sites, ~N^1.5)
-    serial_est = 541.0 * (nsites / 1.024e6) ** 1.5 / 1.6      # fast-math build is ~1.6x quicker
+    return int(max(1, min(ncpu, 64, 0.6 * avail // mem_per_rank)))
+
+
+def reference_sample(workload, target_s, steps=1, warmup=0, serial=True):
+    """The reference's replicated-data SPMD step on all usable host cores, on bounded samples.
+
+    A full step on P cores = rank p (p < P) evaluates cells p mod P and k-block p.  One sample-step: the P workers run
+    ranks p*S of a P*S-way split at the same time (1/S of every core's share of one step); a calibration run with an
+    (almost) empty share gives the unpartitioned per-call overhead t_over (cell lists, trig tables, potp expansion),
+    which a full step pays once:  t_step(P cores) = t_over + S (t_sample - t_over).
+    Serial: the same with one worker alone on the box (rank 0 of a P*S-way split)."""
+    import multiprocessing as mp
+    ms = build_system(workload)
+    nsites = ms.nsites
+    P = _usable_cores(nsites)
+    # serial cost model (survey probe: 541 s at 1.024M TIP4P sites, ~N^1.5; fast-math build ~1.6x quicker) -- sizes S only
+    serial_est = 541.0 * (nsites / 1.024e6) ** 1.5 / 1.6
     S = max(1, int(round(serial_est / (P * target_s))))
     ctx = mp.get_context("spawn")
-    with ctx.Pool(P) as pool:
-        t_over = max(pool.map(_ref_worker, [(n, 0, 1 << 24, True)] * min(P, 2)))
+    with ctx.Pool(P, initializer=_ref_init, initargs=(workload,)) as pool:
+        t_over = max(pool.map(_ref_rank, [(0, 1 << 24)] * min(P, 2)))
         samples = []
-        for _ in range(steps):
-            samples.append(max(pool.map(_ref_worker, [(n, p * S, P * S, True) for p in range(P)])))
-    t_sample = statistics.median(samples)
+        t0 = time.perf_counter()
+        for _ in range(warmup + steps):
+            samples.append(max(pool.map(_ref_rank, [(p * S, P * S) for p in range(P)], chunksize=1)))
+        wall = time.perf_counter() - t0
+        t_solo = pool.apply(_ref_rank, ((0, P * S),)) if serial else None
+    timed = samples[warmup:]
+    t_sample = statistics.mean(timed)
     t_step = t_over + S * max(t_sample - t_over, 0.0)
-    return dict(value=1.0 / t_step, unit="steps/s", cores=P, kind="reference",
-                sample=f"ranks p*{S} (p<{P}) of a {P * S}-way replicated-data SPMD split of one step "
-                       f"(1/{S} of every core's share) + a no-work calibration run; "
-                       f"t_over={t_over:.2f}s t_sample={t_sample:.2f}s -> t_step({P} cores)={t_step:.1f}s; "
-                       f"oracle/_ref/libmoldyref_fast.so = reference force.c/kernel.c/ewald.c, gcc -O2 -ffast-math"), t_step
+    out = dict(value=1.0 / t_step, unit="steps/s", cores=P, kind="reference",
+               sample=f"{len(timed)} timed sample-steps (+{warmup} warm-up): all {P} cores run ranks p*{S} (p<{P}) of a "
+                      f"{P * S}-way replicated-data SPMD split of one step = 1/{S} of every core's share, plus one no-work "
+                      f"calibration; t_over={t_over:.2f}s t_sample={t_sample:.2f}s -> t_step({P} cores)="
+                      f"t_over+{S}(t_sample-t_over)={t_step:.1f}s; oracle/_ref/libmoldyref_fast.so = the reference's "
+                      "force.c/kernel.c/ewald.c, gcc -O2 -ffast-math -funroll-loops (its own flags)",
+               extrapolated=S > 1, sample_fraction=1.0 / S, t_over_s=t_over, t_sample_s=t_sample,
+               full_step_s=t_step, samples_s=timed)
+    if t_solo is not None:
+        t_serial = t_over + P * S * max(t_solo - t_over, 0.0)
+        out["serial"] = {"value": 1.0 / t_serial, "unit": "steps/s", "cores": 1, "full_step_s": t_serial,
+                         "sample": f"one core alone: rank 0 of the {P * S}-way split, {t_solo:.2f}s, extrapolated the same way"}
+    return out, t_sample, wall / max(1, warmup + steps)
+
+
+CONTROL_PROGRAM = """title=bench reference program
+surface-dipole=1
+temperature=300
+subcell=2.5
+lattice-start=1
+sys-spec-file=sys.in
+scale-interval=1000000
+scale-end=0
+step=0.0005
+nsteps={nsteps}
+print-interval=1000000
+average-interval=100000000
+begin-average=100000000
+roll-interval=1
+dump-level=0
+backup-interval=0
+time-unit=4.8888213e-14
+end
+"""
+
+
+def reference_programs(n=4):
+    """The whole reference program on a TIP4P n^3 replica: serial build and the SPMD build (UNCHANGED parallel.c,
+    -DSPMD -DMPI over oracle/mpi_shim) on all cores.  Seconds per MD step = (T(n2 steps) - T(n1 steps)) / (n2 - n1):
+    start-up (lattice read, first force evaluation) cancels.  The reference itself replicates the 256-molecule cell
+    (`a b c alpha beta gamma n n n` lattice line) and derives the Ewald parameters (init_cutoffs)."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    serial, mpi = os.path.join(ref, "moldy_fast"), os.path.join(ref, "moldy_mpi")
+    if not (os.path.exists(serial) and os.path.exists(mpi)):
+        return {"unavailable": "oracle/_ref/moldy_fast / moldy_mpi not built"}
+    eq = open(os.path.join(ROOT, "tests", "golden", "tip4p_256_eq.txt")).read().splitlines()
+    eq[0] = f" Water {256 * n ** 3}"
+    cell = next(i for i, ln in enumerate(eq) if len(ln.split()) == 9 and ln.split()[-1] == "1")
+    t = eq[cell].split()
+    eq[cell] = " ".join(t[:6] + [str(n)] * 3)
+    ncpu = len(os.sched_getaffinity(0))
+    res = {"workload": f"TIP4P {n}x{n}x{n} = {1024 * n ** 3} sites, full MD step of the reference program (leapfrog + forces)"}
+
+    def run(binary, nsteps, np_):
+        with tempfile.TemporaryDirectory() as d:
+            open(os.path.join(d, "sys.in"), "w").write("\n".join(eq) + "\n")
+            open(os.path.join(d, "control"), "w").write(CONTROL_PROGRAM.format(nsteps=nsteps))
+            env = dict(os.environ, MOLDY_MPI_NP=str(np_))
+            t0 = time.perf_counter()
+            r = subprocess.run([binary, "control"], cwd=d, env=env, capture_output=True, text=True, timeout=600)
+            dt = time.perf_counter() - t0
+            if r.returncode != 0:
+                raise RuntimeError(r.stdout[-500:] + r.stderr[-500:])
+            return dt
+    try:
+        a, b = run(serial, 1, 1), run(serial, 3, 1)
+        res["serial"] = {"s_per_step": (b - a) / 2, "steps_per_s": 2 / (b - a), "cores": 1,
+                         "binary": "oracle/_ref/moldy_fast (all sources, gcc -O2 -ffast-math -funroll-loops)"}
+        a, b = run(mpi, 2, ncpu), run(mpi, 10, ncpu)
+        res["mpi_parallel_c"] = {"s_per_step": (b - a) / 8, "steps_per_s": 8 / (b - a), "cores": ncpu,
+                                 "binary": "oracle/_ref/moldy_mpi (-DSPMD -DMPI, unchanged parallel.c, oracle/mpi_shim: "
+                                           "fork + shared-memory MPI_Allreduce/Bcast), MOLDY_MPI_NP=%d" % ncpu}
+        res["speedup_mpi_over_serial"] = res["serial"]["s_per_step"] / res["mpi_parallel_c"]["s_per_step"]
+    except Exception as exc:
+        res["error"] = repr(exc)[:500]
+    return res
 
 
 def run_reference(a):
@@ -153,32 +281,40 @@ def run_reference(a):
     if not ref.available(fast=True):
         emit({"impl": "reference", "unavailable": "oracle/_ref/libmoldyref_fast.so not built"})
         return
-    cb, t_step = reference_sample(a.n, a.cpu_seconds, steps=max(1, min(a.steps, 2)))
-    nsites = 1024 * a.n ** 3
+    ms = build_system(a.workload)
+    cb, t_sample, wall_per_sample = reference_sample(a.workload, a.cpu_seconds, steps=a.steps, warmup=a.warmup)
     line = {"metric": "md_force_steps_per_s", "value": cb["value"], "unit": "steps/s", "n_gpus": a.gpus,
-            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * wall_per_sample, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": workload_config(a.n, nsites, None), "cpu_baseline": cb,
+            "config": workload_config(a.workload, ms), "cpu_baseline": cb,
+            "extrapolated": cb["extrapolated"], "sample_fraction": cb["sample_fraction"],
+            "full_step_ms": 1e3 * cb["full_step_s"],
+            "note": "`steps` sample-steps were run and timed; `ms_per_step` is the measured wall time of one sample-step "
+                    "(1/S of a full step on every core), `value` = 1 / full_step_s is the full-workload rate derived from it",
             "e2e": {"value": cb["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if not a.no_programs:
+        line["reference_program"] = reference_programs()
     emit(line)
 
 
-def workload_config(n, nsites, ms):
-    cfg = {"workload": f"TIP4P water, 256-molecule equilibrated cell replicated {n}x{n}x{n} = {nsites} sites, "
-                       "real-space link-cell + reciprocal-space Ewald (force_calc + ewald)",
-           "l2_flush": "256 MiB device memset between steps, outside the per-step CUDA-event brackets"}
-    if ms is not None:
-        cfg.update({"cutoff_A": ms.control.cutoff, "alpha": ms.control.alpha, "k_cutoff": ms.control.k_cutoff,
-                    "subcell_A": ms.control.subcell})
-    return cfg
-
-
 # --------------------------------------------------------------------------- our arm
+def force_check(block, n):
+    """Reduced description of a result block [fx|fy|fz|pe,pe_recip|stress[9]]: equal across N to ~1e-12."""
+    import numpy as np
+    f = block[:3 * n].reshape(3, n)
+    w = np.sin(0.37 * np.arange(n, dtype=np.float64))
+    s = block[3 * n + 2:3 * n + 11].reshape(3, 3)
+    return {"pe_real": float(block[3 * n]), "pe_recip": float(block[3 * n + 1]),
+            "stress_norm": float(np.linalg.norm(s[np.triu_indices(3)])),
+            "force_rms": float(np.sqrt((f ** 2).mean())), "force_checksum": float((w * f.sum(0)).sum()),
+            "force_net": float(np.abs(f.sum(1)).max())}
+
+
 def run_ours(a):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from moldy_b200 import lib, spmd, systems
+    from moldy_b200 import lib, spmd
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -189,36 +325,75 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    ms = systems.tip4p(a.n)
+    ms = build_system(a.workload)
     N = ms.nsites
     site = ms.make_sites()
+    L = lib.load()
     eng = lib.Engine(local)
     eng.configure(ms)
     eng.set_partition(rank, world)
     st = torch.cuda.current_stream().cuda_stream
-    xyz = torch.from_numpy(np.ascontiguousarray(site[:, :N])).cuda()
-    out = torch.zeros(eng.out_doubles(), dtype=torch.float64, device="cuda")
-    psum = torch.zeros(eng.recip_sum_doubles(), dtype=torch.float64, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    eng.set_sites_device(xyz[0].data_ptr(), xyz[1].data_ptr(), xyz[2].data_ptr(), st)
+    use_peer = world > 1 and a.collective == "peer"
+    NPH = 6
+    if use_peer:
+        peer = lib.Peer(eng, rank, world)
+        handles = [None] * world
+        dist.all_gather_object(handles, peer.handle())
+        peer.open(handles)
+        dist.barrier()
+        peer.sites_host_all(np.ascontiguousarray(site[:, :N]), st)
+        torch.cuda.synchronize()
+        phases = ["cells", "pair", "recip_partial", "sk_allreduce+recip_finish", "force_reduce_scatter", "force_allgather"]
 
-    def step(ev=None):
-        eng.zero_out(out.data_ptr(), st)
-        if ev: ev[0].record()
-        eng.build_cells(st)
-        if ev: ev[1].record()
-        eng.force_real(out.data_ptr(), st)
-        if ev: ev[2].record()
-        spmd.recip_sites(eng, psum, out, st)          # N>1: site partition + all-reduce of S(k)
-        if ev: ev[3].record()
-        if world > 1:
-            dist.all_reduce(out)
-        if ev: ev[4].record()
+        def step(ev=None):
+            if ev: ev[0].record()
+            peer.phase_a(0, st)
+            if ev: ev[1].record()
+            peer.phase_a(4 | lib.REAL, st)
+            if ev: ev[2].record()
+            peer.phase_a(4 | lib.RECIP, st)
+            if ev: ev[3].record()
+            peer.barrier(st)
+            peer.phase_b(lib.REAL | lib.RECIP, st)
+            if ev: ev[4].record()
+            peer.barrier(st)
+            peer.phase_c(st)
+            if ev: ev[5].record()
+            peer.barrier(st)
+            peer.phase_d(st)
+            if ev: ev[6].record()
+
+        def result_block():
+            return eng.read_out(peer.result_ptr(), st)
+    else:
+        xyz = torch.from_numpy(np.ascontiguousarray(site[:, :N])).cuda()
+        out = torch.zeros(eng.out_doubles(), dtype=torch.float64, device="cuda")
+        psum = torch.zeros(eng.recip_sum_doubles(), dtype=torch.float64, device="cuda")
+        eng.set_sites_device(xyz[0].data_ptr(), xyz[1].data_ptr(), xyz[2].data_ptr(), st)
+        phases = ["cells", "pair", "recip", "allreduce", "-", "-"]
+
+        def step(ev=None):
+            eng.zero_out(out.data_ptr(), st)
+            if ev: ev[0].record()
+            eng.build_cells(st)
+            if ev: ev[1].record()
+            eng.force_real(out.data_ptr(), st)
+            if ev: ev[2].record()
+            spmd.recip_sites(eng, psum, out, st)          # N>1: site partition + all-reduce of S(k)
+            if ev: ev[3].record()
+            if world > 1:
+                dist.all_reduce(out)
+            if ev:
+                for k in (4, 5, 6): ev[k].record()
+
+        def result_block():
+            return out.cpu().numpy()
 
     for _ in range(a.warmup):
         step()
     torch.cuda.synchronize()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(a.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(NPH + 1)] for _ in range(a.steps)]
     l0 = eng.launches()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -236,17 +411,28 @@ def run_ours(a):
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if rank == 0 else None
     launches = eng.launches() - l0
-    ph = np.array([[e[k].elapsed_time(e[k + 1]) for k in range(4)] for e in evs])     # ms: cells, pair, recip, allreduce
-    tot_ms = float(sum(e[0].elapsed_time(e[4]) for e in evs))
+    ph = np.array([[e[k].elapsed_time(e[k + 1]) for k in range(NPH)] for e in evs])
+    tot_ms = float(sum(e[0].elapsed_time(e[NPH]) for e in evs))
     t = torch.tensor([tot_ms], dtype=torch.float64, device="cuda")
+    pht = torch.from_numpy(ph.mean(0)).cuda()
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pht, op=dist.ReduceOp.MAX)
     tot_ms = float(t.item())
+    phm = pht.cpu().numpy()
+    block = result_block()
+    chk = force_check(block, N)
+    ident = True
+    if world > 1:
+        h = torch.tensor([chk["force_checksum"], chk["pe_real"], chk["pe_recip"], chk["force_rms"]], dtype=torch.float64, device="cuda")
+        allh = [torch.zeros_like(h) for _ in range(world)]
+        dist.all_gather(allh, h)
+        ident = all(bool(torch.equal(x, allh[0])) for x in allh)
     pairs_rank = eng.pair_count(st)            # pairs handed to kernel() per step by this rank (counting pass, untimed)
-    pr = torch.tensor([pairs_rank], dtype=torch.float64, device="cuda")
+    pr = torch.tensor([pairs_rank, L.mdb_recip_gemm_flop(eng.h)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(pr)
-    pairs = float(pr.item())
+    pairs, gemm_flop = float(pr[0].item()), float(pr[1].item())
     nhkl = eng.n_kvectors()
     ms_step = tot_ms / a.steps
     value = 1e3 / ms_step
@@ -256,63 +442,74 @@ def run_ours(a):
     e2e_mol = measure_e2e_eval_forces(a, ms) if world == 1 else None
 
     if rank == 0:
-        pair_ms = float(ph[:, 1].mean())
-        peak = lib.load().mdb_fp64_peak_probe(local, 100000)
-        achieved = FLOP_PER_PAIR * (pairs / world) / (pair_ms * 1e-3)
+        pair_ms = float(phm[1])
+        recip_ms = float(phm[2] + (phm[3] if use_peer else 0.0))
+        peak = L.mdb_fp64_peak_probe(local, 100000)
+        peak_dmma = L.mdb_dmma_peak_probe(local, 20000)
+        ptname = ["lennard-jones", "buckingham", "mcy", "generic"][ms.sysdef.ptype] if ms.sysdef.ptype < 4 else "generic"
+        fpp = FLOP_PER_PAIR[ptname]
+        achieved = fpp * (pairs / world) / (pair_ms * 1e-3)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(a.workload)
+        except Exception:
+            pass
         split = eng.pair_split()
         roof = {"bound": "fp64",
                 "kernel": ("real-space phase = k_pair_tiled<none,coulomb,newton3> over the charged sites + "
-                           "k_pair_tiled<LJ,no-coulomb,newton3> over the Lennard-Jones sites (+ sublist compaction): "
-                           "the reference's pair set, with the pairs whose charge product / epsilon is exactly zero "
-                           "skipped term by term" if split else
-                           "k_pair_tiled<LJ,coulomb,newton3> (one fused pass over all sites)") +
-                          "; FP64 CUDA cores, no tensor-core or HBM roofline applies (~36 B/site are reused for ~6 300 "
-                          "pair visits; `traffic` is dram read+write bytes of the phase from the ncu capture in profiles/). "
-                          "`achieved` counts SURVEY 8d's 59 flop for every pair the reference hands to kernel() "
-                          "(pairs_per_launch, counted on the device), so skipped zero terms raise it: it is the "
+                           f"k_pair_tiled<{ptname},no-coulomb,newton3> over the sites with a pair potential (+ sublist "
+                           "compaction): the reference's pair set, with the pairs whose charge product / potential "
+                           "amplitude is exactly zero skipped term by term" if split else
+                           f"k_pair_tiled<{ptname},coulomb,newton3> (one fused pass over all sites)") +
+                          "; FP64 CUDA cores, no tensor-core or HBM roofline applies (~36 B/site are reused for thousands of "
+                          "pair visits). `achieved` counts SURVEY 8d's algorithmic flop for every pair the reference hands "
+                          "to kernel() (pairs_per_launch, counted on the device), so skipped zero terms raise it: it is the "
                           "algorithmic rate of the phase, not the FP64 pipe utilisation (profiles/ has that)",
                 "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": "FP64 DFMA rate measured in this run by mdb_fp64_peak_probe (MEASURED_PEAKS.json holds "
                                "no FP64 figure; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2)",
-                "algorithmic_flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs / world,
-                "avg_launch_ms": pair_ms, "split_passes": bool(split), "traffic": TRAFFIC.get(a.n),
+                "peak_dmma_tflops": peak_dmma / 1e12,
+                "algorithmic_flop_per_pair": fpp, "pairs_per_launch": pairs / world,
+                "avg_launch_ms": pair_ms, "split_passes": bool(split),
+                "traffic": traffic["pair_bytes"] if traffic else None,
+                "traffic_source": traffic["source"] if traffic else "no ncu capture of this workload committed (profiles/traffic.json)",
                 "hbm_peak_gbs_measured": peaks.get("hbm_gbs")}
         line = {"metric": "md_force_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(a.n, N, ms),
+                "config": workload_config(a.workload, ms), "collective": "peer" if use_peer else ("nccl" if world > 1 else None),
                 "site_pairs_per_s": pairs / (ms_step * 1e-3), "site_pairs_per_step": pairs,
                 "k_vectors": nhkl, "site_k_terms_per_s": N * nhkl / (ms_step * 1e-3),
-                "phase_ms": {"cells": float(ph[:, 0].mean()), "pair": pair_ms, "recip": float(ph[:, 2].mean()),
-                             "allreduce": float(ph[:, 3].mean())},
-                "recip_roofline": {"bound": "fp64", "kernel": "k_ktables + k_sfac_mma + k_kforce_mma (DMMA.8x8x4, FP64 tensor pipe)",
-                                   "note": "SURVEY 8d's algorithmic 18 flop per (site, k-vector) of the reference's loops over the time of the "
-                                           "factorised GEMMs, which need ~6: a frac above 1 is not a pipe utilisation (DMMA sub-pipe active "
-                                           "74 % / 78 % in k_sfac_mma / k_kforce_mma, profiles/r01_s3_summary.md)",
-                                   "achieved": FLOP_PER_SITEK * N * nhkl / world / (ph[:, 2].mean() * 1e-3) / 1e12,
-                                   "peak": peak / 1e12, "unit": "TFLOP/s",
-                                   "frac": FLOP_PER_SITEK * N * nhkl / world / (ph[:, 2].mean() * 1e-3) / peak},
+                "phase_ms": {nm: float(v) for nm, v in zip(phases, phm) if nm != "-"},
+                "check": dict(chk, ranks_identical=ident),
+                "recip_roofline": {
+                    "bound": "fp64-tensor", "kernel": "k_sfac_mma + k_kforce_mma (mma.sync.m8n8k4.f64 = DMMA.8x8x4) after k_ktables",
+                    "executed_gemm_flop_per_step": gemm_flop,
+                    "achieved": gemm_flop / world / (recip_ms * 1e-3) / 1e12, "peak": peak_dmma / 1e12, "unit": "TFLOP/s",
+                    "frac": gemm_flop / world / (recip_ms * 1e-3) / peak_dmma,
+                    "note": "flop the two GEMM kernels execute (512 per DMMA issued, padding included; mdb_recip_gemm_flop) "
+                            "over the whole k-space phase, against the DMMA.8x8x4 rate measured in this run",
+                    "algorithmic_tflops": FLOP_PER_SITEK * N * nhkl / world / (recip_ms * 1e-3) / 1e12,
+                    "algorithmic_note": "SURVEY 8d's 18 flop per (site, k-vector) of the reference's loops; the factorised "
+                                        "formulation executes fewer, so this rate may exceed the pipe peak"},
                 "roofline": roof, "clocks": clocks, "e2e": e2e, "e2e_eval_forces": e2e_mol, "gpu_launches": int(launches),
                 "wall_s_timed_region": t_wall}
         if world == 1 and not a.no_cpu_baseline:
             from oracle import ref
             if ref.available(fast=True):
-                line["cpu_baseline"], _ = reference_sample(a.n, a.cpu_seconds)
+                line["cpu_baseline"], _, _ = reference_sample(a.workload, max(a.cpu_seconds, 10.0), steps=1, warmup=0)
             else:
                 line["cpu_baseline"] = {"value": None, "unit": "steps/s", "cores": 0, "kind": "reference",
                                         "sample": "oracle/_ref not built on this box"}
         emit(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
-
-
-# dram__bytes_read+write per k_pair launch from the ncu --set full capture committed under profiles/
-TRAFFIC = {10: 73.9e6}     # bytes per step of the two k_pair_tiled launches at n=10 (profiles/r01_s3_summary.md)
 
 
 def measure_e2e(a, ms, site, world, rank, local):
@@ -349,13 +546,14 @@ def measure_e2e(a, ms, site, world, rank, local):
             one()
         dt = (time.perf_counter() - t0) / steps
         return {"value": 1.0 / dt, "unit": "steps/s", "ms_per_step": 1e3 * dt,
-                "h2d_bytes_per_step": 3 * N * 8, "d2h_bytes_per_step": 2 * (3 * N + 16) * 8,
-                "api": "force_calc()+ewald() of libmoldy_b200.so, pinned host site/site_force rows"}
+                "h2d_bytes_per_step": 2 * 3 * N * 8, "d2h_bytes_per_step": 2 * (3 * N + 16) * 8,
+                "api": "force_calc()+ewald() of libmoldy_b200.so, pinned host site/site_force rows (ewald() uploads the "
+                       "rows again to validate the k-space sums started ahead by force_calc)"}
+    import torch.distributed as dist
     from moldy_b200 import spmd
-    ev = spmd.SpmdForces(ms, rank, world, local)
+    ev = spmd.SpmdForces(ms, rank, world, local, nccl=(a.collective == "nccl"))
     hs = torch.from_numpy(np.ascontiguousarray(site[:, :N])).pin_memory()
     ev.step(hs); ev.step(hs)
-    import torch.distributed as dist
     dist.barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -365,9 +563,15 @@ def measure_e2e(a, ms, site, world, rank, local):
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
+    b = torch.tensor(ev.bytes_per_step(), dtype=torch.float64, device="cuda")
+    dist.all_reduce(b)
+    ev.close()
     return {"value": 1.0 / dt, "unit": "steps/s", "ms_per_step": 1e3 * dt,
-            "h2d_bytes_per_step": 3 * N * 8 * world, "d2h_bytes_per_step": (3 * N + 16) * 8 * world,
-            "api": "moldy_b200.spmd.SpmdForces.step(pinned host sites) -> host [forces|pe|stress] on every rank"}
+            "h2d_bytes_per_step": int(b[0].item()), "d2h_bytes_per_step": int(b[1].item()),
+            "api": ("moldy_b200.spmd.SpmdForces.step(pinned host sites): every rank uploads its slice of the site rows, the "
+                    "slices are all-gathered over NVLink, every rank downloads its slice of the summed forces + the scalars "
+                    "(bytes are the totals over all ranks)" if a.collective == "peer" else
+                    "moldy_b200.spmd.SpmdForces(nccl=True): full upload, NCCL all-reduce and full download on every rank")}
 
 
 def measure_e2e_eval_forces(a, ms):

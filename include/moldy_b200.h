@@ -291,6 +291,51 @@ const double *mdb_eval_result(const mdb_engine *e);
 void eval_forces(system_mp sys, spec_mt *species, site_mt *site_info, pot_mt *potpar, double *pe, real *dip_mom,
                  mat_mt stress, vec_mp *force, vec_mp *torque);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Multi-GPU: the reference's replicated-data scheme (every rank holds all sites; par_rsum/par_dsum of the partial force,
+ * stress and energy arrays, src/parallel.c:549-588, call sites src/accel.c:531-535) with the sums done by kernels of the
+ * library's own over NVLink peer memory (mdb_peer.cu).  A peer = one rank = one engine on one GPU plus a window of device
+ * memory the other ranks map: engines of ONE process (mdb_peer_connect) or one process per GPU (mdb_peer_handle, exchange
+ * the 64-byte handles, mdb_peer_open).  Rank r owns the r-th slice of the site batches (real space), of the charged sites
+ * (k-space, the manual's RIL scheme src/moldy.tex:3441-3466) and of the result (sites [bounds[r], bounds[r+1])).
+ * Step = phase A (cells, real-space sum, structure-factor partial sums) | barrier | phase B (structure-factor all-reduce,
+ * energy/stress on rank 0, k-space forces on own sites) | barrier | phase C (reduce-scatter of the forces + the scalars
+ * on every rank) [| barrier | phase D (all-gather of the forces)].  One host thread may drive all ranks of a process if it
+ * enqueues each phase on every rank before the next one; separate processes call mdb_peer_step.  Nothing synchronises
+ * unless stated.  `what`: bit 0 real space, bit 1 reciprocal space (phase A also: bit 2 = continue the phase an earlier
+ * call began, i.e. no new result block and no cell build). */
+#define MDB_MAX_PEERS 16
+#define MDB_PEER_HANDLE_BYTES 64
+typedef struct mdb_peer mdb_peer;
+mdb_peer *mdb_peer_create(mdb_engine *e, int rank, int world);       /* after mdb_configure; sets the engine's partition and sites */
+void      mdb_peer_destroy(mdb_peer *p);
+size_t    mdb_peer_window_bytes(const mdb_peer *p);
+int       mdb_peer_handle(mdb_peer *p, void *handle);                 /* MDB_PEER_HANDLE_BYTES bytes (CUDA IPC)                  */
+int       mdb_peer_open(mdb_peer *p, const void *handles);            /* world * MDB_PEER_HANDLE_BYTES bytes, rank order         */
+int       mdb_peer_connect(mdb_peer *const *peers, int world);        /* same process: all peers, rank order                     */
+int       mdb_peer_set_site_bounds(mdb_peer *p, const long long *bounds);   /* world + 1 values; default nsites r / world        */
+void      mdb_peer_slice(const mdb_peer *p, long long lohi[2]);
+int       mdb_peer_barrier(mdb_peer *p, void *stream);
+int       mdb_peer_error(mdb_peer *p, void *stream);                  /* 1: a barrier timed out (a rank died); synchronises      */
+/* inputs: the rank uploads its own slice over its own PCIe link, the rest comes from the peers after a barrier */
+int       mdb_peer_sites_host_slice(mdb_peer *p, const double *x, const double *y, const double *z, void *stream);
+int       mdb_peer_sites_host_all(mdb_peer *p, const double *x, const double *y, const double *z, void *stream);
+int       mdb_peer_sites_gather(mdb_peer *p, void *stream);
+double   *mdb_peer_sites(mdb_peer *p);                                /* DEVICE [3][nsites]: the engine's site rows              */
+double   *mdb_peer_in(mdb_peer *p);                                   /* DEVICE: generic input block (c-of-m | quaternions)      */
+int       mdb_peer_in_host_slice(mdb_peer *p, const double *h_in, size_t len, void *stream);
+int       mdb_peer_in_gather(mdb_peer *p, size_t len, void *stream);
+/* the step */
+int       mdb_peer_phase_a(mdb_peer *p, int what, void *stream);
+int       mdb_peer_phase_b(mdb_peer *p, int what, void *stream);
+int       mdb_peer_phase_c(mdb_peer *p, void *stream);
+int       mdb_peer_phase_d(mdb_peer *p, void *stream);
+int       mdb_peer_step(mdb_peer *p, int what, int gather, void *stream);   /* A | barrier | B | barrier | C [| barrier | D]     */
+double   *mdb_peer_result(mdb_peer *p);    /* DEVICE result block: own slice + scalars after C, all forces after D               */
+double   *mdb_peer_partial(mdb_peer *p);   /* DEVICE: this rank's partial block of the current step                              */
+int       mdb_peer_read_slice_host(mdb_peer *p, double *fx, double *fy, double *fz, double *scal16, void *stream);
+long      mdb_peer_barriers(const mdb_peer *p);
+
 /* Number of values in which three HOST rows differ (bit for bit) from the sites the engine currently holds; the rows are
  * staged in `d_scratch` (DEVICE, 3*nsites doubles).  Synchronises `stream`; -1 on error.  ewald() of layer (A) validates
  * the k-space sums that force_calc() started ahead of it with this. */
@@ -311,6 +356,9 @@ long   mdb_kernel_launches(const mdb_engine *e);              /* our kernels lau
 int    mdb_too_close(mdb_engine *e, int pair[2], void *stream);/* count of r^2<0.25 inter-molecular pairs */
 size_t mdb_sizeof(const char *struct_name);                   /* "contr_mt", "system_mt", ... */
 double mdb_fp64_peak_probe(int device, int iters);            /* measured DFMA rate, flop/s */
+double mdb_dmma_peak_probe(int device, int iters);            /* measured DMMA.8x8x4 (FP64 tensor pipe) rate, flop/s */
+double mdb_recip_gemm_flop(const mdb_engine *e);              /* flop the k-space GEMM kernels execute per call on this
+                                                                  rank (2 per multiply-add of every DMMA issued)      */
 
 #ifdef __cplusplus
 }

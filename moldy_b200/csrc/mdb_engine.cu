@@ -584,3 +584,46 @@ extern "C" double mdb_fp64_peak_probe(int device, int iters)
    cudaFree(d);
    return best;
 }
+
+// ---- FP64 tensor-pipe probe: mma.sync.m8n8k4.f64 (DMMA.8x8x4) with 8 independent accumulator tiles per warp ----
+__global__ void __launch_bounds__(256) k_dmma_probe(double *out, int iters)
+{
+   double a = 1e-3 * (threadIdx.x % 7 + 1), b = 1e-3 * (threadIdx.x % 5 + 1), c[8][2];
+   for (int k = 0; k < 8; k++) { c[k][0] = k; c[k][1] = k + 1; }
+   for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+         asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                      : "+d"(c[k][0]), "+d"(c[k][1]) : "d"(a), "d"(b));
+   }
+   double s = 0;
+   for (int k = 0; k < 8; k++) s += c[k][0] + c[k][1];
+   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" double mdb_dmma_peak_probe(int device, int iters)
+{
+   if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+   cudaDeviceProp prop;
+   cudaGetDeviceProperties(&prop, device);
+   const int blocks = prop.multiProcessorCount * 2, threads = 256;
+   double *d = nullptr;
+   if (cudaMalloc(&d, sizeof(double) * blocks * threads) != cudaSuccess) return -1.0;
+   cudaEvent_t e0, e1;
+   cudaEventCreate(&e0); cudaEventCreate(&e1);
+   k_dmma_probe<<<blocks, threads>>>(d, iters / 8);
+   double best = 0.0;
+   for (int rep = 0; rep < 5; rep++) {
+      cudaEventRecord(e0);
+      k_dmma_probe<<<blocks, threads>>>(d, iters);
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      // 8 DMMA per iteration per warp, 2*8*8*4 flop each
+      best = std::max(best, 512.0 * 8.0 * (double)iters * blocks * (threads / 32) / (ms * 1e-3));
+   }
+   cudaEventDestroy(e0); cudaEventDestroy(e1);
+   cudaFree(d);
+   return best;
+}

@@ -1267,3 +1267,35 @@ int mdb_launch_recip_finish(mdb_engine *e, const double *d_psum, double *d_out, 
    if (make_plan(e, true, P, st)) return -1;
    return recip_finish(e, P, d_psum, d_out, st);
 }
+
+// Flop the two GEMM kernels execute per call for this rank's share of the charged sites (site partition; with one rank:
+// everything): 512 = 2 x 8 x 8 x 4 per DMMA.8x8x4.
+//   k_sfac_mma: block = column block (<= MC columns, 8 per warp) x l-range (nt n-tiles of 4 slots); per 4 sites every
+//               active warp issues 2 m-tiles x nt n-tiles;
+//   k_kforce_mma: group of 8 columns, nsteps = ceil(max nl / 2) k-steps, 4 accumulator tiles (X, Y, Xz, Yz) per 8 sites.
+// Padding (sites to whole chunks, columns to whole warps, slots to whole tiles) is counted: the pipe executes it.
+extern "C" double mdb_recip_gemm_flop(const mdb_engine *e)
+{
+   const HostTables &T = e->T;
+   const int nvalid = (int)T.hk_valid.size();
+   if (nvalid == 0) return 0.0;
+   const int r = e->ithread, np = e->nthreads;
+   const long nf = e->n_charged_nf, fw = e->n_charged - e->n_charged_nf;
+   const long own_nf = nf * (r + 1) / np - nf * r / np, own_fw = fw * (r + 1) / np - fw * r / np;
+   auto pad = [](long v, long m) { return (v + m - 1) / m * m; };
+   double sfac = 0.0, kf = 0.0;
+   for (int e0 = 0; e0 < nvalid; e0 += MC) {
+      const int ncols = std::min(MC, nvalid - e0), nlmax = T.hk[T.hk_valid[e0]].nl;
+      const int warps = (ncols + 7) / 8;
+      for (int l0 = 0; l0 < nlmax; l0 += 32) {
+         const int nt = (std::min(32, nlmax - l0) + 3) / 4;
+         sfac += 512.0 * warps * 2 * nt * (double)(pad(own_nf, MSC) + pad(own_fw, MSC)) / 4.0;
+      }
+   }
+   for (int v = 0; v < nvalid; v += 8) {
+      int mx = 0;
+      for (int j = 0; j < 8 && v + j < nvalid; j++) mx = std::max(mx, T.hk[T.hk_valid[v + j]].nl);
+      kf += 512.0 * 4 * ((mx + 1) / 2) * (double)(pad(own_nf, 16) + pad(own_fw, 16)) / 8.0;
+   }
+   return sfac + kf;
+}

@@ -104,6 +104,34 @@ def load() -> C.CDLL:
     L.mdb_eval_result_doubles.argtypes = [C.c_void_p]
     L.mdb_eval_forces_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.eval_forces.restype = None
+    L.mdb_sites_differ_host.restype = C.c_long
+    L.mdb_sites_differ_host.argtypes = [C.c_void_p] * 6
+    # multi-GPU peer layer (mdb_peer.cu)
+    L.mdb_peer_create.restype = C.c_void_p
+    L.mdb_peer_create.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.mdb_peer_destroy.argtypes = [C.c_void_p]
+    L.mdb_peer_window_bytes.restype = C.c_size_t
+    L.mdb_peer_window_bytes.argtypes = [C.c_void_p]
+    L.mdb_peer_handle.argtypes = [C.c_void_p, C.c_void_p]
+    L.mdb_peer_open.argtypes = [C.c_void_p, C.c_void_p]
+    L.mdb_peer_connect.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    L.mdb_peer_set_site_bounds.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+    L.mdb_peer_slice.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+    for f in ("mdb_peer_barrier", "mdb_peer_error", "mdb_peer_sites_gather", "mdb_peer_phase_c", "mdb_peer_phase_d"):
+        getattr(L, f).argtypes = [C.c_void_p, C.c_void_p]
+    for f in ("mdb_peer_phase_a", "mdb_peer_phase_b"):
+        getattr(L, f).argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.mdb_peer_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    for f in ("mdb_peer_sites_host_slice", "mdb_peer_sites_host_all"):
+        getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    for f in ("mdb_peer_sites", "mdb_peer_in", "mdb_peer_result", "mdb_peer_partial"):
+        getattr(L, f).restype = C.c_void_p
+        getattr(L, f).argtypes = [C.c_void_p]
+    L.mdb_peer_in_host_slice.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.mdb_peer_in_gather.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+    L.mdb_peer_read_slice_host.argtypes = [C.c_void_p] * 6
+    L.mdb_peer_barriers.restype = C.c_long
+    L.mdb_peer_barriers.argtypes = [C.c_void_p]
     L.kernel.argtypes = [C.c_int, C.c_int, DP, DP, DP, DP, C.c_double, C.c_double, C.c_double, C.c_int,
                          C.POINTER(DP)]
     _LIB = L
@@ -380,6 +408,97 @@ class Engine:
         p = (C.c_int * 2)()
         n = self.L.mdb_too_close(self.h, p, stream)
         return n, (p[0], p[1])
+
+
+PEER_HANDLE_BYTES = 64
+REAL, RECIP = 1, 2
+
+
+class Peer:
+    """One rank of the replicated-data multi-GPU layer (mdb_peer.cu): an Engine plus its peer-mapped window."""
+
+    def __init__(self, eng: Engine, rank: int, world: int):
+        self.L, self.eng, self.rank, self.world = eng.L, eng, rank, world
+        self.h = self.L.mdb_peer_create(eng.h, rank, world)
+        if not self.h:
+            raise RuntimeError("mdb_peer_create failed: " + _err(self.L))
+
+    def close(self):
+        if self.h:
+            self.L.mdb_peer_destroy(self.h)
+            self.h = None
+
+    def _chk(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what}: {_err(self.L)}")
+
+    def handle(self) -> bytes:
+        buf = C.create_string_buffer(PEER_HANDLE_BYTES)
+        self._chk(self.L.mdb_peer_handle(self.h, buf), "mdb_peer_handle")
+        return buf.raw
+
+    def open(self, handles):
+        """handles: the `world` 64-byte IPC handles in rank order (one process per rank)."""
+        blob = b"".join(handles)
+        assert len(blob) == PEER_HANDLE_BYTES * self.world
+        self._chk(self.L.mdb_peer_open(self.h, blob), "mdb_peer_open")
+
+    @staticmethod
+    def connect(peers):
+        """All ranks are engines of this process: map the windows directly."""
+        L = peers[0].L
+        arr = (C.c_void_p * len(peers))(*[p.h for p in peers])
+        if L.mdb_peer_connect(arr, len(peers)):
+            raise RuntimeError("mdb_peer_connect: " + _err(L))
+
+    def set_site_bounds(self, bounds):
+        b = (C.c_longlong * (self.world + 1))(*[int(x) for x in bounds])
+        self._chk(self.L.mdb_peer_set_site_bounds(self.h, b), "mdb_peer_set_site_bounds")
+
+    def slice(self):
+        lohi = (C.c_longlong * 2)()
+        self.L.mdb_peer_slice(self.h, lohi)
+        return int(lohi[0]), int(lohi[1])
+
+    def barrier(self, stream=0):
+        self._chk(self.L.mdb_peer_barrier(self.h, stream), "mdb_peer_barrier")
+
+    def error(self, stream=0) -> int:
+        return self.L.mdb_peer_error(self.h, stream)
+
+    def sites_host_all(self, site_block: np.ndarray, stream=0):
+        r = [site_block.ctypes.data + site_block.strides[0] * i for i in range(3)]
+        self._chk(self.L.mdb_peer_sites_host_all(self.h, r[0], r[1], r[2], stream), "mdb_peer_sites_host_all")
+
+    def sites_host_slice(self, px, py, pz, stream=0):
+        self._chk(self.L.mdb_peer_sites_host_slice(self.h, px, py, pz, stream), "mdb_peer_sites_host_slice")
+
+    def sites_gather(self, stream=0):
+        self._chk(self.L.mdb_peer_sites_gather(self.h, stream), "mdb_peer_sites_gather")
+
+    def phase_a(self, what=REAL | RECIP, stream=0):
+        self._chk(self.L.mdb_peer_phase_a(self.h, what, stream), "mdb_peer_phase_a")
+
+    def phase_b(self, what=REAL | RECIP, stream=0):
+        self._chk(self.L.mdb_peer_phase_b(self.h, what, stream), "mdb_peer_phase_b")
+
+    def phase_c(self, stream=0):
+        self._chk(self.L.mdb_peer_phase_c(self.h, stream), "mdb_peer_phase_c")
+
+    def phase_d(self, stream=0):
+        self._chk(self.L.mdb_peer_phase_d(self.h, stream), "mdb_peer_phase_d")
+
+    def step(self, what=REAL | RECIP, gather=False, stream=0):
+        self._chk(self.L.mdb_peer_step(self.h, what, 1 if gather else 0, stream), "mdb_peer_step")
+
+    def result_ptr(self) -> int:
+        return self.L.mdb_peer_result(self.h)
+
+    def read_slice_host(self, pfx, pfy, pfz, pscal, stream=0):
+        self._chk(self.L.mdb_peer_read_slice_host(self.h, pfx, pfy, pfz, pscal, stream), "mdb_peer_read_slice_host")
+
+    def barriers(self) -> int:
+        return self.L.mdb_peer_barriers(self.h)
 
 
 def unpack(h_out: np.ndarray, n: int):

@@ -62,31 +62,138 @@ def recip_sites(eng, d_psum: torch.Tensor, d_out: torch.Tensor, stream: int, gro
 
 
 class SpmdForces:
-    """Host-buffer front end of the multi-GPU force evaluation (bench.py `e2e`, N>1)."""
+    """Host-buffer front end of the multi-GPU force evaluation, one process per GPU (bench.py `e2e`, N>1).
 
-    def __init__(self, ms: MoldySystem, rank: int, world: int, device: int):
-        self.ms, self.rank, self.world = ms, rank, world
+    The sums run on the library's own peer-memory kernels (mdb_peer.cu): every rank uploads only ITS slice of the
+    site rows over its own PCIe link, the slices are all-gathered over NVLink, and after the step every rank
+    downloads only its slice of the reduced forces (reduce-scatter) plus the 16 scalars.  `nccl=True` keeps the
+    round-1 path (full upload on every rank, NCCL all-reduce, full download) for comparison."""
+
+    def __init__(self, ms: MoldySystem, rank: int, world: int, device: int, nccl: bool = False):
+        self.ms, self.rank, self.world, self.nccl = ms, rank, world, nccl
         torch.cuda.set_device(device)
         self.eng = lib.Engine(device)
         self.eng.configure(ms)
         self.eng.set_partition(rank, world)
-        self.n = ms.nsites
-        self.d_xyz = torch.empty((3, self.n), dtype=torch.float64, device="cuda")
-        self.d_out = torch.zeros(self.eng.out_doubles(), dtype=torch.float64, device="cuda")
-        self.d_psum = torch.zeros(self.eng.recip_sum_doubles(), dtype=torch.float64, device="cuda")
-        self.h_out = torch.empty(self.eng.out_doubles(), dtype=torch.float64).pin_memory()
-        self.eng.set_sites_device(self.d_xyz[0].data_ptr(), self.d_xyz[1].data_ptr(), self.d_xyz[2].data_ptr())
+        self.n = n = ms.nsites
+        self.h_force = torch.zeros((3, n), dtype=torch.float64).pin_memory()
+        self.h_scal = torch.zeros(16, dtype=torch.float64).pin_memory()
+        if nccl:
+            self.d_xyz = torch.empty((3, n), dtype=torch.float64, device="cuda")
+            self.d_out = torch.zeros(self.eng.out_doubles(), dtype=torch.float64, device="cuda")
+            self.d_psum = torch.zeros(self.eng.recip_sum_doubles(), dtype=torch.float64, device="cuda")
+            self.h_out = torch.empty(self.eng.out_doubles(), dtype=torch.float64).pin_memory()
+            self.eng.set_sites_device(self.d_xyz[0].data_ptr(), self.d_xyz[1].data_ptr(), self.d_xyz[2].data_ptr())
+            self.lo, self.hi = 0, n
+            return
+        self.peer = lib.Peer(self.eng, rank, world)
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, self.peer.handle())
+            self.peer.open(handles)
+            dist.barrier()
+        self.lo, self.hi = self.peer.slice()
 
-    def step(self, host_sites: torch.Tensor) -> np.ndarray:
-        """host_sites: pinned [3,N] float64.  Returns the combined block on the host."""
+    def step(self, host_sites: torch.Tensor):
+        """host_sites: pinned [3,N] float64 (only this rank's slice is read).  Returns (forces [3,N] pinned -- this
+        rank's slice [lo,hi) is valid --, scalars[16] = pe_real, pe_recip, stress[9], lo, hi)."""
         st = torch.cuda.current_stream().cuda_stream
-        self.d_xyz.copy_(host_sites, non_blocking=True)
-        self.eng.set_sites_device(self.d_xyz[0].data_ptr(), self.d_xyz[1].data_ptr(), self.d_xyz[2].data_ptr(), st)
-        self.eng.zero_out(self.d_out.data_ptr(), st)
-        self.eng.build_cells(st)
-        self.eng.force_real(self.d_out.data_ptr(), st)
-        recip_sites(self.eng, self.d_psum, self.d_out, st)
-        combine(self.d_out)
-        self.h_out.copy_(self.d_out, non_blocking=True)
-        torch.cuda.synchronize()
-        return self.h_out.numpy()
+        if self.nccl:
+            self.d_xyz.copy_(host_sites, non_blocking=True)
+            self.eng.set_sites_device(self.d_xyz[0].data_ptr(), self.d_xyz[1].data_ptr(), self.d_xyz[2].data_ptr(), st)
+            self.eng.zero_out(self.d_out.data_ptr(), st)
+            self.eng.build_cells(st)
+            self.eng.force_real(self.d_out.data_ptr(), st)
+            recip_sites(self.eng, self.d_psum, self.d_out, st)
+            combine(self.d_out)
+            self.h_out.copy_(self.d_out, non_blocking=True)
+            torch.cuda.synchronize()
+            n = self.n
+            self.h_force.copy_(self.h_out[:3 * n].view(3, n))
+            self.h_scal.copy_(self.h_out[3 * n:])
+            return self.h_force, self.h_scal, 0, n
+        p = self.peer
+        rows = [host_sites[a].data_ptr() for a in range(3)]
+        p.sites_host_slice(rows[0], rows[1], rows[2], st)
+        p.barrier(st)
+        p.sites_gather(st)
+        p.step(lib.REAL | lib.RECIP, False, st)
+        f = [self.h_force[a].data_ptr() for a in range(3)]
+        p.read_slice_host(f[0], f[1], f[2], self.h_scal.data_ptr(), st)
+        return self.h_force, self.h_scal, self.lo, self.hi
+
+    def bytes_per_step(self):
+        """(H2D, D2H) bytes this rank moves per step."""
+        if self.nccl:
+            return 3 * self.n * 8, (3 * self.n + 16) * 8
+        return 3 * (self.hi - self.lo) * 8, (3 * (self.hi - self.lo) + 16) * 8
+
+    def close(self):
+        if not self.nccl:
+            self.peer.close()
+        self.eng.close()
+
+
+class PeerGroup:
+    """All ranks as engines of THIS process (one host thread drives them phase by phase): the form the C library uses
+    behind force_calc()/ewald()/eval_forces() with MOLDY_B200_DEVICES, and what the single-box GPU tests exercise.
+    devices may repeat (several ranks on one GPU: the kernels are the same, the windows are then local)."""
+
+    def __init__(self, ms: MoldySystem, devices):
+        self.ms, self.world, self.n = ms, len(devices), ms.nsites
+        self.engs, self.peers, self.streams = [], [], []
+        for r, d in enumerate(devices):
+            torch.cuda.set_device(d)
+            e = lib.Engine(d)
+            e.configure(ms)
+            self.engs.append(e)
+            self.peers.append(lib.Peer(e, r, self.world))
+            self.streams.append(torch.cuda.Stream(device=d))
+        lib.Peer.connect(self.peers)
+        self.devices = list(devices)
+
+    def _each(self, fn):
+        cur = torch.cuda.current_device()
+        try:
+            for r, p in enumerate(self.peers):
+                fn(p, self.streams[r].cuda_stream)
+        finally:
+            torch.cuda.set_device(cur)         # the library selects each rank's device (cudaSetDevice)
+
+    def set_sites(self, site_block: np.ndarray):
+        blk = np.ascontiguousarray(site_block[:, :self.n])
+        self._keep = blk
+        self._each(lambda p, st: p.sites_host_all(blk, st))
+
+    def step(self, what=lib.REAL | lib.RECIP, gather=True):
+        self._each(lambda p, st: p.phase_a(what, st))
+        self._each(lambda p, st: p.barrier(st))
+        self._each(lambda p, st: p.phase_b(what, st))
+        self._each(lambda p, st: p.barrier(st))
+        self._each(lambda p, st: p.phase_c(st))
+        if gather:
+            self._each(lambda p, st: p.barrier(st))
+            self._each(lambda p, st: p.phase_d(st))
+
+    def result(self, rank=0) -> np.ndarray:
+        """The reduced block of one rank as a host array (after step(gather=True): complete on every rank)."""
+        cur = torch.cuda.current_device()
+        torch.cuda.set_device(self.devices[rank])
+        try:
+            return self.engs[rank].read_out(self.peers[rank].result_ptr(), self.streams[rank].cuda_stream)
+        finally:
+            torch.cuda.set_device(cur)
+
+    def synchronize(self):
+        for s in self.streams:
+            s.synchronize()
+        for r, p in enumerate(self.peers):
+            if p.error(self.streams[r].cuda_stream):
+                raise RuntimeError(f"peer barrier of rank {r} timed out")
+
+    def close(self):
+        self.synchronize()
+        for p in self.peers:
+            p.close()
+        for e in self.engs:
+            e.close()
