@@ -91,6 +91,10 @@ def load() -> C.CDLL:
     L.mdb_sizeof.argtypes = [C.c_char_p]
     L.mdb_fp64_peak_probe.restype = C.c_double
     L.mdb_fp64_peak_probe.argtypes = [C.c_int, C.c_int]
+    L.mdb_dmma_peak_probe.restype = C.c_double
+    L.mdb_dmma_peak_probe.argtypes = [C.c_int, C.c_int]
+    L.mdb_recip_gemm_flop.restype = C.c_double
+    L.mdb_recip_gemm_flop.argtypes = [C.c_void_p]
     L.mdb_control.restype = C.POINTER(abi.contr_mt)
     L.mdb_abi_engine.restype = C.c_void_p
     L.mdb_abi_stream.restype = C.c_void_p
