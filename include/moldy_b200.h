@@ -336,6 +336,29 @@ double   *mdb_peer_partial(mdb_peer *p);   /* DEVICE: this rank's partial block 
 int       mdb_peer_read_slice_host(mdb_peer *p, double *fx, double *fy, double *fz, double *scal16, void *stream);
 long      mdb_peer_barriers(const mdb_peer *p);
 
+/* Several GPUs behind ONE process (mdb_group.cu): P engines + P peers driven by the calling thread; what force_calc()/
+ * ewald()/eval_forces() of layer (A) use when MOLDY_B200_DEVICES names more than one device -- the unmodified Moldy program
+ * (no -DSPMD, nthreads = 1: SURVEY 8b) then runs on all of them.  Both calls block until the results are in host memory.
+ * mdb_group_force_host: forces of the HOST site rows summed over the ranks, WRITTEN into three host rows (each rank copies
+ *   its slice in and out over its own PCIe link), scal16 = [pe_real, pe_recip, stress[9], pad]; c_of_m as mdb_set_com_host
+ *   (molecular cut-off) or NULL; tc/tc_pair as mdb_too_close (may be NULL).
+ * mdb_group_eval_forces_host: contract and result layout of mdb_eval_forces_host; rdf_counts != NULL adds the RDF pass. */
+typedef struct mdb_group mdb_group;
+mdb_group  *mdb_group_create(int ndev, const int *devices);
+void        mdb_group_destroy(mdb_group *g);
+int         mdb_group_size(const mdb_group *g);
+mdb_engine *mdb_group_engine(mdb_group *g, int rank);
+void       *mdb_group_stream(mdb_group *g, int rank);
+int         mdb_group_configure(mdb_group *g, const mdb_config *cfg);
+int         mdb_group_force_host(mdb_group *g, const double *x, const double *y, const double *z, const double *c_of_m, int what,
+                                 double *fx, double *fy, double *fz, double *scal16, int *tc, int tc_pair[2]);
+int         mdb_group_set_species(mdb_group *g, int nspecies, const mdb_species *sp, const double *pfs);
+size_t      mdb_group_eval_result_doubles(const mdb_group *g);
+const double *mdb_group_eval_result(const mdb_group *g);
+int         mdb_group_eval_forces_host(mdb_group *g, const double h[9], const double *const *com, const double *const *quat,
+                                       int surface_dipole, int do_recip, double *h_result, double rdf_limit, int rdf_nbins,
+                                       unsigned long long *rdf_counts, int *tc, int tc_pair[2]);
+
 /* Number of values in which three HOST rows differ (bit for bit) from the sites the engine currently holds; the rows are
  * staged in `d_scratch` (DEVICE, 3*nsites doubles).  Synchronises `stream`; -1 on error.  ewald() of layer (A) validates
  * the k-space sums that force_calc() started ahead of it with this. */

@@ -189,6 +189,13 @@ int mdb_launch_kernel_vec(int jmin, int nnab, double *forceij, double *pe, const
                           const double *nab_chg, double chg, double norm, double alpha, int ptype,
                           double *const *pot);
 
+// pieces of eval_forces() (mdb_molframe.cu), shared with the multi-GPU driver (mdb_group.cu)
+int mdb_evalf_stage_inputs(mdb_engine *e, const double *const *com, const double *const *quat, double *h_in);
+int mdb_evalf_make_sites(mdb_engine *e, const double h[9], const double *d_in, bool second, cudaStream_t st);
+int mdb_evalf_pre(mdb_engine *e, const double h[9], const double *d_in, cudaStream_t st);
+int mdb_evalf_tail(mdb_engine *e, const double h[9], const double *d_in, const double *d_fblock, int m_lo, int m_hi,
+                   int surface_dipole, int do_recip, cudaStream_t st);
+
 #define MDB_CUDA(call)                                                                   \
    do {                                                                                  \
       cudaError_t _e = (call);                                                           \

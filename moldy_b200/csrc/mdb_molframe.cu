@@ -338,10 +338,13 @@ extern "C" size_t mdb_eval_result_doubles(const mdb_engine *e)
    return 3 * (size_t)e->mf.nmols + 3 * (size_t)e->mf.nmols_r + MDB_EVAL_SCALARS;
 }
 
-static int make_all_sites(mdb_engine *e, const double h[9], bool second, cudaStream_t st)
+// ---- the pieces of eval_forces(), shared by the one-GPU path below and the multi-GPU driver (mdb_group.cu) ----------
+// d_in = [scaled c-of-m 3 nmols | quaternions 4 nmols_q] on the device
+
+int mdb_evalf_make_sites(mdb_engine *e, const double h[9], const double *d_in, bool second, cudaStream_t st)
 {
    auto &M = e->mf;
-   const double *d_com = M.d_in, *d_quat = M.d_in + 3 * (size_t)M.nmols;
+   const double *d_com = d_in, *d_quat = d_in + 3 * (size_t)M.nmols;
    for (size_t i = 0; i < M.sp.size(); i++) {
       const mdb_species &s = M.sp[i];
       // first pass: control.molpbc ? MOLPBC : SITEPBC (src/accel.c:500-504); second: framework ? SITEPBC : MOLPBC (:537-542)
@@ -353,56 +356,109 @@ static int make_all_sites(mdb_engine *e, const double h[9], bool second, cudaStr
    return 0;
 }
 
-extern "C" int mdb_eval_forces_host(mdb_engine *e, const double h[9], const double *const *com, const double *const *quat,
-                                    int surface_dipole, int do_recip, double *h_result, void *stream)
+// host staging of the caller's (pageable) per-species arrays into one pinned block, by up to four threads
+int mdb_evalf_stage_inputs(mdb_engine *e, const double *const *com, const double *const *quat, double *h_in)
 {
    auto &M = e->mf;
-   if (!e->configured || M.sp.empty()) { mdb_set_error("mdb_eval_forces_host: mdb_set_species was not called"); return -1; }
-   cudaStream_t st = (cudaStream_t)stream;
-   const size_t n = e->cfg.nsites;
-   // centres of mass and quaternions: the only per-step input (56 B per molecule); staged into pinned memory by up to
-   // four threads (the caller's arrays are pageable)
-   {
-      struct Job { double *dst; const double *src; size_t bytes; };
-      std::vector<Job> jobs;
-      for (size_t i = 0; i < M.sp.size(); i++) {
-         jobs.push_back({M.h_in + 3 * (size_t)M.mol_off[i], com[i], sizeof(double) * 3 * (size_t)M.sp[i].nmols});
-         if (M.quat_off[i] >= 0) {
-            if (!quat || !quat[i]) { mdb_set_error("mdb_eval_forces_host: quaternions missing"); return -1; }
-            jobs.push_back({M.h_in + 3 * (size_t)M.nmols + 4 * (size_t)M.quat_off[i], quat[i],
-                            sizeof(double) * 4 * (size_t)M.sp[i].nmols});
-         }
-      }
-      size_t total = 0;
-      for (auto &j : jobs) total += j.bytes;
-      auto run = [&](int part, int nparts) {
-         for (auto &j : jobs) {
-            const size_t lo = j.bytes / 8 * part / nparts * 8, hi = j.bytes / 8 * (part + 1) / nparts * 8;
-            memcpy((char *)j.dst + lo, (const char *)j.src + lo, hi - lo);
-         }
-      };
-      if (total >= (4u << 20)) {
-         std::thread th[3];
-         for (int k = 1; k < 4; k++) th[k - 1] = std::thread(run, k, 4);
-         run(0, 4);
-         for (auto &t : th) t.join();
-      } else {
-         run(0, 1);
+   struct Job { double *dst; const double *src; size_t bytes; };
+   std::vector<Job> jobs;
+   for (size_t i = 0; i < M.sp.size(); i++) {
+      jobs.push_back({h_in + 3 * (size_t)M.mol_off[i], com[i], sizeof(double) * 3 * (size_t)M.sp[i].nmols});
+      if (M.quat_off[i] >= 0) {
+         if (!quat || !quat[i]) { mdb_set_error("mdb_eval_forces_host: quaternions missing"); return -1; }
+         jobs.push_back({h_in + 3 * (size_t)M.nmols + 4 * (size_t)M.quat_off[i], quat[i],
+                         sizeof(double) * 4 * (size_t)M.sp[i].nmols});
       }
    }
-   MDB_CUDA(cudaMemcpyAsync(M.d_in, M.h_in, sizeof(double) * (3 * (size_t)M.nmols + 4 * (size_t)M.nmols_q),
-                            cudaMemcpyHostToDevice, st));
-   if (make_all_sites(e, h, false, st)) return -1;
-   if (e->cfg.molpbc) {                       // molecular cut-off: the cell build bins by the scaled centres of mass
+   size_t total = 0;
+   for (auto &j : jobs) total += j.bytes;
+   auto run = [&](int part, int nparts) {
+      for (auto &j : jobs) {
+         const size_t lo = j.bytes / 8 * part / nparts * 8, hi = j.bytes / 8 * (part + 1) / nparts * 8;
+         memcpy((char *)j.dst + lo, (const char *)j.src + lo, hi - lo);
+      }
+   };
+   if (total >= (4u << 20)) {
+      std::thread th[3];
+      for (int k = 1; k < 4; k++) th[k - 1] = std::thread(run, k, 4);
+      run(0, 4);
+      for (auto &t : th) t.join();
+   } else {
+      run(0, 1);
+   }
+   return 0;
+}
+
+// sites from the inputs (first make_sites) and, under molecular cut-off, the c-of-m the cell build bins by
+int mdb_evalf_pre(mdb_engine *e, const double h[9], const double *d_in, cudaStream_t st)
+{
+   auto &M = e->mf;
+   if (mdb_evalf_make_sites(e, h, d_in, false, st)) return -1;
+   if (e->cfg.molpbc) {
       if (M.nmols > e->com_cap) {
          if (e->d_com) cudaFree(e->d_com);
          e->d_com = nullptr;
          MDB_CUDA(cudaMalloc(&e->d_com, sizeof(double) * 3 * (size_t)M.nmols));
          e->com_cap = M.nmols;
       }
-      MDB_CUDA(cudaMemcpyAsync(e->d_com, M.d_in, sizeof(double) * 3 * (size_t)M.nmols, cudaMemcpyDeviceToDevice, st));
+      MDB_CUDA(cudaMemcpyAsync(e->d_com, d_in, sizeof(double) * 3 * (size_t)M.nmols, cudaMemcpyDeviceToDevice, st));
       e->com_set = true;
    }
+   return 0;
+}
+
+// After the force sums: second make_sites, dipole moment, and for the molecules [m_lo, m_hi) (global molecule index) the
+// surface-dipole term + mol_force + mol_torque + virial partials -> M.d_res (same layout as the one-GPU result; only the
+// rows of those molecules are written) and the scalars.  d_fblock: result block [fx|fy|fz|16 scalars] holding the COMPLETE
+// site forces of those molecules.
+int mdb_evalf_tail(mdb_engine *e, const double h[9], const double *d_in, const double *d_fblock, int m_lo, int m_hi,
+                   int surface_dipole, int do_recip, cudaStream_t st)
+{
+   auto &M = e->mf;
+   const size_t n = e->cfg.nsites;
+   double *scal = M.d_res + 3 * (size_t)M.nmols + 3 * (size_t)M.nmols_r;
+   MDB_CUDA(cudaMemsetAsync(scal, 0, sizeof(double) * MDB_EVAL_SCALARS, st));
+   double coef = 0.0;
+   if (do_recip) {
+      if (mdb_evalf_make_sites(e, h, d_in, true, st)) return -1;
+      k_dipole_partial<<<DIP_BLOCKS, MB, 0, st>>>(e->d_x, e->d_y, e->d_z, e->d_chg, (int)n, M.d_dpart);
+      k_dipole_finish<<<3, MB, 0, st>>>(M.d_dpart, DIP_BLOCKS, scal);
+      e->launches += 2;
+      if (surface_dipole) coef = 4.0 * MDB_PI / (3.0 * mdb_det3(h));
+   }
+   int nblk = 0;
+   for (size_t i = 0; i < M.sp.size(); i++) {
+      const mdb_species &s = M.sp[i];
+      const int a = std::max(m_lo, M.mol_off[i]) - M.mol_off[i], b = std::min(m_hi, M.mol_off[i] + s.nmols) - M.mol_off[i];
+      if (b <= a) continue;
+      const int cnt = b - a;
+      const size_t so = (size_t)M.site_off[i] + (size_t)a * s.nsites;
+      k_mol_frame<<<(cnt + MB - 1) / MB, MB, 0, st>>>(
+         d_fblock + so, d_fblock + n + so, d_fblock + 2 * n + so, e->d_chg + so, scal, coef,
+         M.quat_off[i] >= 0 ? d_in + 3 * (size_t)M.nmols + 4 * ((size_t)M.quat_off[i] + a) : nullptr,
+         M.d_pfs + 3 * (size_t)M.pfs_off[i], cnt, s.nsites, s.framework, M.d_res + 3 * ((size_t)M.mol_off[i] + a),
+         M.torq_off[i] >= 0 ? M.d_res + 3 * (size_t)M.nmols + 3 * ((size_t)M.torq_off[i] + a) : nullptr,
+         M.d_vpart + 9 * (size_t)nblk);
+      nblk += (cnt + MB - 1) / MB;
+      e->launches++;
+   }
+   k_eval_finish<<<9, MB, 0, st>>>(M.d_vpart, nblk, d_fblock + 3 * n, scal);
+   e->launches++;
+   MDB_CUDA(cudaGetLastError());
+   return 0;
+}
+
+extern "C" int mdb_eval_forces_host(mdb_engine *e, const double h[9], const double *const *com, const double *const *quat,
+                                    int surface_dipole, int do_recip, double *h_result, void *stream)
+{
+   auto &M = e->mf;
+   if (!e->configured || M.sp.empty()) { mdb_set_error("mdb_eval_forces_host: mdb_set_species was not called"); return -1; }
+   cudaStream_t st = (cudaStream_t)stream;
+   // centres of mass and quaternions: the only per-step input (56 B per molecule)
+   if (mdb_evalf_stage_inputs(e, com, quat, M.h_in)) return -1;
+   MDB_CUDA(cudaMemcpyAsync(M.d_in, M.h_in, sizeof(double) * (3 * (size_t)M.nmols + 4 * (size_t)M.nmols_q),
+                            cudaMemcpyHostToDevice, st));
+   if (mdb_evalf_pre(e, h, M.d_in, st)) return -1;
    double *d_out = e->d_out_own;
    if (mdb_zero_out(e, d_out, stream) || mdb_build_cells(e, stream) || mdb_force_real(e, d_out, stream)) return -1;
    if (do_recip && mdb_force_recip(e, d_out, stream)) return -1;
@@ -411,32 +467,7 @@ extern "C" int mdb_eval_forces_host(mdb_engine *e, const double h[9], const doub
       M.rdf_counts = nullptr;
       if (mdb_rdf_counts(e, M.rdf_limit, M.rdf_nbins, dst, stream)) return -1;
    }
-
-   double *scal = M.d_res + 3 * (size_t)M.nmols + 3 * (size_t)M.nmols_r;
-   MDB_CUDA(cudaMemsetAsync(scal, 0, sizeof(double) * MDB_EVAL_SCALARS, st));
-   double coef = 0.0;
-   if (do_recip) {
-      if (make_all_sites(e, h, true, st)) return -1;
-      k_dipole_partial<<<DIP_BLOCKS, MB, 0, st>>>(e->d_x, e->d_y, e->d_z, e->d_chg, (int)n, M.d_dpart);
-      k_dipole_finish<<<3, MB, 0, st>>>(M.d_dpart, DIP_BLOCKS, scal);
-      e->launches += 2;
-      if (surface_dipole) coef = 4.0 * MDB_PI / (3.0 * mdb_det3(h));
-   }
-   for (size_t i = 0; i < M.sp.size(); i++) {
-      const mdb_species &s = M.sp[i];
-      if (s.nmols == 0) continue;
-      const size_t so = M.site_off[i];
-      k_mol_frame<<<(s.nmols + MB - 1) / MB, MB, 0, st>>>(
-         d_out + so, d_out + n + so, d_out + 2 * n + so, e->d_chg + so, scal, coef,
-         M.quat_off[i] >= 0 ? M.d_in + 3 * (size_t)M.nmols + 4 * (size_t)M.quat_off[i] : nullptr,
-         M.d_pfs + 3 * (size_t)M.pfs_off[i], s.nmols, s.nsites, s.framework, M.d_res + 3 * (size_t)M.mol_off[i],
-         M.torq_off[i] >= 0 ? M.d_res + 3 * (size_t)M.nmols + 3 * (size_t)M.torq_off[i] : nullptr,
-         M.d_vpart + 9 * (size_t)M.blk_off[i]);
-      e->launches++;
-   }
-   k_eval_finish<<<9, MB, 0, st>>>(M.d_vpart, M.nblocks, d_out + 3 * n, scal);
-   e->launches++;
-   MDB_CUDA(cudaGetLastError());
+   if (mdb_evalf_tail(e, h, M.d_in, d_out, 0, M.nmols, surface_dipole, do_recip, st)) return -1;
    const size_t nres = mdb_eval_result_doubles(e);
    MDB_CUDA(cudaMemcpyAsync(M.h_res, M.d_res, sizeof(double) * nres, cudaMemcpyDeviceToHost, st));
    MDB_CUDA(cudaStreamSynchronize(st));

@@ -289,7 +289,7 @@ extern "C" int mdb_peer_sites_host_all(mdb_peer *p, const double *x, const doubl
    MDB_CUDA(cudaMemcpyAsync(xyz, x, sizeof(double) * p->n, cudaMemcpyHostToDevice, st));
    MDB_CUDA(cudaMemcpyAsync(xyz + p->n, y, sizeof(double) * p->n, cudaMemcpyHostToDevice, st));
    MDB_CUDA(cudaMemcpyAsync(xyz + 2 * p->n, z, sizeof(double) * p->n, cudaMemcpyHostToDevice, st));
-   p->e->sites_set = true; p->e->cells_valid = false;
+   mdb_set_sites_device(p->e, xyz, xyz + p->n, xyz + 2 * p->n, nullptr);
    return 0;
 }
 // after a barrier: pull the other ranks' slices; the engine then holds all sites
@@ -302,7 +302,8 @@ extern "C" int mdb_peer_sites_gather(mdb_peer *p, void *stream)
       p->e->launches++;
       MDB_CUDA(cudaGetLastError());
    }
-   p->e->sites_set = true; p->e->cells_valid = false;
+   double *xyz = reinterpret_cast<double *>(p->win + p->off_xyz);
+   mdb_set_sites_device(p->e, xyz, xyz + p->n, xyz + 2 * p->n, nullptr);      // (eval_forces switches the engine to its own rows)
    return 0;
 }
 extern "C" double *mdb_peer_sites(mdb_peer *p) { return reinterpret_cast<double *>(p->win + p->off_xyz); }

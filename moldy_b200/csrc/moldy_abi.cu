@@ -92,6 +92,7 @@ const dim_mt pot_dim[][MDB_NPOTP] = {
 // ---- process-wide state (the reference keeps the same in function statics) -----
 struct AbiState {
    mdb_engine *eng = nullptr;
+   mdb_group *group = nullptr;                              // MOLDY_B200_DEVICES names > 1 device: eng = the group's rank 0
    cudaStream_t stream = nullptr, copy_stream = nullptr;   // copy_stream: D2H of the real-space block beside the k-space kernels
    cudaEvent_t ev_real = nullptr, ev_copied = nullptr;
    bool chg_unchecked = false;                              // sync_config(defer_chg): contents of chg[] still to be compared
@@ -117,6 +118,25 @@ struct AbiState {
 };
 static AbiState G;
 
+// MOLDY_B200_DEVICES = "all" | "0-7" | "0,1,4" (a device may repeat: several ranks on one GPU)
+static std::vector<int> parse_devices(const char *s)
+{
+   std::vector<int> d;
+   int ndev = 0;
+   cudaGetDeviceCount(&ndev);
+   if (!strcmp(s, "all")) { for (int i = 0; i < ndev; i++) d.push_back(i); return d; }
+   while (*s) {
+      char *end;
+      const long a = strtol(s, &end, 10);
+      if (end == s) break;
+      long b = a;
+      if (*end == '-') { s = end + 1; b = strtol(s, &end, 10); }
+      for (long v = a; v <= b; v++) d.push_back((int)v);
+      s = *end ? end + 1 : end;
+   }
+   return d;
+}
+
 static void ensure_engine()
 {
    if (G.eng) return;
@@ -124,7 +144,19 @@ static void ensure_engine()
    const char *s = getenv("MOLDY_B200_DEVICE");
    if (!s) s = getenv("LOCAL_RANK");
    if (s) dev = atoi(s);
-   G.eng = mdb_create(dev);
+   const char *many = getenv("MOLDY_B200_DEVICES");
+   std::vector<int> devs = many ? parse_devices(many) : std::vector<int>();
+   if (devs.size() > 1) {
+      if (nthreads > 1) FATAL_MSG("libmoldy_b200: MOLDY_B200_DEVICES drives all GPUs from one process; run Moldy without SPMD");
+      G.group = mdb_group_create((int)devs.size(), devs.data());
+      if (!G.group) FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+      G.eng = mdb_group_engine(G.group, 0);
+      dev = devs[0];
+      cudaSetDevice(dev);
+   } else {
+      if (devs.size() == 1) dev = devs[0];
+      G.eng = mdb_create(dev);
+   }
    if (!G.eng) FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
    if (cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking) != cudaSuccess ||
        cudaStreamCreateWithFlags(&G.copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -199,7 +231,8 @@ static void sync_config(system_mt *system, spec_mt *species, const real *chg, co
    }
    if (!changed) return;
    c.site_type = G.type.data(); c.site_mol = G.mol.data(); c.chg = G.chg.data(); c.potpar = G.potflat.data();
-   if (mdb_configure(G.eng, &c)) FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+   if (G.group ? mdb_group_configure(G.group, &c) : mdb_configure(G.eng, &c)) FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+   if (G.group) cudaSetDevice(G.eng->device);
    G.config_epoch++;
    G.ahead_valid = false;
    G.cfg = c;
@@ -333,6 +366,27 @@ static void real_first_call(system_mt *system, spec_mt *species, const real *chg
    }
 }
 
+// force_calc()/ewald() on all GPUs of the group: slices of the site rows in, slices of the summed forces out (pinned block),
+// then the usual += into the caller's arrays.  what: 1 real space (pe = caller's pe), 2 reciprocal space (pe = caller's pe+1).
+static void group_force(real **site, real **site_force, system_mt *system, int what, double *pe, real (*stress)[3])
+{
+   const int n = system->nsites;
+   int tc = 0, pr[2] = {0, 0};
+   double *h = G.h_out;
+   if (mdb_group_force_host(G.group, site[0], site[1], site[2], control.molpbc ? &system->c_of_m[0][0] : nullptr, what, h, h + n,
+                            h + 2 * (size_t)n, h + 3 * (size_t)n, what == 1 ? &tc : nullptr, pr))
+      FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+   cudaSetDevice(G.eng->device);
+   pull_and_accumulate(site_force, pe, stress, n, G.d_out, h, true);
+   *pe += h[3 * (size_t)n + (what == 1 ? 0 : 1)];
+   if (tc & (1 << 30))
+      message((int *)0, (char *)0, SEV_ERROR, (char *)"Co-ordinate out of range in BIN (fill_cells)");
+   if (tc & ~(1 << 30))                                  /* src/force.c:944-946 */
+      message((int *)0, (char *)0, SEV_WARNING, (char *)"Sites %d and %d closer than %fA.", pr[0], pr[1],
+              sqrt(MDB_TOO_CLOSE));
+   G.sites_fresh = false; G.ahead_valid = false;
+}
+
 extern "C" void force_calc(real **site, real **site_force, system_mt *system, spec_mt *species, real *chg,
                            pot_mt *potpar, double *pe, mat_mt stress)
 {
@@ -344,6 +398,26 @@ extern "C" void force_calc(real **site, real **site_force, system_mt *system, sp
 
    real_first_call(system, species, chg, potpar);
    if (ithread == 0) *pe -= G.eintra;
+
+   if (G.group) {                                        /* all GPUs of MOLDY_B200_DEVICES: complete sums (nthreads = 1) */
+      chg_changed_late(chg, n);
+      group_force(site, site_force, system, 1, pe, stress);
+      if (rdf_due()) {
+         float *rdf_base = rdf_store(mdb_rdf_size(G.eng, control.nbins));
+         if (rdf_base) {
+            std::vector<unsigned long long> cnt(mdb_rdf_size(G.eng, control.nbins), 0ULL);
+            for (int r = 0; r < mdb_group_size(G.group); r++) {
+               mdb_engine *er = mdb_group_engine(G.group, r);
+               cudaSetDevice(er->device);
+               if (mdb_rdf_counts(er, control.limit, control.nbins, cnt.data(), mdb_group_stream(G.group, r)))
+                  FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+            }
+            cudaSetDevice(G.eng->device);
+            rdf_add_counts(system, rdf_base, cnt);
+         }
+      }
+      return;
+   }
 
    auto launch_real = [&]() {
       G.sites_fresh = false;
@@ -473,6 +547,10 @@ extern "C" void ewald(real **site, real **site_force, system_mp system, spec_mt 
       for (int i = 0; i < 3; i++) stress[i][i] += G.sheet_energy / vol;
    }
 
+   if (G.group) {
+      group_force(site, site_force, system, 2, pe, stress);
+      return;
+   }
    bool ahead = G.ahead_valid && G.sites_fresh && G.ahead_sites == (const void *)site[0] &&
                 G.ahead_epoch == G.config_epoch && G.ahead_ithread == ithread && G.ahead_nthreads == nthreads;
    G.ahead_valid = false;
@@ -648,7 +726,9 @@ static void eval_forces_impl(system_mp sys, spec_mt *species, site_mt *site_info
                         !memcmp(sp_new.data(), E.sp.data(), sizeof(mdb_species) * sp_new.size());
       if (!same) {
          E.sp.swap(sp_new); E.pfs.swap(pfs_new);
-         if (mdb_set_species(G.eng, nspecies, E.sp.data(), E.pfs.data())) FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+         if (G.group ? mdb_group_set_species(G.group, nspecies, E.sp.data(), E.pfs.data())
+                     : mdb_set_species(G.eng, nspecies, E.sp.data(), E.pfs.data()))
+            FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
       }
       E.species_epoch = G.config_epoch;
    }
@@ -662,16 +742,21 @@ static void eval_forces_impl(system_mp sys, spec_mt *species, site_mt *site_info
    float *rdf_base = nullptr;
    if (rdf_due() && (rdf_base = rdf_store(mdb_rdf_size(G.eng, control.nbins))) != nullptr) {
       rdf_cnt.assign(mdb_rdf_size(G.eng, control.nbins), 0ULL);   /* binned between the force sums and the second make_sites */
-      mdb_eval_request_rdf(G.eng, control.limit, control.nbins, rdf_cnt.data());
+      if (!G.group) mdb_eval_request_rdf(G.eng, control.limit, control.nbins, rdf_cnt.data());
    }
-   if (mdb_eval_forces_host(G.eng, h9, com.data(), quat.data(), control.surface_dipole ? 1 : 0, do_recip ? 1 : 0,
-                            nullptr, G.stream))
+   int pr[2] = {0, 0}, tc = 0;
+   if (G.group) {
+      if (mdb_group_eval_forces_host(G.group, h9, com.data(), quat.data(), control.surface_dipole ? 1 : 0, do_recip ? 1 : 0, nullptr,
+                                     control.limit, control.nbins, rdf_base ? rdf_cnt.data() : nullptr, &tc, pr))
+         FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+      cudaSetDevice(G.eng->device);
+   } else if (mdb_eval_forces_host(G.eng, h9, com.data(), quat.data(), control.surface_dipole ? 1 : 0, do_recip ? 1 : 0,
+                                   nullptr, G.stream))
       FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
    const double tc2 = now_ms();
    if (rdf_base) rdf_add_counts(sys, rdf_base, rdf_cnt);
 
-   int pr[2];
-   const int tc = mdb_too_close(G.eng, pr, G.stream);
+   if (!G.group) tc = mdb_too_close(G.eng, pr, G.stream);
    if (tc & (1 << 30))
       message((int *)0, (char *)0, SEV_ERROR, (char *)"Co-ordinate out of range in BIN (fill_cells)");
    if (tc & ~(1 << 30))                                  /* src/force.c:944-946 */
@@ -679,7 +764,7 @@ static void eval_forces_impl(system_mp sys, spec_mt *species, site_mt *site_info
               sqrt(MDB_TOO_CLOSE));
 
    /* molecular forces and torques, src/accel.c:564-571 */
-   const double *res = mdb_eval_result(G.eng);            /* pinned: copied straight into the caller's arrays */
+   const double *res = G.group ? mdb_group_eval_result(G.group) : mdb_eval_result(G.eng);   /* pinned: copied straight into the caller's arrays */
    int nmols = 0, nmols_r = 0;
    for (int i = 0; i < nspecies; i++) nmols += species[i].nmols;
    for (int i = 0; i < nspecies; i++) nmols_r += species[i].rdof > 0 ? species[i].nmols : 0;
@@ -753,6 +838,22 @@ extern "C" void eval_forces(system_mp sys, spec_mt *species, site_mt *site_info,
 
 // ---- test/bench accessors ------------------------------------------------------
 extern "C" mdb_engine *mdb_abi_engine(void) { ensure_engine(); return G.eng; }
+extern "C" int mdb_abi_devices(void) { ensure_engine(); return G.group ? mdb_group_size(G.group) : 1; }
+// tests only: drop the engine(s) so that the next call re-reads MOLDY_B200_DEVICE(S)
+extern "C" void mdb_abi_shutdown(void)
+{
+   if (G.stream) cudaStreamSynchronize(G.stream);
+   if (G.group) { mdb_group_destroy(G.group); G.group = nullptr; G.eng = nullptr; }
+   else if (G.eng) { mdb_destroy(G.eng); G.eng = nullptr; }
+   if (G.d_out) cudaFree(G.d_out);
+   if (G.h_out) cudaFreeHost(G.h_out);
+   if (G.d_out2) cudaFree(G.d_out2);
+   if (G.h_out2) cudaFreeHost(G.h_out2);
+   G.d_out = G.h_out = G.d_out2 = G.h_out2 = nullptr; G.out_cap = 0;
+   if (G.stream) { cudaStreamDestroy(G.stream); G.stream = nullptr; }
+   if (G.copy_stream) { cudaStreamDestroy(G.copy_stream); G.copy_stream = nullptr; }
+   G.have_cfg = false; G.type.clear(); G.chg.clear(); G.potflat.clear();
+}
 extern "C" void *mdb_abi_stream(void) { ensure_engine(); return (void *)G.stream; }
 extern "C" void mdb_abi_constants(double out[3]) { out[0] = G.eintra; out[1] = G.self_energy; out[2] = G.sheet_energy; }
 extern "C" void mdb_abi_reset(void)

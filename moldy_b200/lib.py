@@ -248,6 +248,18 @@ def eval_forces_mol(ms: MoldySystem):
     return out
 
 
+def shutdown():
+    """Drop the Moldy-level engine(s); the next call re-reads MOLDY_B200_DEVICE / MOLDY_B200_DEVICES (tests)."""
+    L = load()
+    L.mdb_abi_reset()
+    L.mdb_abi_shutdown()
+
+
+def n_devices() -> int:
+    """Number of GPUs (ranks) behind force_calc()/ewald()/eval_forces() (MOLDY_B200_DEVICES)."""
+    return load().mdb_abi_devices()
+
+
 def reset():
     """Forget the Moldy-level first-call state (lets one test process run several systems)."""
     load().mdb_abi_reset()

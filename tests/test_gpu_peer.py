@@ -98,3 +98,79 @@ def test_one_process_per_gpu_over_cuda_ipc(tmp_path):
     assert res["world"] == ndev
     assert res["force_relrms_vs_record"] < 1e-10 and res["stress_rel"] < 1e-11 and res["proj_rel"] < 1e-10
     assert res["nccl_vs_peer_relrms"] < 1e-11
+
+
+# ---- several GPUs behind Moldy's own entry points (MOLDY_B200_DEVICES; mdb_group.cu) ---------------------------------
+@pytest.fixture
+def abi_devices():
+    """Run the Moldy-level library on the given device list; back to one engine afterwards."""
+    old = os.environ.get("MOLDY_B200_DEVICES")
+
+    def use(devs):
+        lib.shutdown()
+        os.environ["MOLDY_B200_DEVICES"] = devs
+        lib.reset()
+    yield use
+    lib.shutdown()
+    if old is None:
+        os.environ.pop("MOLDY_B200_DEVICES", None)
+    else:
+        os.environ["MOLDY_B200_DEVICES"] = old
+
+
+def _devlists():
+    nd = torch.cuda.device_count()
+    lists = ["0,0", "0,0,0"]
+    if nd >= 2:
+        lists.append("all")
+    return lists
+
+
+@pytest.mark.parametrize("name", ["tip4p", "tip4p_2", "mgcl2", "quartz", "slab_framework", "argon", "tips2_molpbc",
+                                  "tip4p_molpbc_strict", "tips2_strict"])
+def test_force_calc_and_ewald_on_a_device_group(name, abi_devices):
+    """force_calc()+ewald() through the C ABI with MOLDY_B200_DEVICES: same results as the reference's (goldens)."""
+    gold = np.load(os.path.join(GOLD, f"ref_{name}.npz"))
+    for devs in _devlists():
+        abi_devices(devs)
+        assert lib.n_devices() == (torch.cuda.device_count() if devs == "all" else len(devs.split(",")))
+        ms = cases.GOLDEN_CASES[name]()
+        out = lib.eval_forces(ms)
+        assert cases.rel_rms(out["force"], gold["force"]) < 1e-10, devs
+        scale = np.abs(gold["pe"]).max()
+        assert np.abs(out["pe"] - gold["pe"]).max() < 1e-11 * scale, devs
+        iu = np.triu_indices(3)
+        assert np.linalg.norm(out["stress"][iu] - gold["stress"][iu]) < 1e-11 * np.linalg.norm(gold["stress"][iu]), devs
+
+
+@pytest.mark.parametrize("name", ["tip4p", "tip4p_2", "mgcl2", "quartz", "slab_framework", "tips2_molpbc"])
+@pytest.mark.parametrize("sd", [0, 1])
+def test_eval_forces_on_a_device_group(name, sd, abi_devices):
+    """The whole of eval_forces() (src/accel.c:398-617) on several ranks: molecular forces, torques, energies, virial."""
+    g = np.load(os.path.join(GOLD, f"evalf_{name}_sd{sd}.npz"))
+    for devs in _devlists():
+        abi_devices(devs)
+        ms = cases.GOLDEN_CASES[name]()
+        ms.control.surface_dipole = sd
+        mol = lib.eval_forces_mol(ms)
+        assert cases.rel_rms(mol["force"], g["force"]) < 1e-10, devs
+        if g["torque"].size:
+            assert cases.rel_rms(mol["torque"], g["torque"]) < 1e-10, devs
+        assert np.abs(mol["pe"] - g["pe"]).max() < 1e-11 * np.abs(g["pe"]).max(), devs
+        assert np.linalg.norm(mol["stress"] - g["stress"]) < 1e-11 * np.linalg.norm(g["stress"]), devs
+        if "dip_mom" in g.files:
+            assert np.allclose(mol["dip_mom"], g["dip_mom"], rtol=1e-10, atol=1e-9 * np.abs(g["dip_mom"]).max() + 1e-12), devs
+
+
+def test_rdf_pass_on_a_device_group(abi_devices):
+    """force_calc's RDF pass with the batches split over the ranks: the pair counts add up to the reference's."""
+    ref_rdf = np.load(os.path.join(GOLD, "ref_rdf.npz"))
+    abi_devices("0,0,0")
+    for name in ("tip4p", "quartz"):
+        lib.reset()
+        limit, nbins = cases.RDF_CASES[name]
+        ms = cases.GOLDEN_CASES[name]()
+        out = lib.eval_forces(ms, recip=False, rdf=(limit, nbins))
+        rho = ms.nsites / float(np.linalg.det(ms.h))
+        cnt = np.rint(out["rdf"].astype(np.float64) * rho).astype(np.int64)
+        assert np.array_equal(cnt, ref_rdf[name]), name
