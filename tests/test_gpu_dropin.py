@@ -55,13 +55,14 @@ end
 """
 
 
-def _run(binary, tmp, nsteps, every, rdf=0, rdfout=1000000):
-    d = os.path.join(tmp, os.path.basename(binary))
+def _run(binary, tmp, nsteps, every, rdf=0, rdfout=1000000, env=None, tag=""):
+    d = os.path.join(tmp, os.path.basename(binary) + tag)
     os.makedirs(d, exist_ok=True)
     shutil.copy(os.path.join(ROOT, "tests", "golden", "tip4p_256_eq.txt"), d)
     with open(os.path.join(d, "control"), "w") as f:
         f.write(CONTROL.format(nsteps=nsteps, every=every, rdf=rdf, rdfout=rdfout))
-    out = subprocess.run([binary, "control"], cwd=d, capture_output=True, text=True, timeout=240 + nsteps // 4)
+    out = subprocess.run([binary, "control"], cwd=d, capture_output=True, text=True, timeout=240 + nsteps // 4,
+                         env=dict(os.environ, **(env or {})))
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     return out.stdout
 
@@ -154,3 +155,24 @@ def test_rdf_pass_inside_force_calc_prints_the_same_tables(tmp_path, gpu_binary)
             assert ta.shape == tb.shape == (85,)
             assert ta.max() > 0.5
             assert np.allclose(ta, tb, rtol=3e-4, atol=2e-6), (key, np.abs(ta - tb).max())
+
+
+@needs_binaries
+@both
+def test_unmodified_moldy_on_several_gpus(tmp_path, gpu_binary):
+    """MOLDY_B200_DEVICES: the same unmodified program (no -DSPMD, nthreads = 1) with the library driving several ranks
+    -- all GPUs of the box when there is more than one, and three ranks sharing GPU 0 -- prints the same run and RDF
+    tables as the all-CPU binary."""
+    import torch
+    a = _run(REF, str(tmp_path), 40, 10, rdf=2, rdfout=20)
+    va, ra = _current_values(a), _rdf_tables(a)
+    for devs in (["all"] if torch.cuda.device_count() > 1 else []) + ["0,0,0"]:
+        b = _run(gpu_binary, str(tmp_path), 40, 10, rdf=2, rdfout=20, env={"MOLDY_B200_DEVICES": devs}, tag="_" + devs.replace(",", ""))
+        vb, rb = _current_values(b), _rdf_tables(b)
+        assert sorted(va) == sorted(vb) == [10, 20, 30, 40]
+        for step in va:
+            assert np.allclose(va[step], vb[step], rtol=2e-5, atol=2e-2), (devs, step, va[step], vb[step])
+        assert ra and sorted(ra) == sorted(rb)
+        for key in ra:
+            for ta, tb in zip(ra[key], rb[key]):
+                assert np.allclose(ta, tb, rtol=3e-4, atol=2e-6), (devs, key)
