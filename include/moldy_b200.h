@@ -285,6 +285,31 @@ void   mdb_eval_forces_moldy(system_mp sys, spec_mt *species, site_mt *site_info
  * the copy into caller memory. */
 const double *mdb_eval_result(const mdb_engine *e);
 
+/* ---- the NVE leapfrog step of do_step() (src/accel.c:626-827) on a state resident in HBM (mdb_md.cu) ----
+ * Scaled centres of mass, quaternions, linear and angular momenta live on the device between outputs; a step is
+ * leapf_all_coords(step/2) -> eval_forces -> leapf_all_momenta(step/2) x 2 -> framework momenta = 0 -> leapf_all_coords(step/2)
+ * and returns scalars only: [MDB_EVAL_SCALARS as mdb_eval_forces_host | per species MDB_MD_SUMS sums at the end of the step |
+ * per species MDB_MD_SUMS sums at the half step (half_sums != 0; for H_0, src/accel.c:718-726) | count of quaternions whose
+ * norm was off by > 1e-4 (the reference: FATAL)].  Sums of a species: [sum p_i p_j (xx xy xz yy yz zz), p = (h^-1)' mom
+ * (trans_ke / energy_dyad, src/algorith.c:221-284) | sum amom_k^2 (rot_ke :244-257) | sum F_k^2 | sum T_k^2 (mean_square :101)].
+ * Call order: mdb_configure, mdb_set_species, mdb_md_set_dynamics, mdb_md_upload_state, then mdb_md_step per step. */
+typedef struct { double mass, inertia[3]; } mdb_species_dyn;          /* spec->mass, spec->inertia */
+#define MDB_MD_SUMS 15
+int    mdb_md_set_dynamics(mdb_engine *e, const mdb_species_dyn *dyn, int nosymmetric_rot);
+size_t mdb_md_scalars(const mdb_engine *e);
+int    mdb_md_upload_state(mdb_engine *e, const double *const *com, const double *const *quat, const double *const *mom,
+                           const double *const *amom, void *stream);
+int    mdb_md_download_state(mdb_engine *e, double *const *com, double *const *quat, double *const *mom, double *const *amom,
+                             double *const *force, double *const *torque, void *stream);       /* NULL entries are skipped */
+int    mdb_md_step(mdb_engine *e, const double h[9], double step, double ts, int surface_dipole, int do_recip, int half_sums,
+                   double *h_scal, void *stream);
+const double *mdb_md_result(const mdb_engine *e);
+/* the sub-steps, for tests and for hosts that interleave their own work */
+int    mdb_md_coords(mdb_engine *e, const double h[9], double step, double ts, void *stream);
+int    mdb_md_momenta(mdb_engine *e, const double h[9], double step, void *stream);
+int    mdb_md_eval_forces(mdb_engine *e, const double h[9], int surface_dipole, int do_recip, void *stream);
+int    mdb_md_sums_now(mdb_engine *e, const double h[9], double *h_sums, void *stream);
+
 /* Moldy's eval_forces() itself (src/accel.c:398-617) on top of mdb_eval_forces_host: same prototype, same outputs
  * (pe[NPE], dip_mom[3], the full symmetric virial stress, force[ispec][imol], torque[ispec][imol]), same first-call
  * notes.  Linking it in place of accel.c's definition is described in INTEGRATION.md section 5. */
@@ -363,6 +388,15 @@ int         mdb_group_eval_forces_host(mdb_group *g, const double h[9], const do
  * staged in `d_scratch` (DEVICE, 3*nsites doubles).  Synchronises `stream`; -1 on error.  ewald() of layer (A) validates
  * the k-space sums that force_calc() started ahead of it with this. */
 long mdb_sites_differ_host(mdb_engine *e, const double *x, const double *y, const double *z, double *d_scratch, void *stream);
+
+/* Moldy's do_step() (src/accel.c:626-827) for NVE dynamics (const-temp = const-pressure = 0) on top of mdb_md_step: same
+ * prototype (restart_header is only handed on to the host program's dump()), same outputs (meansq_f_t, pe, dip_mom,
+ * stress_vir, sys->H_0 at the first step), the host program's c_of_m / quat / mom / amom arrays advanced in place.
+ * INTEGRATION.md section 6. */
+void do_step(system_mt *sys, spec_mt *species, site_mt *site_info, pot_mt *potpar, vec_mt (*meansq_f_t)[2], double *pe,
+             real *dip_mom, mat_mt stress_vir, void *restart_header, int backup_restart, int init_H_0);
+void mdb_do_step_moldy(system_mt *sys, spec_mt *species, site_mt *site_info, pot_mt *potpar, vec_mt (*meansq_f_t)[2], double *pe,
+                       real *dip_mom, mat_mt stress_vir, void *restart_header, int backup_restart, int init_H_0);
 
 /* Device->host copy of a result block (synchronises `stream`). */
 int  mdb_read_out(mdb_engine *e, const double *d_out, double *h_out, void *stream);

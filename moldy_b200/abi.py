@@ -117,6 +117,14 @@ class dim_mt(C.Structure):
     _fields_ = [("m", C.c_int), ("l", C.c_int), ("t", C.c_int), ("q", C.c_int)]
 
 
+class mdb_species(C.Structure):
+    _fields_ = [("nmols", C.c_int), ("nsites", C.c_int), ("framework", C.c_int), ("rotates", C.c_int), ("rdof", C.c_int)]
+
+
+class mdb_species_dyn(C.Structure):
+    _fields_ = [("mass", C.c_double), ("inertia", C.c_double * 3)]
+
+
 def nsarray(nsites: int) -> int:
     """Row stride of the caller's site[3][nsarray] block (src/accel.c:422)."""
     return ((nsites - 1) | (NCACHE - 1)) + 1 + NLINE

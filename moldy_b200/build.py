@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmoldy_b200.so")
-SOURCES = ["mdb_host.cpp", "mdb_cells.cu", "mdb_pair.cu", "mdb_pair_tiled.cu", "mdb_kspace.cu", "mdb_molframe.cu", "mdb_peer.cu", "mdb_group.cu", "mdb_engine.cu", "moldy_abi.cu"]
+SOURCES = ["mdb_host.cpp", "mdb_cells.cu", "mdb_pair.cu", "mdb_pair_tiled.cu", "mdb_kspace.cu", "mdb_molframe.cu", "mdb_md.cu", "mdb_peer.cu", "mdb_group.cu", "mdb_engine.cu", "moldy_abi.cu"]
 HEADERS = ["mdb_internal.h", "mdb_math.cuh", os.path.join(ROOT, "include", "moldy_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -83,6 +83,8 @@ extern "C" void mdb_destroy(mdb_engine *e)
    FREE(e->mf.d_pfs); FREE(e->mf.d_in); FREE(e->mf.d_res); FREE(e->mf.d_vpart); FREE(e->mf.d_dpart);
    if (e->mf.h_in) cudaFreeHost(e->mf.h_in);
    if (e->mf.h_res) cudaFreeHost(e->mf.h_res);
+   FREE(e->mf.d_mom); FREE(e->mf.d_amom); FREE(e->mf.d_mdpart); FREE(e->mf.d_mdscal);
+   if (e->mf.h_mdscal) cudaFreeHost(e->mf.h_mdscal);
    delete e;
 }
 

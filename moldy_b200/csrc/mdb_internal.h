@@ -152,6 +152,9 @@ struct mdb_engine {
       double *h_in = nullptr, *h_res = nullptr;                                   // pinned
       size_t in_cap = 0, res_cap = 0;
       double rdf_limit = 0.0; int rdf_nbins = 0; unsigned long long *rdf_counts = nullptr;   // one-shot RDF request
+      // resident NVE integrator (mdb_md.cu): momenta, per-species dynamics, sums
+      std::vector<mdb_species_dyn> dyn; int nosymmetric_rot = 0, saxis = 0;
+      double *d_mom = nullptr, *d_amom = nullptr, *d_mdpart = nullptr, *d_mdscal = nullptr, *h_mdscal = nullptr;
    } mf;
 
    // pinned staging for host-facing calls

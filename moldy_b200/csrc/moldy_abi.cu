@@ -664,14 +664,14 @@ static EvalState E;
 // Internal linkage on purpose: when the host program carries its own `eval_forces` symbol (the trampoline of
 // evalf_tramp.c), a call to the exported name from inside the library would bind to the program's definition and
 // recurse; both exported names below call this function directly.
-static void eval_forces_impl(system_mp sys, spec_mt *species, site_mt *site_info, pot_mt *potpar, double *pe,
-                             real *dip_mom, mat_mt stress, vec_mp *force, vec_mp *torque)
+// configuration, first-call constants and notes, species table: everything eval_forces() does before the sites are built
+static void eval_prepare(system_mp sys, spec_mt *species, site_mt *site_info, pot_mt *potpar, double h9[9], double &vol,
+                         bool &do_recip)
 {
    const int n = sys->nsites, nspecies = sys->nspecies;
-   double h9[9];
    for (int i = 0; i < 3; i++)
       for (int j = 0; j < 3; j++) h9[3 * i + j] = sys->h[i][j];
-   const double vol = mdb_det3(h9);
+   vol = mdb_det3(h9);
 
    /* site charges, src/accel.c:473-480; expanded again only when site_info or the species layout changed */
    const double tc0 = now_ms();
@@ -707,7 +707,7 @@ static void eval_forces_impl(system_mp sys, spec_mt *species, site_mt *site_info
            CONV_P_MPA * E.distp / (vol * vol));
       E.init = true;
    }
-   const bool do_recip = control.alpha > MDB_ALPHAMIN;
+   do_recip = control.alpha > MDB_ALPHAMIN;
    real_first_call(sys, species, E.chg.data(), potpar);
    if (do_recip) recip_first_call(sys, species, E.chg.data(), vol);
 
@@ -732,6 +732,50 @@ static void eval_forces_impl(system_mp sys, spec_mt *species, site_mt *site_info
       }
       E.species_epoch = G.config_epoch;
    }
+   if (g_timing) fprintf(stderr, "[moldy_b200] eval_forces: config %.2f ms\n", tc1 - tc0);
+}
+
+// energies, dipole moment and the molecular virial stress from the scalar block of the device
+// (src/force.c:1170, src/ewald.c:427-433, src/accel.c:557, :576-601, :606-608)
+static void eval_finish_scalars(const double *sc, double vol, bool do_recip, double *pe, real *dip_mom, mat_mt stress)
+{
+   pe[0] = sc[12] - G.eintra + E.dist / vol;
+   pe[1] = 0.0;
+   for (int i = 0; i < 3; i++) dip_mom[i] = 0.0;
+   memset(&stress[0][0], 0, sizeof(double) * 9);
+   stress[0][0] = sc[14]; stress[0][1] = sc[15]; stress[0][2] = sc[16];
+   stress[1][1] = sc[18]; stress[1][2] = sc[19]; stress[2][2] = sc[22];
+   if (do_recip) {
+      pe[1] = sc[13] - G.self_energy + G.sheet_energy / vol;
+      for (int i = 0; i < 3; i++) stress[i][i] += G.sheet_energy / vol;
+      for (int i = 0; i < 3; i++) dip_mom[i] = sc[i];
+      if (control.surface_dipole)
+         pe[1] += 2.0 * MDB_PI / (3.0 * vol) * (sc[0] * sc[0] + sc[1] * sc[1] + sc[2] * sc[2]);
+   }
+   for (int i = 0; i < 3; i++)
+      for (int j = i + 1; j < 3; j++) stress[j][i] = stress[i][j];
+   for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) stress[i][j] -= sc[3 + 3 * i + j];
+   for (int i = 0; i < 3; i++) stress[i][i] += E.distp / vol;
+}
+
+static void report_too_close(int tc, const int pr[2])
+{
+   if (tc & (1 << 30))
+      message((int *)0, (char *)0, SEV_ERROR, (char *)"Co-ordinate out of range in BIN (fill_cells)");
+   if (tc & ~(1 << 30))                                  /* src/force.c:944-946 */
+      message((int *)0, (char *)0, SEV_WARNING, (char *)"Sites %d and %d closer than %fA.", pr[0], pr[1],
+              sqrt(MDB_TOO_CLOSE));
+}
+
+static void eval_forces_impl(system_mp sys, spec_mt *species, site_mt *site_info, pot_mt *potpar, double *pe,
+                             real *dip_mom, mat_mt stress, vec_mp *force, vec_mp *torque)
+{
+   const int nspecies = sys->nspecies;
+   double h9[9], vol;
+   bool do_recip;
+   const double tc1 = now_ms();
+   eval_prepare(sys, species, site_info, potpar, h9, vol, do_recip);
    std::vector<const double *> com(nspecies), quat(nspecies);
    for (int i = 0; i < nspecies; i++) {
       com[i] = &species[i].c_of_m[0][0];
@@ -757,11 +801,7 @@ static void eval_forces_impl(system_mp sys, spec_mt *species, site_mt *site_info
    if (rdf_base) rdf_add_counts(sys, rdf_base, rdf_cnt);
 
    if (!G.group) tc = mdb_too_close(G.eng, pr, G.stream);
-   if (tc & (1 << 30))
-      message((int *)0, (char *)0, SEV_ERROR, (char *)"Co-ordinate out of range in BIN (fill_cells)");
-   if (tc & ~(1 << 30))                                  /* src/force.c:944-946 */
-      message((int *)0, (char *)0, SEV_WARNING, (char *)"Sites %d and %d closer than %fA.", pr[0], pr[1],
-              sqrt(MDB_TOO_CLOSE));
+   report_too_close(tc, pr);
 
    /* molecular forces and torques, src/accel.c:564-571 */
    const double *res = G.group ? mdb_group_eval_result(G.group) : mdb_eval_result(G.eng);   /* pinned: copied straight into the caller's arrays */
@@ -796,30 +836,132 @@ static void eval_forces_impl(system_mp sys, spec_mt *species, site_mt *site_info
       }
    }
    const double *sc = res + 3 * (size_t)nmols + 3 * (size_t)nmols_r;
-   /* energies: force_calc's and ewald's constants (src/force.c:1170, src/ewald.c:427-433), surface dipole
-    * (src/accel.c:557), distant potential (:606) */
-   pe[0] = sc[12] - G.eintra + E.dist / vol;
-   pe[1] = 0.0;
-   for (int i = 0; i < 3; i++) dip_mom[i] = 0.0;
-   memset(&stress[0][0], 0, sizeof(double) * 9);
-   stress[0][0] = sc[14]; stress[0][1] = sc[15]; stress[0][2] = sc[16];
-   stress[1][1] = sc[18]; stress[1][2] = sc[19]; stress[2][2] = sc[22];
-   if (do_recip) {
-      pe[1] = sc[13] - G.self_energy + G.sheet_energy / vol;
-      for (int i = 0; i < 3; i++) stress[i][i] += G.sheet_energy / vol;
-      for (int i = 0; i < 3; i++) dip_mom[i] = sc[i];
-      if (control.surface_dipole)
-         pe[1] += 2.0 * MDB_PI / (3.0 * vol) * (sc[0] * sc[0] + sc[1] * sc[1] + sc[2] * sc[2]);
-   }
-   /* site -> molecular virial (src/accel.c:576-601) and distant pressure term (:607-608) */
-   for (int i = 0; i < 3; i++)
-      for (int j = i + 1; j < 3; j++) stress[j][i] = stress[i][j];
-   for (int i = 0; i < 3; i++)
-      for (int j = 0; j < 3; j++) stress[i][j] -= sc[3 + 3 * i + j];
-   for (int i = 0; i < 3; i++) stress[i][i] += E.distp / vol;
+   eval_finish_scalars(sc, vol, do_recip, pe, dip_mom, stress);
    if (g_timing)
-      fprintf(stderr, "[moldy_b200] eval_forces: config %.2f ms, device (H2D .. D2H) %.2f ms, results %.2f ms\n", tc1 - tc0,
-              tc2 - tc1, now_ms() - tc2);
+      fprintf(stderr, "[moldy_b200] eval_forces: device (H2D .. D2H) %.2f ms, results %.2f ms\n", tc2 - tc1, now_ms() - tc2);
+}
+
+// ---- do_step(): the NVE leapfrog step of src/accel.c:626-827 around the device's eval_forces ----------
+// The dynamic state is uploaded from and written back to the host program's arrays on every call, so rescaling, output,
+// dumps and restarts of the host program see and may change it between steps; hosts that keep the state in HBM use
+// mdb_md_step directly.  Thermostat and cell dynamics are outside this row: FATAL (INTEGRATION.md section 6 shows how a
+// host keeps its own do_step for those ensembles).
+#define KB_PROG (1.380658e-23 / (1.6605402e-27 * 1.0e4))                 /* src/defs.h:201-226  kB = _kB / EUNIT */
+extern "C" __attribute__((weak)) void dump(system_mp, spec_mt *, vec_mt *, vec_mt *, mat_mt, double, void *, int);
+
+struct StepState { std::vector<mdb_species_dyn> dyn; long species_epoch = -1; int nosym = -1; double saved_pe = 0; };
+static StepState S;
+
+static void do_step_impl(system_mt *sys, spec_mt *species, site_mt *site_info, pot_mt *potpar, vec_mt (*meansq_f_t)[2],
+                         double *pe, real *dip_mom, mat_mt stress_vir, void *restart_header, int backup_restart, int init_H_0)
+{
+   if (control.const_temp || control.const_pressure)
+      FATAL_MSG("libmoldy_b200: do_step on the device covers NVE dynamics only (const-temp=0, const-pressure=0)");
+   if (G.group) FATAL_MSG("libmoldy_b200: do_step is not available with MOLDY_B200_DEVICES; link eval_forces instead");
+   const int nspecies = sys->nspecies;
+   double h9[9], vol;
+   bool do_recip;
+   eval_prepare(sys, species, site_info, potpar, h9, vol, do_recip);
+   std::vector<mdb_species_dyn> dyn(nspecies);
+   for (int i = 0; i < nspecies; i++)
+      dyn[i] = mdb_species_dyn{species[i].mass, {species[i].inertia[0], species[i].inertia[1], species[i].inertia[2]}};
+   if (S.species_epoch != E.species_epoch || S.nosym != control.nosymmetric_rot || dyn.size() != S.dyn.size() ||
+       memcmp(dyn.data(), S.dyn.data(), sizeof(mdb_species_dyn) * dyn.size())) {
+      if (mdb_md_set_dynamics(G.eng, dyn.data(), control.nosymmetric_rot ? 1 : 0)) FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+      S.dyn = dyn; S.species_epoch = E.species_epoch; S.nosym = control.nosymmetric_rot;
+   }
+   std::vector<const double *> com(nspecies), quat(nspecies), mom(nspecies), amom(nspecies);
+   std::vector<double *> wcom(nspecies), wquat(nspecies), wmom(nspecies), wamom(nspecies), wf(nspecies, nullptr), wt(nspecies, nullptr);
+   for (int i = 0; i < nspecies; i++) {
+      wcom[i] = &species[i].c_of_m[0][0]; wmom[i] = &species[i].mom[0][0];
+      wquat[i] = species[i].quat ? &species[i].quat[0][0] : nullptr;
+      wamom[i] = species[i].quat && species[i].amom ? &species[i].amom[0][0] : nullptr;
+      com[i] = wcom[i]; quat[i] = wquat[i]; mom[i] = wmom[i]; amom[i] = wamom[i];
+   }
+   G.sites_fresh = false; G.ahead_valid = false;
+   std::vector<unsigned long long> rdf_cnt;
+   float *rdf_base = nullptr;
+   if (rdf_due() && (rdf_base = rdf_store(mdb_rdf_size(G.eng, control.nbins))) != nullptr) {
+      rdf_cnt.assign(mdb_rdf_size(G.eng, control.nbins), 0ULL);
+      mdb_eval_request_rdf(G.eng, control.limit, control.nbins, rdf_cnt.data());
+   }
+   const bool want_h0 = control.istep == 1 || init_H_0;
+   if (mdb_md_upload_state(G.eng, com.data(), quat.data(), mom.data(), amom.data(), G.stream) ||
+       mdb_md_step(G.eng, h9, control.step, sys->ts, control.surface_dipole ? 1 : 0, do_recip ? 1 : 0, want_h0 ? 1 : 0, nullptr,
+                   G.stream))
+      FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+   if (rdf_base) rdf_add_counts(sys, rdf_base, rdf_cnt);
+   int pr[2];
+   report_too_close(mdb_too_close(G.eng, pr, G.stream), pr);
+   const bool dump_due = control.dump_interval > 0 && control.dump_level != 0 && control.istep >= control.begin_dump &&
+                         (control.istep - control.begin_dump) % control.dump_interval == 0 && ithread == 0 && dump;
+   std::vector<double> fbuf, tbuf;
+   if (dump_due) {                                         /* the host program's dump wants the forces and torques */
+      fbuf.resize(3 * (size_t)sys->nmols); tbuf.resize(3 * (size_t)std::max(sys->nmols_r, 1));
+      size_t fo = 0, to = 0;
+      for (int i = 0; i < nspecies; i++) {
+         wf[i] = fbuf.data() + fo; fo += 3 * (size_t)species[i].nmols;
+         if (species[i].rdof > 0) { wt[i] = tbuf.data() + to; to += 3 * (size_t)species[i].nmols; }
+      }
+   }
+   if (mdb_md_download_state(G.eng, wcom.data(), wquat.data(), wmom.data(), wamom.data(), wf.data(), wt.data(), G.stream))
+      FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+   const double *r = mdb_md_result(G.eng);
+   const size_t nscal = mdb_md_scalars(G.eng);
+   if (r[nscal - 1] != 0.0)
+      FATAL_MSG("Quaternion %d (%g,%g,%g,%g) - normalisation error in beeman", 0, 0.0, 0.0, 0.0, 0.0);   /* src/leapfrog.c:107 */
+   eval_finish_scalars(r, vol, do_recip, pe, dip_mom, stress_vir);
+   S.saved_pe = pe[0] + pe[1];
+   const double s2 = sys->ts * sys->ts;
+   auto species_ke = [&](const double *sum, const spec_mt &sp, bool rot) {      /* trans_ke + rot_ke, src/algorith.c:221-257 */
+      double ke = (sum[0] + sum[3] + sum[5]) / (2.0 * sp.mass * s2);
+      if (rot && sp.rdof > 0) {
+         double k2 = 0.0;
+         for (int k = 0; k < 3; k++)
+            if (sp.inertia[k] > 1.0e-14) k2 += sum[6 + k] / sp.inertia[k];
+         ke += 0.5 * k2 / s2;
+      }
+      return ke;
+   };
+   if (want_h0) {                                          /* src/accel.c:718-726, kinetic energy at the half step */
+      double ke = 0.0;
+      for (int i = 0; i < nspecies; i++)
+         ke += species_ke(r + MDB_EVAL_SCALARS + MDB_MD_SUMS * ((size_t)nspecies + i), species[i], true);
+      double kc = 0.0;
+      if (sys->hmom)
+         for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) kc += sys->hmom[i][j] * sys->hmom[i][j];
+      sys->H_0 = ke + S.saved_pe + sys->tsmom * sys->tsmom / (2.0 * control.ttmass) + sys->d_of_f * KB_PROG * control.temp * log(sys->ts) +
+                 0.5 / control.pmass * kc;
+   }
+   {  /* src/accel.c:784-790: without GL_THERM the final leapf_nose_therm() is not under `if (control.const_temp)`
+       * (no braces), so the reference runs it in NVE too -- a no-op while tsmom = 0; kept for fidelity */
+      const double scale = 1.0 + sys->tsmom * (0.5 * control.step) / (2.0 * control.ttmass);
+      sys->tsmom /= scale;
+      sys->ts *= scale * scale;
+   }
+   for (int i = 0; i < nspecies; i++) {                    /* mean_square, src/accel.c:806-812 */
+      const double *sum = r + MDB_EVAL_SCALARS + MDB_MD_SUMS * (size_t)i;
+      for (int k = 0; k < 3; k++) {
+         meansq_f_t[i][0][k] = species[i].nmols > 0 ? sum[9 + k] / species[i].nmols : 0.0;
+         meansq_f_t[i][1][k] = species[i].rdof > 0 && species[i].nmols > 0 ? sum[12 + k] / species[i].nmols : 0.0;
+      }
+   }
+   if (dump_due)
+      dump(sys, species, (vec_mt *)fbuf.data(), sys->nmols_r ? (vec_mt *)tbuf.data() : nullptr, stress_vir, pe[0] + pe[1],
+           restart_header, backup_restart);
+}
+
+extern "C" void mdb_do_step_moldy(system_mt *sys, spec_mt *species, site_mt *site_info, pot_mt *potpar, vec_mt (*meansq_f_t)[2],
+                                  double *pe, real *dip_mom, mat_mt stress_vir, void *restart_header, int backup_restart,
+                                  int init_H_0)
+{
+   do_step_impl(sys, species, site_info, potpar, meansq_f_t, pe, dip_mom, stress_vir, restart_header, backup_restart, init_H_0);
+}
+extern "C" void do_step(system_mt *sys, spec_mt *species, site_mt *site_info, pot_mt *potpar, vec_mt (*meansq_f_t)[2], double *pe,
+                        real *dip_mom, mat_mt stress_vir, void *restart_header, int backup_restart, int init_H_0)
+{
+   do_step_impl(sys, species, site_info, potpar, meansq_f_t, pe, dip_mom, stress_vir, restart_header, backup_restart, init_H_0);
 }
 
 // The same function under a name of the library's own: a host program that keeps its own (weakened) eval_forces can
@@ -866,5 +1008,6 @@ extern "C" void mdb_abi_reset(void)
    G.have_cfg = false; G.sites_fresh = false; G.last_sites = nullptr; G.rdf_warned = false;
    if (G.eng && G.stream) cudaStreamSynchronize(G.stream);
    G.ahead_valid = false;
+   S.species_epoch = -1; S.dyn.clear();
    E.init = false; E.species_epoch = -1; E.sp.clear(); E.chg.clear(); E.site_charge.clear(); E.layout.clear();
 }

@@ -108,6 +108,17 @@ def load() -> C.CDLL:
     L.mdb_eval_result_doubles.argtypes = [C.c_void_p]
     L.mdb_eval_forces_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.eval_forces.restype = None
+    L.do_step.restype = None
+    L.mdb_md_scalars.restype = C.c_size_t
+    L.mdb_md_scalars.argtypes = [C.c_void_p]
+    L.mdb_md_set_dynamics.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.mdb_md_upload_state.argtypes = [C.c_void_p] * 6
+    L.mdb_md_download_state.argtypes = [C.c_void_p] * 8
+    L.mdb_md_step.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.mdb_md_coords.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]
+    L.mdb_md_momenta.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    L.mdb_md_eval_forces.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.mdb_md_sums_now.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mdb_sites_differ_host.restype = C.c_long
     L.mdb_sites_differ_host.argtypes = [C.c_void_p] * 6
     # multi-GPU peer layer (mdb_peer.cu)
@@ -245,6 +256,20 @@ def eval_forces_mol(ms: MoldySystem):
     set_thread(0, 1)
     args, out = ms.eval_forces_args()
     L.eval_forces(*args)
+    return out
+
+
+def do_step(ms: MoldySystem, mom, amom, step: float, nsteps: int = 1, resident: bool = False):
+    """Moldy's do_step() (src/accel.c:626-827, NVE) through the library's drop-in symbol, `nsteps` times: centres of mass,
+    quaternions and momenta of `ms` advance in place on the device.  Returns the dict of do_step_args (state arrays, pe,
+    stress, molecular forces/torques of the last step, meansq)."""
+    L = load()
+    args, out, set_control = ms.do_step_args(mom, amom, step)
+    set_control(control())
+    set_thread(0, 1)
+    for k in range(nsteps):
+        control().istep = 2 + k
+        L.do_step(*args)
     return out
 
 
@@ -428,6 +453,68 @@ class Engine:
 
 PEER_HANDLE_BYTES = 64
 REAL, RECIP = 1, 2
+
+
+class MdState:
+    """The resident NVE integrator of an Engine (mdb_md.cu): per-species state arrays in, scalars out."""
+
+    def __init__(self, eng: Engine, ms: MoldySystem, nosymmetric_rot: int = 0):
+        self.eng, self.ms, self.L = eng, ms, eng.L
+        sd = ms.sysdef
+        nsp = len(sd.species)
+        sp = (abi.mdb_species * nsp)()
+        dyn = (abi.mdb_species_dyn * nsp)()
+        pfs = []
+        for i, (s, inert) in enumerate(zip(sd.species, ms.principal_inertia())):
+            sp[i].nmols, sp[i].nsites, sp[i].framework = s.nmols, s.nsites, int(s.framework)
+            sp[i].rotates, sp[i].rdof = int(s.rdof > 0), s.rdof
+            dyn[i].mass = s.mass
+            for k in range(3):
+                dyn[i].inertia[k] = float(inert[k])
+            pfs.append(np.asarray(s.p_f_sites, dtype=np.float64).reshape(-1, 3))
+        pfs = np.ascontiguousarray(np.concatenate(pfs))
+        eng._chk(self.L.mdb_set_species(eng.h, nsp, sp, pfs.ctypes.data), "mdb_set_species")
+        eng._chk(self.L.mdb_md_set_dynamics(eng.h, dyn, nosymmetric_rot), "mdb_md_set_dynamics")
+        self.nsp = nsp
+        self.nscal = self.L.mdb_md_scalars(eng.h)
+
+    def _ptrs(self, arr, width, only_rot=False):
+        out = (C.c_void_p * self.nsp)()
+        m0 = 0
+        for i, s in enumerate(self.ms.sysdef.species):
+            if arr is not None and not (only_rot and not s.rdof):
+                out[i] = arr.ctypes.data + 8 * width * m0
+            m0 += s.nmols
+        return out
+
+    def upload(self, com, quat, mom, amom, stream=0):
+        self._keep = [np.ascontiguousarray(a, dtype=np.float64) for a in (com, quat, mom, amom)]
+        c, q, m, a = self._keep
+        self.eng._chk(self.L.mdb_md_upload_state(self.eng.h, self._ptrs(c, 3), self._ptrs(q, 4, True), self._ptrs(m, 3),
+                                                 self._ptrs(a, 4, True), stream), "mdb_md_upload_state")
+
+    def download(self, stream=0):
+        nm = self.ms.nmols
+        com, quat, mom, amom = np.zeros((nm, 3)), np.zeros((nm, 4)), np.zeros((nm, 3)), np.zeros((nm, 4))
+        force, torque = np.zeros((nm, 3)), np.zeros((nm, 3))
+        self.eng._chk(self.L.mdb_md_download_state(self.eng.h, self._ptrs(com, 3), self._ptrs(quat, 4, True), self._ptrs(mom, 3),
+                                                   self._ptrs(amom, 4, True), self._ptrs(force, 3), self._ptrs(torque, 3, True),
+                                                   stream), "mdb_md_download_state")
+        return dict(com=com, quat=quat, mom=mom, amom=amom, force=force, torque=torque)
+
+    def step(self, step, ts=1.0, surface_dipole=None, half_sums=False, stream=0):
+        h = np.ascontiguousarray(self.ms.h, dtype=np.float64)
+        sd = self.ms.control.surface_dipole if surface_dipole is None else surface_dipole
+        out = np.zeros(self.nscal)
+        self.eng._chk(self.L.mdb_md_step(self.eng.h, h.ctypes.data, step, ts, int(sd), int(self.ms.control.alpha > 1e-7),
+                                         int(half_sums), out.ctypes.data, stream), "mdb_md_step")
+        return out
+
+    def sums_now(self, stream=0):
+        h = np.ascontiguousarray(self.ms.h, dtype=np.float64)
+        out = np.zeros((self.nsp, 15))
+        self.eng._chk(self.L.mdb_md_sums_now(self.eng.h, h.ctypes.data, out.ctypes.data, stream), "mdb_md_sums_now")
+        return out
 
 
 class Peer:

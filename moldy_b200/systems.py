@@ -512,6 +512,69 @@ class MoldySystem:
         self._keep += [sysm, site_info, fptr, tptr]
         return args, dict(pe=pe, dip_mom=dip, stress=stress, force=force, torque=torque[:nmols_r])
 
+    def principal_inertia(self):
+        """Per species: moments of inertia about the axes of the principal frame the sites are given in,
+        sum_s m_s (|r_s|^2 - r_sk^2) (src/startup.c; zero for single-site species)."""
+        sd = self.sysdef
+        out = []
+        for s in sd.species:
+            m = np.asarray(sd.site_mass)[np.asarray(s.site_id)]
+            r = np.asarray(s.p_f_sites, dtype=np.float64)
+            out.append(np.array([(m * ((r ** 2).sum(1) - r[:, k] ** 2)).sum() for k in range(3)]))
+        return out
+
+    def thermal_momenta(self, temperature=300.0, seed=7):
+        """Maxwell-Boltzmann linear momenta (scaled: h' p) and principal-frame angular momenta [0, L1, L2, L3] for a
+        synthetic dynamic state; frameworks at rest."""
+        kB = 1.380658e-23 / (1.6605402e-27 * 1.0e4)                                # src/defs.h:226, amu A^2 ps^-2 per K
+        rng = np.random.default_rng(seed)
+        mom = np.zeros((self.nmols, 3)); amom = np.zeros((self.nmols, 4))
+        m0 = 0
+        for s, inert in zip(self.sysdef.species, self.principal_inertia()):
+            if not s.framework:
+                p = rng.standard_normal((s.nmols, 3)) * np.sqrt(s.mass * kB * temperature)
+                mom[m0:m0 + s.nmols] = p @ self.h                                 # scaled momentum h' p
+                if s.rdof:
+                    amom[m0:m0 + s.nmols, 1:] = rng.standard_normal((s.nmols, 3)) * np.sqrt(np.maximum(inert, 0.0) * kB * temperature)
+            m0 += s.nmols
+        return mom, amom
+
+    def do_step_args(self, mom, amom, step, istep=2):
+        """Argument list of do_step() (src/accel.c:626-637) for this configuration with the given momenta (arrays are
+        updated in place by the call): returns (args, outputs dict incl. the state arrays, setter for `control`)."""
+        args, out = self.eval_forces_args()
+        sysm, spec = args[0]._obj, args[1]
+        sd = self.sysdef
+        com, quat = self._keep[0], self._keep[1]
+        mom = np.ascontiguousarray(mom, dtype=np.float64).copy()
+        amom = np.ascontiguousarray(amom, dtype=np.float64).copy()
+        m0 = 0
+        for i, (s, inert) in enumerate(zip(sd.species, self.principal_inertia())):
+            spec[i].mom = C.cast(mom.ctypes.data + 24 * m0, C.POINTER(abi.vec_mt))
+            for k in range(3):
+                spec[i].inertia[k] = float(inert[k])
+            if s.rdof:
+                spec[i].amom = C.cast(amom.ctypes.data + 32 * m0, C.POINTER(abi.quat_mt))
+            m0 += s.nmols
+        sysm.mom = mom.ctypes.data_as(C.POINTER(abi.vec_mt))
+        sysm.amom = amom.ctypes.data_as(C.POINTER(abi.quat_mt))
+        sysm.ts, sysm.tsmom = 1.0, 0.0
+        hmom = np.zeros((3, 3))
+        sysm.hmom = hmom.ctypes.data_as(C.POINTER(abi.vec_mt))
+        sysm.d_of_f = int(sum(s.nmols * (3 + s.rdof) for s in sd.species if not s.framework))
+        meansq = np.zeros((len(sd.species), 2, 3))
+        self._keep += [mom, amom, meansq, hmom]
+        full = (args[0], args[1], args[2], args[3], meansq.ctypes.data_as(C.POINTER(C.c_double)), args[4], args[5], args[6],
+                None, 0, 0)
+        out.update(com=com, quat=quat, mom=mom, amom=amom, meansq=meansq, sysm=sysm)
+
+        def set_control(c):
+            self.control.fill(c)
+            c.step, c.istep, c.const_temp, c.const_pressure, c.nosymmetric_rot = float(step), int(istep), 0, 0, 0
+            c.dump_interval, c.dump_level = 0, 0
+            c.ttmass, c.rtmass, c.pmass, c.temp = 100.0, 100.0, 100.0, 300.0      # the reference's defaults (src/startup.c)
+        return full, out, set_control
+
     # ---- replication ----
     def replicate(self, nx, ny=None, nz=None, jitter=0.0, seed=0) -> "MoldySystem":
         """Periodic replication nx*ny*nz with optional rigid-molecule jitter (A)."""
