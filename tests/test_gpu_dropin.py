@@ -4,6 +4,10 @@ against libmoldy_b200.so INSTEAD of force.o / kernel.o / ewald.o (oracle/Makefil
 section 2).  It is run next to the all-CPU reference binary oracle/_ref/moldy on the same control
 and sys-spec files:
 
+oracle/_ref/moldy_gpu_dostep goes two levels up: do_step() itself
+(src/accel.c:626-827) is the library's for NVE runs -- leapfrog sub-steps and the kinetic-energy / mean-square sums on
+the device around the device's eval_forces; the program's own do_step stays linked in (renamed) for other ensembles.
+
 oracle/_ref/moldy_gpu_evalf goes one level up: the same unmodified
 sources, but eval_forces() itself (src/accel.c:398-617) is the library's -- accel.c's own definition is weakened with
 objcopy and a one-function trampoline object forwards to libmoldy_b200.so, so only centres of mass and quaternions
@@ -28,6 +32,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "oracle", "_ref", "moldy")
 GPU = os.path.join(ROOT, "oracle", "_ref", "moldy_gpu")
 GPU_EVALF = os.path.join(ROOT, "oracle", "_ref", "moldy_gpu_evalf")
+GPU_DOSTEP = os.path.join(ROOT, "oracle", "_ref", "moldy_gpu_dostep")
 
 CONTROL = """title=drop-in test
 surface-dipole=1
@@ -80,9 +85,9 @@ def _current_values(text):
     return res
 
 
-needs_binaries = pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(GPU) and os.path.exists(GPU_EVALF)),
-                                    reason="oracle/_ref/moldy{,_gpu,_gpu_evalf} not built (make -C oracle ref)")
-both = pytest.mark.parametrize("gpu_binary", [GPU, GPU_EVALF], ids=["force_calc+ewald", "eval_forces"])
+needs_binaries = pytest.mark.skipif(not all(os.path.exists(b) for b in (REF, GPU, GPU_EVALF, GPU_DOSTEP)),
+                                    reason="oracle/_ref/moldy{,_gpu,_gpu_evalf,_gpu_dostep} not built (make -C oracle ref)")
+both = pytest.mark.parametrize("gpu_binary", [GPU, GPU_EVALF, GPU_DOSTEP], ids=["force_calc+ewald", "eval_forces", "do_step"])
 
 
 @needs_binaries
@@ -166,6 +171,8 @@ def test_unmodified_moldy_on_several_gpus(tmp_path, gpu_binary):
     import torch
     a = _run(REF, str(tmp_path), 40, 10, rdf=2, rdfout=20)
     va, ra = _current_values(a), _rdf_tables(a)
+    if gpu_binary == GPU_DOSTEP:
+        pytest.skip("do_step on the device drives one GPU (MOLDY_B200_DEVICES applies to eval_forces and below)")
     for devs in (["all"] if torch.cuda.device_count() > 1 else []) + ["0,0,0"]:
         b = _run(gpu_binary, str(tmp_path), 40, 10, rdf=2, rdfout=20, env={"MOLDY_B200_DEVICES": devs}, tag="_" + devs.replace(",", ""))
         vb, rb = _current_values(b), _rdf_tables(b)
