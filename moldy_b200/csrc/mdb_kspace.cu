@@ -1195,12 +1195,15 @@ static int recip_finish(mdb_engine *e, const RecipPlan &P, const double *d_psum,
          const long nown = std::max(P.nf_hi - P.nf_lo, P.fw_hi - P.fw_lo);
          long best = -1;
          int best_nsb = Q.nsb;
-         for (int nb = Q.nsb; nb >= std::max(4, Q.nsb - 3) && nown > 0; nb--) {
+         // a block lasts as long as its busiest scheduler: the 2 nb consumer warps sit ceil(2 nb / 4) deep on the four
+         // DMMA pipes (measured at 8 ranks: nb = 7 takes as long per block as nb = 8, 192 us)
+         for (int nb = Q.nsb; nb >= std::max(4, Q.nsb - 4) && nown > 0; nb--) {
             const long blocks = (nown + 16 * nb - 1) / (16 * nb), waves = (blocks + nsm - 1) / nsm;
             if (waves > 16) break;                         // many waves: the tail does not matter
-            const long cost = waves * nb;
+            const long cost = waves * ((2 * nb + 3) / 4);
             if (best < 0 || cost < best) { best = cost; best_nsb = nb; }
          }
+         if (getenv("MDB_KF_NSB")) best_nsb = std::min(Q.nsb, std::max(1, atoi(getenv("MDB_KF_NSB"))));
          Q.nsb = best_nsb;
       }
       kshm = stage_bytes + 16 * (size_t)Q.nsb * per_site;

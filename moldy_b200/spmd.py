@@ -45,6 +45,26 @@ def site_slice(nsites: int, rank: int, world: int):
     return nsites * rank // world, nsites * (rank + 1) // world
 
 
+def result_bounds(nsites: int, world: int):
+    """Ownership of the RESULT in the peer layer (mdb_peer.cu, default bounds): rank r reduces the original sites
+    [b[r], b[r+1]) of every force row, every rank sums the 16 scalars."""
+    return [nsites * r // world for r in range(world + 1)]
+
+
+def molecule_bounds(nmols_per_species, nsites_per_species, world: int):
+    """eval_forces() on several ranks (mdb_group.cu): equal numbers of SITES per rank, cut at molecule boundaries.
+    Returns (molecule bounds [world+1], site bounds [world+1])."""
+    site_of_mol = [0]
+    for nm, ns in zip(nmols_per_species, nsites_per_species):
+        for _ in range(nm):
+            site_of_mol.append(site_of_mol[-1] + ns)
+    n, nmols = site_of_mol[-1], len(site_of_mol) - 1
+    import bisect
+    mb = [min(bisect.bisect_left(site_of_mol, n * r // world), nmols) for r in range(world + 1)]
+    mb[world] = nmols
+    return mb, [site_of_mol[m] for m in mb]
+
+
 def column_owner(vpos: int, world: int) -> int:
     """k-space ownership: position of an (h,k) column in the l-count-sorted list, mod P."""
     return vpos % world

@@ -26,7 +26,11 @@ def test_library_exports_every_declared_symbol():
     syms = _declared_symbols()
     for must in ("force_calc", "ewald", "kernel", "poteval", "dist_pot", "potspec", "pot_dim",
                  "mdb_create", "mdb_configure", "mdb_force_real", "mdb_force_recip",
-                 "eval_forces", "mdb_eval_forces_moldy", "mdb_set_species", "mdb_eval_forces_host", "mdb_eval_result"):
+                 "eval_forces", "mdb_eval_forces_moldy", "mdb_set_species", "mdb_eval_forces_host", "mdb_eval_result",
+                 "do_step", "mdb_do_step_moldy", "mdb_md_step", "mdb_md_set_dynamics", "mdb_md_upload_state",
+                 "mdb_peer_create", "mdb_peer_open", "mdb_peer_connect", "mdb_peer_step", "mdb_peer_read_slice_host",
+                 "mdb_group_create", "mdb_group_force_host", "mdb_group_eval_forces_host",
+                 "mdb_sites_differ_host", "mdb_dmma_peak_probe", "mdb_recip_gemm_flop"):
         assert must in syms, f"{must} not parsed from the header"
     for s in syms:
         assert hasattr(L, s), f"libmoldy_b200.so does not export {s}"

@@ -107,13 +107,28 @@ def test_unmodified_moldy_linked_against_the_library_prints_the_same_run(tmp_pat
         assert la and la == lb, (key, la, lb)
 
 
+_REF_NVE = {}
+
+
 @needs_binaries
 @both
 def test_nve_energy_drift_no_worse_than_reference(tmp_path, gpu_binary):
+    """MOLDY_B200_NVE_STEPS=10000 MOLDY_B200_NVE_TRACE=<dir> runs the north_star's 10 000 steps and writes the total-energy
+    traces of both programs (profiles/r02_nve_10k_*.txt are such a run)."""
     nsteps = int(os.environ.get("MOLDY_B200_NVE_STEPS", "2000"))
     every = max(1, nsteps // 20)
-    ea = _current_values(_run(REF, str(tmp_path), nsteps, every))
+    if nsteps not in _REF_NVE:
+        _REF_NVE[nsteps] = _current_values(_run(REF, str(tmp_path), nsteps, every))
+    ea = _REF_NVE[nsteps]
     eb = _current_values(_run(gpu_binary, str(tmp_path), nsteps, every))
+    trace = os.environ.get("MOLDY_B200_NVE_TRACE")
+    if trace:
+        os.makedirs(trace, exist_ok=True)
+        with open(os.path.join(trace, f"nve_{nsteps}_{os.path.basename(gpu_binary)}.txt"), "w") as f:
+            f.write("# step   E_total(reference CPU binary)   E_total(%s)   [kJ/mol]; KE(0) = %.6f\n"
+                    % (os.path.basename(gpu_binary), ea[sorted(ea)[0]][0] + ea[sorted(ea)[0]][1]))
+            for st in sorted(ea):
+                f.write("%d %.6f %.6f\n" % (st, ea[st][3], eb[st][3]))
     steps = sorted(ea)
     tot_a = np.array([ea[s][3] for s in steps])           # "Energy E" column, kJ/mol
     tot_b = np.array([eb[s][3] for s in steps])

@@ -141,3 +141,80 @@ def test_partition_helpers_cover_everything_once():
     owners = [spmd.column_owner(v, 4) for v in range(103)]
     assert sorted(set(owners)) == [0, 1, 2, 3]
     assert max(np.bincount(owners)) - min(np.bincount(owners)) <= 1
+
+
+# ---- the peer layer's scheme (moldy_b200/csrc/mdb_peer.cu) on gloo: reduce-scatter by result slices + all-gather ----
+def _worker_slices(rank, world, port_no, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from moldy_b200 import spmd
+    from oracle import port
+    from tests import cases
+    ms = cases.GOLDEN_CASES["mgcl2"]()
+    n = ms.nsites
+    part = port.run(ms, ithread=rank, nthreads=world)
+    f = torch.from_numpy(part["force"].copy())                        # [3, n] partial
+    scal = torch.zeros(16, dtype=torch.float64)
+    scal[0:2] = torch.from_numpy(part["pe"]); scal[2:11] = torch.from_numpy(part["stress"].reshape(-1))
+    b = spmd.result_bounds(n, world)
+    # phase C: rank r sums slice r of every row in rank order (fixed order: identical bits everywhere); scalars on all ranks
+    red = torch.zeros((3, n), dtype=torch.float64)
+    for r in range(world):
+        piece = f[:, b[r]:b[r + 1]].contiguous()
+        parts = [torch.zeros_like(piece) for _ in range(world)] if rank == r else None
+        dist.gather(piece, parts, dst=r)
+        if rank == r:
+            acc = torch.zeros_like(piece)
+            for p in parts:
+                acc += p
+            red[:, b[r]:b[r + 1]] = acc
+    allscal = [torch.zeros_like(scal) for _ in range(world)]
+    dist.all_gather(allscal, scal)
+    tot = torch.zeros_like(scal)
+    for s_ in allscal:
+        tot += s_
+    # phase D: all-gather of the slices
+    for r in range(world):
+        piece = red[:, b[r]:b[r + 1]].contiguous()
+        dist.broadcast(piece, src=r)
+        red[:, b[r]:b[r + 1]] = piece
+    gathered = [torch.zeros_like(red) for _ in range(world)]
+    dist.all_gather(gathered, red)
+    same = all(torch.equal(gathered[0], g) for g in gathered)
+    if rank == 0:
+        q.put((red.numpy().copy(), tot.numpy().copy(), same))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_reduce_scatter_by_slices_plus_allgather_reproduces_single_rank():
+    from oracle import port
+    from tests import cases
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = _free_port()
+    procs = [ctx.Process(target=_worker_slices, args=(r, world, port_no, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    force, scal, same = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+    assert same
+    ms = cases.GOLDEN_CASES["mgcl2"]()
+    one = port.run(ms)
+    assert cases.rel_rms(force, one["force"]) < 1e-13
+    assert np.allclose(scal[0:2], one["pe"], rtol=1e-12)
+    assert np.allclose(scal[2:11].reshape(3, 3), one["stress"], rtol=1e-11, atol=1e-11 * np.abs(one["stress"]).max())
+
+
+def test_molecule_bounds_cut_at_molecule_boundaries():
+    from moldy_b200 import spmd
+    mb, sb = spmd.molecule_bounds([200, 4, 8], [3, 1, 1], 4)            # MgCl2 cell: 200 waters, 4 Mg, 8 Cl = 612 sites
+    assert mb[0] == 0 and mb[-1] == 212 and sb[0] == 0 and sb[-1] == 612
+    assert all(sb[r] <= sb[r + 1] for r in range(4))
+    assert all(s % 3 == 0 for s in sb if s <= 600)                      # inside the waters a cut never splits a molecule
+    assert max(sb[r + 1] - sb[r] for r in range(4)) - 612 / 4 <= 3      # balanced to within one molecule
+    mb1, sb1 = spmd.molecule_bounds([5], [4], 8)                        # more ranks than molecules: empty shares, no overlap
+    assert mb1[-1] == 5 and sorted(mb1) == mb1
