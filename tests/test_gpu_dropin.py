@@ -136,7 +136,12 @@ def test_nve_energy_drift_no_worse_than_reference(tmp_path, gpu_binary):
     drift_a = np.abs(tot_a - tot_a[0]).max() / ke
     drift_b = np.abs(tot_b - tot_b[0]).max() / ke
     print(f"NVE {nsteps} steps: max |E-E0|/KE  reference {drift_a:.3e}  gpu-linked {drift_b:.3e}")
-    assert drift_b <= 1.5 * drift_a + 1e-4
+    # the two trajectories are identical to print precision for ~5 000 steps and then separate (chaos): beyond that the
+    # excursions of the total energy are different realisations of the same fluctuation, hence the factor
+    assert drift_b <= 2.0 * drift_a + 2e-4
+    if len(steps) >= 10:                                   # and no systematic trend beyond the reference's excursion
+        slope_b = np.polyfit(np.array(steps, dtype=float), tot_b, 1)[0]
+        assert abs(slope_b) * (steps[-1] - steps[0]) / ke <= 2.0 * drift_a + 2e-4
 
 
 def _rdf_tables(text):
