@@ -648,7 +648,7 @@ def build(spec_text: str, control: Control, *, time_unit=1.0e-13, h=None, seed=1
 
 
 def load_textsave(text: str, control: Control, time_unit=KCAL_TIME_UNIT,
-                  auto_cutoffs=True) -> MoldySystem:
+                  auto_cutoffs=True, **units) -> MoldySystem:
     """Read the sys-spec + lattice-start part of a Moldy `text-mode-save` file
     (as written by the reference's print_config, src/output.c:515-606): species
     in their principal frame, then `a b c alpha beta gamma nx ny nz` and one
@@ -656,7 +656,7 @@ def load_textsave(text: str, control: Control, time_unit=KCAL_TIME_UNIT,
     lines = [ln.strip() for ln in text.strip().splitlines() if ln.strip()]
     ends = [i for i, ln in enumerate(lines) if ln.lower() == "end"]
     spec_text = "\n".join(lines[:ends[1] + 1])
-    sd = parse_sysdef(spec_text, time_unit=time_unit)
+    sd = parse_sysdef(spec_text, time_unit=time_unit, **units)
     cell = lines[ends[1] + 1].split()
     a, b, c, al, be, ga = (float(t) for t in cell[:6])
     nx, ny, nz = (int(t) for t in cell[6:9])
@@ -754,6 +754,15 @@ def quartz(n=4, seed=1, jitter=0.03, pinned_cutoff=True) -> MoldySystem:
     ctl = Control(cutoff=8.48 if pinned_cutoff else 0.0, subcell=3.0)
     quat = np.tile([1.0, 0, 0, 0], (len(com), 1))
     return build(sd_text, ctl, time_unit=EV_TIME_UNIT, h=h, com=com, quat=quat)
+
+
+def clay() -> MoldySystem:
+    """The reference's one shipped framework system (src/examples/control.clay): 64 waters + 4 cations around one rigid
+    montmorillonite sheet (framework species, net charge -8), MCY potentials, explicit Ewald parameters, the example's own
+    units.  Configuration: tests/golden/clay_montmorillonite.txt (the sys-spec part of src/examples/control.clay)."""
+    ctl = Control(cutoff=12.6, alpha=0.35, k_cutoff=2.0, subcell=1.8, strict_cutoff=0, surface_dipole=0)
+    return load_textsave(_eq("clay_montmorillonite.txt"), ctl, time_unit=1.0e-12, auto_cutoffs=False,
+                         mass_unit=1.660565e-27, length_unit=1.0e-10, charge_unit=4.298401e-22)
 
 
 def slab(seed=3) -> MoldySystem:

@@ -116,6 +116,7 @@ GOLDEN_CASES = {
     "quartz": systems.quartz,
     "quartz_auto": quartz_auto,
     "slab_framework": systems.slab,
+    "clay": systems.clay,
     "hiw": hiw,
     "morse": morse,
     "morse_nocoul": morse_nocoul,
@@ -132,7 +133,9 @@ EXAMPLE_GOLDENS = {
     "tips2": (125, 94, 968.356089, 570),        # src/examples/tips2-example.out:65-68
     "mgcl2": (3375, 486, 11332.778403, 1484),   # src/examples/mgclh2o-example.out:79-82
     "quartz": (None, None, 457724.399972, 833), # src/examples/quartz-example.out:68-69
+    "clay": (960, 1400, 4773.730122, 381),      # src/examples/clay-example.out:75-79 (framework species)
 }
+CLAY_SHEET_CORRECTION = 201.117                 # "Framework has net electric charge of -8 - correction of 201.117", :77
 
 
 # the example systems exactly as the reference's start-up builds them (box from the
@@ -144,6 +147,7 @@ EXAMPLE_SYSTEMS = {
     "mgcl2": lambda: systems.build(systems.SPEC_MGCL2, Control(cutoff=6.25, k_cutoff=3.0, alpha=0.45, density=1.0),
                                    time_unit=KCAL_TIME_UNIT),
     "quartz": systems.quartz,
+    "clay": systems.clay,
 }
 
 

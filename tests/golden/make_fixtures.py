@@ -13,7 +13,11 @@
    src/rdf.c, compiled in place) for tests/cases.py RDF_CASES, stored as pair counts (histogram * density,
    rounded: the float store holds count/density summed pair by pair).
 
-usage: python tests/golden/make_fixtures.py [--eq] [--ref] [--rdf]
+4. clay_montmorillonite.txt : the one framework system the reference ships (control.clay): the sys-spec +
+   lattice start that follow the control parameters inside src/examples/control.clay, cut out unchanged (input DATA of
+   the example run, in the example's own units).  Pins the framework goldens of that output.
+
+usage: python tests/golden/make_fixtures.py [--eq] [--ref] [--rdf] [--clay]
 """
 import os
 import subprocess
@@ -83,8 +87,18 @@ def make_rdf():
     np.savez_compressed(os.path.join(GOLD, "ref_rdf.npz"), **out)
 
 
+def make_clay():
+    lines = open(os.path.join(EX, "control.clay")).read().splitlines()
+    a = next(i for i, ln in enumerate(lines) if ln.strip() == "end") + 1        # the sys-spec follows the control parameters
+    with open(os.path.join(GOLD, "clay_montmorillonite.txt"), "w") as f:
+        f.write("\n".join(lines[a:]) + "\n")
+    print("wrote clay_montmorillonite.txt", len(lines) - a, "lines")
+
+
 if __name__ == "__main__":
     args = sys.argv[1:] or ["--eq", "--ref", "--rdf"]
+    if "--clay" in args:
+        make_clay()
     if "--rdf" in args:
         make_rdf()
     if "--eq" in args:

@@ -63,7 +63,7 @@ def test_cell_assignment_bit_exact(name, golden_dir):
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["argon", "tip4p", "tips2", "mgcl2", "quartz"])
+@pytest.mark.parametrize("name", ["argon", "tip4p", "tips2", "mgcl2", "quartz", "clay"])
 def test_startup_scalars_match_example_outputs(name):
     """#subcells, #neighbour cells and #k-vectors printed by the reference's 1996
     sample outputs (the only goldens its tree holds for this path)."""
@@ -84,6 +84,8 @@ def test_startup_scalars_match_example_outputs(name):
         c = np.zeros(3)
         lib.load().mdb_abi_constants(c.ctypes.data_as(lib.DP))
         assert abs(c[1] * systems.CONV_E - self_e) < 5e-6
+        if name == "clay":            # framework-charge sheet correction, src/examples/clay-example.out:77
+            assert abs(c[2] * systems.CONV_E / np.linalg.det(ms.h) - cases.CLAY_SHEET_CORRECTION) < 5e-4
 
 
 def test_partition_sums_to_whole():

@@ -45,6 +45,14 @@ def test_startup_scalars_of_example_outputs(name):
         assert abs(out["self_energy"] * systems.CONV_E - self_e) < 5e-6
 
 
+def test_clay_framework_sheet_correction():
+    """src/examples/clay-example.out:77: 'Framework has net electric charge of -8 - correction of 201.117 kJmol(-1)'."""
+    ms = cases.EXAMPLE_SYSTEMS["clay"]()
+    out = port.run(ms)
+    assert abs(out["sheet_energy"] * systems.CONV_E / np.linalg.det(ms.h) - cases.CLAY_SHEET_CORRECTION) < 5e-4
+    assert ms.nsites - ms.nsites_xf == 240 and ms.sysdef.species[-1].framework
+
+
 def test_more_example_scalars():
     # tip4p-example.out:65 "Intramolecular potential energy correction = -255096" (6 sig. digits)
     e = port.constants(cases.EXAMPLE_SYSTEMS["tip4p"]())[0] * systems.CONV_E
