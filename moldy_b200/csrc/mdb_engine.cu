@@ -40,6 +40,7 @@ extern "C" mdb_engine *mdb_create(int device)
 
 static void free_system(mdb_engine *e)
 {
+   e->table_cap.clear(); e->cls_uploaded = false;
    FREE(e->d_type); FREE(e->d_mol); FREE(e->d_chg); FREE(e->d_ptab);
    FREE(e->own_xyz); FREE(e->d_cell); FREE(e->d_order); FREE(e->d_posq);
    FREE(e->d_stype); FREE(e->d_scell); FREE(e->d_sinfo); FREE(e->d_fs); FREE(e->d_com); e->com_cap = 0; e->com_set = false;
@@ -52,7 +53,7 @@ static void free_sublists(mdb_engine *e)
       FREE(S.posq); FREE(S.sinfo); FREE(S.order); FREE(S.start); FREE(S.batches); FREE(S.nbatch); FREE(S.fs);
       S.n = 0; S.batch_cap = 0; S.cap_n = 0; S.cap_cells = 0; S.valid = false;
    }
-   FREE(e->d_cls); FREE(e->d_sub_flag); FREE(e->d_sub_pos); FREE(e->d_sub_scan); FREE(e->d_sub_cols);
+   FREE(e->d_cls); e->table_cap.erase((void *)&e->d_cls); e->cls_uploaded = false; FREE(e->d_sub_flag); FREE(e->d_sub_pos); FREE(e->d_sub_scan); FREE(e->d_sub_cols);
    e->sub_cap = 0; e->sub_cols_cap = 0;
    if (e->aux_stream) { cudaStreamDestroy(e->aux_stream); e->aux_stream = nullptr; }
    if (e->ev_cells) { cudaEventDestroy(e->ev_cells); e->ev_cells = nullptr; }
@@ -63,6 +64,7 @@ static void free_grid(mdb_engine *e)
    FREE(e->d_count); FREE(e->d_start); FREE(e->d_scan_tmp); FREE(e->d_runs); FREE(e->d_runs_half);
    FREE(e->d_batches); FREE(e->d_nbatch); e->batch_cap = 0;
    FREE(e->d_runs_rdf); e->rdf_limit = -1.0;
+   e->table_cap.erase((void *)&e->d_runs); e->table_cap.erase((void *)&e->d_runs_half); e->table_cap.erase((void *)&e->d_runs_rdf);
    e->cells_cap = 0;
 }
 static void free_recip(mdb_engine *e)
@@ -70,7 +72,9 @@ static void free_recip(mdb_engine *e)
    FREE(e->d_hk); FREE(e->d_hk_valid); FREE(e->d_slot_flags); FREE(e->d_ppart);
    FREE(e->d_coef_tot); FREE(e->d_coef_nf); FREE(e->d_kpartials); FREE(e->d_cidx); FREE(e->d_sfac_blocks); FREE(e->d_kf_groups); FREE(e->d_kf_slot_dst); FREE(e->d_ktab); e->ktab_cap = 0;
    FREE(e->d_psum);
-   e->ppart_cap = 0;
+   e->ppart_cap = 0; e->slots_cap = 0;
+   e->table_cap.erase((void *)&e->d_hk); e->table_cap.erase((void *)&e->d_hk_valid);
+   e->table_cap.erase((void *)&e->d_slot_flags); e->table_cap.erase((void *)&e->d_cidx);
 }
 
 extern "C" void mdb_destroy(mdb_engine *e)
@@ -102,13 +106,18 @@ extern "C" void mdb_set_partition(mdb_engine *e, int ithread, int nthreads)
    e->nthreads = nthreads < 1 ? 1 : nthreads;
 }
 
+// (Re)fill a device table.  The allocation is kept while it is large enough: under constant-stress dynamics the cell
+// matrix changes every step and mdb_configure runs every step -- cudaFree/cudaMalloc would synchronise the device each time.
 template <class T>
-static int upload(T **dst, const T *src, size_t n)
+static int upload(mdb_engine *e, T **dst, const T *src, size_t n)
 {
-   if (*dst) cudaFree(*dst);
-   *dst = nullptr;
+   size_t &cap = e->table_cap[(void *)dst];
+   if (*dst && sizeof(T) * n > cap) { cudaFree(*dst); *dst = nullptr; cap = 0; }
    if (n == 0) return 0;
-   MDB_CUDA(cudaMalloc(dst, sizeof(T) * n));
+   if (!*dst) {
+      MDB_CUDA(cudaMalloc(dst, sizeof(T) * n));
+      cap = sizeof(T) * n;
+   }
    MDB_CUDA(cudaMemcpy(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice));
    return 0;
 }
@@ -123,22 +132,32 @@ extern "C" int mdb_configure(mdb_engine *e, const mdb_config *cfg)
       return -1;
    }
    const bool new_system = !e->configured || e->cfg.nsites != n || e->cfg.max_id != cfg->max_id;
+   // the system definition (site ids, molecule map, charges, potential parameters) is static in a run; only the cell
+   // matrix and with it the tables below change under constant-stress dynamics: skip the per-site work then
+   const int np_chk = cfg->max_id * cfg->max_id * MDB_NPOTP;
+   const bool same_def = !new_system && e->cfg.ptype == cfg->ptype && e->cfg.nsites_xf == cfg->nsites_xf &&
+                         (int)e->h_type.size() == n && !memcmp(e->h_type.data(), cfg->site_type, sizeof(int) * n) &&
+                         (cfg->site_mol ? !memcmp(e->h_mol.data(), cfg->site_mol, sizeof(int) * n) : e->mol_is_identity) &&
+                         !memcmp(e->h_chg.data(), cfg->chg, sizeof(double) * n) && (int)e->h_potpar.size() == np_chk &&
+                         !memcmp(e->h_potpar.data(), cfg->potpar, sizeof(double) * np_chk);
    e->cfg = *cfg;
    e->cfg.site_type = nullptr; e->cfg.site_mol = nullptr; e->cfg.chg = nullptr; e->cfg.potpar = nullptr;
    e->cells_valid = false;
 
    // ---- static per-site data ----
-   e->h_type.assign(cfg->site_type, cfg->site_type + n);
-   if (cfg->site_mol) e->h_mol.assign(cfg->site_mol, cfg->site_mol + n);
-   else { e->h_mol.resize(n); for (int i = 0; i < n; i++) e->h_mol[i] = i; }
-   e->h_chg.assign(cfg->chg, cfg->chg + n);
-   const int np = cfg->max_id * cfg->max_id * MDB_NPOTP;
-   e->h_potpar.assign(cfg->potpar, cfg->potpar + np);
-   for (int i = 0; i < n; i++)
-      if (e->h_type[i] < 0 || e->h_type[i] >= cfg->max_id) {
-         mdb_set_error("mdb_configure: site id out of range");
-         return -1;
-      }
+   if (!same_def) {
+      e->h_type.assign(cfg->site_type, cfg->site_type + n);
+      if (cfg->site_mol) e->h_mol.assign(cfg->site_mol, cfg->site_mol + n);
+      else { e->h_mol.resize(n); for (int i = 0; i < n; i++) e->h_mol[i] = i; }
+      e->mol_is_identity = cfg->site_mol == nullptr;
+      e->h_chg.assign(cfg->chg, cfg->chg + n);
+      e->h_potpar.assign(cfg->potpar, cfg->potpar + np_chk);
+      for (int i = 0; i < n; i++)
+         if (e->h_type[i] < 0 || e->h_type[i] >= cfg->max_id) {
+            mdb_set_error("mdb_configure: site id out of range");
+            return -1;
+         }
+   }
    // pair table as the kernel wants it (LJ: sigma^2 and 6 eps precomputed, src/kernel.c:206-210)
    std::vector<double> ptab(e->h_potpar);
    if (cfg->ptype == 0)
@@ -158,10 +177,12 @@ extern "C" int mdb_configure(mdb_engine *e, const mdb_config *cfg)
       MDB_CUDA(cudaMalloc(&e->d_sinfo, sizeof(int2) * (size_t)n));
       e->sites_set = false;
    }
-   if (upload(&e->d_type, e->h_type.data(), n)) return -1;
-   if (upload(&e->d_mol, e->h_mol.data(), n)) return -1;
-   if (upload(&e->d_chg, e->h_chg.data(), n)) return -1;
-   if (upload(&e->d_ptab, ptab.data(), ptab.size())) return -1;
+   if (!same_def) {
+      if (upload(e, &e->d_type, e->h_type.data(), n)) return -1;
+      if (upload(e, &e->d_mol, e->h_mol.data(), n)) return -1;
+      if (upload(e, &e->d_chg, e->h_chg.data(), n)) return -1;
+      if (upload(e, &e->d_ptab, ptab.data(), ptab.size())) return -1;
+   }
 
    // ---- link-cell grid + stencil ----
    std::string err;
@@ -175,9 +196,9 @@ extern "C" int mdb_configure(mdb_engine *e, const mdb_config *cfg)
       MDB_CUDA(cudaMalloc(&e->d_scan_tmp, sizeof(int) * (size_t)(e->cells_cap / 2048 + 2)));
    }
    e->nruns = (int)e->T.runs.size();
-   if (upload(&e->d_runs, e->T.runs.data(), e->T.runs.size())) return -1;
+   if (upload(e, &e->d_runs, e->T.runs.data(), e->T.runs.size())) return -1;
    e->nruns_half = (int)e->T.runs_half.size();
-   if (upload(&e->d_runs_half, e->T.runs_half.data(), e->T.runs_half.size())) return -1;
+   if (upload(e, &e->d_runs_half, e->T.runs_half.data(), e->T.runs_half.size())) return -1;
    {
       const int need = n / MDB_NI + e->T.nx * e->T.ny + 8;
       if (need > e->batch_cap) {
@@ -218,12 +239,17 @@ extern "C" int mdb_configure(mdb_engine *e, const mdb_config *cfg)
       for (int a = 0; a < id; a++)
          for (int b = 0; b < id; b++)
             if (!amp_zero(&e->h_potpar[((size_t)a * id + b) * MDB_NPOTP])) active[a] = 1;
-      std::vector<unsigned char> cls(n);
-      long nc = 0, np2 = 0;
-      for (int i = 0; i < n; i++) {
-         cls[i] = (e->h_chg[i] != 0.0 ? 1 : 0) | (active[e->h_type[i]] ? 2 : 0);
-         nc += cls[i] & 1; np2 += (cls[i] >> 1) & 1;
+      std::vector<unsigned char> &cls = e->h_cls;
+      if (!same_def || (int)cls.size() != n) {
+         cls.resize(n);
+         e->n_cls[0] = e->n_cls[1] = 0;
+         for (int i = 0; i < n; i++) {
+            cls[i] = (e->h_chg[i] != 0.0 ? 1 : 0) | (active[e->h_type[i]] ? 2 : 0);
+            e->n_cls[0] += cls[i] & 1; e->n_cls[1] += (cls[i] >> 1) & 1;
+         }
+         e->cls_uploaded = false;
       }
+      const long nc = e->n_cls[0], np2 = e->n_cls[1];
       // FP64 instructions per visit (profiles/): 22 shared (r^2, 1/r, accumulation), 23 Coulomb, 9..30 potential
       static const double ptc[7] = {9, 19, 27, 30, 12, 0, 40};
       const bool coul = cfg->alpha > 0.0;
@@ -242,8 +268,10 @@ extern "C" int mdb_configure(mdb_engine *e, const mdb_config *cfg)
       }
       for (int k = 0; k < 2; k++) e->sub[k].valid = false;
       if (e->pair_split) {
-         if (new_system || !e->d_cls) { if (upload(&e->d_cls, cls.data(), n)) return -1; }
-         else MDB_CUDA(cudaMemcpy(e->d_cls, cls.data(), n, cudaMemcpyHostToDevice));
+         if (!e->cls_uploaded || !e->d_cls) {
+            if (upload(e, &e->d_cls, cls.data(), n)) return -1;
+            e->cls_uploaded = true;
+         }
          const int ncols = e->T.nx * e->T.ny;
          if (n + 1 > e->sub_cap || new_system || n / 2048 + ncols / 2048 + 4 > e->sub_scan_cap) {
             FREE(e->d_sub_flag); FREE(e->d_sub_pos); FREE(e->d_sub_scan);
@@ -289,24 +317,29 @@ extern "C" int mdb_configure(mdb_engine *e, const mdb_config *cfg)
       for (int s = 0; s < T.nslots; s++) slotinfo[s] = T.slot_flags[s];
       for (size_t i = 0; i < T.hk.size(); i++)
          for (int l = 0; l < T.hk[i].nl; l++) slotinfo[T.nslots + T.hk[i].slot0 + l] = (int)i;
-      std::vector<int> cidx;
-      for (int i = 0; i < n; i++) {
-         if (i == cfg->nsites_xf) e->n_charged_nf = (int)cidx.size();
-         if (e->h_chg[i] != 0.0) cidx.push_back(i);
+      if (!same_def || !e->d_cidx) {
+         std::vector<int> cidx;
+         for (int i = 0; i < n; i++) {
+            if (i == cfg->nsites_xf) e->n_charged_nf = (int)cidx.size();
+            if (e->h_chg[i] != 0.0) cidx.push_back(i);
+         }
+         if (cfg->nsites_xf >= n) e->n_charged_nf = (int)cidx.size();
+         e->n_charged = (int)cidx.size();
+         if (upload(e, &e->d_cidx, cidx.data(), cidx.size())) return -1;
       }
-      if (cfg->nsites_xf >= n) e->n_charged_nf = (int)cidx.size();
-      e->n_charged = (int)cidx.size();
-      if (upload(&e->d_cidx, cidx.data(), cidx.size())) return -1;
-      if (upload(&e->d_hk, T.hk.data(), T.hk.size())) return -1;
-      if (upload(&e->d_hk_valid, T.hk_valid.data(), T.hk_valid.size())) return -1;
-      if (upload(&e->d_slot_flags, slotinfo.data(), slotinfo.size())) return -1;
+      if (upload(e, &e->d_hk, T.hk.data(), T.hk.size())) return -1;
+      if (upload(e, &e->d_hk_valid, T.hk_valid.data(), T.hk_valid.size())) return -1;
+      if (upload(e, &e->d_slot_flags, slotinfo.data(), slotinfo.size())) return -1;
       e->sfac_rank = -1; e->kf_rank = -1;
-      FREE(e->d_coef_tot); FREE(e->d_coef_nf); FREE(e->d_kpartials);
-      MDB_CUDA(cudaMalloc(&e->d_coef_tot, sizeof(double) * 8 * (size_t)std::max(T.nslots, 1)));
-      MDB_CUDA(cudaMalloc(&e->d_coef_nf, sizeof(double) * 8 * (size_t)std::max(T.nslots, 1)));
-      MDB_CUDA(cudaMalloc(&e->d_kpartials, sizeof(double) * 8 * (size_t)(T.nslots / 256 + 1)));
-      FREE(e->d_psum);
-      MDB_CUDA(cudaMalloc(&e->d_psum, sizeof(double) * 8 * (size_t)std::max(T.nslots, 1)));
+      if (T.nslots > e->slots_cap) {                       // grown (never shrunk: a breathing cell changes nslots a little)
+         FREE(e->d_coef_tot); FREE(e->d_coef_nf); FREE(e->d_kpartials); FREE(e->d_psum);
+         const size_t cap = (size_t)std::max(T.nslots, 1) * 5 / 4 + 64;
+         MDB_CUDA(cudaMalloc(&e->d_coef_tot, sizeof(double) * 8 * cap));
+         MDB_CUDA(cudaMalloc(&e->d_coef_nf, sizeof(double) * 8 * cap));
+         MDB_CUDA(cudaMalloc(&e->d_kpartials, sizeof(double) * 8 * (cap / 256 + 1)));
+         MDB_CUDA(cudaMalloc(&e->d_psum, sizeof(double) * 8 * cap));
+         e->slots_cap = (int)cap;
+      }
    } else {
       e->T.nhkl = 0; e->T.hk.clear(); e->T.hk_valid.clear(); e->T.nslots = 0;
    }
@@ -504,7 +537,7 @@ extern "C" int mdb_rdf_counts(mdb_engine *e, double limit, int nbins, unsigned l
       std::vector<StencilRun> runs;
       std::string err;
       if (!mdb_build_rdf_runs(e->cfg, e->T, limit, runs, err)) { mdb_set_error(err); return -1; }
-      if (upload(&e->d_runs_rdf, runs.data(), runs.size())) return -1;
+      if (upload(e, &e->d_runs_rdf, runs.data(), runs.size())) return -1;
       e->nruns_rdf = (int)runs.size(); e->rdf_limit = limit;
       e->rdf_grid[0] = e->T.nx; e->rdf_grid[1] = e->T.ny; e->rdf_grid[2] = e->T.nz;
       memcpy(e->rdf_h, e->cfg.h, sizeof e->rdf_h);

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <map>
 #include <string>
 #include <vector>
 #include "moldy_b200.h"
@@ -90,6 +91,9 @@ struct mdb_engine {
    mdb_config cfg{};
    std::vector<int> h_type, h_mol;
    std::vector<double> h_chg, h_potpar;
+   std::vector<unsigned char> h_cls; long n_cls[2] = {0, 0}; bool cls_uploaded = false, mol_is_identity = false;
+   std::map<void *, size_t> table_cap;    // bytes allocated behind the device tables that upload() refills
+   int slots_cap = 0;
    HostTables T;
    int ithread = 0, nthreads = 1;
    long launches = 0;

@@ -27,6 +27,7 @@
 // out[] is double-buffered by step parity, so a rank may start step n+1 while a peer still reads step n's block; every
 // other window region is protected by the two barriers of the following step.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include "mdb_internal.h"
@@ -54,6 +55,9 @@ struct mdb_peer {
    PeerBounds site_b{}, in_b{};
    double *h_pin = nullptr; size_t pin_cap = 0;         // pinned staging of the host-facing calls
    long barriers = 0;
+   // the structure-factor pass does not need the cell lists: it runs on a side stream beside the (latency-bound) cell
+   // build and sub-list compaction and shares the SMs with the pair kernel afterwards
+   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -177,6 +181,9 @@ extern "C" void mdb_peer_destroy(mdb_peer *p)
    for (int r = 0; r < p->world; r++)
       if (p->ipc && p->opened[r]) cudaIpcCloseMemHandle(p->W.base[r]);
    if (p->win) cudaFree(p->win);
+   if (p->side) cudaStreamDestroy(p->side);
+   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+   if (p->ev_join) cudaEventDestroy(p->ev_join);
    if (p->d_psum_tot) cudaFree(p->d_psum_tot);
    if (p->h_pin) cudaFreeHost(p->h_pin);
    delete p;
@@ -350,13 +357,25 @@ extern "C" int mdb_peer_phase_a(mdb_peer *p, int what, void *stream)
    mdb_set_partition(e, p->rank, p->world);
    if (!(what & 4)) p->parity ^= 1;
    double *out = out_block(p);
+   const bool recip = (what & 2) && e->cfg.do_recip;
+   double *psum = p->world == 1 ? p->d_psum_tot : reinterpret_cast<double *>(p->win + p->off_psum);
+   static const bool no_side = getenv("MDB_PEER_NO_SIDE") != nullptr;
+   const bool fork = recip && (what & 1) && !(what & 4) && !no_side;
+   if (fork) {
+      if (!p->side) {
+         MDB_CUDA(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+         MDB_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+         MDB_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+      }
+      MDB_CUDA(cudaEventRecord(p->ev_fork, st));                   // the sites are complete at this point of `st`
+      MDB_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+      if (mdb_launch_recip_partial(e, psum, p->side)) return -1;
+      MDB_CUDA(cudaEventRecord(p->ev_join, p->side));
+   }
    if (!(what & 4) && (mdb_zero_out(e, out, st) || mdb_build_cells(e, st))) return -1;
    if ((what & 1) && mdb_force_real(e, out, st)) return -1;
-   if ((what & 2) && e->cfg.do_recip) {
-      double *psum = reinterpret_cast<double *>(p->win + p->off_psum);
-      if (p->world == 1) return mdb_launch_recip_partial(e, p->d_psum_tot, st);
-      if (mdb_launch_recip_partial(e, psum, st)) return -1;
-   }
+   if (fork) MDB_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0));
+   else if (recip && mdb_launch_recip_partial(e, psum, st)) return -1;
    return 0;
 }
 
