@@ -214,6 +214,13 @@ int  mdb_zero_out(mdb_engine *e, double *d_out, void *stream);
 int  mdb_build_cells(mdb_engine *e, void *stream);
 int  mdb_force_real(mdb_engine *e, double *d_out, void *stream);
 int  mdb_force_recip(mdb_engine *e, double *d_out, void *stream);
+/* Both sums of one step, overlapped: the k-space kernels run on a high-priority side stream while a small persistent
+ * grid of the pair kernel (`fill_blocks` blocks of `fill_threads` threads; 0, 0 = one block of 64 threads per SM) works
+ * beside them on the same SMs; when they end the rest of the real-space pass runs at full occupancy.  Same sums as
+ * mdb_force_real + mdb_force_recip (the k-space block is added last).  mdb_set_overlap(e, -1, 0) switches the overlap off. */
+int  mdb_set_overlap(mdb_engine *e, int fill_blocks, int fill_threads);
+int  mdb_force_both(mdb_engine *e, double *d_out, void *stream);
+long mdb_overlap_filled(mdb_engine *e);   /* batches the filler drew in the last call (diagnostic; synchronises) */
 
 /* k-space cut by SITES instead of by (h,k) columns (multi-GPU, moldy_b200/spmd.py): pass 1 writes
  * this rank's structure-factor sums (mdb_recip_sum_doubles() doubles) to the DEVICE buffer d_psum,

@@ -79,6 +79,11 @@ static void free_recip(mdb_engine *e)
 
 extern "C" void mdb_destroy(mdb_engine *e)
 {
+   if (e && e->ovl_stream) {
+      cudaSetDevice(e->device);
+      cudaStreamDestroy(e->ovl_stream); cudaEventDestroy(e->ev_ovl_fork); cudaEventDestroy(e->ev_ovl_join);
+      cudaFree(e->d_ovl_q); cudaFree(e->d_out2);
+   }
    if (!e) return;
    cudaSetDevice(e->device);
    free_system(e); free_grid(e); free_recip(e); free_sublists(e);
@@ -437,6 +442,82 @@ extern "C" int mdb_force_recip(mdb_engine *e, double *d_out, void *stream)
    if (!e->configured || !e->sites_set) { mdb_set_error("mdb_force_recip: engine not configured / no sites"); return -1; }
    if (!e->cfg.do_recip) return 0;
    return mdb_launch_recip(e, d_out, (cudaStream_t)stream);
+}
+
+// ---- real space beside k-space -------------------------------------------------------------------------------------
+// DFMA (pair kernel) and DMMA (k-space GEMMs) share one FP64 execution resource per SM sub-partition
+// (profiles/r02_ubench_mix.txt), so running the phases side by side cannot beat the sum of their pipe times -- but each
+// phase alone leaves the pipe idle a quarter to a third of the time (in-order warps waiting on their own latencies).
+// A few pair warps resident beside the GEMM blocks take those slots.
+__global__ void __launch_bounds__(256) k_add_block(double *__restrict__ out, const double *__restrict__ add, size_t n)
+{
+   for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] += add[i];
+}
+
+extern "C" int mdb_set_overlap(mdb_engine *e, int fill_blocks, int fill_threads)
+{
+   if (fill_blocks < 0) { e->ovl_blocks = -1; e->ovl_threads = 0; return 0; }
+   int nsm = 148;
+   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, e->device);
+   e->ovl_blocks = fill_blocks > 0 ? fill_blocks : nsm;
+   e->ovl_threads = fill_threads > 0 ? std::min(128, (fill_threads + 31) / 32 * 32) : 64;
+   return 0;
+}
+
+// batches the filler grid drew in the last mdb_force_both (synchronises the device); -1: no overlapped step yet
+extern "C" long mdb_overlap_filled(mdb_engine *e)
+{
+   if (!e->d_ovl_q) return -1;
+   int q[2] = {0, 0};
+   if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(q, e->d_ovl_q, sizeof q, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+   return q[0];
+}
+
+extern "C" int mdb_force_both(mdb_engine *e, double *d_out, void *stream)
+{
+   cudaStream_t st = (cudaStream_t)stream;
+   if (!e->configured || !e->sites_set) { mdb_set_error("mdb_force_both: engine not configured / no sites"); return -1; }
+   if (e->ovl_blocks == 0) {
+      const char *s = getenv("MDB_OVERLAP");             // "0": off; "blocks,threads": the filler grid
+      int b = 0, t = 0;
+      if (s) { sscanf(s, "%d,%d", &b, &t); if (b <= 0) b = -1; }
+      mdb_set_overlap(e, b, t);
+   }
+   const bool ovl = e->ovl_blocks > 0 && e->cfg.do_recip && e->pair_mode == 4;     // (the filler is a Newton-3 instantiation)
+   if (!ovl) {
+      if (mdb_force_real(e, d_out, stream)) return -1;
+      return mdb_force_recip(e, d_out, stream);
+   }
+   const size_t nd = mdb_out_doubles(e->cfg.nsites);
+   if (!e->ovl_stream) {
+      int lo = 0, hi = 0;
+      MDB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      MDB_CUDA(cudaStreamCreateWithPriority(&e->ovl_stream, cudaStreamNonBlocking, hi));
+      MDB_CUDA(cudaEventCreateWithFlags(&e->ev_ovl_fork, cudaEventDisableTiming));
+      MDB_CUDA(cudaEventCreateWithFlags(&e->ev_ovl_join, cudaEventDisableTiming));
+      MDB_CUDA(cudaMalloc(&e->d_ovl_q, 2 * sizeof(int)));
+   }
+   if (nd > e->out2_cap) {
+      FREE(e->d_out2);
+      MDB_CUDA(cudaMalloc(&e->d_out2, sizeof(double) * nd));
+      e->out2_cap = nd;
+   }
+   MDB_CUDA(cudaMemsetAsync(e->d_ovl_q, 0, 2 * sizeof(int), st));
+   MDB_CUDA(cudaEventRecord(e->ev_ovl_fork, st));                    // the sites are complete at this point of `st`
+   MDB_CUDA(cudaStreamWaitEvent(e->ovl_stream, e->ev_ovl_fork, 0));
+   MDB_CUDA(cudaMemsetAsync(e->d_out2, 0, sizeof(double) * nd, e->ovl_stream));
+   if (mdb_launch_recip(e, e->d_out2, e->ovl_stream)) return -1;
+   MDB_CUDA(cudaMemsetAsync(e->d_ovl_q + 1, 1, sizeof(int), e->ovl_stream));      // stop flag: the filler grid ends
+   MDB_CUDA(cudaEventRecord(e->ev_ovl_join, e->ovl_stream));
+   e->ovl_armed = true;
+   const int rc = mdb_force_real(e, d_out, stream);
+   e->ovl_armed = false;
+   if (rc) return -1;
+   MDB_CUDA(cudaStreamWaitEvent(st, e->ev_ovl_join, 0));
+   k_add_block<<<592, 256, 0, st>>>(d_out, e->d_out2, nd);
+   e->launches++;
+   MDB_CUDA(cudaGetLastError());
+   return 0;
 }
 
 // k-space with the SITE partition (moldy_b200/spmd.py): pass 1 leaves this rank's structure-factor

@@ -161,6 +161,12 @@ struct mdb_engine {
       double *d_mom = nullptr, *d_amom = nullptr, *d_mdpart = nullptr, *d_mdscal = nullptr, *h_mdscal = nullptr;
    } mf;
 
+   // real space beside k-space (mdb_force_both): the k-space chain runs on a high-priority side stream into d_out2, a small
+   // persistent pair grid fills the FP64 issue slots its DMMA stream leaves idle; d_ovl_q = {next batch, stop flag}
+   int ovl_blocks = 0, ovl_threads = 0; bool ovl_armed = false;
+   int *d_ovl_q = nullptr; double *d_out2 = nullptr; size_t out2_cap = 0;
+   cudaStream_t ovl_stream = nullptr; cudaEvent_t ev_ovl_fork = nullptr, ev_ovl_join = nullptr;
+
    // pinned staging for host-facing calls
    double *h_stage = nullptr; size_t stage_cap = 0;
    double *d_out_own = nullptr; size_t out_cap = 0;

@@ -1085,6 +1085,8 @@ static int recip_partial(mdb_engine *e, const RecipPlan &P, double *d_psum, cuda
       size_t &mshm_set = g_shm_set[e->device & 63][1];
       if (mshm > mshm_set) {
          MDB_CUDA(cudaFuncSetAttribute(k_sfac_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mshm));
+         // largest shared-memory carve-out: the pair kernel's filler blocks share the SM (mdb_force_both)
+         MDB_CUDA(cudaFuncSetAttribute(k_sfac_mma, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
          mshm_set = mshm;
       }
       static const int sgroup = getenv("MDB_SFAC_GROUP") ? std::max(1, atoi(getenv("MDB_SFAC_GROUP"))) : 16;
@@ -1211,6 +1213,7 @@ static int recip_finish(mdb_engine *e, const RecipPlan &P, const double *d_psum,
       size_t &kshm_set = g_shm_set[e->device & 63][3];
       if (kshm > kshm_set) {
          MDB_CUDA(cudaFuncSetAttribute(k_kforce_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kshm));
+         MDB_CUDA(cudaFuncSetAttribute(k_kforce_mma, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
          kshm_set = kshm;
       }
       for (int part = 0; part < 2; part++) {

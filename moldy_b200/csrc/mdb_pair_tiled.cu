@@ -99,8 +99,13 @@ struct JBuf {                                  // one lane's neighbour for one s
 
 enum { TM_FORCE = 0, TM_COUNT = 1, TM_RDF = 2 };     // what a visit does
 struct RdfParams { double rbin; int nbins, hist_smem; unsigned long long *counts; };
+// How warps get their batches.  mode 0: warp (block, w) owns batch block * warps + w (one batch per warp).
+// mode 1 ("filler", the QUEUE instantiations): a small persistent grid (one block per SM) draws batches from the counter `next` until the list is
+// exhausted or `stop` is raised; it runs beside the k-space GEMM kernels, whose DMMA stream leaves a quarter of the FP64
+// pipe idle.  mode 2 ("remainder"): the static mapping again, starting at the batch the filler stopped at.
+struct PairQueue { int mode; int *next; const int *stop; int prow0; };
 
-template <int PT, bool COUL, bool STRICT, bool FW, bool N3, int MODE>
+template <int PT, bool COUL, bool STRICT, bool FW, bool N3, int MODE, bool QUEUE = false>
 // (potential-only instantiations fit 128 registers without spills: 4 blocks per SM, 2.10 -> 1.92 ms for the LJ pass;
 //  with the Coulomb term 4 blocks spill and lose, 16.6 -> 17.9 ms)
 __global__ void __launch_bounds__(TW * 32, (COUL || MODE != TM_FORCE) ? MDB_TILED_MINB : MDB_TILED_MINB + 1)
@@ -109,7 +114,7 @@ k_pair_tiled(PairParams P, int nsites, int nout, const double4 *__restrict__ pos
              const int *__restrict__ mol, const StencilRun *__restrict__ runs, const double *__restrict__ ptab,
              const int2 *__restrict__ batches, const int *__restrict__ nbatch_p, int rank, int nranks,
              double *__restrict__ out, double *__restrict__ fs, double *__restrict__ partials,
-             unsigned long long *__restrict__ counters, RdfParams R)
+             unsigned long long *__restrict__ counters, RdfParams R, PairQueue Q)
 {
    constexpr bool COUNT = MODE == TM_COUNT;
    extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -117,15 +122,15 @@ k_pair_tiled(PairParams P, int nsites, int nout, const double4 *__restrict__ pos
    {
       double4 *s_reloc = reinterpret_cast<double4 *>(smem_raw + OFF_RELOC);
       double *s_e2 = reinterpret_cast<double *>(smem_raw + OFF_E2), *s_ptab = reinterpret_cast<double *>(smem_raw + OFF_TAB);
-      for (int k = threadIdx.x; k < 27; k += TW * 32) s_reloc[k] = make_double4(P.reloc[k][0], P.reloc[k][1], P.reloc[k][2], 0.0);
-      for (int k = threadIdx.x; k < 64; k += TW * 32) s_e2[k] = c_exp2tab[k];
+      for (int k = threadIdx.x; k < 27; k += blockDim.x) s_reloc[k] = make_double4(P.reloc[k][0], P.reloc[k][1], P.reloc[k][2], 0.0);
+      for (int k = threadIdx.x; k < 64; k += blockDim.x) s_e2[k] = c_exp2tab[k];
       if (MODE == TM_RDF) {                      // block-local histogram in place of the pair table
          unsigned int *hist = reinterpret_cast<unsigned int *>(s_ptab);
          const int nh = R.hist_smem ? R.nbins * (P.max_id * (P.max_id - 1) / 2) : 0;
-         for (int k = threadIdx.x; k < nh; k += TW * 32) hist[k] = 0u;
+         for (int k = threadIdx.x; k < nh; k += blockDim.x) hist[k] = 0u;
       } else {
          const int ntab = P.max_id * P.max_id * MDB_NPOTP;
-         for (int k = threadIdx.x; k < ntab; k += TW * 32) s_ptab[k] = ptab[k];
+         for (int k = threadIdx.x; k < ntab; k += blockDim.x) s_ptab[k] = ptab[k];
       }
    }
    __syncthreads();
@@ -134,38 +139,11 @@ k_pair_tiled(PairParams P, int nsites, int nout, const double4 *__restrict__ pos
    const unsigned sb = __shfl_sync(0xffffffffu, (unsigned)__cvta_generic_to_shared(smem_raw), 0);
    const unsigned sw = __shfl_sync(0xffffffffu, sb + w * WARP_SM, 0);
 
-   const int nbatch = *nbatch_p;
-   const long b_lo = (long)nbatch * rank / nranks, b_hi = (long)nbatch * (rank + 1) / nranks;
-   const long b = b_lo + (long)blockIdx.x * TW + w;
-   const size_t prow_id = (size_t)blockIdx.x * TW + w;
-   const bool idle = b >= b_hi;
-   if (idle) {                                  // whole warp idle: still publish a zero row
-      if (MODE == TM_FORCE && lane < 7) partials[prow_id * NRED + lane] = 0.0;
-      if (MODE != TM_RDF) return;               // (the RDF pass ends with a block-wide flush)
-   }
-   const int2 bt = idle ? make_int2(0, 1) : batches[b];     // {first sorted site, count | column << 3}
-   const int s0 = bt.x, cnt = bt.y & 7, col = bt.y >> 3;
-   const int cx = col / P.ny, cy = col - cx * P.ny;
-   const int cz_lo = sinfo[s0].y, cz_hi = sinfo[s0 + cnt - 1].y;
-
-   // ---- batch (warp-uniform) data
    double fix[NI], fiy[NI], fiz[NI];
-   if (lane < NI) {
-      const int k = lane, sk = s0 + min(k, cnt - 1);
-      WarpSm *W = reinterpret_cast<WarpSm *>(smem_raw) + w;
-      W->ipos[k] = posq[sk];
-      const int2 si = sinfo[sk];
-      // padded entries never pass the window test; row offset in bytes from the table start
-      W->iint[k] = make_int4(k < cnt ? si.y : BIGZ,
-                             MODE == TM_RDF ? (si.x & 0x3fffffff) : (si.x & 0x3fffffff) * P.max_id * (MDB_NPOTP * 8),
-                             si.x >> 30, k < cnt ? s0 + k : 0x7fffffff);
-   }
-#pragma unroll
-   for (int k = 0; k < NI; k++) fix[k] = fiy[k] = fiz[k] = 0.0;
-   __syncwarp();
    double pe = 0, w00 = 0, w01 = 0, w02 = 0, w11 = 0, w12 = 0, w22 = 0;
    unsigned int visits = 0;
-   const int nruns = idle ? 0 : P.nruns;
+   int s0 = 0, cnt = 1, col = 0, cx = 0, cy = 0, cz_lo = 0, cz_hi = 0, nruns = 0;
+   bool idle = false;
 
    // ---- one step: lane's neighbour j against the NI batch sites --------------------------------
    // u = cz_j - (dzlo - zoff) (or a value no window accepts for padding lanes), wid = dzhi - dzlo:
@@ -298,8 +276,43 @@ k_pair_tiled(PairParams P, int nsites, int nout, const double4 *__restrict__ pos
       }
    };
 
+   for (;;) {                                   // one batch per pass (filler: until the list is exhausted or `stop` is raised)
+   // (bounds and the queue state are re-derived here so that nothing of them stays in registers across the pass)
+   const int nbatch = *nbatch_p;
+   const int b_lo = (int)((long)nbatch * rank / nranks), b_hi = (int)((long)nbatch * (rank + 1) / nranks);
+   int b;
+   if (QUEUE) {
+      int t = 0;
+      if (lane == 0) t = *reinterpret_cast<const volatile int *>(Q.stop) ? 0x3fffffff : atomicAdd(Q.next, 1);
+      b = b_lo + min(__shfl_sync(0xffffffffu, t, 0), 0x3fffffff);
+   } else
+      b = b_lo + (Q.mode == 2 ? min(*Q.next, b_hi - b_lo) : 0) + (int)blockIdx.x * (int)(blockDim.x >> 5) + w;
+   idle = b >= b_hi;
+   if (idle) break;                             // (an idle warp still publishes its zero row below)
+   {
+      const int2 bt = batches[b];               // {first sorted site, count | column << 3}
+      s0 = bt.x; cnt = bt.y & 7; col = bt.y >> 3;
+      cx = col / P.ny; cy = col - cx * P.ny;
+      cz_lo = sinfo[s0].y; cz_hi = sinfo[s0 + cnt - 1].y;
+      // ---- batch (warp-uniform) data
+      if (lane < NI) {
+         const int k = lane, sk = s0 + min(k, cnt - 1);
+         WarpSm *W = reinterpret_cast<WarpSm *>(smem_raw) + w;
+         W->ipos[k] = posq[sk];
+         const int2 si = sinfo[sk];
+         // padded entries never pass the window test; row offset in bytes from the table start
+         W->iint[k] = make_int4(k < cnt ? si.y : BIGZ,
+                                MODE == TM_RDF ? (si.x & 0x3fffffff) : (si.x & 0x3fffffff) * P.max_id * (MDB_NPOTP * 8),
+                                si.x >> 30, k < cnt ? s0 + k : 0x7fffffff);
+      }
+#pragma unroll
+      for (int k = 0; k < NI; k++) fix[k] = fiy[k] = fiz[k] = 0.0;
+      __syncwarp();
+      nruns = P.nruns;
+   }
+
    // ---- Newton-3 prologue: own column, central image, j > s_i (run 0 of the half list starts at dz = 0)
-   if (N3 && !idle) {
+   if (N3) {
       const StencilRun r0 = runs[0];
       const int jb = s0 + 1, je = cstart[col * P.nz + min(cz_hi + r0.dzhi, P.nz - 1) + 1];
       if (lane == 0) sts_i4<OFF_Q>(sw, make_int4(0, -BIGZ, r0.dzhi + BIGZ, 13 | 32));
@@ -399,12 +412,40 @@ k_pair_tiled(PairParams P, int nsites, int nout, const double4 *__restrict__ pos
       }
    }
 
+   // ---- forces on the batch sites: reduce the per-lane partial sums
+   if (MODE == TM_FORCE) {
+      const WarpSm *W = reinterpret_cast<const WarpSm *>(smem_raw) + w;
+#pragma unroll
+      for (int k = 0; k < NI; k++) {
+         const double fx = wsum(fix[k]), fy = wsum(fiy[k]), fz = wsum(fiz[k]);
+         if (lane == 0 && k < cnt) {
+            if (N3) {
+               atomicAdd(&fs[s0 + k], fx);
+               atomicAdd(&fs[(size_t)nsites + s0 + k], fy);
+               atomicAdd(&fs[2 * (size_t)nsites + s0 + k], fz);
+            } else {
+               const int o = order[s0 + k];          // nsites = length of this pass's site list, nout = all sites
+               out[o] += fx;
+               out[(size_t)nout + o] += fy;
+               out[2 * (size_t)nout + o] += fz;
+               const double4 pk4 = W->ipos[k];
+               const double px = pk4.x, py = pk4.y, pz = pk4.z;
+               w00 = fma(px, fx, w00); w01 = fma(py, fx, w01); w02 = fma(pz, fx, w02);
+               w11 = fma(py, fy, w11); w12 = fma(pz, fy, w12); w22 = fma(pz, fz, w22);
+            }
+         }
+      }
+   }
+   if (!QUEUE) break;
+   __syncwarp();                                // the batch data in shared memory are rewritten by the next pass
+   }
+
    if (MODE == TM_RDF) {
       __syncthreads();
       if (R.hist_smem) {
          const unsigned int *hist = reinterpret_cast<const unsigned int *>(smem_raw + OFF_TAB);
          const int nh = R.nbins * (P.max_id * (P.max_id - 1) / 2);
-         for (int k = threadIdx.x; k < nh; k += TW * 32)
+         for (int k = threadIdx.x; k < nh; k += blockDim.x)
             if (hist[k]) atomicAdd(&R.counts[k], (unsigned long long)hist[k]);
       }
       return;
@@ -416,34 +457,11 @@ k_pair_tiled(PairParams P, int nsites, int nout, const double4 *__restrict__ pos
       if (lane == 0) atomicAdd(&counters[0], (unsigned long long)vs * (N3 ? 2ULL : 1ULL));
       return;
    }
-
-   // ---- forces on the batch sites: reduce the per-lane partial sums
-   const WarpSm *W = reinterpret_cast<const WarpSm *>(smem_raw) + w;
-#pragma unroll
-   for (int k = 0; k < NI; k++) {
-      const double fx = wsum(fix[k]), fy = wsum(fiy[k]), fz = wsum(fiz[k]);
-      if (lane == 0 && k < cnt) {
-         if (N3) {
-            atomicAdd(&fs[s0 + k], fx);
-            atomicAdd(&fs[(size_t)nsites + s0 + k], fy);
-            atomicAdd(&fs[2 * (size_t)nsites + s0 + k], fz);
-         } else {
-            const int o = order[s0 + k];          // nsites = length of this pass's site list, nout = all sites
-            out[o] += fx;
-            out[(size_t)nout + o] += fy;
-            out[2 * (size_t)nout + o] += fz;
-            const double4 pk4 = W->ipos[k];
-            const double px = pk4.x, py = pk4.y, pz = pk4.z;
-            w00 = fma(px, fx, w00); w01 = fma(py, fx, w01); w02 = fma(pz, fx, w02);
-            w11 = fma(py, fy, w11); w12 = fma(pz, fy, w12); w22 = fma(pz, fz, w22);
-         }
-      }
-   }
    double v[7] = {pe, w00, w01, w02, w11, w12, w22};
 #pragma unroll
    for (int k = 0; k < 7; k++) {
       const double t = wsum(v[k]);
-      if (lane == 0) partials[prow_id * NRED + k] = t;
+      if (lane == 0) partials[((size_t)Q.prow0 + (size_t)blockIdx.x * (blockDim.x >> 5) + w) * NRED + k] = t;
    }
 }
 
@@ -542,15 +560,23 @@ static SiteList sub_list(const mdb_engine *e, int k)
 }
 
 #define TILED_ARGS P, L.n, c.nsites, L.posq, L.sinfo, L.start, L.order, e->d_mol, runs, e->d_ptab, \
-                   L.batches, L.nbatch, e->ithread, e->nthreads, d_out, L.fs, e->d_partials, e->d_counters, R
+                   L.batches, L.nbatch, e->ithread, e->nthreads, d_out, L.fs, e->d_partials, e->d_counters, R, Q
 
 template <int PT, bool COUL, int MODE>
 static void launch_tiled(bool strict, bool fw, bool n3, dim3 g, cudaStream_t st, PairParams &P, mdb_engine *e, const SiteList &L,
-                         const StencilRun *runs, double *d_out, RdfParams R = RdfParams{0.0, 0, 0, nullptr}, size_t shm_extra = 0)
+                         const StencilRun *runs, double *d_out, RdfParams R = RdfParams{0.0, 0, 0, nullptr}, size_t shm_extra = 0,
+                         PairQueue Q = PairQueue{0, nullptr, nullptr, 0}, int threads = TW * 32)
 {
    const mdb_config &c = e->cfg;
    const size_t shm = TILED_SMEM + (MODE == TM_RDF ? shm_extra : sizeof(double) * MDB_NPOTP * (size_t)c.max_id * c.max_id);
-#define GO(S, F, N) k_pair_tiled<PT, COUL, S, F, N, MODE><<<g, TW * 32, shm, st>>>(TILED_ARGS)
+   // The filler shares its SMs with the k-space GEMM blocks (90-220 KB of shared memory each): an SM has ONE L1/shared split at
+   // a time, so both sides ask for the largest shared-memory carve-out -- otherwise a filler block only gets onto an SM
+   // between two GEMM blocks, when the split can change.
+#define GO(S, F, N) do { if (MODE == TM_FORCE && N && Q.mode == 1) { \
+                           auto kq = k_pair_tiled<PT, COUL, S, F, N, MODE, (MODE == TM_FORCE && N)>; \
+                           cudaFuncSetAttribute(kq, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+                           kq<<<g, threads, shm, st>>>(TILED_ARGS); \
+                        } else k_pair_tiled<PT, COUL, S, F, N, MODE, false><<<g, threads, shm, st>>>(TILED_ARGS); } while (0)
    if (strict && MODE == TM_FORCE) {
       if (fw) { if (n3) GO(true, true, true); else GO(true, true, false); }
       else    { if (n3) GO(true, false, true); else GO(true, false, false); }
@@ -558,6 +584,7 @@ static void launch_tiled(bool strict, bool fw, bool n3, dim3 g, cudaStream_t st,
       if (fw) { if (n3) GO(false, true, true); else GO(false, true, false); }
       else    { if (n3) GO(false, false, true); else GO(false, false, false); }
    }
+   (void)threads;
 #undef GO
 }
 
@@ -625,17 +652,21 @@ int mdb_launch_rdf_tiled(mdb_engine *e, const StencilRun *d_runs, int nruns, dou
    return 0;
 }
 
-// one pass of the force kernel over a site list: pair potential `ptype` (PT_NONE: none) and/or the Coulomb term
-static int pair_pass(mdb_engine *e, const SiteList &L, int ptype, bool coul, double *d_out, cudaStream_t st)
+// one pass of the force kernel over a site list: pair potential `ptype` (PT_NONE: none) and/or the Coulomb term.
+// filler: the pass is split into a small persistent grid that draws batches from a counter until the k-space stream
+// raises the stop flag (mdb_force_both), and a full-size launch for the batches that are left.
+static int pair_pass(mdb_engine *e, const SiteList &L, int ptype, bool coul, double *d_out, cudaStream_t st, bool filler = false)
 {
    const mdb_config &c = e->cfg;
    if (L.n <= 0) return 0;
    const bool n3 = e->pair_mode == 4;
+   filler = filler && n3;
    PairParams P;
    const StencilRun *runs;
    int nblocks;
    tiled_params(e, n3, L.n, P, runs, nblocks);
-   const int nrows_pair = nblocks * TW;
+   const int fill_wpb = filler ? e->ovl_threads / 32 : 0, fill_rows = filler ? e->ovl_blocks * fill_wpb : 0;
+   const int nrows_pair = fill_rows + nblocks * TW;
    const int nblocks_u = (L.n + 255) / 256;
    const int nrows = nrows_pair + (n3 ? nblocks_u : 0);
    if (nrows + RS1 > e->partials_cap) {
@@ -645,21 +676,29 @@ static int pair_pass(mdb_engine *e, const SiteList &L, int ptype, bool coul, dou
    }
    if (n3) MDB_CUDA(cudaMemsetAsync(L.fs, 0, sizeof(double) * 3 * (size_t)L.n, st));
    const bool strict = c.strict_cutoff != 0 && !c.molpbc, fw = c.nsites_xf < c.nsites;   // src/force.c:951
-   dim3 g(nblocks);
-#define PT_CASE(X) case X: if (coul) launch_tiled<X, true, TM_FORCE>(strict, fw, n3, g, st, P, e, L, runs, d_out); \
-                           else launch_tiled<X, false, TM_FORCE>(strict, fw, n3, g, st, P, e, L, runs, d_out); break
-   switch (ptype) {
-      PT_CASE(PT_LJ);
+   const RdfParams R0{0.0, 0, 0, nullptr};
+   auto go = [&](dim3 g, PairQueue Q, int threads) -> int {
+#define PT_CASE(X) case X: if (coul) launch_tiled<X, true, TM_FORCE>(strict, fw, n3, g, st, P, e, L, runs, d_out, R0, 0, Q, threads); \
+                           else launch_tiled<X, false, TM_FORCE>(strict, fw, n3, g, st, P, e, L, runs, d_out, R0, 0, Q, threads); break
+      switch (ptype) {
+         PT_CASE(PT_LJ);
 #ifndef MDB_DEV_LJ_ONLY
-      PT_CASE(PT_E6); PT_CASE(PT_MCY); PT_CASE(PT_GEN); PT_CASE(PT_HIW); PT_CASE(PT_MOR);
+         PT_CASE(PT_E6); PT_CASE(PT_MCY); PT_CASE(PT_GEN); PT_CASE(PT_HIW); PT_CASE(PT_MOR);
 #endif
-      case PT_NONE: launch_tiled<PT_NONE, true, TM_FORCE>(strict, fw, n3, g, st, P, e, L, runs, d_out); break;
-      default:
-         mdb_set_error("KERNEL called with unknown potential type");
-         return -1;
-   }
+         case PT_NONE: launch_tiled<PT_NONE, true, TM_FORCE>(strict, fw, n3, g, st, P, e, L, runs, d_out, R0, 0, Q, threads); break;
+         default:
+            mdb_set_error("KERNEL called with unknown potential type");
+            return -1;
+      }
 #undef PT_CASE
-   e->launches += 1;
+      e->launches += 1;
+      return 0;
+   };
+   if (filler) {
+      if (go(dim3(e->ovl_blocks), PairQueue{1, e->d_ovl_q, e->d_ovl_q + 1, 0}, e->ovl_threads)) return -1;
+      if (go(dim3(nblocks), PairQueue{2, e->d_ovl_q, e->d_ovl_q + 1, fill_rows}, TW * 32)) return -1;
+   } else if (go(dim3(nblocks), PairQueue{0, nullptr, nullptr, 0}, TW * 32))
+      return -1;
    if (n3) {
       k_unsort_virial<<<nblocks_u, 256, 0, st>>>(L.n, c.nsites, L.posq, L.order, L.fs, d_out,
                                                  e->d_partials + (size_t)nrows_pair * NRED);
@@ -679,7 +718,7 @@ int mdb_launch_pair_tiled(mdb_engine *e, double *d_out, cudaStream_t st)
    const bool coul = c.alpha > 0.0;
    if (!e->pair_split) {
       if (mdb_need_batches(e, st)) return -1;
-      return pair_pass(e, full_list(e), c.ptype, coul, d_out, st);
+      return pair_pass(e, full_list(e), c.ptype, coul, d_out, st, e->ovl_armed);
    }
    // split passes: charged x charged with the Coulomb term only, potential x potential with the potential only
    // the potential-site list is compacted on a second stream while the Coulomb pass runs
@@ -697,7 +736,7 @@ int mdb_launch_pair_tiled(mdb_engine *e, double *d_out, cudaStream_t st)
       wait_sub1 = true;
    }
    if (mdb_build_sublist(e, 0, st)) return -1;
-   if (pair_pass(e, sub_list(e, 0), PT_NONE, true, d_out, st)) return -1;
+   if (pair_pass(e, sub_list(e, 0), PT_NONE, true, d_out, st, e->ovl_armed)) return -1;
    if (wait_sub1) MDB_CUDA(cudaStreamWaitEvent(st, e->ev_sub1, 0));
    if (pair_pass(e, sub_list(e, 1), c.ptype, false, d_out, st)) return -1;
    return mdb_launch_too_close_scan(e, st);

@@ -63,7 +63,7 @@ def load() -> C.CDLL:
     L.mdb_set_sites_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mdb_set_sites_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mdb_set_com_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-    for f in ("mdb_zero_out", "mdb_force_real", "mdb_force_recip"):
+    for f in ("mdb_zero_out", "mdb_force_real", "mdb_force_recip", "mdb_force_both"):
         getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.mdb_build_cells.argtypes = [C.c_void_p, C.c_void_p]
     L.mdb_recip_sum_doubles.restype = C.c_size_t
@@ -378,6 +378,19 @@ class Engine:
 
     def force_recip(self, d_out, stream=0):
         self._chk(self.L.mdb_force_recip(self.h, d_out, stream), "mdb_force_recip")
+
+    def force_both(self, d_out, stream=0):
+        """real space + k-space of one step, the pair kernel filling the FP64 issue slots beside the k-space GEMMs."""
+        self._chk(self.L.mdb_force_both(self.h, d_out, stream), "mdb_force_both")
+
+    def set_overlap(self, fill_blocks: int = 0, fill_threads: int = 0):
+        """fill_blocks < 0: off; 0, 0: one 64-thread block of the pair kernel per SM beside the k-space kernels."""
+        self.L.mdb_set_overlap(self.h, int(fill_blocks), int(fill_threads))
+
+    def overlap_filled(self) -> int:
+        self.L.mdb_overlap_filled.restype = C.c_long
+        self.L.mdb_overlap_filled.argtypes = [C.c_void_p]
+        return self.L.mdb_overlap_filled(self.h)
 
     def recip_sum_doubles(self) -> int:
         return self.L.mdb_recip_sum_doubles(self.h)

@@ -30,7 +30,8 @@ def test_library_exports_every_declared_symbol():
                  "do_step", "mdb_do_step_moldy", "mdb_md_step", "mdb_md_set_dynamics", "mdb_md_upload_state",
                  "mdb_peer_create", "mdb_peer_open", "mdb_peer_connect", "mdb_peer_step", "mdb_peer_read_slice_host",
                  "mdb_group_create", "mdb_group_force_host", "mdb_group_eval_forces_host",
-                 "mdb_sites_differ_host", "mdb_dmma_peak_probe", "mdb_recip_gemm_flop"):
+                 "mdb_sites_differ_host", "mdb_dmma_peak_probe", "mdb_recip_gemm_flop",
+                 "mdb_force_both", "mdb_set_overlap", "mdb_overlap_filled"):
         assert must in syms, f"{must} not parsed from the header"
     for s in syms:
         assert hasattr(L, s), f"libmoldy_b200.so does not export {s}"
