@@ -106,9 +106,10 @@ struct RdfParams { double rbin; int nbins, hist_smem; unsigned long long *counts
 struct PairQueue { int mode; int *next; const int *stop; int prow0; };
 
 template <int PT, bool COUL, bool STRICT, bool FW, bool N3, int MODE, bool QUEUE = false>
-// (potential-only instantiations fit 128 registers without spills: 4 blocks per SM, 2.10 -> 1.92 ms for the LJ pass;
-//  with the Coulomb term 4 blocks spill and lose, 16.6 -> 17.9 ms)
-__global__ void __launch_bounds__(TW * 32, (COUL || MODE != TM_FORCE) ? MDB_TILED_MINB : MDB_TILED_MINB + 1)
+// (the power-law potential-only instantiations fit 128 registers without spills: 4 blocks per SM, 2.10 -> 1.92 ms for the LJ
+//  pass; with the Coulomb term 4 blocks spill and lose, 16.6 -> 17.9 ms; the exponential potentials alone (MCY: 200-300
+//  bytes of spills, LDL/STL inside the hot loop at 128 registers) stay at 3 blocks as well)
+__global__ void __launch_bounds__(TW * 32, (COUL || MODE != TM_FORCE || (PT != PT_LJ && PT != PT_HIW)) ? MDB_TILED_MINB : MDB_TILED_MINB + 1)
 k_pair_tiled(PairParams P, int nsites, int nout, const double4 *__restrict__ posq, const int2 *__restrict__ sinfo,
              const int *__restrict__ cstart, const int *__restrict__ order,
              const int *__restrict__ mol, const StencilRun *__restrict__ runs, const double *__restrict__ ptab,

@@ -1,17 +1,21 @@
 """Quick device-side timing of the hot-path phases (cells / pair / recip) with
-CUDA events on the launching stream.  usage: python scripts/perf_probe.py [n=5] [reps=3]"""
+CUDA events on the launching stream.  usage: python scripts/perf_probe.py [n=5 | tip4p_10 | quartz_48 | mgcl2_7 ...] [reps=3]"""
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from moldy_b200 import lib, systems
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+arg = sys.argv[1] if len(sys.argv) > 1 else "5"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 t0 = time.time()
-ms = systems.tip4p(n)
+if arg.isdigit():
+    n = int(arg); ms = systems.tip4p(n)
+else:
+    from tests import cases
+    n = arg; ms = cases.LARGE_CASES[arg]()
 site = ms.make_sites()
-print(f"tip4p n={n}: N={ms.nsites} rc={ms.control.cutoff:.3f} alpha={ms.control.alpha:.5f} kc={ms.control.k_cutoff:.4f} (built in {time.time()-t0:.1f}s)")
+print(f"{n}: N={ms.nsites} rc={ms.control.cutoff:.3f} alpha={ms.control.alpha:.5f} kc={ms.control.k_cutoff:.4f} (built in {time.time()-t0:.1f}s)")
 eng = lib.Engine(0)
 t0 = time.time(); eng.configure(ms); print(f"configure {time.time()-t0:.2f}s  grid={eng.grid()} nabors={2*eng.n_neighbour_cells()} nhkl={eng.n_kvectors()}")
 N = ms.nsites
