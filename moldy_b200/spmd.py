@@ -1,26 +1,31 @@
 """Replicated-data multi-GPU layer, modelled on parallel.c's par_rsum/par_dsum
 (src/parallel.c:549-588; call sites src/accel.c:531-535).
 
-One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch).  Every rank
-holds all N positions and the full cell-sorted SoA (the cell build is
-replicated: ~0.1 ms at 10^6 sites); rank r of P owns
+The sums themselves are kernels of the C library (moldy_b200/csrc/mdb_peer.cu: flag barrier, structure-factor
+all-reduce, force reduce-scatter and all-gather over NVLink/NVSwitch peer memory); this module is the Python front end:
+`SpmdForces` = one process per GPU (torchrun; CUDA-IPC windows exchanged through torch.distributed, which is used for that
+hand-shake only), `PeerGroup` = all ranks as engines of one process (what the library does itself behind
+force_calc()/ewald()/eval_forces() with MOLDY_B200_DEVICES, moldy_b200/csrc/mdb_group.cu).  `combine`/`recip_sites` and
+`SpmdForces(nccl=True)` keep the round-1 path (packed NCCL all-reduce) for comparison and for the gloo tests.
 
-  * real space:  the r-th contiguous slice of the cell-sorted sites (full
-    stencil, owner-computes: its partial force array is non-zero only there),
-  * k-space:     its slice of the (charged) sites for ALL k-vectors -- the manual's
-    "RIL" scheme (src/moldy.tex:3441-3466): the 8*nslots structure-factor sums are
-    all-reduced between the two passes (0.6-1.2 MB), so both the structure-factor
-    pass and the back-projection scale with 1/P.  (Moldy's shipped scheme, a block
-    of k-vectors per rank for all sites, src/ewald.c:495-496, is what the library
-    does when it is driven through force_calc()/ewald() with ithread/nthreads,
-    because no exchange is available there before the final sums.)
+Every rank holds all N positions and the full cell-sorted SoA (the cell build is replicated: ~0.1 ms at 10^6 sites);
+rank r of P owns
 
-Real space follows the reference's scheme (cells `icell = ithread mod nthreads`,
-src/force.c:856) with a different but equally disjoint assignment.  The partial [forces | pe | stress] blocks are
-combined by ONE packed all-reduce (the reference issues three,
-src/accel.c:532-534); NCCL returns bit-identical sums on all ranks, which is what
-Moldy's DESYNC check (src/main.c:262-273) relies on.  Constants the reference
-adds on rank 0 only (eintra, self/sheet energy) are not part of this block.
+  * real space:  the r-th contiguous slice of the BATCHES of the cell-sorted sites (default kernel: the reference's half
+    list with Newton's third law, so its partial force array also holds what its batches add to the neighbours j of
+    other slices -- the partial arrays of all ranks are summed, as par_rsum does; pair mode 3 is the full stencil,
+    owner-computes),
+  * k-space:     its slice of the (charged) sites for ALL k-vectors -- the manual's "RIL" scheme
+    (src/moldy.tex:3441-3466): the 8*nslots structure-factor sums are all-reduced between the two passes (0.6-1.2 MB),
+    so both the structure-factor pass and the back-projection scale with 1/P.  (Moldy's shipped scheme, a block of
+    k-vectors per rank for all sites, src/ewald.c:495-496, is what the library does when it is driven through
+    force_calc()/ewald() with ithread/nthreads, because no exchange is available there before the final sums.)
+  * the result:  the r-th slice of the sites of every force row (reduce-scatter; the 16 scalars are summed by every rank).
+
+Real space follows the reference's scheme (cells `icell = ithread mod nthreads`, src/force.c:856) with a different but
+equally disjoint assignment.  The sums are formed in rank order on every rank, so all ranks hold identical bits, which
+is what Moldy's DESYNC check (src/main.c:262-273) relies on.  Constants the reference adds on rank 0 only (eintra,
+self/sheet energy) are not part of the block.
 """
 from __future__ import annotations
 
