@@ -163,7 +163,11 @@ struct mdb_engine {
 
    // real space beside k-space (mdb_force_both): the k-space chain runs on a high-priority side stream into d_out2, a small
    // persistent pair grid fills the FP64 issue slots its DMMA stream leaves idle; d_ovl_q = {next batch, stop flag}
-   int ovl_blocks = 0, ovl_threads = 0; bool ovl_armed = false;
+   int ovl_blocks = -2, ovl_threads = 0; bool ovl_armed = false;     // -2: not chosen yet (MDB_OVERLAP), -1: off, 0: k-space first with the set-up behind it, > 0: filler grid
+   // an event the pair passes wait for, after the (launch-latency-bound) cell build and sub-list compaction are enqueued: a
+   // k-space kernel on a side stream then hides that set-up, and the pair kernel does not share the SMs with it (two
+   // FP64-bound kernels side by side lose ~7 % against the same two in sequence, profiles/r02_summary.md)
+   cudaEvent_t pre_pair_wait = nullptr;
    int *d_ovl_q = nullptr; double *d_out2 = nullptr; size_t out2_cap = 0;
    cudaStream_t ovl_stream = nullptr; cudaEvent_t ev_ovl_fork = nullptr, ev_ovl_join = nullptr;
 

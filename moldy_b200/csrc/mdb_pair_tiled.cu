@@ -719,6 +719,7 @@ int mdb_launch_pair_tiled(mdb_engine *e, double *d_out, cudaStream_t st)
    const bool coul = c.alpha > 0.0;
    if (!e->pair_split) {
       if (mdb_need_batches(e, st)) return -1;
+      if (e->pre_pair_wait) MDB_CUDA(cudaStreamWaitEvent(st, e->pre_pair_wait, 0));
       return pair_pass(e, full_list(e), c.ptype, coul, d_out, st, e->ovl_armed);
    }
    // split passes: charged x charged with the Coulomb term only, potential x potential with the potential only
@@ -737,6 +738,7 @@ int mdb_launch_pair_tiled(mdb_engine *e, double *d_out, cudaStream_t st)
       wait_sub1 = true;
    }
    if (mdb_build_sublist(e, 0, st)) return -1;
+   if (e->pre_pair_wait) MDB_CUDA(cudaStreamWaitEvent(st, e->pre_pair_wait, 0));
    if (pair_pass(e, sub_list(e, 0), PT_NONE, true, d_out, st, e->ovl_armed)) return -1;
    if (wait_sub1) MDB_CUDA(cudaStreamWaitEvent(st, e->ev_sub1, 0));
    if (pair_pass(e, sub_list(e, 1), c.ptype, false, d_out, st)) return -1;

@@ -363,7 +363,10 @@ extern "C" int mdb_peer_phase_a(mdb_peer *p, int what, void *stream)
    const bool fork = recip && (what & 1) && !(what & 4) && !no_side;
    if (fork) {
       if (!p->side) {
-         MDB_CUDA(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+         int lo = 0, hi = 0;                          // MDB_PEER_SIDE_PRIO=1: the structure-factor blocks go first
+         static const bool prio = getenv("MDB_PEER_SIDE_PRIO") && atoi(getenv("MDB_PEER_SIDE_PRIO")) != 0;
+         MDB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+         MDB_CUDA(cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, prio ? hi : lo));
          MDB_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
          MDB_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
       }
@@ -373,7 +376,12 @@ extern "C" int mdb_peer_phase_a(mdb_peer *p, int what, void *stream)
       MDB_CUDA(cudaEventRecord(p->ev_join, p->side));
    }
    if (!(what & 4) && (mdb_zero_out(e, out, st) || mdb_build_cells(e, st))) return -1;
-   if ((what & 1) && mdb_force_real(e, out, st)) return -1;
+   // the pair passes start when the structure-factor pass has ended (MDB_PEER_SHARE=1: beside it, as measured in round 2)
+   static const bool share = getenv("MDB_PEER_SHARE") && atoi(getenv("MDB_PEER_SHARE")) != 0;
+   if (fork && !share) e->pre_pair_wait = p->ev_join;
+   const int rc_real = (what & 1) ? mdb_force_real(e, out, st) : 0;
+   e->pre_pair_wait = nullptr;
+   if (rc_real) return -1;
    if (fork) MDB_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0));
    else if (recip && mdb_launch_recip_partial(e, psum, st)) return -1;
    return 0;

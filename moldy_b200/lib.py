@@ -384,7 +384,7 @@ class Engine:
         self._chk(self.L.mdb_force_both(self.h, d_out, stream), "mdb_force_both")
 
     def set_overlap(self, fill_blocks: int = 0, fill_threads: int = 0):
-        """fill_blocks < 0: off; 0, 0: one 64-thread block of the pair kernel per SM beside the k-space kernels."""
+        """fill_blocks < 0: one stream; 0: k-space first on a side stream, set-up behind it (default); > 0: filler grid."""
         self.L.mdb_set_overlap(self.h, int(fill_blocks), int(fill_threads))
 
     def overlap_filled(self) -> int:

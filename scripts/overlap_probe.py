@@ -39,7 +39,7 @@ def both():
 
 t0, f0, pe0, s0 = run(seq)
 print(f"{wl} n={n} N={N} nsb={os.environ.get('MDB_KF_NSB','-')}: sequential {t0:.3f} ms  pe {pe0}")
-for fb, ft in [(-1, 0), (148, 64), (148, 128), (296, 64), (296, 128), (444, 64)]:
+for fb, ft in [(-1, 0), (0, 0), (148, 64), (148, 128), (296, 64), (296, 128), (444, 64)]:
     eng.set_overlap(fb, ft)
     t, f, pe, s = run(both)
     err = np.linalg.norm(f - f0) / np.linalg.norm(f0)

@@ -35,7 +35,7 @@ def _run(ms, both, fill=(0, 0), mode=4):
 
 
 @pytest.mark.parametrize("name", ["tip4p", "tip4p_2", "mgcl2", "quartz", "slab_framework", "tips2_strict", "morse", "argon"])
-@pytest.mark.parametrize("fill", [(0, 0), (7, 128), (1000, 32)])
+@pytest.mark.parametrize("fill", [(0, 0), (148, 64), (7, 128), (1000, 32)])
 def test_force_both_equals_the_two_phases_and_the_reference(name, fill):
     ms = cases.GOLDEN_CASES[name]()
     f0, pe0, s0 = _run(ms, False)
@@ -63,7 +63,7 @@ def test_force_both_at_benchmark_size_takes_a_share_in_the_filler():
         pytest.skip("large fixture not generated")
     g = np.load(path)
     ms = cases.LARGE_CASES["tip4p_10"]()
-    f, pe, s = _run(ms, True)
+    f, pe, s = _run(ms, True, (296, 128))
     smp = g["sample"]
     assert cases.rel_rms(f[:, smp], g["fsample"]) < 1e-10
     assert np.abs((f ** 2).sum(1) / g["fsq"] - 1).max() < 1e-10
