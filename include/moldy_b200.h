@@ -223,7 +223,12 @@ int  mdb_force_recip(mdb_engine *e, double *d_out, void *stream);
  * mdb_set_overlap(e, -1, 0): one stream, real space then k-space.  MDB_OVERLAP=-1 | 0 | blocks,threads sets the default. */
 int  mdb_set_overlap(mdb_engine *e, int fill_blocks, int fill_threads);
 int  mdb_force_both(mdb_engine *e, double *d_out, void *stream);
-long mdb_overlap_filled(mdb_engine *e);   /* batches the filler drew in the last call (diagnostic; synchronises) */
+long mdb_overlap_filled(mdb_engine *e);
+/* Exponential potentials (Buckingham, generic, Morse, MCY): stencil runs whose every cell pair is further apart than 52 decay
+ * lengths (exp(-r/rho) < 2.6e-23 of its amplitude for every site-type pair) are evaluated without the exponentials.  Default
+ * on (MDB_PAIR_FAR=0 or mdb_set_pair_far(e, 0) before mdb_configure: every run with the full potential). */
+void mdb_set_pair_far(mdb_engine *e, int on);
+int  mdb_pair_far_runs(const mdb_engine *e);   /* batches the filler drew in the last call (diagnostic; synchronises) */
 
 /* k-space cut by SITES instead of by (h,k) columns (multi-GPU, moldy_b200/spmd.py): pass 1 writes
  * this rank's structure-factor sums (mdb_recip_sum_doubles() doubles) to the DEVICE buffer d_psum,

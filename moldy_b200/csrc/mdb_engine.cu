@@ -64,6 +64,8 @@ static void free_grid(mdb_engine *e)
    FREE(e->d_count); FREE(e->d_start); FREE(e->d_scan_tmp); FREE(e->d_runs); FREE(e->d_runs_half);
    FREE(e->d_batches); FREE(e->d_nbatch); e->batch_cap = 0;
    FREE(e->d_runs_rdf); e->rdf_limit = -1.0;
+   FREE(e->d_runs_near); FREE(e->d_runs_far); FREE(e->d_ptab_far); e->far_ptype = -1;
+   e->table_cap.erase((void *)&e->d_runs_near); e->table_cap.erase((void *)&e->d_runs_far); e->table_cap.erase((void *)&e->d_ptab_far);
    e->table_cap.erase((void *)&e->d_runs); e->table_cap.erase((void *)&e->d_runs_half); e->table_cap.erase((void *)&e->d_runs_rdf);
    e->cells_cap = 0;
 }
@@ -105,6 +107,11 @@ extern "C" void mdb_set_pair_mode(mdb_engine *e, int mode)
    e->cells_valid = false;
 }
 
+// far stencil runs of the exponential potentials without the exponentials (default on; MDB_PAIR_FAR=0); takes effect at the
+// next mdb_configure.  mdb_pair_far_runs: how many of the half list's runs the current configuration treats that way.
+extern "C" void mdb_set_pair_far(mdb_engine *e, int on) { e->far_enable = on ? 1 : 0; }
+extern "C" int mdb_pair_far_runs(const mdb_engine *e) { return e->far_ptype >= 0 ? e->nruns_far : 0; }
+
 extern "C" void mdb_set_partition(mdb_engine *e, int ithread, int nthreads)
 {
    e->ithread = ithread;
@@ -124,6 +131,68 @@ static int upload(mdb_engine *e, T **dst, const T *src, size_t n)
       cap = sizeof(T) * n;
    }
    MDB_CUDA(cudaMemcpy(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice));
+   return 0;
+}
+
+// ---- far stencil runs of the exponential potentials (see mdb_internal.h) ---------------------------------------------
+// kernel.c's forms: Buckingham -p0/r^6 + p1 exp(-p2 r); generic p0 exp(-p1 r) + p2/r^12 - p3/r^4 - p4/r^6 - p5/r^8; Morse/BIG
+// p0 exp((p1 - r) p2) - p3/r^6 + p4 (exp(-2 p5 (r - p6)) - 2 exp(-p5 (r - p6))); MCY p0 exp(-p1 r) - p2 exp(-p3 r)
+// (src/kernel.c:230-355).  PT_HIW rows are p0/r^4 + p1/r^6 + p2/r^12.
+static constexpr double FAR_EXPONENT = 52.0;    // e^-52 = 2.6e-23 of the amplitude: below rounding in every sum it enters
+static int mdb_split_far_runs(mdb_engine *e)
+{
+   const mdb_config &c = e->cfg;
+   e->far_ptype = -1; e->nruns_near = e->nruns_far = 0; e->r_far = 0.0;
+   if (e->far_enable < 0) e->far_enable = !(getenv("MDB_PAIR_FAR") && atoi(getenv("MDB_PAIR_FAR")) == 0);
+   const int pt = c.ptype, id = c.max_id;
+   if (!e->far_enable || c.molpbc || e->T.runs_half.empty() || !(pt == 1 || pt == 2 || pt == 3 || pt == 6)) return 0;
+   double r_far = 0.0;
+   bool any = false;
+   std::vector<double> far(e->h_potpar.size(), 0.0);
+   for (int a = 0; a < id; a++)
+      for (int b = 0; b < id; b++) {
+         const double *p = &e->h_potpar[((size_t)a * id + b) * MDB_NPOTP];
+         double *q = &far[((size_t)a * id + b) * MDB_NPOTP];
+         auto term = [&](double amp, double decay, double shift) {         // amp exp(-decay (r - shift))
+            if (amp == 0.0) return true;
+            if (!(decay > 0.0)) return false;
+            r_far = std::max(r_far, shift + FAR_EXPONENT / decay);
+            any = true;
+            return true;
+         };
+         bool ok = true;
+         if (pt == 1) { ok = term(p[1], p[2], 0.0); q[1] = -p[0]; }
+         else if (pt == 2) { ok = term(p[0], p[1], 0.0) && term(p[2], p[3], 0.0); }
+         else if (pt == 3) { ok = term(p[0], p[1], 0.0) && p[5] == 0.0; q[0] = -p[3]; q[1] = -p[4]; q[2] = p[2]; }
+         else { ok = term(p[0], p[2], p[1]) && term(p[4], p[5], p[6]); q[1] = -p[3]; }
+         if (!ok) return 0;
+      }
+   if (!any) return 0;
+   // lower bound of the distance between a point of a cell and a point of the cell (dx,dy,dz) away: |h d| - longest diagonal
+   const double inv[3] = {1.0 / e->T.nx, 1.0 / e->T.ny, 1.0 / e->T.nz};
+   auto len = [&](double x, double y, double z) {
+      double v[3];
+      for (int i = 0; i < 3; i++) v[i] = c.h[3 * i] * x * inv[0] + c.h[3 * i + 1] * y * inv[1] + c.h[3 * i + 2] * z * inv[2];
+      return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+   };
+   double diag = 0.0;
+   for (int sgn = 0; sgn < 4; sgn++) diag = std::max(diag, len(1.0, (sgn & 1) ? -1.0 : 1.0, (sgn & 2) ? -1.0 : 1.0));
+   std::vector<StencilRun> nearv, farv;
+   for (size_t r = 0; r < e->T.runs_half.size(); r++) {
+      const StencilRun &run = e->T.runs_half[r];
+      double dmin = 1e300;
+      for (int dz = run.dzlo; dz <= run.dzhi; dz++) dmin = std::min(dmin, len(run.dx, run.dy, dz));
+      if (r > 0 && dmin - diag >= r_far) farv.push_back(run); else nearv.push_back(run);      // run 0 is the prologue's
+   }
+   if (farv.empty()) return 0;
+   bool rest = false;                              // anything left of the potential out there?
+   for (double v : far) rest |= v != 0.0;
+   if (upload(e, &e->d_runs_near, nearv.data(), nearv.size())) return -1;
+   if (upload(e, &e->d_runs_far, farv.data(), farv.size())) return -1;
+   if (upload(e, &e->d_ptab_far, far.data(), far.size())) return -1;
+   e->nruns_near = (int)nearv.size(); e->nruns_far = (int)farv.size();
+   e->far_ptype = rest ? 4 /* PT_HIW */ : 7 /* PT_NONE */;
+   e->r_far = r_far;
    return 0;
 }
 
@@ -204,6 +273,7 @@ extern "C" int mdb_configure(mdb_engine *e, const mdb_config *cfg)
    if (upload(e, &e->d_runs, e->T.runs.data(), e->T.runs.size())) return -1;
    e->nruns_half = (int)e->T.runs_half.size();
    if (upload(e, &e->d_runs_half, e->T.runs_half.data(), e->T.runs_half.size())) return -1;
+   if (mdb_split_far_runs(e)) return -1;
    {
       const int need = n / MDB_NI + e->T.nx * e->T.ny + 8;
       if (need > e->batch_cap) {

@@ -115,6 +115,12 @@ struct mdb_engine {
    int2 *d_sinfo = nullptr;               // {type | framework bit 30, z index of the cell}, cell-sorted
    StencilRun *d_runs = nullptr, *d_runs_half = nullptr;
    int nruns = 0, nruns_half = 0;
+   // Exponential potentials (Buckingham, generic, Morse/BIG, MCY) with a cut-off of many decay lengths: the stencil runs whose
+   // EVERY cell pair is further apart than r_far, where exp(-r/rho) has fallen below e^-52 = 2.6e-23 of its amplitude for
+   // all site-type pairs, are walked by a second launch with the power-law rest of the potential (as PT_HIW rows) or with the
+   // Coulomb term alone.  far_ptype < 0: no such runs / not applicable.
+   StencilRun *d_runs_near = nullptr, *d_runs_far = nullptr; int nruns_near = 0, nruns_far = 0;
+   int far_ptype = -1, far_enable = -1; double *d_ptab_far = nullptr; double r_far = 0.0;
    int2 *d_batches = nullptr; int *d_nbatch = nullptr; int batch_cap = 0;   // i-site batches of the tiled pair kernel
    double *d_fs = nullptr;                // [3N] cell-sorted force accumulator (Newton-3 mode)
    int pair_mode = -1;                    // 2: per-thread full stencil, 3: tiled full stencil, 4: tiled Newton-3

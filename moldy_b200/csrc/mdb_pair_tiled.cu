@@ -103,7 +103,9 @@ struct RdfParams { double rbin; int nbins, hist_smem; unsigned long long *counts
 // mode 1 ("filler", the QUEUE instantiations): a small persistent grid (one block per SM) draws batches from the counter `next` until the list is
 // exhausted or `stop` is raised; it runs beside the k-space GEMM kernels, whose DMMA stream leaves a quarter of the FP64
 // pipe idle.  mode 2 ("remainder"): the static mapping again, starting at the batch the filler stopped at.
-struct PairQueue { int mode; int *next; const int *stop; int prow0; };
+struct PairQueue { int mode; int *next; const int *stop; int prow0; int nopro; };
+// nopro = 1: a launch over a subset of the stencil runs that does not contain run 0 (the far runs): no Newton-3 prologue, and
+// its first run is an ordinary one.
 
 template <int PT, bool COUL, bool STRICT, bool FW, bool N3, int MODE, bool QUEUE = false>
 // (the power-law potential-only instantiations fit 128 registers without spills: 4 blocks per SM, 2.10 -> 1.92 ms for the LJ
@@ -313,7 +315,7 @@ k_pair_tiled(PairParams P, int nsites, int nout, const double4 *__restrict__ pos
    }
 
    // ---- Newton-3 prologue: own column, central image, j > s_i (run 0 of the half list starts at dz = 0)
-   if (N3) {
+   if (N3 && !Q.nopro) {
       const StencilRun r0 = runs[0];
       const int jb = s0 + 1, je = cstart[col * P.nz + min(cz_hi + r0.dzhi, P.nz - 1) + 1];
       if (lane == 0) sts_i4<OFF_Q>(sw, make_int4(0, -BIGZ, r0.dzhi + BIGZ, 13 | 32));
@@ -350,7 +352,7 @@ k_pair_tiled(PairParams P, int nsites, int nout, const double4 *__restrict__ pos
                const int zoff = kk * P.nz;
                const int a = max(z0, zoff), bb = min(z1, zoff + P.nz - 1);
                // Newton-3: the central piece of run 0 is the prologue's
-               if (a <= bb && !(N3 && r == 0 && kk == 0)) {
+               if (a <= bb && !(N3 && r == 0 && kk == 0 && !Q.nopro)) {
                   const int jb = cstart[colb + a - zoff], jn = cstart[colb + bb - zoff + 1];
                   js3[kk + 1] = jb; cnt3[kk + 1] = jn - jb;
                   img3[kk + 1] = (9 * (ii + 1) + 3 * (jj + 1) + (kk + 1)) | (selfcol << 5);
@@ -560,13 +562,13 @@ static SiteList sub_list(const mdb_engine *e, int k)
    return SiteList{S.n, S.posq, S.sinfo, S.start, S.order, S.batches, S.nbatch, S.fs};
 }
 
-#define TILED_ARGS P, L.n, c.nsites, L.posq, L.sinfo, L.start, L.order, e->d_mol, runs, e->d_ptab, \
+#define TILED_ARGS P, L.n, c.nsites, L.posq, L.sinfo, L.start, L.order, e->d_mol, runs, (ptab_dev ? ptab_dev : e->d_ptab), \
                    L.batches, L.nbatch, e->ithread, e->nthreads, d_out, L.fs, e->d_partials, e->d_counters, R, Q
 
 template <int PT, bool COUL, int MODE>
 static void launch_tiled(bool strict, bool fw, bool n3, dim3 g, cudaStream_t st, PairParams &P, mdb_engine *e, const SiteList &L,
                          const StencilRun *runs, double *d_out, RdfParams R = RdfParams{0.0, 0, 0, nullptr}, size_t shm_extra = 0,
-                         PairQueue Q = PairQueue{0, nullptr, nullptr, 0}, int threads = TW * 32)
+                         PairQueue Q = PairQueue{0, nullptr, nullptr, 0, 0}, int threads = TW * 32, const double *ptab_dev = nullptr)
 {
    const mdb_config &c = e->cfg;
    const size_t shm = TILED_SMEM + (MODE == TM_RDF ? shm_extra : sizeof(double) * MDB_NPOTP * (size_t)c.max_id * c.max_id);
@@ -667,7 +669,12 @@ static int pair_pass(mdb_engine *e, const SiteList &L, int ptype, bool coul, dou
    int nblocks;
    tiled_params(e, n3, L.n, P, runs, nblocks);
    const int fill_wpb = filler ? e->ovl_threads / 32 : 0, fill_rows = filler ? e->ovl_blocks * fill_wpb : 0;
-   const int nrows_pair = fill_rows + nblocks * TW;
+   // exponential potentials: the runs beyond r_far get their own launch with what is left of the potential there
+   // (mdb_split_far_runs; nothing at all for a potential-only pass whose rest is zero)
+   const bool far = n3 && e->far_ptype >= 0 && ptype == c.ptype;
+   const bool far_launch = far && (coul || e->far_ptype != PT_NONE);
+   const int far_row0 = fill_rows + nblocks * TW;
+   const int nrows_pair = far_row0 + (far_launch ? nblocks * TW : 0);
    const int nblocks_u = (L.n + 255) / 256;
    const int nrows = nrows_pair + (n3 ? nblocks_u : 0);
    if (nrows + RS1 > e->partials_cap) {
@@ -678,15 +685,15 @@ static int pair_pass(mdb_engine *e, const SiteList &L, int ptype, bool coul, dou
    if (n3) MDB_CUDA(cudaMemsetAsync(L.fs, 0, sizeof(double) * 3 * (size_t)L.n, st));
    const bool strict = c.strict_cutoff != 0 && !c.molpbc, fw = c.nsites_xf < c.nsites;   // src/force.c:951
    const RdfParams R0{0.0, 0, 0, nullptr};
-   auto go = [&](dim3 g, PairQueue Q, int threads) -> int {
-#define PT_CASE(X) case X: if (coul) launch_tiled<X, true, TM_FORCE>(strict, fw, n3, g, st, P, e, L, runs, d_out, R0, 0, Q, threads); \
-                           else launch_tiled<X, false, TM_FORCE>(strict, fw, n3, g, st, P, e, L, runs, d_out, R0, 0, Q, threads); break
-      switch (ptype) {
+   auto go = [&](int pt, dim3 g, PairQueue Q, int threads, const double *ptab_dev) -> int {
+#define PT_CASE(X) case X: if (coul) launch_tiled<X, true, TM_FORCE>(strict, fw, n3, g, st, P, e, L, runs, d_out, R0, 0, Q, threads, ptab_dev); \
+                           else launch_tiled<X, false, TM_FORCE>(strict, fw, n3, g, st, P, e, L, runs, d_out, R0, 0, Q, threads, ptab_dev); break
+      switch (pt) {
          PT_CASE(PT_LJ);
 #ifndef MDB_DEV_LJ_ONLY
          PT_CASE(PT_E6); PT_CASE(PT_MCY); PT_CASE(PT_GEN); PT_CASE(PT_HIW); PT_CASE(PT_MOR);
 #endif
-         case PT_NONE: launch_tiled<PT_NONE, true, TM_FORCE>(strict, fw, n3, g, st, P, e, L, runs, d_out, R0, 0, Q, threads); break;
+         case PT_NONE: launch_tiled<PT_NONE, true, TM_FORCE>(strict, fw, n3, g, st, P, e, L, runs, d_out, R0, 0, Q, threads, ptab_dev); break;
          default:
             mdb_set_error("KERNEL called with unknown potential type");
             return -1;
@@ -695,11 +702,16 @@ static int pair_pass(mdb_engine *e, const SiteList &L, int ptype, bool coul, dou
       e->launches += 1;
       return 0;
    };
+   if (far) { runs = e->d_runs_near; P.nruns = e->nruns_near; }
    if (filler) {
-      if (go(dim3(e->ovl_blocks), PairQueue{1, e->d_ovl_q, e->d_ovl_q + 1, 0}, e->ovl_threads)) return -1;
-      if (go(dim3(nblocks), PairQueue{2, e->d_ovl_q, e->d_ovl_q + 1, fill_rows}, TW * 32)) return -1;
-   } else if (go(dim3(nblocks), PairQueue{0, nullptr, nullptr, 0}, TW * 32))
+      if (go(ptype, dim3(e->ovl_blocks), PairQueue{1, e->d_ovl_q, e->d_ovl_q + 1, 0, 0}, e->ovl_threads, nullptr)) return -1;
+      if (go(ptype, dim3(nblocks), PairQueue{2, e->d_ovl_q, e->d_ovl_q + 1, fill_rows, 0}, TW * 32, nullptr)) return -1;
+   } else if (go(ptype, dim3(nblocks), PairQueue{0, nullptr, nullptr, 0, 0}, TW * 32, nullptr))
       return -1;
+   if (far_launch) {
+      runs = e->d_runs_far; P.nruns = e->nruns_far;
+      if (go(e->far_ptype, dim3(nblocks), PairQueue{0, nullptr, nullptr, far_row0, 1}, TW * 32, e->d_ptab_far)) return -1;
+   }
    if (n3) {
       k_unsort_virial<<<nblocks_u, 256, 0, st>>>(L.n, c.nsites, L.posq, L.order, L.fs, d_out,
                                                  e->d_partials + (size_t)nrows_pair * NRED);

@@ -387,6 +387,15 @@ class Engine:
         """fill_blocks < 0: one stream; 0: k-space first on a side stream, set-up behind it (default); > 0: filler grid."""
         self.L.mdb_set_overlap(self.h, int(fill_blocks), int(fill_threads))
 
+    def set_pair_far(self, on: bool):
+        """before configure(): far stencil runs of the exponential potentials without their exponentials (default on)."""
+        self.L.mdb_set_pair_far.argtypes = [C.c_void_p, C.c_int]
+        self.L.mdb_set_pair_far(self.h, int(on))
+
+    def pair_far_runs(self) -> int:
+        self.L.mdb_pair_far_runs.argtypes = [C.c_void_p]
+        return self.L.mdb_pair_far_runs(self.h)
+
     def overlap_filled(self) -> int:
         self.L.mdb_overlap_filled.restype = C.c_long
         self.L.mdb_overlap_filled.argtypes = [C.c_void_p]

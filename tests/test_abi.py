@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
                  "mdb_peer_create", "mdb_peer_open", "mdb_peer_connect", "mdb_peer_step", "mdb_peer_read_slice_host",
                  "mdb_group_create", "mdb_group_force_host", "mdb_group_eval_forces_host",
                  "mdb_sites_differ_host", "mdb_dmma_peak_probe", "mdb_recip_gemm_flop",
-                 "mdb_force_both", "mdb_set_overlap", "mdb_overlap_filled"):
+                 "mdb_force_both", "mdb_set_overlap", "mdb_overlap_filled", "mdb_set_pair_far", "mdb_pair_far_runs"):
         assert must in syms, f"{must} not parsed from the header"
     for s in syms:
         assert hasattr(L, s), f"libmoldy_b200.so does not export {s}"

@@ -67,3 +67,41 @@ def test_force_both_at_benchmark_size_takes_a_share_in_the_filler():
     smp = g["sample"]
     assert cases.rel_rms(f[:, smp], g["fsample"]) < 1e-10
     assert np.abs((f ** 2).sum(1) / g["fsq"] - 1).max() < 1e-10
+
+
+def _run_far(ms, far):
+    eng = lib.Engine(0)
+    eng.set_pair_far(far)
+    eng.configure(ms)
+    nfar = eng.pair_far_runs()
+    eng.set_sites_host(ms.make_sites())
+    st = torch.cuda.current_stream().cuda_stream
+    out = torch.zeros(eng.out_doubles(), dtype=torch.float64, device="cuda")
+    eng.build_cells(st)
+    eng.force_real(out.data_ptr(), st)
+    torch.cuda.synchronize()
+    res = lib.unpack(out.cpu().numpy(), ms.nsites) + (eng.pair_count(st), nfar)
+    eng.close()
+    return res
+
+
+def test_far_runs_of_the_buckingham_potential_without_the_exponential():
+    """quartz at the benchmark size (995 328 ions, cut-off of ~80 decay lengths of the O-O repulsion): the stencil runs beyond
+    52 decay lengths are walked with -C/r^6 + Coulomb only (PT_HIW rows).  Same forces, energy, stress and pair count as with
+    the full potential on every run; the comparison with the compiled reference's record is test_gpu_large's."""
+    ms = cases.LARGE_CASES["quartz_48"]()
+    f0, pe0, s0, n0, far0 = _run_far(ms, False)
+    f1, pe1, s1, n1, far1 = _run_far(ms, True)
+    assert far0 == 0 and far1 > 0
+    assert n0 == n1
+    assert cases.rel_rms(f1, f0) < 1e-13
+    assert abs(pe1[0] - pe0[0]) <= 1e-13 * abs(pe0[0])
+    assert np.abs(s1 - s0).max() <= 1e-13 * np.abs(s0).max()
+
+
+@pytest.mark.parametrize("name", ["quartz", "morse", "mgcl2", "morse_nocoul"])
+def test_far_run_switch_is_neutral_where_no_run_is_far(name):
+    ms = cases.GOLDEN_CASES[name]()
+    f0, pe0, s0, n0, far0 = _run_far(ms, False)
+    f1, pe1, s1, n1, far1 = _run_far(ms, True)
+    assert cases.rel_rms(f1, f0) < 1e-13 and n0 == n1 and far0 == 0
