@@ -171,8 +171,9 @@ struct mdb_engine {
    // persistent pair grid fills the FP64 issue slots its DMMA stream leaves idle; d_ovl_q = {next batch, stop flag}
    int ovl_blocks = -2, ovl_threads = 0; bool ovl_armed = false;     // -2: not chosen yet (MDB_OVERLAP), -1: off, 0: k-space first with the set-up behind it, > 0: filler grid
    // an event the pair passes wait for, after the (launch-latency-bound) cell build and sub-list compaction are enqueued: a
-   // k-space kernel on a side stream then hides that set-up, and the pair kernel does not share the SMs with it (two
-   // FP64-bound kernels side by side lose ~7 % against the same two in sequence, profiles/r02_summary.md)
+   // k-space kernel on a side stream then hides that set-up and the pair kernel does not share the SMs with it (on one GPU two
+   // FP64-bound kernels side by side lose up to 7 % against the same two in sequence, profiles/r02_summary.md; at 8 GPUs
+   // waiting and sharing measured the same, 3.339 ms for phase A)
    cudaEvent_t pre_pair_wait = nullptr;
    int *d_ovl_q = nullptr; double *d_out2 = nullptr; size_t out2_cap = 0;
    cudaStream_t ovl_stream = nullptr; cudaEvent_t ev_ovl_fork = nullptr, ev_ovl_join = nullptr;
