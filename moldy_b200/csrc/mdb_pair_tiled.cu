@@ -46,8 +46,9 @@ static constexpr int OFF_Q = 0, OFF_PRE = OFF_Q + 16 * NSLOT, OFF_IPOS = OFF_PRE
                      OFF_IINT = OFF_IPOS + 32 * NI, WARP_SM = OFF_IINT + 16 * NI;
 static_assert(sizeof(WarpSm) == WARP_SM && WARP_SM % 16 == 0, "WarpSm layout");
 static constexpr int OFF_RELOC = TW * WARP_SM;           // double4[27]: image translations
-static constexpr int OFF_E2 = OFF_RELOC + 32 * 28;       // double[64]: 2^(j/64), mdb_exp_tab_v
-static constexpr int OFF_TAB = OFF_E2 + 8 * 64;          // pair-parameter table
+static constexpr int NE2 = MDB_EXP_F32TAIL ? 256 : 64;    // entries of the exp table in shared memory
+static constexpr int OFF_E2 = OFF_RELOC + 32 * 28;       // double[NE2]: 2^(j/NE2), mdb_exp_tab_v / mdb_exp_tab8_v
+static constexpr int OFF_TAB = OFF_E2 + 8 * NE2;         // pair-parameter table
 static constexpr size_t TILED_SMEM = OFF_TAB;
 
 template <int OFF> __device__ __forceinline__ int lds_i(unsigned a)
@@ -126,7 +127,7 @@ k_pair_tiled(PairParams P, int nsites, int nout, const double4 *__restrict__ pos
       double4 *s_reloc = reinterpret_cast<double4 *>(smem_raw + OFF_RELOC);
       double *s_e2 = reinterpret_cast<double *>(smem_raw + OFF_E2), *s_ptab = reinterpret_cast<double *>(smem_raw + OFF_TAB);
       for (int k = threadIdx.x; k < 27; k += blockDim.x) s_reloc[k] = make_double4(P.reloc[k][0], P.reloc[k][1], P.reloc[k][2], 0.0);
-      for (int k = threadIdx.x; k < 64; k += blockDim.x) s_e2[k] = c_exp2tab[k];
+      for (int k = threadIdx.x; k < NE2; k += blockDim.x) s_e2[k] = MDB_EXP_F32TAIL ? c_exp2tab256[k & (MDB_EXP_F32TAIL ? 255 : 0)] : c_exp2tab[k & 63];
       if (MODE == TM_RDF) {                      // block-local histogram in place of the pair table
          unsigned int *hist = reinterpret_cast<unsigned int *>(s_ptab);
          const int nh = R.hist_smem ? R.nbins * (P.max_id * (P.max_id - 1) / 2) : 0;
