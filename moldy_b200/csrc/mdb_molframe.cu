@@ -315,6 +315,7 @@ extern "C" int mdb_set_species(mdb_engine *e, int nspecies, const mdb_species *s
       if (M.h_res) cudaFreeHost(M.h_res);
       M.d_res = M.h_res = nullptr; M.res_cap = 0;
       MDB_CUDA(cudaMalloc(&M.d_res, sizeof(double) * need_res));
+      MDB_CUDA(cudaMemset(M.d_res, 0, sizeof(double) * need_res));    // forces/torques read back before the first evaluation are 0, not noise
       MDB_CUDA(cudaMallocHost(&M.h_res, sizeof(double) * need_res));
       M.res_cap = need_res;
    }

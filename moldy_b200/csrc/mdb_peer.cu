@@ -110,9 +110,16 @@ __global__ void __launch_bounds__(256) k_peer_sum(PeerWin W, int world, size_t s
       int s = 0;
       while (i >= R.len[s]) { i -= R.len[s]; s++; }
       const long long idx = R.start[s] + i;
+      // all peers' values are requested before the first add: `world` NVLink round trips in flight per thread instead of
+      // one after the other; the sum itself stays in rank order (identical bits on every rank)
+      double v[MAXP];
+#pragma unroll
+      for (int p = 0; p < MAXP; p++)
+         v[p] = p < world ? __ldcg(reinterpret_cast<const double *>(W.base[p] + src_off) + idx) : 0.0;
       double acc = 0.0;
-      for (int p = 0; p < world; p++)
-         acc += __ldcg(reinterpret_cast<const double *>(W.base[p] + src_off) + idx);
+#pragma unroll
+      for (int p = 0; p < MAXP; p++)
+         if (p < world) acc += v[p];
       dst[idx - dst_base] = acc;
    }
 }
