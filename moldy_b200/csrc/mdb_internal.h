@@ -205,7 +205,10 @@ int mdb_launch_batches(mdb_engine *e, cudaStream_t st);
 int mdb_need_batches(mdb_engine *e, cudaStream_t st);     // batches of the full cell-sorted list, built once per cell build
 int mdb_build_sublist(mdb_engine *e, int k, cudaStream_t st);
 int mdb_launch_too_close_scan(mdb_engine *e, cudaStream_t st);
-static constexpr int MDB_NI = 4;          // i-sites per warp in the tiled pair kernel
+#ifndef MDB_NI_SITES
+#define MDB_NI_SITES 4
+#endif
+static constexpr int MDB_NI = MDB_NI_SITES;   // i-sites per warp in the tiled pair kernel (2..4)
 int mdb_launch_recip(mdb_engine *e, double *d_out, cudaStream_t st);
 int mdb_launch_recip_partial(mdb_engine *e, double *d_psum, cudaStream_t st);
 int mdb_launch_recip_finish(mdb_engine *e, const double *d_psum, double *d_out, cudaStream_t st);
