@@ -96,6 +96,7 @@ extern "C" void mdb_destroy(mdb_engine *e)
    if (e->mf.h_res) cudaFreeHost(e->mf.h_res);
    FREE(e->mf.d_mom); FREE(e->mf.d_amom); FREE(e->mf.d_mdpart); FREE(e->mf.d_mdscal);
    if (e->mf.h_mdscal) cudaFreeHost(e->mf.h_mdscal);
+   if (e->mf.h_state) cudaFreeHost(e->mf.h_state);
    delete e;
 }
 

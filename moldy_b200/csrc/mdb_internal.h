@@ -165,6 +165,7 @@ struct mdb_engine {
       // resident NVE integrator (mdb_md.cu): momenta, per-species dynamics, sums
       std::vector<mdb_species_dyn> dyn; int nosymmetric_rot = 0, saxis = 0;
       double *d_mom = nullptr, *d_amom = nullptr, *d_mdpart = nullptr, *d_mdscal = nullptr, *h_mdscal = nullptr;
+      double *h_state = nullptr; size_t state_cap = 0;      // pinned staging of the state arrays (upload/download)
    } mf;
 
    // real space beside k-space (mdb_force_both): the k-space chain runs on a high-priority side stream into d_out2, a small

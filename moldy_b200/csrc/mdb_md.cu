@@ -18,6 +18,7 @@
 #include <float.h>
 #include <math.h>
 #include <algorithm>
+#include <thread>
 #include <vector>
 #include "mdb_internal.h"
 
@@ -235,6 +236,49 @@ extern "C" size_t mdb_md_scalars(const mdb_engine *e) { return MDB_EVAL_SCALARS 
 
 // the dynamic state, per species HOST arrays as Moldy holds them: c_of_m[nmols][3] (scaled), quat[nmols][4], mom[nmols][3],
 // amom[nmols][4]; quat/amom NULL for species without quaternions
+// Host <-> device transfer of the per-species state arrays.  The caller's arrays are pageable (Moldy's own malloc'ed
+// c_of_m/quat/mom/amom): cudaMemcpy from them runs at 2-3 GB/s, which cost the do_step() of the C ABI 24 ms per step at
+// 256 000 molecules.  They are staged through ONE pinned block instead: up to six host threads copy the pieces, the device
+// copies then run at PCIe speed.  Layout of the block: [c-of-m 3 nmols | quaternions 4 nmols_q | mom 3 nmols | amom 4 nmols_q
+// | force 3 nmols | torque 3 nmols_r].
+struct CopyJob { double *dst; const double *src; size_t bytes; };
+static void run_jobs(const std::vector<CopyJob> &jobs)
+{
+   size_t total = 0;
+   for (auto &j : jobs) total += j.bytes;
+   auto run = [&](int part, int nparts) {
+      for (auto &j : jobs) {
+         const size_t lo = j.bytes / 8 * part / nparts * 8, hi = j.bytes / 8 * (part + 1) / nparts * 8;
+         if (j.src) memcpy((char *)j.dst + lo, (const char *)j.src + lo, hi - lo);
+         else memset((char *)j.dst + lo, 0, hi - lo);
+      }
+   };
+   if (total >= (4u << 20)) {
+      std::thread th[5];
+      for (int k = 1; k < 6; k++) th[k - 1] = std::thread(run, k, 6);
+      run(0, 6);
+      for (auto &t : th) t.join();
+   } else {
+      run(0, 1);
+   }
+}
+static int state_block(mdb_engine *e, size_t off[6])
+{
+   auto &M = e->mf;
+   const size_t nm = (size_t)M.nmols, nq = (size_t)M.nmols_q, nr = (size_t)M.nmols_r;
+   off[0] = 0; off[1] = 3 * nm; off[2] = off[1] + 4 * nq; off[3] = off[2] + 3 * nm; off[4] = off[3] + 4 * nq; off[5] = off[4] + 3 * nm;
+   const size_t need = off[5] + 3 * nr + 8;
+   if (need > M.state_cap) {
+      if (M.h_state) cudaFreeHost(M.h_state);
+      M.h_state = nullptr; M.state_cap = 0;
+      MDB_CUDA(cudaMallocHost(&M.h_state, sizeof(double) * need));
+      M.state_cap = need;
+   }
+   return 0;
+}
+
+// the dynamic state, per species HOST arrays as Moldy holds them: c_of_m[nmols][3] (scaled), quat[nmols][4], mom[nmols][3],
+// amom[nmols][4]; quat/amom NULL for species without quaternions.  Returns when the state is on the device.
 extern "C" int mdb_md_upload_state(mdb_engine *e, const double *const *com, const double *const *quat, const double *const *mom,
                                    const double *const *amom, void *stream)
 {
@@ -242,20 +286,27 @@ extern "C" int mdb_md_upload_state(mdb_engine *e, const double *const *com, cons
    cudaStream_t st = (cudaStream_t)stream;
    if (!M.d_mom) { mdb_set_error("mdb_md_upload_state: mdb_md_set_dynamics was not called"); return -1; }
    MDB_CUDA(cudaSetDevice(e->device));
+   size_t off[6];
+   if (state_block(e, off)) return -1;
+   double *h = M.h_state;
+   std::vector<CopyJob> jobs;
    for (size_t i = 0; i < M.sp.size(); i++) {
       const size_t nm = (size_t)M.sp[i].nmols;
       if (nm == 0) continue;
-      MDB_CUDA(cudaMemcpyAsync(M.d_in + 3 * (size_t)M.mol_off[i], com[i], sizeof(double) * 3 * nm, cudaMemcpyHostToDevice, st));
-      MDB_CUDA(cudaMemcpyAsync(M.d_mom + 3 * (size_t)M.mol_off[i], mom[i], sizeof(double) * 3 * nm, cudaMemcpyHostToDevice, st));
+      jobs.push_back({h + off[0] + 3 * (size_t)M.mol_off[i], com[i], sizeof(double) * 3 * nm});
+      jobs.push_back({h + off[2] + 3 * (size_t)M.mol_off[i], mom[i], sizeof(double) * 3 * nm});
       if (M.quat_off[i] >= 0) {
-         MDB_CUDA(cudaMemcpyAsync(M.d_in + 3 * (size_t)M.nmols + 4 * (size_t)M.quat_off[i], quat[i], sizeof(double) * 4 * nm,
-                                  cudaMemcpyHostToDevice, st));
-         if (amom && amom[i])
-            MDB_CUDA(cudaMemcpyAsync(M.d_amom + 4 * (size_t)M.quat_off[i], amom[i], sizeof(double) * 4 * nm, cudaMemcpyHostToDevice, st));
-         else
-            MDB_CUDA(cudaMemsetAsync(M.d_amom + 4 * (size_t)M.quat_off[i], 0, sizeof(double) * 4 * nm, st));
+         if (!quat || !quat[i]) { mdb_set_error("mdb_md_upload_state: quaternions missing"); return -1; }
+         jobs.push_back({h + off[1] + 4 * (size_t)M.quat_off[i], quat[i], sizeof(double) * 4 * nm});
+         jobs.push_back({h + off[3] + 4 * (size_t)M.quat_off[i], amom && amom[i] ? amom[i] : nullptr, sizeof(double) * 4 * nm});
       }
    }
+   run_jobs(jobs);
+   const size_t nm = (size_t)M.nmols, nq = (size_t)M.nmols_q;
+   MDB_CUDA(cudaMemcpyAsync(M.d_in, h + off[0], sizeof(double) * (3 * nm + 4 * nq), cudaMemcpyHostToDevice, st));
+   MDB_CUDA(cudaMemcpyAsync(M.d_mom, h + off[2], sizeof(double) * 3 * nm, cudaMemcpyHostToDevice, st));
+   if (nq) MDB_CUDA(cudaMemcpyAsync(M.d_amom, h + off[3], sizeof(double) * 4 * nq, cudaMemcpyHostToDevice, st));
+   MDB_CUDA(cudaStreamSynchronize(st));                   // the staging block is free again
    return 0;
 }
 
@@ -265,20 +316,33 @@ extern "C" int mdb_md_download_state(mdb_engine *e, double *const *com, double *
    auto &M = e->mf;
    cudaStream_t st = (cudaStream_t)stream;
    MDB_CUDA(cudaSetDevice(e->device));
+   size_t off[6];
+   if (state_block(e, off)) return -1;
+   double *h = M.h_state;
+   const size_t nm = (size_t)M.nmols, nq = (size_t)M.nmols_q, nr = (size_t)M.nmols_r;
+   bool want_f = false, want_t = false;
+   for (size_t i = 0; i < M.sp.size(); i++) { want_f |= force && force[i]; want_t |= torque && torque[i]; }
+   MDB_CUDA(cudaMemcpyAsync(h + off[0], M.d_in, sizeof(double) * (3 * nm + 4 * nq), cudaMemcpyDeviceToHost, st));
+   MDB_CUDA(cudaMemcpyAsync(h + off[2], M.d_mom, sizeof(double) * 3 * nm, cudaMemcpyDeviceToHost, st));
+   if (nq) MDB_CUDA(cudaMemcpyAsync(h + off[3], M.d_amom, sizeof(double) * 4 * nq, cudaMemcpyDeviceToHost, st));
+   if (want_f) MDB_CUDA(cudaMemcpyAsync(h + off[4], M.d_res, sizeof(double) * 3 * nm, cudaMemcpyDeviceToHost, st));
+   if (want_t && nr) MDB_CUDA(cudaMemcpyAsync(h + off[5], M.d_res + 3 * nm, sizeof(double) * 3 * nr, cudaMemcpyDeviceToHost, st));
+   MDB_CUDA(cudaStreamSynchronize(st));
+   std::vector<CopyJob> jobs;
    for (size_t i = 0; i < M.sp.size(); i++) {
-      const size_t nm = (size_t)M.sp[i].nmols;
-      if (nm == 0) continue;
-      if (com && com[i]) MDB_CUDA(cudaMemcpyAsync(com[i], M.d_in + 3 * (size_t)M.mol_off[i], sizeof(double) * 3 * nm, cudaMemcpyDeviceToHost, st));
-      if (mom && mom[i]) MDB_CUDA(cudaMemcpyAsync(mom[i], M.d_mom + 3 * (size_t)M.mol_off[i], sizeof(double) * 3 * nm, cudaMemcpyDeviceToHost, st));
-      if (force && force[i]) MDB_CUDA(cudaMemcpyAsync(force[i], M.d_res + 3 * (size_t)M.mol_off[i], sizeof(double) * 3 * nm, cudaMemcpyDeviceToHost, st));
+      const size_t n = (size_t)M.sp[i].nmols;
+      if (n == 0) continue;
+      if (com && com[i]) jobs.push_back({com[i], h + off[0] + 3 * (size_t)M.mol_off[i], sizeof(double) * 3 * n});
+      if (mom && mom[i]) jobs.push_back({mom[i], h + off[2] + 3 * (size_t)M.mol_off[i], sizeof(double) * 3 * n});
+      if (force && force[i]) jobs.push_back({force[i], h + off[4] + 3 * (size_t)M.mol_off[i], sizeof(double) * 3 * n});
       if (M.quat_off[i] >= 0) {
-         if (quat && quat[i]) MDB_CUDA(cudaMemcpyAsync(quat[i], M.d_in + 3 * (size_t)M.nmols + 4 * (size_t)M.quat_off[i], sizeof(double) * 4 * nm, cudaMemcpyDeviceToHost, st));
-         if (amom && amom[i]) MDB_CUDA(cudaMemcpyAsync(amom[i], M.d_amom + 4 * (size_t)M.quat_off[i], sizeof(double) * 4 * nm, cudaMemcpyDeviceToHost, st));
+         if (quat && quat[i]) jobs.push_back({quat[i], h + off[1] + 4 * (size_t)M.quat_off[i], sizeof(double) * 4 * n});
+         if (amom && amom[i]) jobs.push_back({amom[i], h + off[3] + 4 * (size_t)M.quat_off[i], sizeof(double) * 4 * n});
       }
       if (M.torq_off[i] >= 0 && torque && torque[i])
-         MDB_CUDA(cudaMemcpyAsync(torque[i], M.d_res + 3 * (size_t)M.nmols + 3 * (size_t)M.torq_off[i], sizeof(double) * 3 * nm, cudaMemcpyDeviceToHost, st));
+         jobs.push_back({torque[i], h + off[5] + 3 * (size_t)M.torq_off[i], sizeof(double) * 3 * n});
    }
-   MDB_CUDA(cudaStreamSynchronize(st));
+   run_jobs(jobs);
    return 0;
 }
 
