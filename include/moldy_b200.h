@@ -214,6 +214,13 @@ int  mdb_zero_out(mdb_engine *e, double *d_out, void *stream);
 int  mdb_build_cells(mdb_engine *e, void *stream);
 int  mdb_force_real(mdb_engine *e, double *d_out, void *stream);
 int  mdb_force_recip(mdb_engine *e, double *d_out, void *stream);
+/* k-space forces in `n` slices of the charged sites (1..8; default 1), an event after each, so that a host-facing caller can
+ * bring a slice home while the next one is computed (force_calc()/ewald() of layer (A) do).  After mdb_force_recip:
+ * mdb_kforce_slices fills the events (cudaEvent_t, recorded on the launching stream) and the exclusive upper bounds of the
+ * original site indices whose k-space forces are complete at each event; returns the number of slices (0: not cut). */
+void mdb_set_kforce_slices(mdb_engine *e, int n);
+int  mdb_kforce_slices(const mdb_engine *e, void **events, int *site_hi);
+
 /* Both sums of one step on two streams.  Default (mdb_set_overlap(e, 0, 0)): the k-space kernels go first on a side stream
  * while the cell build and the sub-list compaction (launch-latency-bound) are enqueued behind them; the pair passes follow.
  * With a filler grid (`fill_blocks` > 0 blocks of `fill_threads` threads of the pair kernel, persistent, drawing batches

@@ -97,6 +97,7 @@ extern "C" void mdb_destroy(mdb_engine *e)
    FREE(e->mf.d_mom); FREE(e->mf.d_amom); FREE(e->mf.d_mdpart); FREE(e->mf.d_mdscal);
    if (e->mf.h_mdscal) cudaFreeHost(e->mf.h_mdscal);
    if (e->mf.h_state) cudaFreeHost(e->mf.h_state);
+   for (auto &ev : e->kf_ev) if (ev) cudaEventDestroy(ev);
    delete e;
 }
 
@@ -402,6 +403,7 @@ extern "C" int mdb_configure(mdb_engine *e, const mdb_config *cfg)
          if (cfg->nsites_xf >= n) e->n_charged_nf = (int)cidx.size();
          e->n_charged = (int)cidx.size();
          if (upload(e, &e->d_cidx, cidx.data(), cidx.size())) return -1;
+         e->h_cidx = cidx;
       }
       if (upload(e, &e->d_hk, T.hk.data(), T.hk.size())) return -1;
       if (upload(e, &e->d_hk_valid, T.hk_valid.data(), T.hk_valid.size())) return -1;
@@ -506,6 +508,16 @@ extern "C" int mdb_force_real(mdb_engine *e, double *d_out, void *stream)
    if (e->pair_mode >= 3) return mdb_launch_pair_tiled(e, d_out, (cudaStream_t)stream);
    e->pair_evals++;
    return mdb_launch_pair(e, d_out, (cudaStream_t)stream);
+}
+
+// k-space forces in slices (see mdb_engine::kf_chunks): set before mdb_force_recip; afterwards mdb_kforce_slices returns the
+// number of slices, their events (recorded on the launching stream) and the exclusive upper bounds of the ORIGINAL site
+// indices whose k-space forces are complete at each event (the last one is nsites).  0 slices: the launch was not cut.
+extern "C" void mdb_set_kforce_slices(mdb_engine *e, int n) { e->kf_chunks = std::max(1, std::min(n, (int)mdb_engine::KF_MAXCH)); }
+extern "C" int mdb_kforce_slices(const mdb_engine *e, void **events, int *site_hi)
+{
+   for (int k = 0; k < e->kf_nch; k++) { events[k] = (void *)e->kf_ev[k]; site_hi[k] = e->kf_site_hi[k]; }
+   return e->kf_nch;
 }
 
 extern "C" int mdb_force_recip(mdb_engine *e, double *d_out, void *stream)

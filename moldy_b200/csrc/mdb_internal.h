@@ -152,6 +152,11 @@ struct mdb_engine {
    double *d_kpartials = nullptr;
    double *d_psum = nullptr;              // [2][nslots][4] structure-factor sums (non-framework, framework)
    int n_slabs = 0, n_slabs_nf = 0, slab_sites = 0;
+   // k_kforce_mma launched in `kf_chunks` slices of the (non-framework) charged sites, an event after each: the host-facing
+   // layer brings a slice of the k-space forces home and adds it to the caller's array while the next slice is computed
+   static constexpr int KF_MAXCH = 8;
+   int kf_chunks = 1, kf_nch = 0; cudaEvent_t kf_ev[KF_MAXCH] = {}; int kf_site_hi[KF_MAXCH] = {};
+   std::vector<int> h_cidx;
 
    // eval_forces() on the device (mdb_molframe.cu): species table and molecular-frame buffers
    struct MolFrame {

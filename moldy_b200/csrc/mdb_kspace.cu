@@ -1216,13 +1216,35 @@ static int recip_finish(mdb_engine *e, const RecipPlan &P, const double *d_psum,
          MDB_CUDA(cudaFuncSetAttribute(k_kforce_mma, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
          kshm_set = kshm;
       }
+      // the non-framework sites in kf_chunks slices of whole blocks, an event after each (kf_site_hi: the forces of the
+      // ORIGINAL sites below it are complete then -- d_cidx ascends); the framework sites go with the last slice
+      const int nch = std::max(1, std::min(e->kf_chunks, (int)mdb_engine::KF_MAXCH));
+      const bool events = nch > 1 && P.col_nranks == 1 && (int)e->h_cidx.size() == e->n_charged && Q.ngroups > 0;
+      e->kf_nch = 0;
       for (int part = 0; part < 2; part++) {
-         Q.c0 = part == 0 ? P.nf_lo : P.fw_lo; Q.c1 = part == 0 ? P.nf_hi : P.fw_hi;
-         if (Q.c1 <= Q.c0 || Q.ngroups == 0) continue;
-         const int spb = 16 * Q.nsb;
-         k_kforce_mma<<<(Q.c1 - Q.c0 + spb - 1) / spb, 64 * Q.nsb + 32, kshm, st>>>(
-            Q, e->d_cidx, e->d_x, e->d_y, e->d_z, e->d_chg, part == 0 ? blk_tot : blk_nf, d_out);
-         e->launches++;
+         const int c0 = part == 0 ? P.nf_lo : P.fw_lo, c1 = part == 0 ? P.nf_hi : P.fw_hi;
+         if (c1 <= c0 || Q.ngroups == 0) continue;
+         const int spb = 16 * Q.nsb, nblk = (c1 - c0 + spb - 1) / spb, parts = part == 0 && events ? nch : 1;
+         for (int k = 0; k < parts; k++) {
+            const long b_lo = (long)nblk * k / parts, b_hi = (long)nblk * (k + 1) / parts;
+            if (b_hi <= b_lo) continue;
+            Q.c0 = c0 + (int)b_lo * spb; Q.c1 = std::min(c1, c0 + (int)b_hi * spb);
+            k_kforce_mma<<<(unsigned)(b_hi - b_lo), 64 * Q.nsb + 32, kshm, st>>>(
+               Q, e->d_cidx, e->d_x, e->d_y, e->d_z, e->d_chg, part == 0 ? blk_tot : blk_nf, d_out);
+            e->launches++;
+            if (events && part == 0 && k + 1 < parts) {
+               if (!e->kf_ev[e->kf_nch]) MDB_CUDA(cudaEventCreateWithFlags(&e->kf_ev[e->kf_nch], cudaEventDisableTiming));
+               MDB_CUDA(cudaEventRecord(e->kf_ev[e->kf_nch], st));
+               e->kf_site_hi[e->kf_nch] = Q.c1 < e->n_charged ? e->h_cidx[Q.c1] : c.nsites;
+               e->kf_nch++;
+            }
+         }
+      }
+      if (events) {                                      // the last slice (and the framework sites): everything is complete
+         if (!e->kf_ev[e->kf_nch]) MDB_CUDA(cudaEventCreateWithFlags(&e->kf_ev[e->kf_nch], cudaEventDisableTiming));
+         MDB_CUDA(cudaEventRecord(e->kf_ev[e->kf_nch], st));
+         e->kf_site_hi[e->kf_nch] = c.nsites;
+         e->kf_nch++;
       }
       MDB_CUDA(cudaGetLastError());
       return 0;

@@ -95,6 +95,11 @@ struct AbiState {
    mdb_group *group = nullptr;                              // MOLDY_B200_DEVICES names > 1 device: eng = the group's rank 0
    cudaStream_t stream = nullptr, copy_stream = nullptr;   // copy_stream: D2H of the real-space block beside the k-space kernels
    cudaEvent_t ev_real = nullptr, ev_copied = nullptr;
+   // look-ahead k-space sum in slices: slice k of the forces is copied home on copy_stream behind its event and added to the
+   // caller's rows by ewald() while slice k+1 is computed; check_stream carries ewald()'s validation upload of the site rows
+   cudaStream_t check_stream = nullptr;
+   int ahead_nslice = 0; int ahead_hi[8] = {0}; cudaEvent_t ev_slice[8] = {nullptr};
+   int kf_slices = -1, kf_min_sites = 200000;          // MOLDY_B200_KF_SLICES (default 4) for systems of >= kf_min_sites sites
    bool chg_unchecked = false;                              // sync_config(defer_chg): contents of chg[] still to be compared
    bool real_init = false, recip_init = false;
    double eintra = 0, self_energy = 0, sheet_energy = 0;
@@ -303,6 +308,26 @@ static void pull_and_accumulate(real **site_force, double *pe, real (*stress)[3]
    stress[1][1] += sc[6]; stress[1][2] += sc[7]; stress[2][2] += sc[10];
 }
 
+// site_force[a][lo..hi) += rows of a pinned result block, on up to six threads
+static void accumulate_rows(real **site_force, const double *h_src, int n, size_t lo, size_t hi)
+{
+   if (hi <= lo) return;
+   auto add_part = [&](int a, int part, int nparts) {
+      const size_t l = lo + (hi - lo) * part / nparts, h = lo + (hi - lo) * (part + 1) / nparts;
+      real *dst = site_force[a];
+      const double *src = h_src + (size_t)a * n;
+      for (size_t i = l; i < h; i++) dst[i] += src[i];
+   };
+   if (hi - lo >= 65536) {
+      std::thread th[5];
+      for (int k = 1; k < 6; k++) th[k - 1] = std::thread(add_part, k / 2, k % 2, 2);
+      add_part(0, 0, 2);
+      for (auto &t : th) t.join();
+   } else {
+      for (int a = 0; a < 3; a++) add_part(a, 0, 1);
+   }
+}
+
 /* Radial distribution functions, src/force.c:1302-1313 + src/rdf.c:94-108.  The pairs are binned on the device;
  * count/density is added to the host program's float histograms in one step (the reference adds 1/density pair by
  * pair in single precision, so it rounds differently). */
@@ -451,9 +476,37 @@ extern "C" void force_calc(real **site, real **site_force, system_mt *system, sp
    G.ahead_valid = false;
    if (control.alpha > MDB_ALPHAMIN && !getenv("MOLDY_B200_NO_AHEAD")) {
       if (!G.ev_ahead) cudaEventCreateWithFlags(&G.ev_ahead, cudaEventDisableTiming);
-      if (mdb_zero_out(G.eng, G.d_out2, G.stream) || mdb_force_recip(G.eng, G.d_out2, G.stream))
-         FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
-      cudaMemcpyAsync(G.h_out2, G.d_out2, sizeof(double) * mdb_out_doubles(n), cudaMemcpyDeviceToHost, G.stream);
+      if (G.kf_slices < 0) {
+         G.kf_slices = getenv("MOLDY_B200_KF_SLICES") ? atoi(getenv("MOLDY_B200_KF_SLICES")) : 4;
+         G.kf_min_sites = 200000;
+      }
+      mdb_set_kforce_slices(G.eng, n >= G.kf_min_sites ? G.kf_slices : 1);
+      const int rc_recip = mdb_zero_out(G.eng, G.d_out2, G.stream) || mdb_force_recip(G.eng, G.d_out2, G.stream);
+      mdb_set_kforce_slices(G.eng, 1);
+      if (rc_recip) FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+      void *evs[8];
+      G.ahead_nslice = mdb_kforce_slices(G.eng, evs, G.ahead_hi);
+      if (G.ahead_nslice > 1) {
+         // slice k of the k-space forces goes home behind its event while slice k+1 is computed; ewald() adds them one by one
+         size_t lo = 0;
+         for (int k = 0; k < G.ahead_nslice; k++) {
+            const size_t hi = (size_t)G.ahead_hi[k];
+            cudaStreamWaitEvent(G.copy_stream, (cudaEvent_t)evs[k], 0);
+            for (int a = 0; a < 3 && hi > lo; a++)
+               cudaMemcpyAsync(G.h_out2 + (size_t)a * n + lo, G.d_out2 + (size_t)a * n + lo, sizeof(double) * (hi - lo),
+                               cudaMemcpyDeviceToHost, G.copy_stream);
+            if (k == G.ahead_nslice - 1)
+               cudaMemcpyAsync(G.h_out2 + 3 * (size_t)n, G.d_out2 + 3 * (size_t)n, sizeof(double) * (mdb_out_doubles(n) - 3 * (size_t)n),
+                               cudaMemcpyDeviceToHost, G.copy_stream);
+            if (!G.ev_slice[k]) cudaEventCreateWithFlags(&G.ev_slice[k], cudaEventDisableTiming);
+            cudaEventRecord(G.ev_slice[k], G.copy_stream);
+            lo = hi;
+         }
+         cudaStreamWaitEvent(G.stream, G.ev_slice[G.ahead_nslice - 1], 0);
+      } else {
+         G.ahead_nslice = 0;
+         cudaMemcpyAsync(G.h_out2, G.d_out2, sizeof(double) * mdb_out_doubles(n), cudaMemcpyDeviceToHost, G.stream);
+      }
       cudaEventRecord(G.ev_ahead, G.stream);
       G.ahead_valid = true; G.ahead_sites = (const void *)site[0]; G.ahead_epoch = G.config_epoch;
       G.ahead_ithread = ithread; G.ahead_nthreads = nthreads;
@@ -558,12 +611,30 @@ extern "C" void ewald(real **site, real **site_force, system_mp system, spec_mt 
       /* ewald(site,...) must compute from the sites it is passed (src/ewald.c:280): the rows go up again on the copy
        * stream while the kernels started by force_calc run (G.d_out is free by now) and are compared bit for bit on
        * the device with the sites those kernels used; any difference discards the look-ahead result. */
-      const long nd = mdb_sites_differ_host(G.eng, site[0], site[1], site[2], G.d_out, G.copy_stream);
+      if (!G.check_stream) cudaStreamCreateWithFlags(&G.check_stream, cudaStreamNonBlocking);
+      const long nd = mdb_sites_differ_host(G.eng, site[0], site[1], site[2], G.d_out, G.check_stream);
       if (nd != 0) {
          if (g_timing) fprintf(stderr, "[moldy_b200] ewald: sites changed since force_calc (%ld values), recomputing\n", nd);
          cudaEventSynchronize(G.ev_ahead);
          ahead = false;
       }
+   }
+   if (ahead && G.ahead_nslice > 1) {                    /* started by force_calc in slices: add each as it arrives */
+      const double t0 = now_ms();
+      size_t lo = 0;
+      for (int k = 0; k < G.ahead_nslice; k++) {
+         if (cudaEventSynchronize(G.ev_slice[k]) != cudaSuccess) FATAL_MSG("libmoldy_b200: k-space kernels failed");
+         accumulate_rows(site_force, G.h_out2, n, lo, (size_t)G.ahead_hi[k]);
+         lo = (size_t)G.ahead_hi[k];
+      }
+      if (cudaEventSynchronize(G.ev_ahead) != cudaSuccess) FATAL_MSG("libmoldy_b200: k-space kernels failed");
+      if (g_timing) fprintf(stderr, "[moldy_b200] ewald: %d slices of the look-ahead k-space sum added in %.2f ms\n", G.ahead_nslice, now_ms() - t0);
+      G.sites_fresh = false;
+      const double *sc = G.h_out2 + 3 * (size_t)n;
+      stress[0][0] += sc[2]; stress[0][1] += sc[3]; stress[0][2] += sc[4];
+      stress[1][1] += sc[6]; stress[1][2] += sc[7]; stress[2][2] += sc[10];
+      *pe += sc[1];
+      return;
    }
    if (ahead) {                                          /* started by force_calc: wait and add */
       const double t0 = now_ms();
@@ -994,8 +1065,12 @@ extern "C" void mdb_abi_shutdown(void)
    G.d_out = G.h_out = G.d_out2 = G.h_out2 = nullptr; G.out_cap = 0;
    if (G.stream) { cudaStreamDestroy(G.stream); G.stream = nullptr; }
    if (G.copy_stream) { cudaStreamDestroy(G.copy_stream); G.copy_stream = nullptr; }
+   if (G.check_stream) { cudaStreamDestroy(G.check_stream); G.check_stream = nullptr; }
+   for (auto &ev : G.ev_slice) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
    G.have_cfg = false; G.type.clear(); G.chg.clear(); G.potflat.clear();
 }
+// tests: slices of the look-ahead k-space sum and the smallest system they are used for
+extern "C" void mdb_abi_set_kf_slices(int nslices, int min_sites) { G.kf_slices = nslices; G.kf_min_sites = min_sites; }
 extern "C" void *mdb_abi_stream(void) { ensure_engine(); return (void *)G.stream; }
 extern "C" void mdb_abi_constants(double out[3]) { out[0] = G.eintra; out[1] = G.self_energy; out[2] = G.sheet_energy; }
 extern "C" void mdb_abi_reset(void)

@@ -105,3 +105,24 @@ def test_far_run_switch_is_neutral_where_no_run_is_far(name):
     f0, pe0, s0, n0, far0 = _run_far(ms, False)
     f1, pe1, s1, n1, far1 = _run_far(ms, True)
     assert cases.rel_rms(f1, f0) < 1e-13 and n0 == n1 and far0 == 0
+
+
+@pytest.mark.parametrize("name", ["tip4p_2", "mgcl2", "slab_framework"])
+def test_lookahead_kspace_sum_in_slices_through_the_c_abi(name):
+    """force_calc() starts ewald()'s k-space kernels ahead; for large systems the force kernel is cut into slices of the
+    charged sites and ewald() adds each slice to the caller's rows while the next is computed.  Forced here on small
+    golden systems (4 and 3 slices, no size threshold): same result as the reference's record."""
+    L = lib.load()
+    gold = np.load(os.path.join(GOLD, f"ref_{name}.npz"))
+    for ns in (4, 3, 1):
+        L.mdb_abi_set_kf_slices(ns, 0)
+        try:
+            ms = cases.GOLDEN_CASES[name]()
+            lib.reset()
+            out = lib.eval_forces(ms)
+        finally:
+            L.mdb_abi_set_kf_slices(4, 200000)
+        assert cases.rel_rms(out["force"], gold["force"]) < 1e-10, ns
+        assert (np.abs(out["pe"] - gold["pe"]) / np.abs(gold["pe"])).max() < 1e-11, ns
+        iu = np.triu_indices(3)
+        assert np.linalg.norm(out["stress"][iu] - gold["stress"][iu]) / np.linalg.norm(gold["stress"][iu]) < 1e-11, ns
