@@ -372,6 +372,7 @@ double   *mdb_peer_sites(mdb_peer *p);                                /* DEVICE 
 double   *mdb_peer_in(mdb_peer *p);                                   /* DEVICE: generic input block (c-of-m | quaternions)      */
 int       mdb_peer_in_host_slice(mdb_peer *p, const double *h_in, size_t len, void *stream);
 int       mdb_peer_in_gather(mdb_peer *p, size_t len, void *stream);
+int       mdb_peer_in_gather_bounds(mdb_peer *p, size_t off_doubles, long long row_len, const long long *bounds, void *stream);
 /* the step */
 int       mdb_peer_phase_a(mdb_peer *p, int what, void *stream);
 int       mdb_peer_phase_b(mdb_peer *p, int what, void *stream);
@@ -405,6 +406,20 @@ const double *mdb_group_eval_result(const mdb_group *g);
 int         mdb_group_eval_forces_host(mdb_group *g, const double h[9], const double *const *com, const double *const *quat,
                                        int surface_dipole, int do_recip, double *h_result, double rdf_limit, int rdf_nbins,
                                        unsigned long long *rdf_counts, int *tc, int tc_pair[2]);
+/* The resident NVE step (mdb_md_step) on a device group: every rank moves its share of the molecules, the [c-of-m |
+ * quaternions] block is all-gathered over NVLink after the first half step of the co-ordinates, the sums are added on the
+ * host.  Call order: mdb_group_configure, mdb_group_set_species, mdb_group_md_set_dynamics, mdb_group_md_upload_state,
+ * then mdb_group_md_step per step (scalars: layout of mdb_md_step; rdf_counts as mdb_group_eval_forces_host). */
+int         mdb_group_too_close(mdb_group *g, int tc_pair[2]);          /* as mdb_too_close, over all ranks */
+int         mdb_group_md_set_dynamics(mdb_group *g, const mdb_species_dyn *dyn, int nosymmetric_rot);
+int         mdb_group_md_upload_state(mdb_group *g, const double *const *com, const double *const *quat, const double *const *mom,
+                                      const double *const *amom);
+int         mdb_group_md_download_state(mdb_group *g, double *const *com, double *const *quat, double *const *mom, double *const *amom,
+                                        double *const *force, double *const *torque);
+size_t      mdb_group_md_scalars(const mdb_group *g);
+const double *mdb_group_md_result(const mdb_group *g);
+int         mdb_group_md_step(mdb_group *g, const double h[9], double step, double ts, int surface_dipole, int do_recip,
+                              int half_sums, double *h_scal, double rdf_limit, int rdf_nbins, unsigned long long *rdf_counts);
 
 /* Number of values in which three HOST rows differ (bit for bit) from the sites the engine currently holds; the rows are
  * staged in `d_scratch` (DEVICE, 3*nsites doubles).  Synchronises `stream`; -1 on error.  ewald() of layer (A) validates

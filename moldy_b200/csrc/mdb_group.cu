@@ -25,6 +25,10 @@ struct mdb_group {
    size_t in_cap = 0, res_cap = 0;
    std::vector<int> mol_lo;                                         // molecule bounds of the ranks (eval_forces)
    bool species_set = false;
+   // resident NVE step: molecule bounds as element bounds of the c-of-m row and of the quaternion row, staging
+   long long com_b[MDB_MAX_PEERS + 1] = {0}, quat_b[MDB_MAX_PEERS + 1] = {0};
+   double *h_md = nullptr, *h_state = nullptr; size_t md_cap = 0, state_cap = 0;
+   bool md_set = false;
 };
 
 #define GFOR(r) for (int r = 0; r < g->world; r++)
@@ -63,6 +67,8 @@ extern "C" void mdb_group_destroy(mdb_group *g)
    if (g->h_in) cudaFreeHost(g->h_in);
    if (g->h_res) cudaFreeHost(g->h_res);
    if (g->h_scal) cudaFreeHost(g->h_scal);
+   if (g->h_md) cudaFreeHost(g->h_md);
+   if (g->h_state) cudaFreeHost(g->h_state);
    delete g;
 }
 
@@ -246,5 +252,201 @@ extern "C" int mdb_group_eval_forces_host(mdb_group *g, const double h[9], const
    }
    if (h_result) memcpy(h_result, g->h_res, sizeof(double) * mdb_eval_result_doubles(e0));
    (void)n;
+   return 0;
+}
+
+// TOO_CLOSE count / example pair / bin-error bit over all ranks (as mdb_too_close)
+extern "C" int mdb_group_too_close(mdb_group *g, int tc_pair[2])
+{
+   int tc = 0;
+   GFOR(r) {
+      int pr[2];
+      if (cudaSetDevice(g->dev[r]) != cudaSuccess) return -1;
+      const int t = mdb_too_close(g->eng[r], pr, g->st[r]);
+      if (t < 0) return -1;
+      if ((t & ~(1 << 30)) && tc_pair) { tc_pair[0] = pr[0]; tc_pair[1] = pr[1]; }
+      tc = ((tc & ~(1 << 30)) + (t & ~(1 << 30))) | ((tc | t) & (1 << 30));
+   }
+   return tc;
+}
+
+// ---- the NVE step with the state resident on the GPUs of the group (mdb_md.cu on every rank's share of the molecules) ---
+// Every rank keeps the whole [c-of-m | quaternions] block in its peer window and the momenta of ITS molecules; a step is
+//   coords(step/2) on own molecules -> barrier, all-gather of the block -> make_sites, phases A | B | C, molecular forces and
+//   torques of own molecules -> momenta(step/2) x 2 [sums at the half step] -> coords(step/2) -> sums;
+// the per-rank sums (kinetic-energy dyads, mean squares, virial pieces) are added on the host.
+extern "C" int mdb_group_md_set_dynamics(mdb_group *g, const mdb_species_dyn *dyn, int nosymmetric_rot)
+{
+   if (!g->species_set) { mdb_set_error("mdb_group_md_set_dynamics: mdb_group_set_species was not called"); return -1; }
+   GFOR(r) { MDB_CUDA(cudaSetDevice(g->dev[r])); if (mdb_md_set_dynamics(g->eng[r], dyn, nosymmetric_rot)) return -1; }
+   const auto &M = g->eng[0]->mf;
+   for (int r = 0; r <= g->world; r++) {
+      const int m = g->mol_lo[r];
+      long long q = 0;                                    // molecules with quaternions below molecule m
+      for (size_t i = 0; i < M.sp.size(); i++)
+         if (M.quat_off[i] >= 0) q += std::max(0, std::min(m, M.mol_off[i] + M.sp[i].nmols) - M.mol_off[i]);
+      g->com_b[r] = 3LL * m; g->quat_b[r] = 4LL * q;
+   }
+   const size_t ns = mdb_md_scalars(g->eng[0]) * (size_t)g->world;
+   if (ns > g->md_cap) {
+      if (g->h_md) cudaFreeHost(g->h_md);
+      MDB_CUDA(cudaHostAlloc(&g->h_md, sizeof(double) * (ns + mdb_md_scalars(g->eng[0])), cudaHostAllocPortable));
+      g->md_cap = ns;
+   }
+   g->md_set = true;
+   return 0;
+}
+
+extern "C" int mdb_group_md_upload_state(mdb_group *g, const double *const *com, const double *const *quat, const double *const *mom,
+                                         const double *const *amom)
+{
+   if (!g->md_set) { mdb_set_error("mdb_group_md_upload_state: mdb_group_md_set_dynamics was not called"); return -1; }
+   const auto &M0 = g->eng[0]->mf;
+   const size_t len_in = 3 * (size_t)M0.nmols + 4 * (size_t)M0.nmols_q;
+   GFOR(r) {
+      MDB_CUDA(cudaSetDevice(g->dev[r]));
+      if (mdb_md_upload_state(g->eng[r], com, quat, mom, amom, g->st[r])) return -1;
+      MDB_CUDA(cudaMemcpyAsync(mdb_peer_in(g->peer[r]), g->eng[r]->mf.d_in, sizeof(double) * len_in, cudaMemcpyDeviceToDevice, g->st[r]));
+   }
+   GFOR(r) { MDB_CUDA(cudaSetDevice(g->dev[r])); MDB_CUDA(cudaStreamSynchronize(g->st[r])); }
+   return 0;
+}
+
+static int gather_state(mdb_group *g)
+{
+   const auto &M0 = g->eng[0]->mf;
+   if (barrier_all(g)) return -1;
+   GFOR(r) {
+      if (mdb_peer_in_gather_bounds(g->peer[r], 0, 3LL * M0.nmols, g->com_b, g->st[r])) return -1;
+      if (M0.nmols_q > 0 && mdb_peer_in_gather_bounds(g->peer[r], 3 * (size_t)M0.nmols, 4LL * M0.nmols_q, g->quat_b, g->st[r])) return -1;
+   }
+   return 0;
+}
+
+extern "C" size_t mdb_group_md_scalars(const mdb_group *g) { return mdb_md_scalars(g->eng[0]); }
+extern "C" const double *mdb_group_md_result(const mdb_group *g) { return g->h_md + mdb_md_scalars(g->eng[0]) * (size_t)g->world; }
+
+// One NVE step (contract of mdb_md_step; h_scal may be NULL: mdb_group_md_result).  Blocks until the scalars are on the host.
+extern "C" int mdb_group_md_step(mdb_group *g, const double h[9], double step, double ts, int surface_dipole, int do_recip,
+                                 int half_sums, double *h_scal, double rdf_limit, int rdf_nbins, unsigned long long *rdf_counts)
+{
+   if (g->peer.empty() || !g->md_set) { mdb_set_error("mdb_group_md_step: group not configured"); return -1; }
+   const int what = 1 | (do_recip ? 2 : 0);
+   const size_t ns = mdb_md_scalars(g->eng[0]);
+   auto each = [&](auto fn) -> int {
+      GFOR(r) { MDB_CUDA(cudaSetDevice(g->dev[r])); if (fn(r, g->eng[r], g->mol_lo[r], g->mol_lo[r + 1], g->st[r])) return -1; }
+      return 0;
+   };
+   if (each([&](int r, mdb_engine *e, int lo, int hi, cudaStream_t st) { return mdb_md_coords_range(e, h, 0.5 * step, ts, mdb_peer_in(g->peer[r]), lo, hi, st); })) return -1;
+   if (gather_state(g)) return -1;
+   if (each([&](int r, mdb_engine *e, int, int, cudaStream_t st) { return mdb_evalf_pre(e, h, mdb_peer_in(g->peer[r]), st); })) return -1;
+   GFOR(r) if (mdb_peer_phase_a(g->peer[r], what, g->st[r])) return -1;
+   if (barrier_all(g)) return -1;
+   GFOR(r) if (mdb_peer_phase_b(g->peer[r], what, g->st[r])) return -1;
+   if (barrier_all(g)) return -1;
+   GFOR(r) if (mdb_peer_phase_c(g->peer[r], g->st[r])) return -1;
+   if (rdf_counts) GFOR(r) {
+      MDB_CUDA(cudaSetDevice(g->dev[r]));
+      if (mdb_rdf_counts(g->eng[r], rdf_limit, rdf_nbins, rdf_counts, g->st[r])) return -1;
+   }
+   if (each([&](int r, mdb_engine *e, int lo, int hi, cudaStream_t st) {
+          return mdb_evalf_tail(e, h, mdb_peer_in(g->peer[r]), mdb_peer_result(g->peer[r]), lo, hi, surface_dipole, do_recip, st); })) return -1;
+   if (each([&](int, mdb_engine *e, int lo, int hi, cudaStream_t st) { return mdb_md_momenta_range(e, h, 0.5 * step * ts, lo, hi, st); })) return -1;
+   if (half_sums && each([&](int, mdb_engine *e, int lo, int hi, cudaStream_t st) { return mdb_md_sums_range(e, h, 1, false, lo, hi, st); })) return -1;
+   if (each([&](int, mdb_engine *e, int lo, int hi, cudaStream_t st) { return mdb_md_momenta_range(e, h, 0.5 * step * ts, lo, hi, st); })) return -1;
+   GFOR(r) {                                               /* framework constraint, src/accel.c:751-755 */
+      auto &M = g->eng[r]->mf;
+      MDB_CUDA(cudaSetDevice(g->dev[r]));
+      for (size_t i = 0; i < M.sp.size(); i++)
+         if (M.sp[i].framework && M.sp[i].nmols > 0)
+            MDB_CUDA(cudaMemsetAsync(M.d_mom + 3 * (size_t)M.mol_off[i], 0, sizeof(double) * 3 * (size_t)M.sp[i].nmols, g->st[r]));
+   }
+   if (each([&](int r, mdb_engine *e, int lo, int hi, cudaStream_t st) { return mdb_md_coords_range(e, h, 0.5 * step, ts, mdb_peer_in(g->peer[r]), lo, hi, st); })) return -1;
+   if (each([&](int, mdb_engine *e, int lo, int hi, cudaStream_t st) { return mdb_md_sums_range(e, h, 0, true, lo, hi, st); })) return -1;
+   GFOR(r) {
+      auto &M = g->eng[r]->mf;
+      MDB_CUDA(cudaSetDevice(g->dev[r]));
+      MDB_CUDA(cudaMemcpyAsync(M.d_mdscal, M.d_res + 3 * (size_t)M.nmols + 3 * (size_t)M.nmols_r, sizeof(double) * MDB_EVAL_SCALARS,
+                               cudaMemcpyDeviceToDevice, g->st[r]));
+      MDB_CUDA(cudaMemcpyAsync(g->h_md + ns * (size_t)r, M.d_mdscal, sizeof(double) * ns, cudaMemcpyDeviceToHost, g->st[r]));
+   }
+   GFOR(r) { MDB_CUDA(cudaSetDevice(g->dev[r])); MDB_CUDA(cudaStreamSynchronize(g->st[r])); }
+   GFOR(r) if (mdb_peer_error(g->peer[r], g->st[r]) != 0) { mdb_set_error("mdb_group: a peer barrier timed out"); return -1; }
+   // combine: energies, dipole moment and stress of the force evaluation are complete and identical on every rank, its
+   // virial pieces (3..11), all sums over molecules and the bad-quaternion counts add up
+   double *out = g->h_md + ns * (size_t)g->world;
+   memcpy(out, g->h_md, sizeof(double) * ns);
+   unsigned int bad_tot = 0;
+   GFOR(r) {
+      const double *sr = g->h_md + ns * (size_t)r;
+      unsigned int bad;
+      memcpy(&bad, sr + ns - 1, sizeof bad);
+      bad_tot += bad;
+      if (bad) { MDB_CUDA(cudaSetDevice(g->dev[r])); MDB_CUDA(cudaMemsetAsync(g->eng[r]->mf.d_mdscal + ns - 1, 0, sizeof(double), g->st[r])); }
+      if (r == 0) continue;
+      for (int k = 3; k < 12; k++) out[k] += sr[k];
+      for (size_t k = MDB_EVAL_SCALARS; k + 1 < ns; k++) out[k] += sr[k];
+   }
+   out[ns - 1] = (double)bad_tot;
+   if (h_scal) memcpy(h_scal, out, sizeof(double) * ns);
+   return 0;
+}
+
+// The state (and, if asked for, the molecular forces and torques of the last step) back into the caller's per-species arrays:
+// every rank sends the rows of its own molecules through one pinned block.
+extern "C" int mdb_group_md_download_state(mdb_group *g, double *const *com, double *const *quat, double *const *mom, double *const *amom,
+                                           double *const *force, double *const *torque)
+{
+   if (!g->md_set) { mdb_set_error("mdb_group_md_download_state: group not configured"); return -1; }
+   const auto &M0 = g->eng[0]->mf;
+   const size_t nm = (size_t)M0.nmols, nq = (size_t)M0.nmols_q, nr = (size_t)M0.nmols_r;
+   const size_t off[6] = {0, 3 * nm, 3 * nm + 4 * nq, 6 * nm + 4 * nq, 6 * nm + 8 * nq, 9 * nm + 8 * nq};
+   const size_t need = off[5] + 3 * nr + 8;
+   if (need > g->state_cap) {
+      if (g->h_state) cudaFreeHost(g->h_state);
+      g->h_state = nullptr; g->state_cap = 0;
+      MDB_CUDA(cudaHostAlloc(&g->h_state, sizeof(double) * need, cudaHostAllocPortable));
+      g->state_cap = need;
+   }
+   double *hs = g->h_state;
+   GFOR(r) {
+      auto &M = g->eng[r]->mf;
+      const double *in = mdb_peer_in(g->peer[r]);
+      MDB_CUDA(cudaSetDevice(g->dev[r]));
+      const int m_lo = g->mol_lo[r], m_hi = g->mol_lo[r + 1];
+      for (size_t i = 0; i < M.sp.size(); i++) {
+         const int a = std::max(m_lo, M.mol_off[i]) - M.mol_off[i], b = std::min(m_hi, M.mol_off[i] + M.sp[i].nmols) - M.mol_off[i];
+         if (b <= a) continue;
+         const size_t cnt = (size_t)(b - a), mo = (size_t)M.mol_off[i] + a;
+         auto d2h = [&](double *dst, const double *src, size_t n) { return cudaMemcpyAsync(dst, src, sizeof(double) * n, cudaMemcpyDeviceToHost, g->st[r]); };
+         MDB_CUDA(d2h(hs + off[0] + 3 * mo, in + 3 * mo, 3 * cnt));
+         MDB_CUDA(d2h(hs + off[2] + 3 * mo, M.d_mom + 3 * mo, 3 * cnt));
+         MDB_CUDA(d2h(hs + off[4] + 3 * mo, M.d_res + 3 * mo, 3 * cnt));
+         if (M.quat_off[i] >= 0) {
+            const size_t qo = (size_t)M.quat_off[i] + a;
+            MDB_CUDA(d2h(hs + off[1] + 4 * qo, in + 3 * nm + 4 * qo, 4 * cnt));
+            MDB_CUDA(d2h(hs + off[3] + 4 * qo, M.d_amom + 4 * qo, 4 * cnt));
+         }
+         if (M.torq_off[i] >= 0) {
+            const size_t to = (size_t)M.torq_off[i] + a;
+            MDB_CUDA(d2h(hs + off[5] + 3 * to, M.d_res + 3 * nm + 3 * to, 3 * cnt));
+         }
+      }
+   }
+   GFOR(r) { MDB_CUDA(cudaSetDevice(g->dev[r])); MDB_CUDA(cudaStreamSynchronize(g->st[r])); }
+   std::vector<MdbCopyJob> jobs;
+   for (size_t i = 0; i < M0.sp.size(); i++) {
+      const size_t n = (size_t)M0.sp[i].nmols, mo = (size_t)M0.mol_off[i];
+      if (n == 0) continue;
+      if (com && com[i]) jobs.push_back({com[i], hs + off[0] + 3 * mo, sizeof(double) * 3 * n});
+      if (mom && mom[i]) jobs.push_back({mom[i], hs + off[2] + 3 * mo, sizeof(double) * 3 * n});
+      if (force && force[i]) jobs.push_back({force[i], hs + off[4] + 3 * mo, sizeof(double) * 3 * n});
+      if (M0.quat_off[i] >= 0) {
+         if (quat && quat[i]) jobs.push_back({quat[i], hs + off[1] + 4 * (size_t)M0.quat_off[i], sizeof(double) * 4 * n});
+         if (amom && amom[i]) jobs.push_back({amom[i], hs + off[3] + 4 * (size_t)M0.quat_off[i], sizeof(double) * 4 * n});
+      }
+      if (M0.torq_off[i] >= 0 && torque && torque[i]) jobs.push_back({torque[i], hs + off[5] + 3 * (size_t)M0.torq_off[i], sizeof(double) * 3 * n});
+   }
+   mdb_run_copy_jobs(jobs);
    return 0;
 }

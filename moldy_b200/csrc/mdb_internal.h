@@ -222,6 +222,13 @@ int mdb_launch_kernel_vec(int jmin, int nnab, double *forceij, double *pe, const
                           const double *nab_chg, double chg, double norm, double alpha, int ptype,
                           double *const *pot);
 
+// pieces of the NVE step (mdb_md.cu) on a range of molecules, shared with the multi-GPU driver (mdb_group.cu)
+struct MdbCopyJob { double *dst; const double *src; size_t bytes; };     // src == nullptr: zero fill
+void mdb_run_copy_jobs(const std::vector<MdbCopyJob> &jobs);            // host copies on up to six threads
+int mdb_md_coords_range(mdb_engine *e, const double h[9], double step, double ts, double *d_in, int m_lo, int m_hi, cudaStream_t st);
+int mdb_md_momenta_range(mdb_engine *e, const double h[9], double step, int m_lo, int m_hi, cudaStream_t st);
+int mdb_md_sums_range(mdb_engine *e, const double h[9], int slot, bool with_forces, int m_lo, int m_hi, cudaStream_t st);
+
 // pieces of eval_forces() (mdb_molframe.cu), shared with the multi-GPU driver (mdb_group.cu)
 int mdb_evalf_stage_inputs(mdb_engine *e, const double *const *com, const double *const *quat, double *h_in);
 int mdb_evalf_make_sites(mdb_engine *e, const double h[9], const double *d_in, bool second, cudaStream_t st);

@@ -241,8 +241,8 @@ extern "C" size_t mdb_md_scalars(const mdb_engine *e) { return MDB_EVAL_SCALARS 
 // 256 000 molecules.  They are staged through ONE pinned block instead: up to six host threads copy the pieces, the device
 // copies then run at PCIe speed.  Layout of the block: [c-of-m 3 nmols | quaternions 4 nmols_q | mom 3 nmols | amom 4 nmols_q
 // | force 3 nmols | torque 3 nmols_r].
-struct CopyJob { double *dst; const double *src; size_t bytes; };
-static void run_jobs(const std::vector<CopyJob> &jobs)
+typedef MdbCopyJob CopyJob;
+void mdb_run_copy_jobs(const std::vector<MdbCopyJob> &jobs)
 {
    size_t total = 0;
    for (auto &j : jobs) total += j.bytes;
@@ -301,7 +301,7 @@ extern "C" int mdb_md_upload_state(mdb_engine *e, const double *const *com, cons
          jobs.push_back({h + off[3] + 4 * (size_t)M.quat_off[i], amom && amom[i] ? amom[i] : nullptr, sizeof(double) * 4 * nm});
       }
    }
-   run_jobs(jobs);
+   mdb_run_copy_jobs(jobs);
    const size_t nm = (size_t)M.nmols, nq = (size_t)M.nmols_q;
    MDB_CUDA(cudaMemcpyAsync(M.d_in, h + off[0], sizeof(double) * (3 * nm + 4 * nq), cudaMemcpyHostToDevice, st));
    MDB_CUDA(cudaMemcpyAsync(M.d_mom, h + off[2], sizeof(double) * 3 * nm, cudaMemcpyHostToDevice, st));
@@ -342,15 +342,15 @@ extern "C" int mdb_md_download_state(mdb_engine *e, double *const *com, double *
       if (M.torq_off[i] >= 0 && torque && torque[i])
          jobs.push_back({torque[i], h + off[5] + 3 * (size_t)M.torq_off[i], sizeof(double) * 3 * n});
    }
-   run_jobs(jobs);
+   mdb_run_copy_jobs(jobs);
    return 0;
 }
 
-// leapf_all_coords(step) of src/accel.c:360-372 on the resident state
-extern "C" int mdb_md_coords(mdb_engine *e, const double h[9], double step, double ts, void *stream)
+// leapf_all_coords(step) of src/accel.c:360-372 on the resident state; the _range forms work on the molecules [m_lo, m_hi)
+// of the state block d_in (a rank's share in a device group, mdb_group.cu)
+int mdb_md_coords_range(mdb_engine *e, const double h[9], double step, double ts, double *d_in, int m_lo, int m_hi, cudaStream_t st)
 {
    auto &M = e->mf;
-   cudaStream_t st = (cudaStream_t)stream;
    double ht[9], G[9], Gi[9];
    for (int i = 0; i < 3; i++)
       for (int j = 0; j < 3; j++) ht[3 * j + i] = h[3 * i + j];
@@ -359,7 +359,8 @@ extern "C" int mdb_md_coords(mdb_engine *e, const double h[9], double step, doub
    unsigned int *bad = reinterpret_cast<unsigned int *>(M.d_mdscal + mdb_md_scalars(e) - 1);
    for (size_t i = 0; i < M.sp.size(); i++) {
       const mdb_species &s = M.sp[i];
-      if (s.nmols == 0) continue;
+      const int a = std::max(m_lo, M.mol_off[i]) - M.mol_off[i], b = std::min(m_hi, M.mol_off[i] + s.nmols) - M.mol_off[i];
+      if (b <= a) continue;
       Mat3 GI;
       const double f = step / (M.dyn[i].mass * ts);                 /* mat_sca_mul(step/(mass*s), Ginv, Ginv), :142 */
       for (int k = 0; k < 9; k++) GI.m[k] = f * Gi[k];
@@ -367,40 +368,48 @@ extern "C" int mdb_md_coords(mdb_engine *e, const double h[9], double step, doub
       rinertia(M.dyn[i].inertia, R.ri);
       R.saxis = M.saxis; R.symmetric = M.nosymmetric_rot ? 0 : 1;
       const bool rot = s.rdof > 0 && M.quat_off[i] >= 0;
-      k_leap_coords<<<(s.nmols + MB - 1) / MB, MB, 0, st>>>(
-         GI, R, step / ts, s.nmols, M.d_in + 3 * (size_t)M.mol_off[i], M.d_mom + 3 * (size_t)M.mol_off[i],
-         rot ? M.d_in + 3 * (size_t)M.nmols + 4 * (size_t)M.quat_off[i] : nullptr,
-         rot ? M.d_amom + 4 * (size_t)M.quat_off[i] : nullptr, bad);
+      k_leap_coords<<<(b - a + MB - 1) / MB, MB, 0, st>>>(
+         GI, R, step / ts, b - a, d_in + 3 * ((size_t)M.mol_off[i] + a), M.d_mom + 3 * ((size_t)M.mol_off[i] + a),
+         rot ? d_in + 3 * (size_t)M.nmols + 4 * ((size_t)M.quat_off[i] + a) : nullptr,
+         rot ? M.d_amom + 4 * ((size_t)M.quat_off[i] + a) : nullptr, bad);
       e->launches++;
    }
    MDB_CUDA(cudaGetLastError());
    return 0;
 }
+extern "C" int mdb_md_coords(mdb_engine *e, const double h[9], double step, double ts, void *stream)
+{
+   return mdb_md_coords_range(e, h, step, ts, e->mf.d_in, 0, e->mf.nmols, (cudaStream_t)stream);
+}
 
 // leapf_all_momenta(step) of src/accel.c:376-388 (the caller passes step*ts) from the forces/torques of the last eval
-extern "C" int mdb_md_momenta(mdb_engine *e, const double h[9], double step, void *stream)
+int mdb_md_momenta_range(mdb_engine *e, const double h[9], double step, int m_lo, int m_hi, cudaStream_t st)
 {
    auto &M = e->mf;
-   cudaStream_t st = (cudaStream_t)stream;
    Mat3 HT;
    for (int i = 0; i < 3; i++)
       for (int j = 0; j < 3; j++) HT.m[3 * j + i] = step * h[3 * i + j];         /* transpose + mat_sca_mul, :154-155 */
    for (size_t i = 0; i < M.sp.size(); i++) {
       const mdb_species &s = M.sp[i];
-      if (s.nmols == 0) continue;
+      const int a = std::max(m_lo, M.mol_off[i]) - M.mol_off[i], b = std::min(m_hi, M.mol_off[i] + s.nmols) - M.mol_off[i];
+      if (b <= a) continue;
       const bool rot = s.rdof > 0 && M.quat_off[i] >= 0 && M.torq_off[i] >= 0;
-      k_leap_momenta<<<(s.nmols + MB - 1) / MB, MB, 0, st>>>(
-         HT, step, s.nmols, M.d_mom + 3 * (size_t)M.mol_off[i], M.d_res + 3 * (size_t)M.mol_off[i],
-         rot ? M.d_amom + 4 * (size_t)M.quat_off[i] : nullptr,
-         rot ? M.d_res + 3 * (size_t)M.nmols + 3 * (size_t)M.torq_off[i] : nullptr);
+      k_leap_momenta<<<(b - a + MB - 1) / MB, MB, 0, st>>>(
+         HT, step, b - a, M.d_mom + 3 * ((size_t)M.mol_off[i] + a), M.d_res + 3 * ((size_t)M.mol_off[i] + a),
+         rot ? M.d_amom + 4 * ((size_t)M.quat_off[i] + a) : nullptr,
+         rot ? M.d_res + 3 * (size_t)M.nmols + 3 * ((size_t)M.torq_off[i] + a) : nullptr);
       e->launches++;
    }
    MDB_CUDA(cudaGetLastError());
    return 0;
 }
+extern "C" int mdb_md_momenta(mdb_engine *e, const double h[9], double step, void *stream)
+{
+   return mdb_md_momenta_range(e, h, step, 0, e->mf.nmols, (cudaStream_t)stream);
+}
 
 // sums of the momenta (and, with_forces, of the molecular forces/torques) per species -> d_mdscal[slot]
-static int md_sums(mdb_engine *e, const double h[9], int slot, bool with_forces, cudaStream_t st)
+int mdb_md_sums_range(mdb_engine *e, const double h[9], int slot, bool with_forces, int m_lo, int m_hi, cudaStream_t st)
 {
    auto &M = e->mf;
    Mat3 HI;
@@ -408,19 +417,24 @@ static int md_sums(mdb_engine *e, const double h[9], int slot, bool with_forces,
    for (size_t i = 0; i < M.sp.size(); i++) {
       const mdb_species &s = M.sp[i];
       double *dst = M.d_mdscal + MDB_EVAL_SCALARS + NSUM * ((size_t)slot * M.sp.size() + i);
-      if (s.nmols == 0) { MDB_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * NSUM, st)); continue; }
-      const int nb = (s.nmols + MB - 1) / MB;
+      const int a = std::max(m_lo, M.mol_off[i]) - M.mol_off[i], b = std::min(m_hi, M.mol_off[i] + s.nmols) - M.mol_off[i];
+      if (b <= a) { MDB_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * NSUM, st)); continue; }
+      const int nb = (b - a + MB - 1) / MB;
       const bool rot = s.rdof > 0 && M.quat_off[i] >= 0;
-      k_md_sums<<<nb, MB, 0, st>>>(HI, s.nmols, M.d_mom + 3 * (size_t)M.mol_off[i],
-                                   rot ? M.d_amom + 4 * (size_t)M.quat_off[i] : nullptr,
-                                   with_forces ? M.d_res + 3 * (size_t)M.mol_off[i] : nullptr,
-                                   with_forces && M.torq_off[i] >= 0 ? M.d_res + 3 * (size_t)M.nmols + 3 * (size_t)M.torq_off[i] : nullptr,
+      k_md_sums<<<nb, MB, 0, st>>>(HI, b - a, M.d_mom + 3 * ((size_t)M.mol_off[i] + a),
+                                   rot ? M.d_amom + 4 * ((size_t)M.quat_off[i] + a) : nullptr,
+                                   with_forces ? M.d_res + 3 * ((size_t)M.mol_off[i] + a) : nullptr,
+                                   with_forces && M.torq_off[i] >= 0 ? M.d_res + 3 * (size_t)M.nmols + 3 * ((size_t)M.torq_off[i] + a) : nullptr,
                                    M.d_mdpart);
       k_md_sums_finish<<<NSUM, MB, 0, st>>>(M.d_mdpart, nb, dst);
       e->launches += 2;
    }
    MDB_CUDA(cudaGetLastError());
    return 0;
+}
+static int md_sums(mdb_engine *e, const double h[9], int slot, bool with_forces, cudaStream_t st)
+{
+   return mdb_md_sums_range(e, h, slot, with_forces, 0, e->mf.nmols, st);
 }
 
 // eval_forces() on the resident state: no input upload, no force download (mdb_molframe.cu pieces)

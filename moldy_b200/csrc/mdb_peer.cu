@@ -347,6 +347,22 @@ extern "C" int mdb_peer_in_gather(mdb_peer *p, size_t len, void *stream)
    return 0;
 }
 
+// all-gather of ONE row of `row_len` doubles at `off_doubles` of the input block, owned in the pieces bounds[r] .. bounds[r+1]
+// (the resident NVE step of a device group: every rank moves its own molecules and pulls the others')
+extern "C" int mdb_peer_in_gather_bounds(mdb_peer *p, size_t off_doubles, long long row_len, const long long *bounds, void *stream)
+{
+   if (p->world == 1 || row_len <= 0) return 0;
+   if (off_doubles + (size_t)row_len > p->in_cap) { mdb_set_error("mdb_peer_in_gather_bounds: row outside the window"); return -1; }
+   MDB_CUDA(cudaSetDevice(p->e->device));
+   PeerBounds B{};
+   for (int r = 0; r <= p->world; r++) B.lo[r] = bounds[r];
+   k_peer_gather<<<grid_for(row_len), 256, 0, (cudaStream_t)stream>>>(p->W, p->rank, p->world, p->off_in + sizeof(double) * off_doubles, 1,
+                                                                      row_len, B);
+   p->e->launches++;
+   MDB_CUDA(cudaGetLastError());
+   return 0;
+}
+
 // ---- the step ----------------------------------------------------------------------------------------------------
 static double *out_block(mdb_peer *p) { return reinterpret_cast<double *>(p->win + p->off_out[p->parity]); }
 

@@ -928,7 +928,6 @@ static void do_step_impl(system_mt *sys, spec_mt *species, site_mt *site_info, p
 {
    if (control.const_temp || control.const_pressure)
       FATAL_MSG("libmoldy_b200: do_step on the device covers NVE dynamics only (const-temp=0, const-pressure=0)");
-   if (G.group) FATAL_MSG("libmoldy_b200: do_step is not available with MOLDY_B200_DEVICES; link eval_forces instead");
    const int nspecies = sys->nspecies;
    double h9[9], vol;
    bool do_recip;
@@ -938,7 +937,9 @@ static void do_step_impl(system_mt *sys, spec_mt *species, site_mt *site_info, p
       dyn[i] = mdb_species_dyn{species[i].mass, {species[i].inertia[0], species[i].inertia[1], species[i].inertia[2]}};
    if (S.species_epoch != E.species_epoch || S.nosym != control.nosymmetric_rot || dyn.size() != S.dyn.size() ||
        memcmp(dyn.data(), S.dyn.data(), sizeof(mdb_species_dyn) * dyn.size())) {
-      if (mdb_md_set_dynamics(G.eng, dyn.data(), control.nosymmetric_rot ? 1 : 0)) FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+      if (G.group ? mdb_group_md_set_dynamics(G.group, dyn.data(), control.nosymmetric_rot ? 1 : 0)
+                  : mdb_md_set_dynamics(G.eng, dyn.data(), control.nosymmetric_rot ? 1 : 0))
+         FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
       S.dyn = dyn; S.species_epoch = E.species_epoch; S.nosym = control.nosymmetric_rot;
    }
    std::vector<const double *> com(nspecies), quat(nspecies), mom(nspecies), amom(nspecies);
@@ -954,16 +955,25 @@ static void do_step_impl(system_mt *sys, spec_mt *species, site_mt *site_info, p
    float *rdf_base = nullptr;
    if (rdf_due() && (rdf_base = rdf_store(mdb_rdf_size(G.eng, control.nbins))) != nullptr) {
       rdf_cnt.assign(mdb_rdf_size(G.eng, control.nbins), 0ULL);
-      mdb_eval_request_rdf(G.eng, control.limit, control.nbins, rdf_cnt.data());
+      if (!G.group) mdb_eval_request_rdf(G.eng, control.limit, control.nbins, rdf_cnt.data());
    }
    const bool want_h0 = control.istep == 1 || init_H_0;
-   if (mdb_md_upload_state(G.eng, com.data(), quat.data(), mom.data(), amom.data(), G.stream) ||
-       mdb_md_step(G.eng, h9, control.step, sys->ts, control.surface_dipole ? 1 : 0, do_recip ? 1 : 0, want_h0 ? 1 : 0, nullptr,
-                   G.stream))
-      FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
-   if (rdf_base) rdf_add_counts(sys, rdf_base, rdf_cnt);
    int pr[2];
-   report_too_close(mdb_too_close(G.eng, pr, G.stream), pr);
+   if (G.group) {                                          /* all GPUs of MOLDY_B200_DEVICES: every rank moves its molecules */
+      if (mdb_group_md_upload_state(G.group, com.data(), quat.data(), mom.data(), amom.data()) ||
+          mdb_group_md_step(G.group, h9, control.step, sys->ts, control.surface_dipole ? 1 : 0, do_recip ? 1 : 0, want_h0 ? 1 : 0,
+                            nullptr, control.limit, control.nbins, rdf_base ? rdf_cnt.data() : nullptr))
+         FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+      if (rdf_base) rdf_add_counts(sys, rdf_base, rdf_cnt);
+      report_too_close(mdb_group_too_close(G.group, pr), pr);
+   } else {
+      if (mdb_md_upload_state(G.eng, com.data(), quat.data(), mom.data(), amom.data(), G.stream) ||
+          mdb_md_step(G.eng, h9, control.step, sys->ts, control.surface_dipole ? 1 : 0, do_recip ? 1 : 0, want_h0 ? 1 : 0, nullptr,
+                      G.stream))
+         FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
+      if (rdf_base) rdf_add_counts(sys, rdf_base, rdf_cnt);
+      report_too_close(mdb_too_close(G.eng, pr, G.stream), pr);
+   }
    const bool dump_due = control.dump_interval > 0 && control.dump_level != 0 && control.istep >= control.begin_dump &&
                          (control.istep - control.begin_dump) % control.dump_interval == 0 && ithread == 0 && dump;
    std::vector<double> fbuf, tbuf;
@@ -975,10 +985,11 @@ static void do_step_impl(system_mt *sys, spec_mt *species, site_mt *site_info, p
          if (species[i].rdof > 0) { wt[i] = tbuf.data() + to; to += 3 * (size_t)species[i].nmols; }
       }
    }
-   if (mdb_md_download_state(G.eng, wcom.data(), wquat.data(), wmom.data(), wamom.data(), wf.data(), wt.data(), G.stream))
+   if (G.group ? mdb_group_md_download_state(G.group, wcom.data(), wquat.data(), wmom.data(), wamom.data(), wf.data(), wt.data())
+               : mdb_md_download_state(G.eng, wcom.data(), wquat.data(), wmom.data(), wamom.data(), wf.data(), wt.data(), G.stream))
       FATAL_MSG("libmoldy_b200: %s", mdb_last_error());
-   const double *r = mdb_md_result(G.eng);
-   const size_t nscal = mdb_md_scalars(G.eng);
+   const double *r = G.group ? mdb_group_md_result(G.group) : mdb_md_result(G.eng);
+   const size_t nscal = G.group ? mdb_group_md_scalars(G.group) : mdb_md_scalars(G.eng);
    if (r[nscal - 1] != 0.0)
       FATAL_MSG("Quaternion %d (%g,%g,%g,%g) - normalisation error in beeman", 0, 0.0, 0.0, 0.0, 0.0);   /* src/leapfrog.c:107 */
    eval_finish_scalars(r, vol, do_recip, pe, dip_mom, stress_vir);

@@ -191,8 +191,6 @@ def test_unmodified_moldy_on_several_gpus(tmp_path, gpu_binary):
     import torch
     a = _run(REF, str(tmp_path), 40, 10, rdf=2, rdfout=20)
     va, ra = _current_values(a), _rdf_tables(a)
-    if gpu_binary == GPU_DOSTEP:
-        pytest.skip("do_step on the device drives one GPU (MOLDY_B200_DEVICES applies to eval_forces and below)")
     for devs in (["all"] if torch.cuda.device_count() > 1 else []) + ["0,0,0"]:
         b = _run(gpu_binary, str(tmp_path), 40, 10, rdf=2, rdfout=20, env={"MOLDY_B200_DEVICES": devs}, tag="_" + devs.replace(",", ""))
         vb, rb = _current_values(b), _rdf_tables(b)

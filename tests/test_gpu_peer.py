@@ -174,3 +174,30 @@ def test_rdf_pass_on_a_device_group(abi_devices):
         rho = ms.nsites / float(np.linalg.det(ms.h))
         cnt = np.rint(out["rdf"].astype(np.float64) * rho).astype(np.int64)
         assert np.array_equal(cnt, ref_rdf[name]), name
+
+
+@pytest.mark.parametrize("name", ["tip4p", "mgcl2", "tip4p_2"])
+def test_do_step_on_a_device_group(name, abi_devices):
+    """The NVE do_step() of the library with MOLDY_B200_DEVICES: every rank moves its share of the
+    molecules, the c-of-m / quaternion block is all-gathered, the kinetic-energy and mean-square sums are added over the
+    ranks.  Same trajectory, energies, stress and sums as on one engine (and, through it, as the reference's do_step:
+    tests/test_gpu_md.py)."""
+    step, nsteps = 0.0005, 3
+    ms = cases.GOLDEN_CASES[name]()
+    mom, amom = ms.thermal_momenta(seed=11)
+    lib.shutdown()
+    os.environ.pop("MOLDY_B200_DEVICES", None)
+    lib.reset()
+    want = lib.do_step(cases.GOLDEN_CASES[name](), mom, amom, step, nsteps=nsteps)
+    for devs in _devlists():
+        abi_devices(devs)
+        got = lib.do_step(cases.GOLDEN_CASES[name](), mom, amom, step, nsteps=nsteps)
+        assert np.abs(got["com"] - want["com"]).max() < 1e-11, devs
+        assert np.abs(got["mom"] - want["mom"]).max() < 1e-11 * np.abs(want["mom"]).max(), devs
+        assert np.abs(got["quat"] - want["quat"]).max() < 1e-11, devs
+        if want["amom"].size:
+            assert np.abs(got["amom"] - want["amom"]).max() < 1e-11 * max(np.abs(want["amom"]).max(), 1e-300), devs
+        assert np.abs(got["pe"] - want["pe"]).max() < 1e-11 * np.abs(want["pe"]).max(), devs
+        assert np.linalg.norm(got["stress"] - want["stress"]) < 1e-10 * np.linalg.norm(want["stress"]), devs
+        assert np.allclose(got["meansq"], want["meansq"], rtol=1e-10, atol=1e-12 * np.abs(want["meansq"]).max()), devs
+        assert np.allclose(got["dip_mom"], want["dip_mom"], rtol=1e-9, atol=1e-9 * np.abs(want["dip_mom"]).max() + 1e-12), devs
