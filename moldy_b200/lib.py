@@ -317,7 +317,9 @@ class Engine:
         if rc != 0:
             raise RuntimeError(f"{what}: {_err(self.L)}")
 
-    def configure(self, ms: MoldySystem):
+    @staticmethod
+    def make_config(ms: MoldySystem):
+        """mdb_config of a system + the arrays it points into (keep them alive while it is used)."""
         cfg = mdb_config()
         sd = ms.sysdef
         ids = np.ascontiguousarray(ms.site_ids(), dtype=np.int32)
@@ -337,7 +339,10 @@ class Engine:
         cfg.strict_cutoff = c.strict_cutoff
         cfg.do_recip = int(c.alpha > 1e-7)
         cfg.molpbc, cfg.nmols = int(c.molpbc), ms.nmols
-        self._keep = (ids, mol, chg, pot)
+        return cfg, (ids, mol, chg, pot)
+
+    def configure(self, ms: MoldySystem):
+        cfg, self._keep = Engine.make_config(ms)
         self._chk(self.L.mdb_configure(self.h, C.byref(cfg)), "mdb_configure")
         self.n = ms.nsites
 
@@ -537,6 +542,84 @@ class MdState:
         out = np.zeros((self.nsp, 15))
         self.eng._chk(self.L.mdb_md_sums_now(self.eng.h, h.ctypes.data, out.ctypes.data, stream), "mdb_md_sums_now")
         return out
+
+
+class GroupMd:
+    """The resident NVE step on a device group (mdb_group.cu: mdb_group_md_step): one process, several GPUs, every rank
+    moving its share of the molecules.  devices may repeat (ranks sharing a GPU)."""
+
+    def __init__(self, ms: MoldySystem, devices, nosymmetric_rot: int = 0):
+        self.L, self.ms = load(), ms
+        L = self.L
+        L.mdb_group_create.restype = C.c_void_p
+        L.mdb_group_create.argtypes = [C.c_int, IP]
+        for f in ("mdb_group_destroy", "mdb_group_size"):
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.mdb_group_configure.argtypes = [C.c_void_p, C.POINTER(mdb_config)]
+        L.mdb_group_set_species.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.mdb_group_md_set_dynamics.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.mdb_group_md_upload_state.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        L.mdb_group_md_download_state.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        L.mdb_group_md_scalars.restype = C.c_size_t
+        L.mdb_group_md_scalars.argtypes = [C.c_void_p]
+        L.mdb_group_md_step.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                        C.c_double, C.c_int, C.c_void_p]
+        dev = (C.c_int * len(devices))(*devices)
+        self.g = L.mdb_group_create(len(devices), dev)
+        if not self.g:
+            raise RuntimeError("mdb_group_create: " + _err(L))
+        cfg, self._keep = Engine.make_config(ms)
+        self._chk(L.mdb_group_configure(self.g, C.byref(cfg)), "mdb_group_configure")
+        sd = ms.sysdef
+        nsp = len(sd.species)
+        sp = (abi.mdb_species * nsp)()
+        dyn = (abi.mdb_species_dyn * nsp)()
+        pfs = []
+        for i, (s, inert) in enumerate(zip(sd.species, ms.principal_inertia())):
+            sp[i].nmols, sp[i].nsites, sp[i].framework = s.nmols, s.nsites, int(s.framework)
+            sp[i].rotates, sp[i].rdof = int(s.rdof > 0), s.rdof
+            dyn[i].mass = s.mass
+            for k in range(3):
+                dyn[i].inertia[k] = float(inert[k])
+            pfs.append(np.asarray(s.p_f_sites, dtype=np.float64).reshape(-1, 3))
+        pfs = np.ascontiguousarray(np.concatenate(pfs))
+        self._chk(L.mdb_group_set_species(self.g, nsp, sp, pfs.ctypes.data), "mdb_group_set_species")
+        self._chk(L.mdb_group_md_set_dynamics(self.g, dyn, nosymmetric_rot), "mdb_group_md_set_dynamics")
+        self.nsp, self.nscal = nsp, L.mdb_group_md_scalars(self.g)
+
+    def _chk(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what}: {_err(self.L)}")
+
+    _ptrs = MdState._ptrs
+
+    def upload(self, com, quat, mom, amom):
+        self._state = [np.ascontiguousarray(a, dtype=np.float64) for a in (com, quat, mom, amom)]
+        c, q, m, a = self._state
+        self._chk(self.L.mdb_group_md_upload_state(self.g, self._ptrs(c, 3), self._ptrs(q, 4, True), self._ptrs(m, 3),
+                                                   self._ptrs(a, 4, True)), "mdb_group_md_upload_state")
+
+    def download(self):
+        nm = self.ms.nmols
+        com, quat, mom, amom = np.zeros((nm, 3)), np.zeros((nm, 4)), np.zeros((nm, 3)), np.zeros((nm, 4))
+        force, torque = np.zeros((nm, 3)), np.zeros((nm, 3))
+        self._chk(self.L.mdb_group_md_download_state(self.g, self._ptrs(com, 3), self._ptrs(quat, 4, True), self._ptrs(mom, 3),
+                                                     self._ptrs(amom, 4, True), self._ptrs(force, 3), self._ptrs(torque, 3, True)),
+                  "mdb_group_md_download_state")
+        return dict(com=com, quat=quat, mom=mom, amom=amom, force=force, torque=torque)
+
+    def step(self, step, ts=1.0, half_sums=False):
+        h = np.ascontiguousarray(self.ms.h, dtype=np.float64)
+        out = np.zeros(self.nscal)
+        self._chk(self.L.mdb_group_md_step(self.g, h.ctypes.data, step, ts, int(self.ms.control.surface_dipole),
+                                           int(self.ms.control.alpha > 1e-7), int(half_sums), out.ctypes.data, 0.0, 0, None),
+                  "mdb_group_md_step")
+        return out
+
+    def close(self):
+        if self.g:
+            self.L.mdb_group_destroy(self.g)
+            self.g = None
 
 
 class Peer:
