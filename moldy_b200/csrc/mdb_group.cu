@@ -11,6 +11,8 @@
 //                              ITS molecules from the reduce-scatter, and returns their molecular forces and torques.
 #include <string.h>
 #include <algorithm>
+#include <stdlib.h>
+#include <thread>
 #include <vector>
 #include "mdb_internal.h"
 
@@ -29,6 +31,7 @@ struct mdb_group {
    long long com_b[MDB_MAX_PEERS + 1] = {0}, quat_b[MDB_MAX_PEERS + 1] = {0};
    double *h_md = nullptr, *h_state = nullptr; size_t md_cap = 0, state_cap = 0;
    bool md_set = false;
+   long md_steps = 0;                                               // steps since the dynamics were set (the first one allocates)
 };
 
 #define GFOR(r) for (int r = 0; r < g->world; r++)
@@ -293,7 +296,7 @@ extern "C" int mdb_group_md_set_dynamics(mdb_group *g, const mdb_species_dyn *dy
       MDB_CUDA(cudaHostAlloc(&g->h_md, sizeof(double) * (ns + mdb_md_scalars(g->eng[0])), cudaHostAllocPortable));
       g->md_cap = ns;
    }
-   g->md_set = true;
+   g->md_set = true; g->md_steps = 0;
    return 0;
 }
 
@@ -337,6 +340,49 @@ extern "C" int mdb_group_md_step(mdb_group *g, const double h[9], double step, d
       GFOR(r) { MDB_CUDA(cudaSetDevice(g->dev[r])); if (fn(r, g->eng[r], g->mol_lo[r], g->mol_lo[r + 1], g->st[r])) return -1; }
       return 0;
    };
+   // One host thread per rank once the buffers exist and every rank has a device of its own: each enqueues its whole step (the
+   // barriers are kernels, nothing in the sequence blocks), so the ~70 launches per rank and step no longer queue behind one
+   // another on one thread.  (Ranks sharing a device stay on the phase-by-phase path: a device-wide call of one rank could
+   // wait there for a barrier kernel whose partner is not enqueued yet.)
+   bool distinct = g->world > 1;
+   GFOR(r) for (int q = 0; q < r; q++) distinct = distinct && g->dev[q] != g->dev[r];
+   static const bool threads_env = !(getenv("MDB_GROUP_THREADS") && atoi(getenv("MDB_GROUP_THREADS")) == 0);
+   const bool threaded = distinct && threads_env && !rdf_counts && g->md_steps > 0;
+   g->md_steps++;
+   if (threaded) {
+      const auto &M0 = g->eng[0]->mf;
+      std::vector<int> rc(g->world, 0);
+      auto seq = [&](int r) {
+         mdb_engine *e = g->eng[r];
+         mdb_peer *p = g->peer[r];
+         cudaStream_t st = g->st[r];
+         const int lo = g->mol_lo[r], hi = g->mol_lo[r + 1];
+         auto &M = e->mf;
+         int bad = cudaSetDevice(g->dev[r]) != cudaSuccess;
+         bad = bad || mdb_md_coords_range(e, h, 0.5 * step, ts, mdb_peer_in(p), lo, hi, st) || mdb_peer_barrier(p, st) ||
+               mdb_peer_in_gather_bounds(p, 0, 3LL * M0.nmols, g->com_b, st) ||
+               (M0.nmols_q > 0 && mdb_peer_in_gather_bounds(p, 3 * (size_t)M0.nmols, 4LL * M0.nmols_q, g->quat_b, st)) ||
+               mdb_evalf_pre(e, h, mdb_peer_in(p), st) || mdb_peer_phase_a(p, what, st) || mdb_peer_barrier(p, st) ||
+               mdb_peer_phase_b(p, what, st) || mdb_peer_barrier(p, st) || mdb_peer_phase_c(p, st) ||
+               mdb_evalf_tail(e, h, mdb_peer_in(p), mdb_peer_result(p), lo, hi, surface_dipole, do_recip, st) ||
+               mdb_md_momenta_range(e, h, 0.5 * step * ts, lo, hi, st) || (half_sums && mdb_md_sums_range(e, h, 1, false, lo, hi, st)) ||
+               mdb_md_momenta_range(e, h, 0.5 * step * ts, lo, hi, st);
+         for (size_t i = 0; !bad && i < M.sp.size(); i++)
+            if (M.sp[i].framework && M.sp[i].nmols > 0)
+               bad = cudaMemsetAsync(M.d_mom + 3 * (size_t)M.mol_off[i], 0, sizeof(double) * 3 * (size_t)M.sp[i].nmols, st) != cudaSuccess;
+         bad = bad || mdb_md_coords_range(e, h, 0.5 * step, ts, mdb_peer_in(p), lo, hi, st) || mdb_md_sums_range(e, h, 0, true, lo, hi, st) ||
+               cudaMemcpyAsync(M.d_mdscal, M.d_res + 3 * (size_t)M.nmols + 3 * (size_t)M.nmols_r, sizeof(double) * MDB_EVAL_SCALARS,
+                               cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+               cudaMemcpyAsync(g->h_md + ns * (size_t)r, M.d_mdscal, sizeof(double) * ns, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+               cudaStreamSynchronize(st) != cudaSuccess;
+         rc[r] = bad;
+      };
+      std::vector<std::thread> th;
+      for (int r = 1; r < g->world; r++) th.emplace_back(seq, r);
+      seq(0);
+      for (auto &t : th) t.join();
+      GFOR(r) if (rc[r]) { if (!*mdb_last_error()) mdb_set_error("mdb_group_md_step: a rank failed"); return -1; }
+   } else {
    if (each([&](int r, mdb_engine *e, int lo, int hi, cudaStream_t st) { return mdb_md_coords_range(e, h, 0.5 * step, ts, mdb_peer_in(g->peer[r]), lo, hi, st); })) return -1;
    if (gather_state(g)) return -1;
    if (each([&](int r, mdb_engine *e, int, int, cudaStream_t st) { return mdb_evalf_pre(e, h, mdb_peer_in(g->peer[r]), st); })) return -1;
@@ -371,6 +417,7 @@ extern "C" int mdb_group_md_step(mdb_group *g, const double h[9], double step, d
       MDB_CUDA(cudaMemcpyAsync(g->h_md + ns * (size_t)r, M.d_mdscal, sizeof(double) * ns, cudaMemcpyDeviceToHost, g->st[r]));
    }
    GFOR(r) { MDB_CUDA(cudaSetDevice(g->dev[r])); MDB_CUDA(cudaStreamSynchronize(g->st[r])); }
+   }
    GFOR(r) if (mdb_peer_error(g->peer[r], g->st[r]) != 0) { mdb_set_error("mdb_group: a peer barrier timed out"); return -1; }
    // combine: energies, dipole moment and stress of the force evaluation are complete and identical on every rank, its
    // virial pieces (3..11), all sums over molecules and the bad-quaternion counts add up
