@@ -31,7 +31,7 @@ struct mdb_group {
    long long com_b[MDB_MAX_PEERS + 1] = {0}, quat_b[MDB_MAX_PEERS + 1] = {0};
    double *h_md = nullptr, *h_state = nullptr; size_t md_cap = 0, state_cap = 0;
    bool md_set = false;
-   long md_steps = 0;                                               // steps since the dynamics were set (the first one allocates)
+   long md_steps = 0, ev_calls = 0;                                 // steps / evaluations since the set-up (the first one allocates)
 };
 
 #define GFOR(r) for (int r = 0; r < g->world; r++)
@@ -179,7 +179,7 @@ extern "C" int mdb_group_set_species(mdb_group *g, int nspecies, const mdb_speci
       MDB_CUDA(cudaHostAlloc(&g->h_res, sizeof(double) * need_res, cudaHostAllocPortable));
       g->res_cap = need_res;
    }
-   g->species_set = true;
+   g->species_set = true; g->ev_calls = 0;
    return 0;
 }
 
@@ -198,6 +198,28 @@ extern "C" int mdb_group_eval_forces_host(mdb_group *g, const double h[9], const
    const size_t len_in = 3 * (size_t)M0.nmols + 4 * (size_t)M0.nmols_q, n = g->peer_n;
    const int what = 1 | (do_recip ? 2 : 0);
    if (mdb_evalf_stage_inputs(e0, com, quat, g->h_in)) return -1;
+   // one host thread per rank for the launches up to the reduce-scatter, as in mdb_group_md_step (every rank on its own GPU,
+   // buffers allocated by an earlier call, no RDF pass)
+   bool distinct = g->world > 1;
+   GFOR(r) for (int q = 0; q < r; q++) distinct = distinct && g->dev[q] != g->dev[r];
+   static const bool threads_env = !(getenv("MDB_GROUP_THREADS") && atoi(getenv("MDB_GROUP_THREADS")) == 0);
+   const bool threaded = distinct && threads_env && !rdf_counts && g->ev_calls > 0;
+   g->ev_calls++;
+   if (threaded) {
+      std::vector<int> rc(g->world, 0);
+      auto seq = [&](int r) {
+         mdb_peer *p = g->peer[r];
+         cudaStream_t st = g->st[r];
+         rc[r] = cudaSetDevice(g->dev[r]) != cudaSuccess || mdb_peer_in_host_slice(p, g->h_in, len_in, st) || mdb_peer_barrier(p, st) ||
+                 mdb_peer_in_gather(p, len_in, st) || mdb_evalf_pre(g->eng[r], h, mdb_peer_in(p), st) || mdb_peer_phase_a(p, what, st) ||
+                 mdb_peer_barrier(p, st) || mdb_peer_phase_b(p, what, st) || mdb_peer_barrier(p, st) || mdb_peer_phase_c(p, st);
+      };
+      std::vector<std::thread> th;
+      for (int r = 1; r < g->world; r++) th.emplace_back(seq, r);
+      seq(0);
+      for (auto &t : th) t.join();
+      GFOR(r) if (rc[r]) { if (!*mdb_last_error()) mdb_set_error("mdb_group_eval_forces_host: a rank failed"); return -1; }
+   } else {
    GFOR(r) if (mdb_peer_in_host_slice(g->peer[r], g->h_in, len_in, g->st[r])) return -1;
    if (barrier_all(g)) return -1;
    GFOR(r) if (mdb_peer_in_gather(g->peer[r], len_in, g->st[r])) return -1;
@@ -207,6 +229,7 @@ extern "C" int mdb_group_eval_forces_host(mdb_group *g, const double h[9], const
    GFOR(r) if (mdb_peer_phase_b(g->peer[r], what, g->st[r])) return -1;
    if (barrier_all(g)) return -1;
    GFOR(r) if (mdb_peer_phase_c(g->peer[r], g->st[r])) return -1;
+   }
    // RDF pass of force_calc (src/force.c:1302-1313) on this step's cell lists, before the second make_sites replaces the
    // sites; every rank bins its share of the batches (blocks on each rank in turn: all barriers above are enqueued)
    if (rdf_counts) GFOR(r) {
