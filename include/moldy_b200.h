@@ -235,6 +235,9 @@ long mdb_overlap_filled(mdb_engine *e);
  * lengths (exp(-r/rho) < 2.6e-23 of its amplitude for every site-type pair) are evaluated without the exponentials.  Default
  * on (MDB_PAIR_FAR=0 or mdb_set_pair_far(e, 0) before mdb_configure: every run with the full potential). */
 void mdb_set_pair_far(mdb_engine *e, int on);
+/* host only: that distance for a potential table (max_id x max_id rows of MDB_NPOTP parameters as pot_mt.p holds them) and,
+ * if rest != NULL, the power-law rest of the potential as rows of the p0/r^4 + p1/r^6 + p2/r^12 form; 0 = not applicable */
+double mdb_far_radius(int ptype, int max_id, const double *potpar, double *rest);
 int  mdb_pair_far_runs(const mdb_engine *e);   /* batches the filler drew in the last call (diagnostic; synchronises) */
 
 /* k-space cut by SITES instead of by (h,k) columns (multi-GPU, moldy_b200/spmd.py): pass 1 writes

@@ -140,7 +140,6 @@ static int upload(mdb_engine *e, T **dst, const T *src, size_t n)
 // kernel.c's forms: Buckingham -p0/r^6 + p1 exp(-p2 r); generic p0 exp(-p1 r) + p2/r^12 - p3/r^4 - p4/r^6 - p5/r^8; Morse/BIG
 // p0 exp((p1 - r) p2) - p3/r^6 + p4 (exp(-2 p5 (r - p6)) - 2 exp(-p5 (r - p6))); MCY p0 exp(-p1 r) - p2 exp(-p3 r)
 // (src/kernel.c:230-355).  PT_HIW rows are p0/r^4 + p1/r^6 + p2/r^12.
-static constexpr double FAR_EXPONENT = 52.0;    // e^-52 = 2.6e-23 of the amplitude: below rounding in every sum it enters
 static int mdb_split_far_runs(mdb_engine *e)
 {
    const mdb_config &c = e->cfg;
@@ -148,28 +147,9 @@ static int mdb_split_far_runs(mdb_engine *e)
    if (e->far_enable < 0) e->far_enable = !(getenv("MDB_PAIR_FAR") && atoi(getenv("MDB_PAIR_FAR")) == 0);
    const int pt = c.ptype, id = c.max_id;
    if (!e->far_enable || c.molpbc || e->T.runs_half.empty() || !(pt == 1 || pt == 2 || pt == 3 || pt == 6)) return 0;
-   double r_far = 0.0;
-   bool any = false;
    std::vector<double> far(e->h_potpar.size(), 0.0);
-   for (int a = 0; a < id; a++)
-      for (int b = 0; b < id; b++) {
-         const double *p = &e->h_potpar[((size_t)a * id + b) * MDB_NPOTP];
-         double *q = &far[((size_t)a * id + b) * MDB_NPOTP];
-         auto term = [&](double amp, double decay, double shift) {         // amp exp(-decay (r - shift))
-            if (amp == 0.0) return true;
-            if (!(decay > 0.0)) return false;
-            r_far = std::max(r_far, shift + FAR_EXPONENT / decay);
-            any = true;
-            return true;
-         };
-         bool ok = true;
-         if (pt == 1) { ok = term(p[1], p[2], 0.0); q[1] = -p[0]; }
-         else if (pt == 2) { ok = term(p[0], p[1], 0.0) && term(p[2], p[3], 0.0); }
-         else if (pt == 3) { ok = term(p[0], p[1], 0.0) && p[5] == 0.0; q[0] = -p[3]; q[1] = -p[4]; q[2] = p[2]; }
-         else { ok = term(p[0], p[2], p[1]) && term(p[4], p[5], p[6]); q[1] = -p[3]; }
-         if (!ok) return 0;
-      }
-   if (!any) return 0;
+   const double r_far = mdb_far_radius(pt, id, e->h_potpar.data(), far.data());
+   if (!(r_far > 0.0)) return 0;
    // lower bound of the distance between a point of a cell and a point of the cell (dx,dy,dz) away: |h d| - longest diagonal
    const double inv[3] = {1.0 / e->T.nx, 1.0 / e->T.ny, 1.0 / e->T.nz};
    auto len = [&](double x, double y, double z) {

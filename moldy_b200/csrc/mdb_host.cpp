@@ -339,3 +339,36 @@ bool mdb_build_recip_tables(const mdb_config &c, HostTables &T, std::string &err
    (void)err;
    return true;
 }
+
+// Distance beyond which every exponential of an exponential pair potential (src/kernel.c:230-355) has fallen below
+// e^-52 = 2.6e-23 of its amplitude for all site-type pairs, and the power-law rest of the potential as PT_HIW rows
+// (p0/r^4 + p1/r^6 + p2/r^12) in `rest` (max_id^2 x MDB_NPOTP, may be NULL).  0: not applicable (no exponential term, a
+// non-positive decay constant, or a term the rows cannot express).  Host only; mdb_split_far_runs (mdb_engine.cu) uses it.
+//   Buckingham -p0/r^6 + p1 exp(-p2 r); MCY p0 exp(-p1 r) - p2 exp(-p3 r); generic p0 exp(-p1 r) + p2/r^12 - p3/r^4 - p4/r^6
+//   - p5/r^8; Morse/BIG p0 exp((p1 - r) p2) - p3/r^6 + p4 (exp(-2 p5 (r - p6)) - 2 exp(-p5 (r - p6)))
+extern "C" double mdb_far_radius(int ptype, int max_id, const double *potpar, double *rest)
+{
+   const double FAR_EXPONENT = 52.0;
+   if (!(ptype == 1 || ptype == 2 || ptype == 3 || ptype == 6) || max_id <= 0 || !potpar) return 0.0;
+   double r_far = 0.0;
+   bool any = false;
+   for (int a = 0; a < max_id; a++)
+      for (int b = 0; b < max_id; b++) {
+         const double *p = potpar + ((size_t)a * max_id + b) * MDB_NPOTP;
+         double q[MDB_NPOTP] = {0};
+         bool ok = true;
+         auto term = [&](double amp, double decay, double shift) {         // amp exp(-decay (r - shift))
+            if (amp == 0.0) return;
+            if (!(decay > 0.0)) { ok = false; return; }
+            r_far = std::max(r_far, shift + FAR_EXPONENT / decay);
+            any = true;
+         };
+         if (ptype == 1) { term(p[1], p[2], 0.0); q[1] = -p[0]; }
+         else if (ptype == 2) { term(p[0], p[1], 0.0); term(p[2], p[3], 0.0); }
+         else if (ptype == 3) { term(p[0], p[1], 0.0); ok = ok && p[5] == 0.0; q[0] = -p[3]; q[1] = -p[4]; q[2] = p[2]; }
+         else { term(p[0], p[2], p[1]); term(p[4], p[5], p[6]); q[1] = -p[3]; }
+         if (!ok) return 0.0;
+         if (rest) memcpy(rest + ((size_t)a * max_id + b) * MDB_NPOTP, q, sizeof q);
+      }
+   return any ? r_far : 0.0;
+}

@@ -79,3 +79,41 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("oracle/", "ORACLE_DOC/") or f in ("systems.py",), f
+
+
+def test_far_radius_of_the_exponential_potentials():
+    """mdb_far_radius (host only): the distance beyond which exp(-r/rho) is below e^-52 of its amplitude for every
+    site-type pair, and the power-law rest of the potential as p0/r^4 + p1/r^6 + p2/r^12 rows (far-run launch)."""
+    import ctypes as C
+    import numpy as np
+    L = lib.load()
+    L.mdb_far_radius.restype = C.c_double
+    L.mdb_far_radius.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    NP = 8
+
+    def call(ptype, rows):
+        mid = int(round(len(rows) ** 0.5))
+        pot = np.zeros((mid * mid, NP))
+        for k, r in enumerate(rows):
+            pot[k, :len(r)] = r
+        rest = np.full((mid * mid, NP), np.nan)
+        return L.mdb_far_radius(ptype, mid, pot.ctypes.data, rest.ctypes.data), rest
+
+    # Buckingham (ptype 1): -p0/r^6 + p1 exp(-p2 r); the slowest decay of a pair WITH an exponential sets the radius
+    r, rest = call(1, [(0, 0, 0), (133.5, 18003.0, 4.873), (133.5, 18003.0, 4.873), (175.0, 1388.8, 2.76)])
+    assert abs(r - 52.0 / 2.76) < 1e-12
+    assert np.array_equal(rest[3, :3], [0.0, -175.0, 0.0]) and np.array_equal(rest[0], np.zeros(NP))
+    # no exponential anywhere, a zero decay constant with an amplitude, or a non-exponential potential type: not applicable
+    assert call(1, [(1.0, 0.0, 0.0)])[0] == 0.0
+    assert call(1, [(1.0, 5.0, 0.0)])[0] == 0.0
+    assert call(0, [(1.0, 3.0)])[0] == 0.0 and call(4, [(1.0, 1.0, 1.0)])[0] == 0.0
+    # MCY (2): both exponentials count, nothing is left of the potential beyond
+    r, rest = call(2, [(1.0e6, 5.15, 0.0, 0.0), (600.0, 2.76, 270.0, 2.23), (600.0, 2.76, 270.0, 2.23), (0, 0, 0, 0)])
+    assert abs(r - 52.0 / 2.23) < 1e-12 and not rest.any()
+    # generic (3): p0 exp(-p1 r) + p2/r^12 - p3/r^4 - p4/r^6 - p5/r^8 -> rows (-p3, -p4, p2); an r^-8 term cannot be expressed
+    r, rest = call(3, [(10.0, 4.0, 7.0, 3.0, 5.0, 0.0)])
+    assert abs(r - 13.0) < 1e-12 and np.array_equal(rest[0, :3], [-3.0, -5.0, 7.0])
+    assert call(3, [(10.0, 4.0, 7.0, 3.0, 5.0, 1.0)])[0] == 0.0
+    # Morse / BIG (6): p0 exp((p1 - r) p2) - p3/r^6 + p4 (exp(-2 p5 (r - p6)) - 2 exp(-p5 (r - p6)))
+    r, rest = call(6, [(2.0, 3.0, 6.0, 11.0, 0.5, 2.0, 1.5)])
+    assert abs(r - max(3.0 + 52.0 / 6.0, 1.5 + 52.0 / 2.0)) < 1e-12 and np.array_equal(rest[0, :3], [0.0, -11.0, 0.0])
