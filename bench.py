@@ -482,7 +482,14 @@ def run_ours(a):
                 "avg_launch_ms": pair_ms, "split_passes": bool(split),
                 "traffic": traffic["pair_bytes"] if traffic else None,
                 "traffic_source": traffic["source"] if traffic else "no ncu capture of this workload committed (profiles/traffic.json)",
-                "hbm_peak_gbs_measured": peaks.get("hbm_gbs")}
+                "hbm_peak_gbs_measured": peaks.get("hbm_gbs"),
+                "instruction_accounting": {
+                    "source": "static: SASS of the hot loops + ncu captures of round 2 (profiles/r02_summary.md), not measured in this run",
+                    "fp64_instructions_per_visit": {"coulomb_only": 48.8, "lennard_jones_only": 27.3, "buckingham_coulomb": 68.8, "mcy_only": 52.3},
+                    "masked_visit_fraction": 0.12,
+                    "fp64_pipe_cycles_over_elapsed": "0.82-0.86 for the Coulomb pass (195 FP64 instructions per 128 visits weighted 3.2 / 2.15 / "
+                                                     "2.32 cycles by operand count, of 573 cycles per step); running the pair kernel beside the "
+                                                     "k-space GEMMs on the same SMs conserves total time (profiles/r02_overlap_probe.txt)"}}
         line = {"metric": "md_force_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
