@@ -503,6 +503,7 @@ extern "C" int mdb_kforce_slices(const mdb_engine *e, void **events, int *site_h
 extern "C" int mdb_force_recip(mdb_engine *e, double *d_out, void *stream)
 {
    if (!e->configured || !e->sites_set) { mdb_set_error("mdb_force_recip: engine not configured / no sites"); return -1; }
+   e->kf_nch = 0;
    if (!e->cfg.do_recip) return 0;
    return mdb_launch_recip(e, d_out, (cudaStream_t)stream);
 }

@@ -323,16 +323,52 @@ extern "C" int mdb_group_md_set_dynamics(mdb_group *g, const mdb_species_dyn *dy
    return 0;
 }
 
+// pinned staging block of the group: [c-of-m 3 nmols | quaternions 4 nmols_q | mom 3 nmols | amom 4 nmols_q | force | torque]
+static int group_state_block(mdb_group *g, size_t off[6])
+{
+   const auto &M0 = g->eng[0]->mf;
+   const size_t nm = (size_t)M0.nmols, nq = (size_t)M0.nmols_q, nr = (size_t)M0.nmols_r;
+   off[0] = 0; off[1] = 3 * nm; off[2] = off[1] + 4 * nq; off[3] = off[2] + 3 * nm; off[4] = off[3] + 4 * nq; off[5] = off[4] + 3 * nm;
+   const size_t need = off[5] + 3 * nr + 8;
+   if (need > g->state_cap) {
+      if (g->h_state) cudaFreeHost(g->h_state);
+      g->h_state = nullptr; g->state_cap = 0;
+      MDB_CUDA(cudaHostAlloc(&g->h_state, sizeof(double) * need, cudaHostAllocPortable));
+      g->state_cap = need;
+   }
+   return 0;
+}
+
+// The caller's per-species arrays are staged ONCE in pinned memory (six host threads); every rank then copies the block over
+// its own PCIe link, all ranks at the same time.
 extern "C" int mdb_group_md_upload_state(mdb_group *g, const double *const *com, const double *const *quat, const double *const *mom,
                                          const double *const *amom)
 {
    if (!g->md_set) { mdb_set_error("mdb_group_md_upload_state: mdb_group_md_set_dynamics was not called"); return -1; }
    const auto &M0 = g->eng[0]->mf;
-   const size_t len_in = 3 * (size_t)M0.nmols + 4 * (size_t)M0.nmols_q;
+   const size_t nm = (size_t)M0.nmols, nq = (size_t)M0.nmols_q;
+   size_t off[6];
+   if (group_state_block(g, off)) return -1;
+   double *hs = g->h_state;
+   std::vector<MdbCopyJob> jobs;
+   for (size_t i = 0; i < M0.sp.size(); i++) {
+      const size_t n = (size_t)M0.sp[i].nmols;
+      if (n == 0) continue;
+      jobs.push_back({hs + off[0] + 3 * (size_t)M0.mol_off[i], com[i], sizeof(double) * 3 * n});
+      jobs.push_back({hs + off[2] + 3 * (size_t)M0.mol_off[i], mom[i], sizeof(double) * 3 * n});
+      if (M0.quat_off[i] >= 0) {
+         if (!quat || !quat[i]) { mdb_set_error("mdb_group_md_upload_state: quaternions missing"); return -1; }
+         jobs.push_back({hs + off[1] + 4 * (size_t)M0.quat_off[i], quat[i], sizeof(double) * 4 * n});
+         jobs.push_back({hs + off[3] + 4 * (size_t)M0.quat_off[i], amom && amom[i] ? amom[i] : nullptr, sizeof(double) * 4 * n});
+      }
+   }
+   mdb_run_copy_jobs(jobs);
    GFOR(r) {
+      auto &M = g->eng[r]->mf;
       MDB_CUDA(cudaSetDevice(g->dev[r]));
-      if (mdb_md_upload_state(g->eng[r], com, quat, mom, amom, g->st[r])) return -1;
-      MDB_CUDA(cudaMemcpyAsync(mdb_peer_in(g->peer[r]), g->eng[r]->mf.d_in, sizeof(double) * len_in, cudaMemcpyDeviceToDevice, g->st[r]));
+      MDB_CUDA(cudaMemcpyAsync(mdb_peer_in(g->peer[r]), hs + off[0], sizeof(double) * (3 * nm + 4 * nq), cudaMemcpyHostToDevice, g->st[r]));
+      MDB_CUDA(cudaMemcpyAsync(M.d_mom, hs + off[2], sizeof(double) * 3 * nm, cudaMemcpyHostToDevice, g->st[r]));
+      if (nq) MDB_CUDA(cudaMemcpyAsync(M.d_amom, hs + off[3], sizeof(double) * 4 * nq, cudaMemcpyHostToDevice, g->st[r]));
    }
    GFOR(r) { MDB_CUDA(cudaSetDevice(g->dev[r])); MDB_CUDA(cudaStreamSynchronize(g->st[r])); }
    return 0;
@@ -469,15 +505,9 @@ extern "C" int mdb_group_md_download_state(mdb_group *g, double *const *com, dou
 {
    if (!g->md_set) { mdb_set_error("mdb_group_md_download_state: group not configured"); return -1; }
    const auto &M0 = g->eng[0]->mf;
-   const size_t nm = (size_t)M0.nmols, nq = (size_t)M0.nmols_q, nr = (size_t)M0.nmols_r;
-   const size_t off[6] = {0, 3 * nm, 3 * nm + 4 * nq, 6 * nm + 4 * nq, 6 * nm + 8 * nq, 9 * nm + 8 * nq};
-   const size_t need = off[5] + 3 * nr + 8;
-   if (need > g->state_cap) {
-      if (g->h_state) cudaFreeHost(g->h_state);
-      g->h_state = nullptr; g->state_cap = 0;
-      MDB_CUDA(cudaHostAlloc(&g->h_state, sizeof(double) * need, cudaHostAllocPortable));
-      g->state_cap = need;
-   }
+   const size_t nm = (size_t)M0.nmols;
+   size_t off[6];
+   if (group_state_block(g, off)) return -1;
    double *hs = g->h_state;
    GFOR(r) {
       auto &M = g->eng[r]->mf;

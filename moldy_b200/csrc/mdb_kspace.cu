@@ -1117,6 +1117,7 @@ static int recip_partial(mdb_engine *e, const RecipPlan &P, double *d_psum, cuda
 static int recip_finish(mdb_engine *e, const RecipPlan &P, const double *d_psum, double *d_out, cudaStream_t st)
 {
    const mdb_config &c = e->cfg;
+   e->kf_nch = 0;                                   // (slices of the force kernel: set again below when it is cut)
    const HostTables &T = e->T;
    SfinArgs F;
    kspace_params(e, F.K);
