@@ -682,6 +682,7 @@ extern "C" double dist_pot(real *p, double rc, int ptype)
    switch (ptype) {
       default:
          FATAL_MSG("KERNEL called with unknown potential type %d", ptype);
+         return 0.0;                                       /* (a host whose message() returns) */
       case 0: { double s2 = p[1] * p[1] / rc; return p[0] * s2 * s2 * s2 / 3.0; }
       case 1:
          if (p[2] > tol) return p[0] / (3.0 * rc3) - p[1] * exp(-p[2] * rc) * exp_tail(p[2]);
